@@ -1,0 +1,252 @@
+"""Host-side mirror of the reference's five stage wrappers + frame driver, over the C ABI (include/pcop.h).
+
+Method names follow the reference's free functions (minibot_cr18/src/obstacle_detection.cpp):
+  crop                         <- build_initial_occupancy_grid_dataset crop loop   (od.cpp:195-215)
+  downsample_cloud             <- downsample_cloud                                 (od.cpp:271-296)
+  remove_statistical_outliers  <- remove_statistical_outliers                      (od.cpp:316-340)
+  segment_plane_and_extract_indices <- same name                                   (od.cpp:342-428)
+  extract_euclidian_clusters   <- same name (sic)                                  (od.cpp:430-455)
+  centroid_radius              <- PointWithRad/PointIndicesArray output            (msg/*.msg, od.cpp:806-814)
+  process / process_batch      <- cloud_cb's process branch                        (od.cpp:699-927)
+
+There is no CPU fallback: constructing an ObstacleProcessor without a usable B200-class device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _ctypes_abi as abi
+from ._ctypes_abi import FrameResult, Params
+from .result import Frame
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcop.so")
+_lib = None
+
+EXPORTS = [
+    "pcop_abi_version", "pcop_global_error", "pcop_last_error", "pcop_params_init_code_defaults",
+    "pcop_params_init_params_yaml", "pcop_create", "pcop_destroy", "pcop_set_params", "pcop_process",
+    "pcop_process_batch", "pcop_last_elapsed_us", "pcop_stage_times_us", "pcop_last_launch_count",
+    "pcop_last_algorithmic_bytes", "pcop_crop", "pcop_voxel", "pcop_sor", "pcop_plane", "pcop_cluster",
+    "pcop_centroid_radius",
+]
+
+
+class PcopError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"pcop status {status}: {message}")
+        self.status = status
+
+
+def load_library():
+    """Load libpcop.so (building it in-tree if missing).  Raises if the CUDA library cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from ._build import build_cuda
+        build_cuda()
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint32
+    pi32, pu32 = C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
+    L.pcop_abi_version.restype = C.c_int
+    L.pcop_global_error.restype = C.c_char_p
+    L.pcop_last_error.restype = C.c_char_p
+    L.pcop_last_error.argtypes = [vp]
+    L.pcop_params_init_code_defaults.argtypes = [C.POINTER(Params)]
+    L.pcop_params_init_params_yaml.argtypes = [C.POINTER(Params)]
+    L.pcop_create.argtypes = [C.POINTER(Params), C.c_int, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.pcop_destroy.argtypes = [vp]
+    L.pcop_set_params.argtypes = [vp, C.POINTER(Params)]
+    L.pcop_process.argtypes = [vp, vp, i32, C.POINTER(FrameResult)]
+    L.pcop_process_batch.argtypes = [vp, vp, C.c_size_t, vp, i32, C.POINTER(FrameResult)]
+    L.pcop_last_elapsed_us.restype = C.c_float
+    L.pcop_last_elapsed_us.argtypes = [vp]
+    L.pcop_stage_times_us.argtypes = [vp, C.POINTER(C.c_float)]
+    L.pcop_last_launch_count.restype = C.c_int64
+    L.pcop_last_launch_count.argtypes = [vp]
+    L.pcop_last_algorithmic_bytes.restype = C.c_double
+    L.pcop_last_algorithmic_bytes.argtypes = [vp]
+    L.pcop_crop.argtypes = [vp, vp, i32, vp, vp, pi32]
+    L.pcop_voxel.argtypes = [vp, vp, i32, vp, vp, pi32, pu32]
+    L.pcop_sor.argtypes = [vp, vp, i32, vp, vp, pi32, pu32]
+    L.pcop_plane.argtypes = [vp, vp, i32, vp, vp, pi32, pi32, vp, vp, vp, vp, vp, pi32, pu32]
+    L.pcop_cluster.argtypes = [vp, vp, i32, vp, vp, pi32, pi32]
+    L.pcop_centroid_radius.argtypes = [vp, vp, i32, vp, vp, i32, vp]
+    _lib = L
+    return L
+
+
+def params_yaml() -> Params:
+    """Parameter values of the reference's minibot_cr18/params.yaml."""
+    p = Params()
+    load_library().pcop_params_init_params_yaml(C.byref(p))
+    return p
+
+
+def params_code_defaults() -> Params:
+    """Defaults of the nh.param(...) calls at od.cpp:940-975."""
+    p = Params()
+    load_library().pcop_params_init_code_defaults(C.byref(p))
+    return p
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("cloud must be [n, 4] float32 (pcl::PointXYZ layout)")
+    return a
+
+
+class ObstacleProcessor:
+    """One handle = one device = one caller at a time (the reference node is single-threaded, od.cpp:1014)."""
+
+    def __init__(self, params: Params, max_points: int, max_batch: int = 1, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.params = params.copy()
+        self.max_points, self.max_batch, self.device = int(max_points), int(max_batch), int(device)
+        st = self._lib.pcop_create(C.byref(self.params), device, max_points, max_batch, C.byref(self._h))
+        if st != abi.OK:
+            raise PcopError(st, (self._lib.pcop_global_error() or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.pcop_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st):
+        if st != abi.OK:
+            raise PcopError(st, (self._lib.pcop_last_error(self._h) or b"").decode())
+
+    def set_params(self, params: Params):
+        self._check(self._lib.pcop_set_params(self._h, C.byref(params)))
+        self.params = params.copy()
+
+    # ---- whole pipeline ------------------------------------------------------------
+    def process(self, cloud) -> Frame:
+        cloud = _f32(cloud)
+        r = FrameResult()
+        self._check(self._lib.pcop_process(self._h, cloud.ctypes.data_as(C.c_void_p), cloud.shape[0], C.byref(r)))
+        return Frame.from_c(r)
+
+    def process_batch_raw(self, ptr: int, frame_stride_points: int, counts: np.ndarray):
+        """Frames at a raw host or device address; returns the ctypes result array (valid until the next call)."""
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        res = (FrameResult * len(counts))()
+        self._check(self._lib.pcop_process_batch(self._h, C.c_void_p(ptr), frame_stride_points,
+                                                 counts.ctypes.data_as(C.c_void_p), len(counts), res))
+        return res
+
+    def process_batch(self, clouds, counts=None):
+        """clouds: float32 [B, n, 4] (host).  Returns a list of Frame."""
+        clouds = np.ascontiguousarray(clouds, dtype=np.float32)
+        assert clouds.ndim == 3 and clouds.shape[2] == 4
+        if counts is None:
+            counts = np.full(clouds.shape[0], clouds.shape[1], np.int32)
+        res = self.process_batch_raw(clouds.ctypes.data, clouds.shape[1], counts)
+        return [Frame.from_c(r) for r in res]
+
+    # ---- timing / accounting of the last call ----------------------------------------
+    @property
+    def last_elapsed_us(self) -> float:
+        return float(self._lib.pcop_last_elapsed_us(self._h))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._lib.pcop_last_launch_count(self._h))
+
+    @property
+    def last_algorithmic_bytes(self) -> float:
+        return float(self._lib.pcop_last_algorithmic_bytes(self._h))
+
+    def stage_times_us(self):
+        us = (C.c_float * len(abi.STAGE_NAMES))()
+        self._check(self._lib.pcop_stage_times_us(self._h, us))
+        return dict(zip(abi.STAGE_NAMES, [float(x) for x in us]))
+
+    # ---- the five wrappers, stage-isolated -------------------------------------------
+    def crop(self, cloud):
+        cloud = _f32(cloud)
+        n = cloud.shape[0]
+        out = np.empty((max(n, 1), 4), np.float32)
+        kept = np.empty(max(n, 1), np.int32)
+        m = C.c_int32()
+        self._check(self._lib.pcop_crop(self._h, cloud.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p),
+                                        kept.ctypes.data_as(C.c_void_p), C.byref(m)))
+        return out[:m.value].copy(), kept[:m.value].copy()
+
+    def downsample_cloud(self, cloud):
+        cloud = _f32(cloud)
+        n = cloud.shape[0]
+        out = np.empty((max(n, 1), 4), np.float32)
+        keys = np.empty(max(n, 1), np.uint32)
+        v, w = C.c_int32(), C.c_uint32()
+        self._check(self._lib.pcop_voxel(self._h, cloud.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p),
+                                         keys.ctypes.data_as(C.c_void_p), C.byref(v), C.byref(w)))
+        return out[:v.value].copy(), keys[:v.value].copy(), w.value
+
+    def remove_statistical_outliers(self, cloud):
+        cloud = _f32(cloud)
+        n = cloud.shape[0]
+        out = np.empty((max(n, 1), 4), np.float32)
+        kept = np.empty(max(n, 1), np.int32)
+        s, w = C.c_int32(), C.c_uint32()
+        self._check(self._lib.pcop_sor(self._h, cloud.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p),
+                                       kept.ctypes.data_as(C.c_void_p), C.byref(s), C.byref(w)))
+        return out[:s.value].copy(), kept[:s.value].copy(), w.value
+
+    def segment_plane_and_extract_indices(self, cloud):
+        cloud = _f32(cloud)
+        n = cloud.shape[0]
+        vp = C.c_void_p
+        rem = np.empty((max(n, 1), 4), np.float32)
+        src = np.empty(max(n, 1), np.int32)
+        inl = np.empty(max(n, 1), np.int32)
+        pp = np.zeros(abi.MAX_PASSES, np.int32)
+        pi = np.zeros(abi.MAX_PASSES, np.int32)
+        pc = np.zeros((abi.MAX_PASSES, 4), np.float32)
+        lc = np.zeros(4, np.float32)
+        p, npass, ninl, w = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint32()
+        self._check(self._lib.pcop_plane(self._h, cloud.ctypes.data_as(vp), n, rem.ctypes.data_as(vp),
+                                         src.ctypes.data_as(vp), C.byref(p), C.byref(npass), pp.ctypes.data_as(vp),
+                                         pi.ctypes.data_as(vp), pc.ctypes.data_as(vp), lc.ctypes.data_as(vp),
+                                         inl.ctypes.data_as(vp), C.byref(ninl), C.byref(w)))
+        return dict(remaining=rem[:p.value].copy(), src=src[:p.value].copy(), n_passes=npass.value, pass_points=pp,
+                    pass_inliers=pi, pass_coeff=pc, last_coeff=lc, inliers=inl[:ninl.value].copy(), warnings=w.value)
+
+    def extract_euclidian_clusters(self, cloud):
+        cloud = _f32(cloud)
+        n = cloud.shape[0]
+        offs = np.zeros(n + 2, np.int32)
+        idx = np.zeros(n + 1, np.int32)
+        c, l = C.c_int32(), C.c_int32()
+        self._check(self._lib.pcop_cluster(self._h, cloud.ctypes.data_as(C.c_void_p), n,
+                                           offs.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p),
+                                           C.byref(c), C.byref(l)))
+        return offs[:c.value + 1].copy(), idx[:l.value].copy()
+
+    def centroid_radius(self, cloud, offsets, indices):
+        cloud = _f32(cloud)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        indices = np.ascontiguousarray(indices, np.int32)
+        c = len(offsets) - 1
+        out = np.zeros((max(c, 1), 4), np.float32)
+        self._check(self._lib.pcop_centroid_radius(self._h, cloud.ctypes.data_as(C.c_void_p), cloud.shape[0],
+                                                   offsets.ctypes.data_as(C.c_void_p),
+                                                   indices.ctypes.data_as(C.c_void_p), c,
+                                                   out.ctypes.data_as(C.c_void_p)))
+        return out[:c].copy()

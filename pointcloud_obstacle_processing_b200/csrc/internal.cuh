@@ -1,0 +1,147 @@
+// Host-side interfaces between the stage translation units.
+#pragma once
+#include "common.cuh"
+
+struct pcop_handle;
+
+namespace pcop {
+
+// records the error text in the handle (and the thread's global error slot); returns PCOP_ERR_CUDA
+int fail_cuda(pcop_handle* h, cudaError_t e, const char* expr, const char* file, int line);
+
+struct Ctx {
+  cudaStream_t stream;
+  int B;    // frames in the wave
+  int cap;  // per-frame capacity (points)
+  int64_t* launches;
+};
+
+inline void count_launch(const Ctx& c, int n = 1) { *c.launches += n; }
+
+// ---- batched stable LSD radix sort of (key32, val32) pairs ---------------------
+struct SortBufs {
+  uint32_t* key[2];  // [B*cap] ping-pong
+  uint32_t* val[2];
+  uint32_t* hist;    // [B][RS_MAX_PASSES][RS_BINS]  (becomes exclusive bin bases)
+  uint32_t* desc;    // [RS_MAX_PASSES][B][tiles][RS_BINS] look-back descriptors
+  uint32_t* maxkey;  // [B]  written (atomicMax) by the kernel that produced the keys
+  int* npass;        // [B]  passes actually needed for this frame (>= 1)
+};
+size_t sort_desc_bytes(int B, int cap);
+// Sorts frame f's `count[f]` pairs that sit in key[0]/val[0] (val[0] is ignored and taken as
+// 0..count-1 when iota_vals).  Frame f's result is in key[npass[f]&1] / val[npass[f]&1].
+void radix_sort_batched(const Ctx& c, const SortBufs& s, const int* count, bool iota_vals);
+// zero maxkey before a key-producing kernel
+void sort_reset_maxkey(const Ctx& c, const SortBufs& s);
+
+// ---- stages ---------------------------------------------------------------------
+struct CropArgs {
+  const float4* in;
+  size_t in_stride;  // points between frames of `in`
+  const int* n_in;   // [B]
+  float4* out;       // [B*cap]
+  int* kept_idx;     // [B*cap]
+  int* n_out;        // [B]
+  MinMax* minmax;    // [B] of the kept points
+  unsigned* desc;    // [B*tiles] compaction descriptors (zeroed here)
+  float lim[6];      // x_min,x_max,y_min,y_max,z_min,z_max
+};
+void run_crop(const Ctx& c, const CropArgs& a);
+
+// min/max of an arbitrary frame-strided cloud (used when crop is disabled and by ECE)
+void run_minmax(const Ctx& c, const float4* pts, size_t stride, const int* n, MinMax* minmax);
+
+struct VoxelArgs {
+  const float4* in;  // [B*stride]
+  size_t in_stride;
+  const int* n_in;
+  const MinMax* minmax;
+  float leaf;
+  VoxelFrame* vf;      // [B]
+  SortBufs sort;
+  unsigned* desc;      // compaction descriptors [B*tiles]
+  int* run_start;      // [B*cap]
+  float4* out;         // [B*cap]
+  uint32_t* out_keys;  // [B*cap]
+  int* n_out;          // [B]
+  uint32_t* warnings;  // [B]
+};
+void run_voxel(const Ctx& c, const VoxelArgs& a);
+
+// Uniform grid over a frame-strided cloud: cell >= `cell`*(1+2^-8) per axis (<= 1024 cells per axis),
+// points radix-sorted by cell key; sorted_pts[j] = {x,y,z, original index}.  parent/csize (optional)
+// are initialised for the union-find.  Sorted keys: sort.key[sort.npass[f]&1].
+void run_grid_sort(const Ctx& c, const float4* in, size_t in_stride, const int* n_in, float cell, MinMax* minmax,
+                   EceFrame* ef, const SortBufs& sort, float4* sorted_pts, int* parent, int* csize);
+
+struct SorArgs {
+  const float4* in;
+  size_t in_stride;
+  const int* n_in;
+  int meanK;
+  double mul;
+  float cell;  // grid cell for the k-NN search (speed only)
+  MinMax* minmax;
+  EceFrame* gf;
+  SortBufs sort;
+  float4* sorted_pts;  // [B*cap]
+  float* dist;         // [B*cap] mean k-NN distance per point (original order)
+  double* partial;     // [B][chunks][2]
+  double* thr;         // [B]
+  unsigned* desc;
+  float4* out;
+  int* kept_idx;
+  int* n_out;
+  uint32_t* warnings;
+};
+void run_sor(const Ctx& c, const SorArgs& a);
+
+struct PlaneArgs {
+  const float4* in;  // plane-loop input (S points per frame)
+  size_t in_stride;
+  const int* n_in;
+  float4* buf[2];  // [B*cap] ping-pong clouds
+  int* src[2];     // [B*cap] index into `in` of each remaining point
+  int* inlier_idx; // [B*cap] last pass' inliers
+  PlaneFrame* pf;  // [B]
+  double* partial; // [B][chunks][10]
+  unsigned* desc;  // compaction descriptors
+  int* n_tmp;      // [B] count written by the extraction
+  int* n_active;   // device counter (one int per pass slot, [64])
+  int* h_n_active; // pinned host mirror
+  const int* rng;  // [RNG_TABLE] rnd() values
+  PlaneConst pc;
+  uint32_t* warnings;
+  // outputs
+  int* n_out;  // [B] remaining count
+};
+// returns cudaSuccess or the first failing runtime error (synchronises once per pass)
+cudaError_t run_plane(const Ctx& c, const PlaneArgs& a);
+// copies each frame's remaining cloud (planar_cloud_y) + source indices out of the ping-pong buffers
+void run_plane_finalize(const Ctx& c, const PlaneArgs& a, float4* out, int* out_src);
+
+struct ClusterArgs {
+  const float4* in;  // remaining cloud, frame f at in + f*in_stride
+  size_t in_stride;
+  const int* n_in;
+  float tol;
+  int min_size, max_size;
+  MinMax* minmax;
+  EceFrame* ef;
+  SortBufs sort;
+  float4* sorted_pts;  // [B*cap] xyz + original index in w
+  int* parent;         // [B*cap]
+  int* csize;          // [B*cap]
+  int* roots;          // [B*cap]
+  int* rank_of;        // [B*cap]
+  unsigned* desc;
+  int* offsets;  // [B*(cap+1)]
+  int* indices;  // [B*cap]
+  int* n_clusters;
+  int* n_cluster_pts;
+  float4* obstacles;  // [B*cap]
+};
+void run_cluster(const Ctx& c, const ClusterArgs& a);
+void run_centroid_radius(const Ctx& c, const ClusterArgs& a);
+
+}  // namespace pcop

@@ -1,0 +1,1135 @@
+// C ABI of the library (include/pcop.h): handle, memory, wave scheduling, result packing.
+//
+// A call processes its frames in waves of up to max_batch frames.  Within a wave every stage
+// is one set of launches over all frames (blockIdx.y = frame); the only host synchronisations
+// are one per RANSAC pass (the loop count is data dependent, od.cpp:379) and two for the
+// result copy (sizes, then payload).  Requested outputs of all frames of a wave are packed on
+// the device into one contiguous buffer and come back in a single device->host copy.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "internal.cuh"
+#include "primitives.cuh"
+
+using namespace pcop;
+
+namespace {
+
+enum {  // rows of the per-frame count table (device: d_counts[row*maxB + f])
+  CNT_IN = 0,
+  CNT_CROP,
+  CNT_VOX,
+  CNT_SOR,
+  CNT_REM,
+  CNT_CLUS,
+  CNT_CLPTS,
+  CNT_TMP,
+  CNT_NINL,   // inliers of the last segment() call
+  CNT_CLUS1,  // C + 1 (CSR offsets length)
+  CNT_ROWS
+};
+
+enum {  // packed output arrays
+  PK_CROP_KEPT = 0,
+  PK_VOX_KEYS,
+  PK_VOX_PTS,
+  PK_SOR_KEPT,
+  PK_INLIERS,
+  PK_REM_PTS,
+  PK_REM_SRC,
+  PK_OFFSETS,
+  PK_INDICES,
+  PK_OBSTACLES,
+  PK_N
+};
+const int kPkElem[PK_N] = {4, 4, 16, 4, 4, 16, 4, 4, 4, 16};
+const int kPkCount[PK_N] = {CNT_CROP, CNT_VOX, CNT_VOX, CNT_SOR, CNT_NINL, CNT_REM, CNT_REM, CNT_CLUS1, CNT_CLPTS, CNT_CLUS};
+const uint32_t kPkMask[PK_N] = {PCOP_OUT_CROP,      PCOP_OUT_VOXEL,     PCOP_OUT_VOXEL,    PCOP_OUT_SOR,
+                                PCOP_OUT_PLANE,     PCOP_OUT_REMAINING, PCOP_OUT_REMAINING, PCOP_OUT_CLUSTERS,
+                                PCOP_OUT_CLUSTERS,  PCOP_OUT_OBSTACLES};
+
+struct PlaneRecord {
+  int n_passes;
+  int n_inliers_last;
+  float4 coeff;
+  int pass_points[PCOP_MAX_PLANE_PASSES_RECORDED];
+  int pass_inliers[PCOP_MAX_PLANE_PASSES_RECORDED];
+  float4 pass_coeff[PCOP_MAX_PLANE_PASSES_RECORDED];
+};
+
+struct PackMeta {  // device -> host in one copy
+  unsigned long long base[PK_N];  // byte offset of each array inside the pack buffer
+  unsigned long long total_bytes;
+  int total[PK_N];  // elements
+};
+
+thread_local std::string g_global_error;
+
+}  // namespace
+
+struct pcop_handle {
+  pcop_params params;
+  int device = 0;
+  int cap = 0;
+  int maxB = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::vector<void*> dev_allocs;
+  std::vector<void*> host_allocs;
+
+  // device
+  float4 *d_in = nullptr, *d_crop = nullptr, *d_vox = nullptr, *d_sor = nullptr, *d_pbuf[2] = {nullptr, nullptr},
+         *d_rem = nullptr, *d_sorted = nullptr, *d_obst = nullptr;
+  int *d_crop_kept = nullptr, *d_run_start = nullptr, *d_sor_kept = nullptr, *d_psrc[2] = {nullptr, nullptr},
+      *d_rem_src = nullptr, *d_inliers = nullptr, *d_parent = nullptr, *d_csize = nullptr, *d_roots = nullptr,
+      *d_rank = nullptr, *d_indices = nullptr, *d_offsets = nullptr;
+  uint32_t* d_vox_keys = nullptr;
+  float* d_sor_dist = nullptr;
+  SortBufs sort{};
+  unsigned* d_desc = nullptr;
+  int* d_counts = nullptr;        // [CNT_ROWS][maxB]
+  uint32_t* d_warnings = nullptr; // [maxB]
+  MinMax* d_minmax = nullptr;
+  VoxelFrame* d_vf = nullptr;
+  EceFrame* d_ef = nullptr;
+  PlaneFrame* d_pf = nullptr;
+  PlaneRecord* d_prec = nullptr;
+  double* d_partial = nullptr;  // [maxB][chunks][10]
+  double* d_thr = nullptr;
+  int* d_n_active = nullptr;
+  int* d_rng = nullptr;
+  int* d_pack_off = nullptr;  // [PK_N][maxB]
+  PackMeta* d_meta = nullptr;
+  unsigned char* d_pack = nullptr;
+  size_t pack_cap = 0;
+  uint32_t alloc_outputs = 0;
+
+  // pinned host
+  int* h_n_active = nullptr;
+  int* h_counts = nullptr;  // [CNT_ROWS][maxB]
+  uint32_t* h_warnings = nullptr;
+  PlaneRecord* h_prec = nullptr;
+  PackMeta* h_meta = nullptr;
+  int* h_n_in = nullptr;  // staging for the per-frame input sizes
+  unsigned char* h_pack = nullptr;
+  size_t h_pack_cap = 0;
+
+  // timing
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stage[PCOP_N_STAGES][2] = {};
+  bool stage_used[PCOP_N_STAGES] = {};
+  float stage_us[PCOP_N_STAGES] = {};
+  float last_elapsed_us = 0.f;
+  int64_t launches = 0;
+  double alg_bytes = 0.0;
+
+  int* cnt(int row) { return d_counts + (size_t)row * maxB; }
+};
+
+namespace pcop {
+int fail_cuda(pcop_handle* h, cudaError_t e, const char* expr, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, expr);
+  if (h) h->err = buf;
+  g_global_error = buf;
+  return PCOP_ERR_CUDA;
+}
+}  // namespace pcop
+
+namespace {
+
+int fail(pcop_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_global_error = msg;
+  return code;
+}
+
+// boost::mt19937 (== std::mt19937 algorithm) restated; rnd() = uniform_int<>(0, INT_MAX) = raw >> 1
+void fill_rng_table(uint32_t seed, int* out, int count) {
+  uint32_t mt[624];
+  mt[0] = seed;
+  for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+  int pos = 624;
+  for (int k = 0; k < count; ++k) {
+    if (pos >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      pos = 0;
+    }
+    uint32_t y = mt[pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    out[k] = (int)(y >> 1);
+  }
+}
+
+int validate_params(pcop_handle* h, const pcop_params& p) {
+  if (p.enable_voxel && !(p.downsample_size > 0.0f)) return fail(h, PCOP_ERR_BAD_PARAM, "downsample_size must be > 0");
+  if (p.enable_sor && (p.statistical_outlier_meanK < 1 || p.statistical_outlier_meanK > 63))
+    return fail(h, PCOP_ERR_BAD_PARAM, "statistical_outlier_meanK must be in [1, 63]");
+  if (p.enable_plane && (p.plane_max_iterations < 0 || p.plane_max_iterations + 1 > PCOP_MAX_HYPOTHESES))
+    return fail(h, PCOP_ERR_BAD_PARAM, "plane_max_iterations must be in [0, 63]");
+  if (p.enable_plane && !(p.plane_probability > 0.0 && p.plane_probability < 1.0))
+    return fail(h, PCOP_ERR_BAD_PARAM, "plane_probability must be in (0, 1)");
+  if (p.enable_cluster && !(p.euc_cluster_tolerance > 0.0f))
+    return fail(h, PCOP_ERR_BAD_PARAM, "euc_cluster_tolerance must be > 0");
+  return PCOP_OK;
+}
+
+uint32_t effective_outputs(const pcop_params& p) {
+  uint32_t m = p.outputs;
+  if (p.publish_point_clouds) m |= PCOP_OUT_ALL;  // od.cpp:945: intermediates wanted
+  if (!p.enable_crop) m &= ~(uint32_t)PCOP_OUT_CROP;
+  if (!p.enable_voxel) m &= ~(uint32_t)PCOP_OUT_VOXEL;
+  if (!p.enable_sor) m &= ~(uint32_t)PCOP_OUT_SOR;
+  if (!p.enable_plane) m &= ~(uint32_t)PCOP_OUT_PLANE;
+  if (!p.enable_cluster) m &= ~(uint32_t)(PCOP_OUT_CLUSTERS | PCOP_OUT_OBSTACLES);
+  return m;
+}
+
+size_t pack_capacity_bytes(uint32_t mask, int B, int cap) {
+  size_t bytes = 0;
+  for (int k = 0; k < PK_N; ++k)
+    if (mask & kPkMask[k]) bytes += ((size_t)B * (cap + 1)) * kPkElem[k] + 256;
+  return bytes + 256;
+}
+
+template <class T>
+int dalloc(pcop_handle* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail_cuda(h, e, "cudaMalloc", __FILE__, __LINE__);
+  h->dev_allocs.push_back(q);
+  *p = (T*)q;
+  return PCOP_OK;
+}
+template <class T>
+int halloc(pcop_handle* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaHostAlloc(&q, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc", __FILE__, __LINE__);
+  h->host_allocs.push_back(q);
+  *p = (T*)q;
+  return PCOP_OK;
+}
+#define TRY(x)                      \
+  do {                              \
+    int _s = (x);                   \
+    if (_s != PCOP_OK) return _s;   \
+  } while (0)
+
+int ensure_pack_capacity(pcop_handle* h, uint32_t mask) {
+  const size_t need = pack_capacity_bytes(mask, h->maxB, h->cap);
+  if (need <= h->pack_cap) return PCOP_OK;
+  if (h->d_pack) cudaFree(h->d_pack);  // not tracked in dev_allocs
+  h->d_pack = nullptr;
+  h->pack_cap = 0;
+  cudaError_t e = cudaMalloc((void**)&h->d_pack, need);
+  if (e != cudaSuccess) return fail_cuda(h, e, "cudaMalloc(pack)", __FILE__, __LINE__);
+  h->pack_cap = need;
+  return PCOP_OK;
+}
+
+int ensure_host_pack(pcop_handle* h, size_t need) {
+  if (need <= h->h_pack_cap) return PCOP_OK;
+  size_t ncap = std::max<size_t>(need, h->h_pack_cap * 2);
+  ncap = std::max<size_t>(ncap, 1 << 20);
+  unsigned char* q = nullptr;
+  cudaError_t e = cudaHostAlloc((void**)&q, ncap, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(pack)", __FILE__, __LINE__);
+  if (h->h_pack) {
+    memcpy(q, h->h_pack, h->h_pack_cap);
+    cudaFreeHost(h->h_pack);
+  }
+  h->h_pack = q;
+  h->h_pack_cap = ncap;
+  return PCOP_OK;
+}
+
+// ---- small kernels owned by the API layer -----------------------------------------
+__global__ void k_copy_counts(const int* __restrict__ src, int* __restrict__ dst, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < B) dst[f] = src[f];
+}
+
+__global__ void k_zero_u32(uint32_t* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0u;
+}
+
+// cloud copy for a disabled plane stage: remaining = input, src = identity
+__global__ void __launch_bounds__(CT_THREADS)
+    k_copy_cloud(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, float4* __restrict__ out,
+                 int* __restrict__ out_src, int cap) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const int n = n_in[f];
+  if (tile * CT_TILE >= n) return;
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int i = ct_index(tile, k);
+    if (i < n) {
+      out[(size_t)f * cap + i] = __ldg(in + (size_t)f * in_stride + i);
+      out_src[(size_t)f * cap + i] = i;
+    }
+  }
+}
+
+__global__ void k_plane_record(const PlaneFrame* __restrict__ pf, PlaneRecord* __restrict__ rec, int* __restrict__ n_inl,
+                               int* __restrict__ n_clus, int* __restrict__ n_clus1, int plane_enabled, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  PlaneRecord r;
+  r.n_passes = 0;
+  r.n_inliers_last = 0;
+  r.coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < PCOP_MAX_PLANE_PASSES_RECORDED; ++k) {
+    r.pass_points[k] = 0;
+    r.pass_inliers[k] = 0;
+    r.pass_coeff[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (plane_enabled) {
+    const PlaneFrame& P = pf[f];
+    r.n_passes = P.n_passes;
+    r.n_inliers_last = P.n_inliers_last;
+    r.coeff = P.coeff_ref;
+    for (int k = 0; k < PCOP_MAX_PLANE_PASSES_RECORDED; ++k) {
+      r.pass_points[k] = P.pass_points[k];
+      r.pass_inliers[k] = P.pass_inliers[k];
+      r.pass_coeff[k] = P.pass_coeff[k];
+    }
+  }
+  rec[f] = r;
+  n_inl[f] = r.n_inliers_last;
+  n_clus1[f] = n_clus[f] + 1;
+}
+
+// exclusive scans over the frames of every requested output's count row + array base offsets
+__global__ void k_pack_scan(const int* __restrict__ counts, int maxB, int B, uint32_t mask, int* __restrict__ pack_off,
+                            PackMeta* __restrict__ meta) {
+  __shared__ int total[PK_N];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kPkCountD[PK_N] = {CNT_CROP, CNT_VOX, CNT_VOX, CNT_SOR, CNT_NINL, CNT_REM, CNT_REM, CNT_CLUS1, CNT_CLPTS, CNT_CLUS};
+  const uint32_t kPkMaskD[PK_N] = {PCOP_OUT_CROP,     PCOP_OUT_VOXEL,     PCOP_OUT_VOXEL,     PCOP_OUT_SOR,
+                                   PCOP_OUT_PLANE,    PCOP_OUT_REMAINING, PCOP_OUT_REMAINING, PCOP_OUT_CLUSTERS,
+                                   PCOP_OUT_CLUSTERS, PCOP_OUT_OBSTACLES};
+  const int kPkElemD[PK_N] = {4, 4, 16, 4, 4, 16, 4, 4, 4, 16};
+  for (int k = warp; k < PK_N; k += blockDim.x / 32) {
+    int run = 0;
+    if (mask & kPkMaskD[k]) {
+      const int* row = counts + (size_t)kPkCountD[k] * maxB;
+      for (int base = 0; base < B; base += 32) {
+        const int f = base + lane;
+        const int v = (f < B) ? row[f] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += up;
+        }
+        if (f < B) pack_off[(size_t)k * maxB + f] = run + incl - v;
+        run += __shfl_sync(FULL, incl, 31);
+      }
+    }
+    if (lane == 0) total[k] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long off = 0;
+    for (int k = 0; k < PK_N; ++k) {
+      meta->base[k] = off;
+      meta->total[k] = total[k];
+      off += ((unsigned long long)total[k] * kPkElemD[k] + 255ull) & ~255ull;
+    }
+    meta->total_bytes = off;
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+    k_pack(const T* __restrict__ src, size_t frame_stride, const int* __restrict__ count, const int* __restrict__ pack_off,
+           const PackMeta* __restrict__ meta, int which, unsigned char* __restrict__ pack) {
+  const int f = blockIdx.y;
+  const int n = count[f];
+  T* dst = reinterpret_cast<T*>(pack + meta->base[which]) + pack_off[f];
+  const T* s = src + (size_t)f * frame_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = s[i];
+}
+
+struct StageTimer {
+  pcop_handle* h;
+  int stage;
+  StageTimer(pcop_handle* hh, int s) : h(hh), stage(s) {
+    cudaEventRecord(h->ev_stage[s][0], h->stream);
+    h->stage_used[s] = true;
+  }
+  ~StageTimer() { cudaEventRecord(h->ev_stage[stage][1], h->stream); }
+};
+
+Ctx make_ctx(pcop_handle* h, int B) { return Ctx{h->stream, B, h->cap, &h->launches}; }
+
+PlaneConst make_plane_const(const pcop_params& p) {
+  PlaneConst pc;
+  pc.thr = p.plane_segment_dist_thres;
+  pc.eps_angle = (double)p.plane_segment_angle;  // od.cpp:371: the int is handed to setEpsAngle as radians
+  pc.cos_eps = std::cos(pc.eps_angle);
+  for (int a = 0; a < 3; ++a) pc.axis[a] = (double)p.plane_axis[a];
+  pc.keep_fraction = p.plane_keep_fraction;
+  pc.max_iterations = p.plane_max_iterations;
+  pc.probability = p.plane_probability;
+  pc.log_probability = 0.0;
+  pc.optimize = p.optimize_coefficients ? 1 : 0;
+  return pc;
+}
+
+PlaneArgs make_plane_args(pcop_handle* h, const float4* in, size_t stride, const int* n_in) {
+  PlaneArgs a{};
+  a.in = in;
+  a.in_stride = stride;
+  a.n_in = n_in;
+  a.buf[0] = h->d_pbuf[0];
+  a.buf[1] = h->d_pbuf[1];
+  a.src[0] = h->d_psrc[0];
+  a.src[1] = h->d_psrc[1];
+  a.inlier_idx = h->d_inliers;
+  a.pf = h->d_pf;
+  a.partial = h->d_partial;
+  a.desc = h->d_desc;
+  a.n_tmp = h->cnt(CNT_TMP);
+  a.n_active = h->d_n_active;
+  a.h_n_active = h->h_n_active;
+  a.rng = h->d_rng;
+  a.pc = make_plane_const(h->params);
+  a.warnings = h->d_warnings;
+  a.n_out = h->cnt(CNT_REM);
+  return a;
+}
+
+ClusterArgs make_cluster_args(pcop_handle* h, const float4* in, size_t stride, const int* n_in) {
+  ClusterArgs a{};
+  a.in = in;
+  a.in_stride = stride;
+  a.n_in = n_in;
+  a.tol = h->params.euc_cluster_tolerance;
+  a.min_size = h->params.euc_min_cluster_size;
+  a.max_size = h->params.euc_max_cluster_size;
+  a.minmax = h->d_minmax;
+  a.ef = h->d_ef;
+  a.sort = h->sort;
+  a.sorted_pts = h->d_sorted;
+  a.parent = h->d_parent;
+  a.csize = h->d_csize;
+  a.roots = h->d_roots;
+  a.rank_of = h->d_rank;
+  a.desc = h->d_desc;
+  a.offsets = h->d_offsets;
+  a.indices = h->d_indices;
+  a.n_clusters = h->cnt(CNT_CLUS);
+  a.n_cluster_pts = h->cnt(CNT_CLPTS);
+  a.obstacles = h->d_obst;
+  return a;
+}
+
+CropArgs make_crop_args(pcop_handle* h, const float4* in, size_t stride, const int* n_in) {
+  CropArgs a{};
+  a.in = in;
+  a.in_stride = stride;
+  a.n_in = n_in;
+  a.out = h->d_crop;
+  a.kept_idx = h->d_crop_kept;
+  a.n_out = h->cnt(CNT_CROP);
+  a.minmax = h->d_minmax;
+  a.desc = h->d_desc;
+  const pcop_params& p = h->params;
+  a.lim[0] = p.x_min;
+  a.lim[1] = p.x_max;
+  a.lim[2] = p.y_min;
+  a.lim[3] = p.y_max;
+  a.lim[4] = p.z_min;
+  a.lim[5] = p.z_max;
+  return a;
+}
+
+VoxelArgs make_voxel_args(pcop_handle* h, const float4* in, size_t stride, const int* n_in) {
+  VoxelArgs a{};
+  a.in = in;
+  a.in_stride = stride;
+  a.n_in = n_in;
+  a.minmax = h->d_minmax;
+  a.leaf = h->params.downsample_size;
+  a.vf = h->d_vf;
+  a.sort = h->sort;
+  a.desc = h->d_desc;
+  a.run_start = h->d_run_start;
+  a.out = h->d_vox;
+  a.out_keys = h->d_vox_keys;
+  a.n_out = h->cnt(CNT_VOX);
+  a.warnings = h->d_warnings;
+  return a;
+}
+
+SorArgs make_sor_args(pcop_handle* h, const float4* in, size_t stride, const int* n_in) {
+  SorArgs a{};
+  a.in = in;
+  a.in_stride = stride;
+  a.n_in = n_in;
+  a.meanK = h->params.statistical_outlier_meanK;
+  a.mul = (double)h->params.statistical_outlier_stdDevThres;
+  // search-grid cell: a speed knob only (the k-NN result is exact for any cell size)
+  a.cell = (h->params.enable_voxel && h->params.downsample_size > 0.0f) ? 3.0f * h->params.downsample_size : 0.05f;
+  a.minmax = h->d_minmax;
+  a.gf = h->d_ef;
+  a.sort = h->sort;
+  a.sorted_pts = h->d_sorted;
+  a.dist = h->d_sor_dist;
+  a.partial = h->d_partial;
+  a.thr = h->d_thr;
+  a.desc = h->d_desc;
+  a.out = h->d_sor;
+  a.kept_idx = h->d_sor_kept;
+  a.n_out = h->cnt(CNT_SOR);
+  a.warnings = h->d_warnings;
+  return a;
+}
+
+bool is_device_pointer(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// All stages of one wave.  `in`/`stride` already on the device; counts row CNT_IN already set.
+int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride) {
+  const pcop_params& p = h->params;
+  Ctx c = make_ctx(h, B);
+  const int tiles = cdiv(h->cap, CT_TILE);
+  k_zero_u32<<<cdiv(B, 256), 256, 0, h->stream>>>(h->d_warnings, B);
+  count_launch(c);
+
+  const float4* cur = in;
+  size_t cur_stride = stride;
+  const int* cur_n = h->cnt(CNT_IN);
+  bool have_minmax = false;
+
+  {
+    StageTimer t(h, PCOP_STAGE_CROP);
+    if (p.enable_crop) {
+      run_crop(c, make_crop_args(h, cur, cur_stride, cur_n));
+      cur = h->d_crop;
+      cur_stride = h->cap;
+      cur_n = h->cnt(CNT_CROP);
+      have_minmax = true;
+    } else {
+      k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_CROP), B);
+      count_launch(c);
+    }
+  }
+  {
+    StageTimer t(h, PCOP_STAGE_VOXEL);
+    if (p.enable_voxel) {
+      if (!have_minmax) run_minmax(c, cur, cur_stride, cur_n, h->d_minmax);
+      run_voxel(c, make_voxel_args(h, cur, cur_stride, cur_n));
+      cur = h->d_vox;
+      cur_stride = h->cap;
+      cur_n = h->cnt(CNT_VOX);
+    } else {
+      k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_VOX), B);
+      count_launch(c);
+    }
+  }
+  {
+    StageTimer t(h, PCOP_STAGE_SOR);
+    if (p.enable_sor) {
+      run_sor(c, make_sor_args(h, cur, cur_stride, cur_n));
+      cur = h->d_sor;
+      cur_stride = h->cap;
+      cur_n = h->cnt(CNT_SOR);
+    } else {
+      k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_SOR), B);
+      count_launch(c);
+    }
+  }
+  {
+    StageTimer t(h, PCOP_STAGE_PLANE);
+    if (p.enable_plane) {
+      PlaneArgs a = make_plane_args(h, cur, cur_stride, cur_n);
+      cudaError_t e = run_plane(c, a);
+      if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
+      run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
+    } else {
+      k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_REM), B);
+      k_copy_cloud<<<dim3(tiles, B), CT_THREADS, 0, h->stream>>>(cur, cur_stride, cur_n, h->d_rem, h->d_rem_src, h->cap);
+      count_launch(c, 2);
+    }
+  }
+  ClusterArgs ca = make_cluster_args(h, h->d_rem, h->cap, h->cnt(CNT_REM));
+  {
+    StageTimer t(h, PCOP_STAGE_CLUSTER);
+    if (p.enable_cluster) {
+      run_cluster(c, ca);
+    } else {
+      cudaMemsetAsync(h->cnt(CNT_CLUS), 0, sizeof(int) * B, h->stream);
+      cudaMemsetAsync(h->cnt(CNT_CLPTS), 0, sizeof(int) * B, h->stream);
+    }
+  }
+  {
+    StageTimer t(h, PCOP_STAGE_CENTROID);
+    if (p.enable_cluster) run_centroid_radius(c, ca);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(h, e, "stage launches", __FILE__, __LINE__);
+  return PCOP_OK;
+}
+
+// pack + copy back the requested outputs of a wave; fills out[0..B)
+int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop_frame_result* out_all, int w0,
+                 std::vector<size_t>* ptr_fixups) {
+  pcop_frame_result* out = out_all + w0;
+  Ctx c = make_ctx(h, B);
+  StageTimer t(h, PCOP_STAGE_D2H);
+  k_plane_record<<<cdiv(B, 128), 128, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS),
+                                                      h->cnt(CNT_CLUS1), h->params.enable_plane ? 1 : 0, B);
+  k_pack_scan<<<1, 320, 0, h->stream>>>(h->d_counts, h->maxB, B, mask, h->d_pack_off, h->d_meta);
+  count_launch(c, 2);
+  const void* srcs[PK_N] = {h->d_crop_kept, h->d_vox_keys, h->d_vox,     h->d_sor_kept, h->d_inliers,
+                            h->d_rem,       h->d_rem_src,  h->d_offsets, h->d_indices,  h->d_obst};
+  const size_t strides[PK_N] = {(size_t)h->cap, (size_t)h->cap, (size_t)h->cap,     (size_t)h->cap, (size_t)h->cap,
+                                (size_t)h->cap, (size_t)h->cap, (size_t)h->cap + 1, (size_t)h->cap, (size_t)h->cap};
+  const int gx = std::min(cdiv(h->cap, 256), 64);
+  for (int k = 0; k < PK_N; ++k) {
+    if (!(mask & kPkMask[k])) continue;
+    const int* cnt = h->cnt(kPkCount[k]);
+    const int* off = h->d_pack_off + (size_t)k * h->maxB;
+    if (kPkElem[k] == 16)
+      k_pack<float4><<<dim3(gx, B), 256, 0, h->stream>>>((const float4*)srcs[k], strides[k], cnt, off, h->d_meta, k,
+                                                         h->d_pack);
+    else
+      k_pack<int><<<dim3(gx, B), 256, 0, h->stream>>>((const int*)srcs[k], strides[k], cnt, off, h->d_meta, k, h->d_pack);
+    count_launch(c);
+  }
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int) * CNT_ROWS * h->maxB, cudaMemcpyDeviceToHost,
+                                h->stream));
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_warnings, h->d_warnings, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_prec, h->d_prec, sizeof(PlaneRecord) * B, cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_meta, h->d_meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  const PackMeta meta = *h->h_meta;
+  const size_t base_off = (*h_pack_used + 255) & ~(size_t)255;
+  TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
+  if (meta.total_bytes) {
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, h->d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
+  // the second sync happens in the caller after the stage-timer event is recorded
+  *h_pack_used = base_off + meta.total_bytes;
+
+  size_t run[PK_N] = {0};
+  auto H = [&](int row, int f) { return h->h_counts[(size_t)row * h->maxB + f]; };
+  for (int f = 0; f < B; ++f) {
+    pcop_frame_result& r = out[f];
+    memset(&r, 0, sizeof(r));
+    r.status = PCOP_OK;
+    r.warnings = h->h_warnings[f];
+    r.n_input = H(CNT_IN, f);
+    r.n_crop = H(CNT_CROP, f);
+    r.n_voxel = H(CNT_VOX, f);
+    r.n_sor = H(CNT_SOR, f);
+    r.n_remaining = H(CNT_REM, f);
+    r.n_clusters = H(CNT_CLUS, f);
+    r.n_cluster_points = H(CNT_CLPTS, f);
+    const PlaneRecord& pr = h->h_prec[f];
+    r.n_plane_passes = pr.n_passes;
+    r.n_plane_inliers = pr.n_inliers_last;
+    memcpy(r.plane_coeff, &pr.coeff, 16);
+    memcpy(r.plane_pass_points, pr.pass_points, sizeof(pr.pass_points));
+    memcpy(r.plane_pass_inliers, pr.pass_inliers, sizeof(pr.pass_inliers));
+    memcpy(r.plane_pass_coeff, pr.pass_coeff, sizeof(pr.pass_coeff));
+    const void** slots[PK_N] = {(const void**)&r.crop_kept_idx,    (const void**)&r.voxel_keys,
+                                (const void**)&r.voxel_centroids,  (const void**)&r.sor_kept_idx,
+                                (const void**)&r.plane_inlier_idx, (const void**)&r.remaining_cloud,
+                                (const void**)&r.remaining_src_idx, (const void**)&r.cluster_offsets,
+                                (const void**)&r.cluster_indices,  (const void**)&r.obstacles};
+    for (int k = 0; k < PK_N; ++k) {
+      if (!(mask & kPkMask[k])) continue;
+      // store the byte offset now; turned into a pointer once the host buffer can no longer move
+      const size_t off = base_off + (size_t)meta.base[k] + run[k] * kPkElem[k];
+      *slots[k] = (const void*)(uintptr_t)(off + 1);  // +1 so that offset 0 is distinguishable from NULL
+      ptr_fixups->push_back((size_t)((const unsigned char*)slots[k] - (const unsigned char*)out_all));
+      run[k] += (size_t)H(kPkCount[k], f);
+    }
+    // algorithmic bytes
+    double b = 0.0;
+    const pcop_params& p = h->params;
+    if (p.enable_crop) b += 16.0 * r.n_input + 20.0 * r.n_crop;
+    if (p.enable_voxel) b += 16.0 * r.n_crop + 20.0 * r.n_voxel;
+    if (p.enable_sor) b += 16.0 * r.n_voxel + 20.0 * r.n_sor;
+    if (p.enable_plane) {
+      int pk = r.n_sor;
+      const int np = std::min(r.n_plane_passes, (int)PCOP_MAX_PLANE_PASSES_RECORDED);
+      for (int k = 0; k < np; ++k) {
+        const int ik = r.plane_pass_inliers[k];
+        b += 16.0 * pk + 16.0 * (pk - ik) + 4.0 * ik + 16.0;
+        pk -= ik;
+      }
+    }
+    if (p.enable_cluster) {
+      b += 16.0 * r.n_remaining + 4.0 * r.n_cluster_points + 4.0 * (r.n_clusters + 1);
+      b += 16.0 * r.n_remaining + 4.0 * r.n_cluster_points + 16.0 * r.n_clusters;
+    }
+    h->alg_bytes += b;
+  }
+  return PCOP_OK;
+}
+
+int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n, int32_t batch,
+                 pcop_frame_result* out) {
+  if (!h) return fail(nullptr, PCOP_ERR_BAD_PARAM, "null handle");
+  if (!xyzw || !n || !out || batch < 0) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  for (int f = 0; f < batch; ++f) {
+    if (n[f] < 0) return fail(h, PCOP_ERR_BAD_PARAM, "negative point count");
+    if (n[f] > h->cap) return fail(h, PCOP_ERR_CAPACITY, "frame has more points than max_points");
+    if ((size_t)n[f] > frame_stride_points && batch > 1) return fail(h, PCOP_ERR_BAD_PARAM, "frame_stride_points < n");
+  }
+  const uint32_t mask = effective_outputs(h->params);
+  TRY(ensure_pack_capacity(h, mask));
+  h->launches = 0;
+  h->alg_bytes = 0.0;
+  for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] = 0.f;
+  const bool on_device = is_device_pointer(xyzw);
+  size_t h_pack_used = 0;
+  std::vector<size_t> fixups;
+  fixups.reserve((size_t)batch * 6);
+  PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[0], h->stream));
+  for (int w0 = 0; w0 < batch; w0 += h->maxB) {
+    const int B = std::min(h->maxB, batch - w0);
+    for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_used[s] = false;
+    const float4* in;
+    size_t stride;
+    {
+      StageTimer t(h, PCOP_STAGE_H2D);
+      memcpy(h->h_n_in, n + w0, sizeof(int) * B);
+      PCOP_CUDA_TRY(cudaMemcpyAsync(h->cnt(CNT_IN), h->h_n_in, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+      if (on_device) {
+        in = reinterpret_cast<const float4*>(xyzw) + (size_t)w0 * frame_stride_points;
+        stride = frame_stride_points;
+      } else {
+        const float* src = xyzw + (size_t)w0 * frame_stride_points * 4;
+        bool uniform = true;
+        for (int f = 1; f < B; ++f) uniform = uniform && (n[w0 + f] == n[w0]);
+        if (B > 0 && uniform && n[w0] > 0) {
+          PCOP_CUDA_TRY(cudaMemcpy2DAsync(h->d_in, (size_t)h->cap * 16, src, frame_stride_points * 16, (size_t)n[w0] * 16,
+                                          B, cudaMemcpyHostToDevice, h->stream));
+        } else {
+          for (int f = 0; f < B; ++f)
+            if (n[w0 + f] > 0)
+              PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_in + (size_t)f * h->cap, src + (size_t)f * frame_stride_points * 4,
+                                            (size_t)n[w0 + f] * 16, cudaMemcpyHostToDevice, h->stream));
+        }
+        in = h->d_in;
+        stride = h->cap;
+      }
+    }
+    TRY(run_wave_stages(h, B, in, stride));
+    TRY(collect_wave(h, B, mask, &h_pack_used, out, w0, &fixups));
+    PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < PCOP_N_STAGES; ++s) {
+      if (!h->stage_used[s]) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev_stage[s][0], h->ev_stage[s][1]) == cudaSuccess) h->stage_us[s] += ms * 1000.f;
+    }
+  }
+  PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[1], h->stream));
+  PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_call[1]));
+  float ms = 0.f;
+  PCOP_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]));
+  h->last_elapsed_us = ms * 1000.f;
+  // the host pack buffer is final now: turn the stored offsets into pointers
+  for (size_t fx : fixups) {
+    const void** slot = (const void**)((unsigned char*)out + fx);
+    const size_t off = (size_t)(uintptr_t)(*slot) - 1;
+    *slot = h->h_pack + off;
+  }
+  return PCOP_OK;
+}
+
+// upload a single cloud into d_in as frame 0 and set a count row
+int upload_single(pcop_handle* h, const float* xyzw, int32_t n, int count_row) {
+  if (n < 0) return fail(h, PCOP_ERR_BAD_PARAM, "negative point count");
+  if (n > h->cap) return fail(h, PCOP_ERR_CAPACITY, "cloud has more points than max_points");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  h->h_n_in[0] = n;
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->cnt(count_row), h->h_n_in, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (n > 0) PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_in, xyzw, (size_t)n * 16, cudaMemcpyDefault, h->stream));
+  k_zero_u32<<<1, 32, 0, h->stream>>>(h->d_warnings, 1);
+  return PCOP_OK;
+}
+
+int download(pcop_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!dst || bytes == 0) return PCOP_OK;
+  PCOP_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return PCOP_OK;
+}
+
+int fetch_count(pcop_handle* h, int row, int32_t* out) {
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->cnt(row), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = h->h_counts[0];
+  return PCOP_OK;
+}
+
+int fetch_warnings(pcop_handle* h, uint32_t* w) {
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_warnings, h->d_warnings, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (w) *w = h->h_warnings[0];
+  return PCOP_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int pcop_abi_version(void) { return PCOP_ABI_VERSION; }
+const char* pcop_global_error(void) { return g_global_error.c_str(); }
+const char* pcop_last_error(const pcop_handle* h) { return h ? h->err.c_str() : g_global_error.c_str(); }
+
+void pcop_params_init_code_defaults(pcop_params* p) {
+  memset(p, 0, sizeof(*p));
+  // od.cpp:948-953
+  p->x_min = -1.0f; p->x_max = 1.0f; p->y_min = -0.5f; p->y_max = 0.6f; p->z_min = 0.0f; p->z_max = -0.5f;
+  p->downsample_size = 0.015f;                   // od.cpp:964
+  p->statistical_outlier_meanK = 15;             // od.cpp:966
+  p->statistical_outlier_stdDevThres = 1.0f;     // od.cpp:967
+  p->plane_segment_dist_thres = 0.040f;          // od.cpp:969
+  p->plane_segment_angle = 20;                   // od.cpp:970
+  p->euc_cluster_tolerance = 0.4f;               // od.cpp:972
+  p->euc_min_cluster_size = 5;                   // od.cpp:973
+  p->euc_max_cluster_size = 20000;               // od.cpp:974
+  p->plane_axis[0] = 0.0f; p->plane_axis[1] = 0.0f; p->plane_axis[2] = 1.0f;  // od.cpp:769
+  p->plane_keep_fraction = 0.3;                  // od.cpp:379
+  p->plane_max_iterations = 50;                  // pcl::SACSegmentation default
+  p->plane_probability = 0.99;                   // pcl::SACSegmentation default
+  p->ransac_seed = 12345u;                       // pcl::SampleConsensusModel rng seed
+  p->optimize_coefficients = 1;                  // od.cpp:365
+  p->enable_crop = p->enable_voxel = p->enable_sor = p->enable_plane = p->enable_cluster = 1;
+  p->publish_point_clouds = 1;                   // od.cpp:945
+  p->outputs = PCOP_OUT_DEFAULT;
+  p->accumulate_count = 2;                       // od.cpp:940
+  p->block_size = 0.15f;                         // od.cpp:955
+  p->dev_percent = 0.5f;                         // od.cpp:956
+  p->grid_opacity = 0;                           // od.cpp:946
+  p->downsample_input_data = 1;                  // od.cpp:943
+  p->passthrough_filter_enable = 1;              // od.cpp:944
+  p->convex_hull_alpha = 180.0f;                 // od.cpp:975
+}
+
+void pcop_params_init_params_yaml(pcop_params* p) {
+  pcop_params_init_code_defaults(p);
+  // minibot_cr18/params.yaml:2-31
+  p->x_min = 0.0f; p->x_max = 4.5f; p->y_min = 0.0f; p->y_max = 3.78f; p->z_min = -0.5f; p->z_max = 0.25f;
+  p->accumulate_count = 200;
+  p->block_size = 0.0375f;
+  p->dev_percent = 0.9f;
+  p->grid_opacity = 0;
+  p->downsample_size = 0.015f;
+  p->statistical_outlier_meanK = 15;
+  p->statistical_outlier_stdDevThres = 4.0f;
+  p->plane_segment_dist_thres = 0.040f;
+  p->plane_segment_angle = 20;
+  p->euc_cluster_tolerance = 0.4f;
+  p->euc_min_cluster_size = 5;
+  p->euc_max_cluster_size = 20000;
+  p->convex_hull_alpha = 180.0f;
+  p->publish_point_clouds = 1;
+}
+
+int pcop_create(const pcop_params* params, int device, size_t max_points, int max_batch, pcop_handle** out) {
+  if (!params || !out || max_points == 0 || max_points > (size_t)(1u << 30) || max_batch < 1)
+    return fail(nullptr, PCOP_ERR_BAD_PARAM, "pcop_create: bad argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, PCOP_ERR_CUDA, "pcop_create: no CUDA device (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, PCOP_ERR_BAD_PARAM, "pcop_create: bad device index");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail_cuda(nullptr, e, "props", __FILE__, __LINE__);
+  if (prop.major != 10)
+    return fail(nullptr, PCOP_ERR_CUDA, "pcop_create: device is not sm_100-class (kernels are built for sm_100a only)");
+  pcop_handle* h = new pcop_handle();
+  h->params = *params;
+  h->device = device;
+  h->cap = (int)max_points;
+  h->maxB = max_batch;
+  int st = validate_params(h, *params);
+  if (st != PCOP_OK) {
+    g_global_error = h->err;
+    delete h;
+    return st;
+  }
+  auto bail = [&](int code) {
+    g_global_error = h->err;
+    pcop_destroy(h);
+    return code;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(fail_cuda(h, e, "cudaSetDevice", __FILE__, __LINE__));
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(fail_cuda(h, e, "cudaStreamCreate", __FILE__, __LINE__));
+  const size_t BC = (size_t)h->maxB * h->cap;
+  const int B = h->maxB;
+  const int chunks = cdiv(h->cap, TS_CHUNK);
+  const int tiles = cdiv(h->cap, CT_TILE);
+#define A(x)                         \
+  do {                               \
+    int _s = (x);                    \
+    if (_s != PCOP_OK) return bail(_s); \
+  } while (0)
+  A(dalloc(h, &h->d_in, BC));
+  A(dalloc(h, &h->d_crop, BC));
+  A(dalloc(h, &h->d_vox, BC));
+  A(dalloc(h, &h->d_sor, BC));
+  A(dalloc(h, &h->d_pbuf[0], BC));
+  A(dalloc(h, &h->d_pbuf[1], BC));
+  A(dalloc(h, &h->d_rem, BC));
+  A(dalloc(h, &h->d_sorted, BC));
+  A(dalloc(h, &h->d_obst, BC));
+  A(dalloc(h, &h->d_crop_kept, BC));
+  A(dalloc(h, &h->d_run_start, BC));
+  A(dalloc(h, &h->d_sor_kept, BC));
+  A(dalloc(h, &h->d_psrc[0], BC));
+  A(dalloc(h, &h->d_psrc[1], BC));
+  A(dalloc(h, &h->d_rem_src, BC));
+  A(dalloc(h, &h->d_inliers, BC));
+  A(dalloc(h, &h->d_parent, BC));
+  A(dalloc(h, &h->d_csize, BC));
+  A(dalloc(h, &h->d_roots, BC));
+  A(dalloc(h, &h->d_rank, BC));
+  A(dalloc(h, &h->d_indices, BC));
+  A(dalloc(h, &h->d_offsets, BC + B));
+  A(dalloc(h, &h->d_vox_keys, BC));
+  A(dalloc(h, &h->d_sor_dist, BC));
+  A(dalloc(h, &h->sort.key[0], BC));
+  A(dalloc(h, &h->sort.key[1], BC));
+  A(dalloc(h, &h->sort.val[0], BC));
+  A(dalloc(h, &h->sort.val[1], BC));
+  A(dalloc(h, &h->sort.hist, (size_t)B * RS_MAX_PASSES * RS_BINS));
+  {
+    unsigned char* d = nullptr;
+    A(dalloc(h, &d, sort_desc_bytes(B, h->cap)));
+    h->sort.desc = (uint32_t*)d;
+  }
+  A(dalloc(h, &h->sort.maxkey, B));
+  A(dalloc(h, &h->sort.npass, B));
+  A(dalloc(h, &h->d_desc, (size_t)B * tiles));
+  A(dalloc(h, &h->d_counts, (size_t)CNT_ROWS * B));
+  A(dalloc(h, &h->d_warnings, B));
+  A(dalloc(h, &h->d_minmax, B));
+  A(dalloc(h, &h->d_vf, B));
+  A(dalloc(h, &h->d_ef, B));
+  A(dalloc(h, &h->d_pf, B));
+  A(dalloc(h, &h->d_prec, B));
+  A(dalloc(h, &h->d_partial, (size_t)B * chunks * 10));
+  A(dalloc(h, &h->d_thr, B));
+  A(dalloc(h, &h->d_n_active, 64));
+  A(dalloc(h, &h->d_rng, RNG_TABLE));
+  A(dalloc(h, &h->d_pack_off, (size_t)PK_N * B));
+  A(dalloc(h, &h->d_meta, 1));
+  A(halloc(h, &h->h_n_active, 16));
+  A(halloc(h, &h->h_counts, (size_t)CNT_ROWS * B));
+  A(halloc(h, &h->h_warnings, B));
+  A(halloc(h, &h->h_prec, B));
+  A(halloc(h, &h->h_meta, 1));
+  A(halloc(h, &h->h_n_in, (size_t)B + 16));
+#undef A
+  if ((e = cudaMemset(h->d_counts, 0, sizeof(int) * CNT_ROWS * B)) != cudaSuccess)
+    return bail(fail_cuda(h, e, "memset", __FILE__, __LINE__));
+  if ((e = cudaMemset(h->d_pf, 0, sizeof(PlaneFrame) * B)) != cudaSuccess)
+    return bail(fail_cuda(h, e, "memset", __FILE__, __LINE__));
+  {
+    std::vector<int> tbl(RNG_TABLE);
+    fill_rng_table(params->ransac_seed, tbl.data(), RNG_TABLE);
+    if ((e = cudaMemcpy(h->d_rng, tbl.data(), sizeof(int) * RNG_TABLE, cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail(fail_cuda(h, e, "rng upload", __FILE__, __LINE__));
+  }
+  for (int i = 0; i < 2; ++i)
+    if ((e = cudaEventCreate(&h->ev_call[i])) != cudaSuccess) return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
+  for (int s = 0; s < PCOP_N_STAGES; ++s)
+    for (int i = 0; i < 2; ++i)
+      if ((e = cudaEventCreate(&h->ev_stage[s][i])) != cudaSuccess)
+        return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
+  st = ensure_pack_capacity(h, effective_outputs(h->params));
+  if (st != PCOP_OK) return bail(st);
+  *out = h;
+  return PCOP_OK;
+}
+
+void pcop_destroy(pcop_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->dev_allocs) cudaFree(p);
+  for (void* p : h->host_allocs) cudaFreeHost(p);
+  if (h->d_pack) cudaFree(h->d_pack);
+  if (h->h_pack) cudaFreeHost(h->h_pack);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
+  for (int s = 0; s < PCOP_N_STAGES; ++s)
+    for (int i = 0; i < 2; ++i)
+      if (h->ev_stage[s][i]) cudaEventDestroy(h->ev_stage[s][i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int pcop_set_params(pcop_handle* h, const pcop_params* params) {
+  if (!h || !params) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  int st = validate_params(h, *params);
+  if (st != PCOP_OK) return st;
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  if (params->ransac_seed != h->params.ransac_seed) {
+    std::vector<int> tbl(RNG_TABLE);
+    fill_rng_table(params->ransac_seed, tbl.data(), RNG_TABLE);
+    PCOP_CUDA_TRY(cudaMemcpy(h->d_rng, tbl.data(), sizeof(int) * RNG_TABLE, cudaMemcpyHostToDevice));
+  }
+  h->params = *params;
+  return ensure_pack_capacity(h, effective_outputs(h->params));
+}
+
+int pcop_process(pcop_handle* h, const float* xyzw, int32_t n, pcop_frame_result* out) {
+  return process_impl(h, xyzw, (size_t)(n > 0 ? n : 1), &n, 1, out);
+}
+
+int pcop_process_batch(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n, int32_t batch,
+                       pcop_frame_result* out) {
+  return process_impl(h, xyzw, frame_stride_points, n, batch, out);
+}
+
+float pcop_last_elapsed_us(const pcop_handle* h) { return h ? h->last_elapsed_us : 0.f; }
+int pcop_stage_times_us(const pcop_handle* h, float us[PCOP_N_STAGES]) {
+  if (!h || !us) return PCOP_ERR_BAD_PARAM;
+  for (int s = 0; s < PCOP_N_STAGES; ++s) us[s] = h->stage_us[s];
+  return PCOP_OK;
+}
+int64_t pcop_last_launch_count(const pcop_handle* h) { return h ? h->launches : 0; }
+double pcop_last_algorithmic_bytes(const pcop_handle* h) { return h ? h->alg_bytes : 0.0; }
+
+// ---- stage-isolated entry points -------------------------------------------------------
+int pcop_crop(pcop_handle* h, const float* xyzw, int32_t n, float* out_xyzw, int32_t* kept_idx, int32_t* m) {
+  if (!h || !xyzw || !m) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  TRY(upload_single(h, xyzw, n, CNT_IN));
+  Ctx c = make_ctx(h, 1);
+  run_crop(c, make_crop_args(h, h->d_in, h->cap, h->cnt(CNT_IN)));
+  TRY(fetch_count(h, CNT_CROP, m));
+  TRY(download(h, out_xyzw, h->d_crop, (size_t)*m * 16));
+  TRY(download(h, kept_idx, h->d_crop_kept, (size_t)*m * 4));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+int pcop_voxel(pcop_handle* h, const float* xyzw, int32_t m, float* out_xyzw, uint32_t* out_keys, int32_t* v,
+               uint32_t* warnings) {
+  if (!h || !xyzw || !v) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  if (!(h->params.downsample_size > 0.0f)) return fail(h, PCOP_ERR_BAD_PARAM, "downsample_size must be > 0");
+  TRY(upload_single(h, xyzw, m, CNT_CROP));
+  Ctx c = make_ctx(h, 1);
+  run_minmax(c, h->d_in, h->cap, h->cnt(CNT_CROP), h->d_minmax);
+  run_voxel(c, make_voxel_args(h, h->d_in, h->cap, h->cnt(CNT_CROP)));
+  TRY(fetch_count(h, CNT_VOX, v));
+  TRY(fetch_warnings(h, warnings));
+  TRY(download(h, out_xyzw, h->d_vox, (size_t)*v * 16));
+  TRY(download(h, out_keys, h->d_vox_keys, (size_t)*v * 4));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+int pcop_sor(pcop_handle* h, const float* xyzw, int32_t v, float* out_xyzw, int32_t* kept_idx, int32_t* s,
+             uint32_t* warnings) {
+  if (!h || !xyzw || !s) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  if (h->params.statistical_outlier_meanK < 1 || h->params.statistical_outlier_meanK > 63)
+    return fail(h, PCOP_ERR_BAD_PARAM, "statistical_outlier_meanK must be in [1, 63]");
+  TRY(upload_single(h, xyzw, v, CNT_VOX));
+  Ctx c = make_ctx(h, 1);
+  run_sor(c, make_sor_args(h, h->d_in, h->cap, h->cnt(CNT_VOX)));
+  TRY(fetch_count(h, CNT_SOR, s));
+  TRY(fetch_warnings(h, warnings));
+  TRY(download(h, out_xyzw, h->d_sor, (size_t)*s * 16));
+  TRY(download(h, kept_idx, h->d_sor_kept, (size_t)*s * 4));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+int pcop_plane(pcop_handle* h, const float* xyzw, int32_t s, float* remaining_xyzw, int32_t* remaining_src_idx,
+               int32_t* p, int32_t* n_passes, int32_t* pass_points, int32_t* pass_inliers, float* pass_coeff,
+               float* last_coeff, int32_t* inlier_idx, int32_t* n_inliers, uint32_t* warnings) {
+  if (!h || !xyzw || !p) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  TRY(upload_single(h, xyzw, s, CNT_SOR));
+  Ctx c = make_ctx(h, 1);
+  PlaneArgs a = make_plane_args(h, h->d_in, h->cap, h->cnt(CNT_SOR));
+  cudaError_t e = run_plane(c, a);
+  if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
+  run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
+  k_plane_record<<<1, 32, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS), h->cnt(CNT_CLUS1), 1, 1);
+  TRY(fetch_count(h, CNT_REM, p));
+  TRY(fetch_warnings(h, warnings));
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_prec, h->d_prec, sizeof(PlaneRecord), cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  const PlaneRecord& r = h->h_prec[0];
+  if (n_passes) *n_passes = r.n_passes;
+  if (pass_points) memcpy(pass_points, r.pass_points, sizeof(r.pass_points));
+  if (pass_inliers) memcpy(pass_inliers, r.pass_inliers, sizeof(r.pass_inliers));
+  if (pass_coeff) memcpy(pass_coeff, r.pass_coeff, sizeof(r.pass_coeff));
+  if (last_coeff) memcpy(last_coeff, &r.coeff, 16);
+  if (n_inliers) *n_inliers = r.n_inliers_last;
+  TRY(download(h, remaining_xyzw, h->d_rem, (size_t)*p * 16));
+  TRY(download(h, remaining_src_idx, h->d_rem_src, (size_t)*p * 4));
+  TRY(download(h, inlier_idx, h->d_inliers, (size_t)r.n_inliers_last * 4));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+int pcop_cluster(pcop_handle* h, const float* xyzw, int32_t p, int32_t* cluster_offsets, int32_t* cluster_indices,
+                 int32_t* c_out, int32_t* l_out) {
+  if (!h || !xyzw || !c_out || !l_out) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  if (!(h->params.euc_cluster_tolerance > 0.0f)) return fail(h, PCOP_ERR_BAD_PARAM, "euc_cluster_tolerance must be > 0");
+  TRY(upload_single(h, xyzw, p, CNT_REM));
+  Ctx c = make_ctx(h, 1);
+  run_cluster(c, make_cluster_args(h, h->d_in, h->cap, h->cnt(CNT_REM)));
+  TRY(fetch_count(h, CNT_CLUS, c_out));
+  TRY(fetch_count(h, CNT_CLPTS, l_out));
+  TRY(download(h, cluster_offsets, h->d_offsets, (size_t)(*c_out + 1) * 4));
+  TRY(download(h, cluster_indices, h->d_indices, (size_t)*l_out * 4));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+int pcop_centroid_radius(pcop_handle* h, const float* xyzw, int32_t p, const int32_t* cluster_offsets,
+                         const int32_t* cluster_indices, int32_t c_in, float* obstacles) {
+  if (!h || !xyzw || !cluster_offsets || !cluster_indices || !obstacles || c_in < 0)
+    return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  if (c_in > h->cap) return fail(h, PCOP_ERR_CAPACITY, "too many clusters");
+  TRY(upload_single(h, xyzw, p, CNT_REM));
+  const int l = cluster_offsets[c_in];
+  if (l < 0 || l > h->cap) return fail(h, PCOP_ERR_CAPACITY, "cluster index list longer than max_points");
+  h->h_n_in[1] = c_in;
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->cnt(CNT_CLUS), h->h_n_in + 1, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_offsets, cluster_offsets, (size_t)(c_in + 1) * 4, cudaMemcpyDefault, h->stream));
+  if (l > 0) PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_indices, cluster_indices, (size_t)l * 4, cudaMemcpyDefault, h->stream));
+  Ctx c = make_ctx(h, 1);
+  run_centroid_radius(c, make_cluster_args(h, h->d_in, h->cap, h->cnt(CNT_REM)));
+  TRY(download(h, obstacles, h->d_obst, (size_t)c_in * 16));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+// Batched, stable, least-significant-digit radix sort of (key32, val32) pairs, onesweep style:
+// one histogram kernel for all digits, then one kernel per 8-bit digit in which every 2048-key
+// tile ranks its keys (warp match_any multi-split), learns its per-digit global offset by
+// decoupled look-back over the earlier tiles of the same frame, stages the tile in shared
+// memory in sorted order and writes it out in coalesced runs.
+//
+// Frames are independent segments: blockIdx.y = frame.  A frame only runs the passes its
+// largest key needs (npass[f], from the atomicMax the key-producing kernel left in maxkey[f]);
+// its result sits in buffer npass[f] & 1.
+//
+// Used by VoxelGrid (voxel keys), the ECE hash grid (cell keys), the canonical
+// cluster ordering (size desc) and the CSR build (cluster rank).
+#include "internal.cuh"
+#include "primitives.cuh"
+
+namespace pcop {
+
+namespace {
+
+__global__ void k_sort_reset(uint32_t* maxkey, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < B) maxkey[f] = 0u;
+}
+
+// npass from maxkey; zero this frame's histograms
+__global__ void k_sort_setup(const uint32_t* __restrict__ maxkey, int* __restrict__ npass, uint32_t* __restrict__ hist,
+                             int B) {
+  const int f = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const uint32_t mk = maxkey[f];
+    const int bits = 32 - __clz((int)(mk | 1u));
+    npass[f] = max(1, cdiv(bits, RS_RADIX_BITS));
+  }
+  for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_BINS; i += blockDim.x)
+    hist[(size_t)f * RS_MAX_PASSES * RS_BINS + i] = 0u;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_sort_hist(const uint32_t* __restrict__ keys, const int* __restrict__ count,
+                                                           const int* __restrict__ npass, uint32_t* __restrict__ hist,
+                                                           int cap) {
+  const int f = blockIdx.y;
+  const int n = count[f];
+  const int base = blockIdx.x * RS_TILE;
+  if (base >= n) return;
+  const int np = npass[f];
+  __shared__ uint32_t sh[RS_MAX_PASSES * RS_BINS];
+  for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_BINS; i += RS_THREADS) sh[i] = 0u;
+  __syncthreads();
+  const uint32_t* k = keys + (size_t)f * cap;
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const int i = base + it * RS_THREADS + threadIdx.x;
+    if (i < n) {
+      const uint32_t key = k[i];
+      for (int p = 0; p < np; ++p) atomicAdd(&sh[p * RS_BINS + ((key >> (p * RS_RADIX_BITS)) & (RS_BINS - 1))], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t* gh = hist + (size_t)f * RS_MAX_PASSES * RS_BINS;
+  for (int i = threadIdx.x; i < np * RS_BINS; i += RS_THREADS) {
+    const uint32_t v = sh[i];
+    if (v) atomicAdd(&gh[i], v);
+  }
+}
+
+// exclusive scan of each (frame, pass) histogram, in place; blockDim = 256 = RS_BINS
+__global__ void __launch_bounds__(RS_BINS) k_sort_scan(uint32_t* __restrict__ hist, const int* __restrict__ npass) {
+  const int f = blockIdx.y, p = blockIdx.x;
+  if (p >= npass[f]) return;
+  uint32_t* h = hist + ((size_t)f * RS_MAX_PASSES + p) * RS_BINS;
+  __shared__ uint32_t wsum[RS_BINS / 32];
+  const uint32_t v = h[threadIdx.x];
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(FULL, incl, o);
+    if (lane_id() >= o) incl += up;
+  }
+  if (lane_id() == 31) wsum[warp_id()] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int w = 0; w < warp_id(); ++w) wbase += wsum[w];
+  h[threadIdx.x] = wbase + incl - v;
+}
+
+struct PassSmem {
+  uint32_t warp_hist[RS_THREADS / 32][RS_BINS];  // per-warp digit counts -> exclusive across warps
+  uint32_t tile_off[RS_BINS];                    // exclusive scan of the tile histogram
+  uint32_t glob_base[RS_BINS];                   // global output slot of the tile's first key of each digit
+  uint32_t skey[RS_TILE];
+  uint32_t sval[RS_TILE];
+  uint32_t wsum[RS_BINS / 32];
+};
+
+__global__ void __launch_bounds__(RS_THREADS)
+    k_sort_pass(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, const int* __restrict__ count, const int* __restrict__ npass,
+                const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ desc, int pass, int cap, int tiles,
+                int iota_vals) {
+  const int f = blockIdx.y;
+  const int n = count[f];
+  const int tile = blockIdx.x;
+  const int tbase = tile * RS_TILE;
+  if (tbase >= n) return;
+  if (pass >= npass[f]) return;
+  __shared__ PassSmem sm;
+  const int lane = lane_id(), warp = warp_id();
+  const int shift = pass * RS_RADIX_BITS;
+  // buffers of this pass: even passes read buffer 0
+  const uint32_t* kin = ((pass & 1) ? key_b : key_a) + (size_t)f * cap;
+  const uint32_t* vin = ((pass & 1) ? val_b : val_a) + (size_t)f * cap;
+  uint32_t* kout = ((pass & 1) ? key_a : key_b) + (size_t)f * cap;
+  uint32_t* vout = ((pass & 1) ? val_a : val_b) + (size_t)f * cap;
+
+  for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_BINS; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0u;
+  __syncthreads();
+
+  // warp-striped: warp w owns tile elements [w*256, w*256+256); item k of lane l = w*256 + k*32 + l
+  uint32_t key[RS_ITEMS], val[RS_ITEMS];
+  uint32_t rank[RS_ITEMS];
+  bool valid[RS_ITEMS];
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int i = tbase + warp * (32 * RS_ITEMS) + k * 32 + lane;
+    valid[k] = i < n;
+    key[k] = valid[k] ? kin[i] : 0xffffffffu;
+    val[k] = valid[k] ? ((iota_vals && pass == 0) ? (uint32_t)i : vin[i]) : 0u;
+  }
+  // rank keys inside the warp, digit by digit, rows in order => stable
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const uint32_t d = (key[k] >> shift) & (RS_BINS - 1);
+    const unsigned vm = __ballot_sync(FULL, valid[k]);
+    unsigned m = __match_any_sync(FULL, valid[k] ? d : (RS_BINS + lane));  // invalid lanes match nobody
+    m &= vm;
+    uint32_t before = 0;
+    if (valid[k]) before = sm.warp_hist[warp][d];
+    __syncwarp();
+    if (valid[k]) {
+      rank[k] = before + __popc(m & lanemask_lt());
+      if ((m & lanemask_lt()) == 0u) sm.warp_hist[warp][d] = before + __popc(m);  // lowest lane of the group
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread d: exclusive scan of digit d over the 8 warps, tile count, look-back
+  {
+    const int d = threadIdx.x;
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; ++w) {
+      const uint32_t c = sm.warp_hist[w][d];
+      sm.warp_hist[w][d] = run;
+      run += c;
+    }
+    const uint32_t tile_count = run;
+    // tile-local exclusive scan over digits
+    uint32_t incl = tile_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) sm.wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (int w = 0; w < warp; ++w) wb += sm.wsum[w];
+    sm.tile_off[d] = wb + incl - tile_count;
+
+    // decoupled look-back for digit d over the earlier tiles of this frame
+    unsigned* dd = desc + (((size_t)pass * gridDim.y + f) * tiles) * RS_BINS + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st_volatile_u32(dd, LB_PREFIX | tile_count);
+    } else {
+      st_volatile_u32(dd + (size_t)tile * RS_BINS, LB_AGG | tile_count);
+      for (int t = tile - 1; t >= 0; --t) {
+        unsigned v = ld_volatile_u32(dd + (size_t)t * RS_BINS);
+        while ((v >> 30) == 0u) v = ld_volatile_u32(dd + (size_t)t * RS_BINS);
+        excl += v & LB_VALUE;
+        if ((v >> 30) == 2u) break;
+      }
+      st_volatile_u32(dd + (size_t)tile * RS_BINS, LB_PREFIX | (excl + tile_count));
+    }
+    sm.glob_base[d] = bin_base[((size_t)f * RS_MAX_PASSES + pass) * RS_BINS + d] + excl;
+  }
+  __syncthreads();
+
+  // stage the tile in sorted order
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    if (valid[k]) {
+      const uint32_t d = (key[k] >> shift) & (RS_BINS - 1);
+      const uint32_t p = sm.tile_off[d] + sm.warp_hist[warp][d] + rank[k];
+      sm.skey[p] = key[k];
+      sm.sval[p] = val[k];
+    }
+  }
+  __syncthreads();
+  const int tile_n = min(RS_TILE, n - tbase);
+  for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+    const uint32_t kk = sm.skey[i];
+    const uint32_t d = (kk >> shift) & (RS_BINS - 1);
+    const uint32_t g = sm.glob_base[d] + ((uint32_t)i - sm.tile_off[d]);
+    kout[g] = kk;
+    vout[g] = sm.sval[i];
+  }
+}
+
+}  // namespace
+
+size_t sort_desc_bytes(int B, int cap) {
+  return (size_t)RS_MAX_PASSES * B * cdiv(cap, RS_TILE) * RS_BINS * sizeof(uint32_t);
+}
+
+void sort_reset_maxkey(const Ctx& c, const SortBufs& s) {
+  k_sort_reset<<<cdiv(c.B, 256), 256, 0, c.stream>>>(s.maxkey, c.B);
+  count_launch(c);
+}
+
+void radix_sort_batched(const Ctx& c, const SortBufs& s, const int* count, bool iota_vals) {
+  const int tiles = cdiv(c.cap, RS_TILE);
+  cudaMemsetAsync(s.desc, 0, sort_desc_bytes(c.B, c.cap), c.stream);
+  k_sort_setup<<<c.B, 256, 0, c.stream>>>(s.maxkey, s.npass, s.hist, c.B);
+  k_sort_hist<<<dim3(tiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], count, s.npass, s.hist, c.cap);
+  k_sort_scan<<<dim3(RS_MAX_PASSES, c.B), RS_BINS, 0, c.stream>>>(s.hist, s.npass);
+  count_launch(c, 3);
+  for (int p = 0; p < RS_MAX_PASSES; ++p) {
+    k_sort_pass<<<dim3(tiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.key[1], s.val[1], count, s.npass,
+                                                               s.hist, s.desc, p, c.cap, tiles, iota_vals ? 1 : 0);
+    count_launch(c);
+  }
+}
+
+}  // namespace pcop

@@ -1,0 +1,439 @@
+// Euclidean cluster extraction (reference: extract_euclidian_clusters od.cpp:430-455 with the
+// kd-tree of od.cpp:791-792 -> pcl::EuclideanClusterExtraction) and per-cluster
+// centroid + bounding radius (msg/PointWithRad.msg:1-4; distance arithmetic od.cpp:457-464).
+//
+// The kd-tree radius search is replaced by a uniform grid with cell >= tolerance*(1+2^-8):
+// points are radix-sorted by cell key, every point tests the 13 "forward" neighbour cells plus
+// the rest of its own cell with the exact float predicate d2 < r2, and matching pairs are merged
+// in an atomic-min union-find whose roots are the smallest original index of each component, so
+// labels are deterministic.  Clusters = connected components, filtered by size, ordered by
+// size descending then smallest index ascending, indices ascending inside a cluster.
+#include "internal.cuh"
+#include "primitives.cuh"
+
+namespace pcop {
+
+namespace {
+
+constexpr int ECE_MAX_DIM = 1024;  // cells per axis (30-bit keys)
+
+__global__ void k_ece_setup(const MinMax* __restrict__ minmax, const int* __restrict__ n_in, float tol,
+                            EceFrame* __restrict__ ef, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  EceFrame e;
+  const float cell_min = tol * 1.00390625f;  // tolerance * (1 + 2^-8): see DESIGN.md "grid guarantee"
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float mn = ord2f(minmax[f].mn[a]);
+    float mx = ord2f(minmax[f].mx[a]);
+    if (n_in[f] <= 0 || !(mx >= mn)) {
+      mn = 0.0f;
+      mx = 0.0f;
+    }
+    const float ext = mx - mn;
+    float cell = fmaxf(cell_min, ext / (float)(ECE_MAX_DIM - 1));
+    if (!(cell > 0.0f) || !(cell < 3.0e38f)) cell = 1.0f;
+    e.mn[a] = mn;
+    e.inv[a] = 1.0f / cell;
+    int d = (int)floorf(ext * e.inv[a]) + 1;
+    e.dim[a] = min(max(d, 1), ECE_MAX_DIM);
+  }
+  ef[f] = e;
+}
+
+__device__ __forceinline__ int cell_coord(float x, float mn, float inv, int dim) {
+  const float s = floorf((x - mn) * inv);
+  int c = (s == s) ? (int)fminf(fmaxf(s, 0.0f), (float)(dim - 1)) : 0;
+  return c;
+}
+
+__global__ void __launch_bounds__(CT_THREADS)
+    k_ece_keys(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in,
+               const EceFrame* __restrict__ ef, uint32_t* __restrict__ keys, uint32_t* __restrict__ maxkey,
+               int* __restrict__ parent, int* __restrict__ csize, int cap) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const int n = n_in[f];
+  if (tile * CT_TILE >= n) return;
+  const EceFrame e = ef[f];
+  const float4* src = in + (size_t)f * in_stride;
+  uint32_t mk = 0;
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int i = ct_index(tile, k);
+    if (i < n) {
+      const float4 p = __ldg(src + i);
+      const int cx = cell_coord(p.x, e.mn[0], e.inv[0], e.dim[0]);
+      const int cy = cell_coord(p.y, e.mn[1], e.inv[1], e.dim[1]);
+      const int cz = cell_coord(p.z, e.mn[2], e.inv[2], e.dim[2]);
+      const uint32_t key = (uint32_t)cx + (uint32_t)e.dim[0] * ((uint32_t)cy + (uint32_t)e.dim[1] * (uint32_t)cz);
+      keys[(size_t)f * cap + i] = key;
+      if (parent) {
+        parent[(size_t)f * cap + i] = i;
+        csize[(size_t)f * cap + i] = 0;
+      }
+      mk = max(mk, key);
+    }
+  }
+  mk = __reduce_max_sync(FULL, mk);
+  if (lane_id() == 0 && mk) atomicMax(&maxkey[f], mk);
+}
+
+// sorted copy of the cloud: xyz + original index in w
+__global__ void __launch_bounds__(CT_THREADS)
+    k_ece_gather(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in,
+                 const uint32_t* __restrict__ val0, const uint32_t* __restrict__ val1, const int* __restrict__ npass,
+                 float4* __restrict__ sorted_pts, int cap) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const int n = n_in[f];
+  if (tile * CT_TILE >= n) return;
+  const uint32_t* vs = ((npass[f] & 1) ? val1 : val0) + (size_t)f * cap;
+  const float4* src = in + (size_t)f * in_stride;
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int j = ct_index(tile, k);
+    if (j < n) {
+      const uint32_t i = vs[j];
+      float4 p = __ldg(src + i);
+      p.w = __uint_as_float(i);
+      sorted_pts[(size_t)f * cap + j] = p;
+    }
+  }
+}
+
+__device__ __forceinline__ int uf_find(int* parent, int v) {
+  // path halving with atomicMin: parents only ever decrease, so a stale read is still an ancestor
+  int p = parent[v];
+  while (p != v) {
+    const int gp = parent[p];
+    if (gp != p) atomicMin(&parent[v], gp);
+    v = p;
+    p = gp;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(&parent[a], b);  // hook the larger root under the smaller
+    if (old == a) return;
+    a = old;  // a was no longer a root: merge its (former) parent with b instead
+  }
+}
+
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+    k_ece_union(const float4* __restrict__ sorted_pts, const uint32_t* __restrict__ key0,
+                const uint32_t* __restrict__ key1, const int* __restrict__ npass, const int* __restrict__ n_in,
+                const EceFrame* __restrict__ ef, int* __restrict__ parent, float r2, int cap) {
+  const int f = blockIdx.y;
+  const int n = n_in[f];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t* ks = ((npass[f] & 1) ? key1 : key0) + (size_t)f * cap;
+  const float4* sp = sorted_pts + (size_t)f * cap;
+  int* par = parent + (size_t)f * cap;
+  const EceFrame e = ef[f];
+  const float4 p = sp[j];
+  const int pi = (int)__float_as_uint(p.w);
+  const uint32_t key = ks[j];
+  const int cx = (int)(key % (uint32_t)e.dim[0]);
+  const int cy = (int)((key / (uint32_t)e.dim[0]) % (uint32_t)e.dim[1]);
+  const int cz = (int)(key / ((uint32_t)e.dim[0] * (uint32_t)e.dim[1]));
+  const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, e.dim[0] - 1);
+
+  // own row: the rest of the own cell and the +x cell directly follow j in sorted order
+  {
+    const uint32_t hi_key = key - (uint32_t)cx + (uint32_t)x_hi;
+    for (int q = j + 1; q < n && ks[q] <= hi_key; ++q) {
+      const float4 o = sp[q];
+      if (dist2(p.x, p.y, p.z, o.x, o.y, o.z) < r2) uf_union(par, pi, (int)__float_as_uint(o.w));
+    }
+  }
+  // the four forward rows: (dy,dz) = (+1,0), (-1,+1), (0,+1), (+1,+1)
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int dy = (r == 0) ? 1 : (r - 2);
+    const int dz = (r == 0) ? 0 : 1;
+    const int yy = cy + dy, zz = cz + dz;
+    if (yy < 0 || yy >= e.dim[1] || zz >= e.dim[2]) continue;
+    const uint32_t row = (uint32_t)e.dim[0] * ((uint32_t)yy + (uint32_t)e.dim[1] * (uint32_t)zz);
+    const uint32_t lo_key = row + (uint32_t)x_lo, hi_key = row + (uint32_t)x_hi;
+    for (int q = lower_bound_u32(ks, n, lo_key); q < n && ks[q] <= hi_key; ++q) {
+      const float4 o = sp[q];
+      if (dist2(p.x, p.y, p.z, o.x, o.y, o.z) < r2) uf_union(par, pi, (int)__float_as_uint(o.w));
+    }
+  }
+}
+
+// label = root; component sizes (warp-aggregated atomics)
+__global__ void __launch_bounds__(256) k_ece_flatten(int* __restrict__ parent, int* __restrict__ csize,
+                                                       const int* __restrict__ n_in, int cap) {
+  const int f = blockIdx.y;
+  const int n = n_in[f];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  int* par = parent + (size_t)f * cap;
+  int root = -1 - (int)threadIdx.x;  // unique dummy for idle lanes
+  if (valid) {
+    root = par[i];
+    while (true) {
+      const int up = par[root];
+      if (up == root) break;
+      root = up;
+    }
+    par[i] = root;
+  }
+  const unsigned m = __match_any_sync(FULL, root);
+  if (valid && (m & lanemask_lt()) == 0u) atomicAdd(&csize[(size_t)f * cap + root], __popc(m));
+}
+
+// kept roots in ascending index order + their sort key (n - size: ascending key = descending size)
+__global__ void __launch_bounds__(CT_THREADS)
+    k_ece_roots(const int* __restrict__ parent, const int* __restrict__ csize, const int* __restrict__ n_in,
+                int min_size, int max_size, int* __restrict__ roots, uint32_t* __restrict__ keys,
+                uint32_t* __restrict__ maxkey, int* __restrict__ n_clusters, unsigned* __restrict__ desc, int cap,
+                int tiles) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const int n = n_in[f];
+  if (tile * CT_TILE >= n) {
+    if (tile == 0 && threadIdx.x == 0) n_clusters[f] = 0;
+    return;
+  }
+  __shared__ CompactSmem sm;
+  bool keep[CT_ITEMS];
+  unsigned pos[CT_ITEMS];
+  int sz[CT_ITEMS];
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int i = ct_index(tile, k);
+    keep[k] = false;
+    sz[k] = 0;
+    if (i < n && parent[(size_t)f * cap + i] == i) {
+      sz[k] = csize[(size_t)f * cap + i];
+      keep[k] = sz[k] >= min_size && sz[k] <= max_size;
+    }
+  }
+  const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm);
+  uint32_t mk = 0;
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    if (keep[k]) {
+      roots[(size_t)f * cap + pos[k]] = ct_index(tile, k);
+      const uint32_t key = (uint32_t)(n - sz[k]);
+      keys[(size_t)f * cap + pos[k]] = key;
+      mk = max(mk, key);
+    }
+  }
+  mk = __reduce_max_sync(FULL, mk);
+  if (lane_id() == 0 && mk) atomicMax(&maxkey[f], mk);
+  if ((tile + 1) * CT_TILE >= n && threadIdx.x == 0) n_clusters[f] = (int)incl_total;
+}
+
+// one block per frame: walk the size-sorted roots, assign ranks and CSR offsets
+__global__ void __launch_bounds__(256)
+    k_ece_rank(const int* __restrict__ roots, const uint32_t* __restrict__ val0, const uint32_t* __restrict__ val1,
+               const int* __restrict__ npass, const int* __restrict__ csize, const int* __restrict__ n_clusters,
+               int* __restrict__ rank_of, int* __restrict__ offsets, int* __restrict__ n_cluster_pts, int cap) {
+  const int f = blockIdx.x;
+  const int C = n_clusters[f];
+  const uint32_t* vs = ((npass[f] & 1) ? val1 : val0) + (size_t)f * cap;
+  int* offs = offsets + (size_t)f * (cap + 1);
+  __shared__ int wsum[8];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < C; base += 256) {
+    const int r = base + threadIdx.x;
+    int sz = 0, root = -1;
+    if (r < C) {
+      root = roots[(size_t)f * cap + vs[r]];
+      sz = csize[(size_t)f * cap + root];
+      rank_of[(size_t)f * cap + root] = r;
+    }
+    int incl = sz;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(FULL, incl, o);
+      if (lane_id() >= o) incl += up;
+    }
+    if (lane_id() == 31) wsum[warp_id()] = incl;
+    __syncthreads();
+    int wb = carry;
+    for (int w = 0; w < warp_id(); ++w) wb += wsum[w];
+    if (r < C) offs[r] = wb + incl - sz;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = wb + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    offs[C] = carry;
+    n_cluster_pts[f] = carry;
+  }
+}
+
+// per point: sort key = rank of its cluster, or C for points outside every kept cluster
+__global__ void __launch_bounds__(CT_THREADS)
+    k_ece_member_keys(const int* __restrict__ parent, const int* __restrict__ csize, const int* __restrict__ rank_of,
+                      const int* __restrict__ n_in, const int* __restrict__ n_clusters, int min_size, int max_size,
+                      uint32_t* __restrict__ keys, uint32_t* __restrict__ maxkey, int cap) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const int n = n_in[f];
+  if (tile * CT_TILE >= n) return;
+  const uint32_t C = (uint32_t)n_clusters[f];
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int i = ct_index(tile, k);
+    if (i < n) {
+      const int root = parent[(size_t)f * cap + i];
+      const int sz = csize[(size_t)f * cap + root];
+      const bool kept = sz >= min_size && sz <= max_size;
+      keys[(size_t)f * cap + i] = kept ? (uint32_t)rank_of[(size_t)f * cap + root] : C;
+    }
+  }
+  if (tile == 0 && threadIdx.x == 0 && C) atomicMax(&maxkey[f], C);
+}
+
+// the first L sorted values are the CSR indices
+__global__ void __launch_bounds__(256)
+    k_ece_indices(const uint32_t* __restrict__ val0, const uint32_t* __restrict__ val1, const int* __restrict__ npass,
+                  const int* __restrict__ n_cluster_pts, int* __restrict__ indices, int cap) {
+  const int f = blockIdx.y;
+  const int L = n_cluster_pts[f];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= L) return;
+  const uint32_t* vs = ((npass[f] & 1) ? val1 : val0) + (size_t)f * cap;
+  indices[(size_t)f * cap + j] = (int)vs[j];
+}
+
+// one block per cluster (grid-stride over the frame's clusters): centroid in double, then radius
+__global__ void __launch_bounds__(256)
+    k_centroid_radius(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ offsets,
+                      const int* __restrict__ indices, const int* __restrict__ n_clusters, float4* __restrict__ obstacles,
+                      int cap) {
+  const int f = blockIdx.y;
+  const int C = n_clusters[f];
+  const float4* src = in + (size_t)f * in_stride;
+  const int* offs = offsets + (size_t)f * (cap + 1);
+  const int* idx = indices + (size_t)f * cap;
+  __shared__ double sh[8][3];
+  __shared__ float shc[3];
+  __shared__ float shr[8];
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const int b = offs[c], e = offs[c + 1];
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int j = b + threadIdx.x; j < e; j += blockDim.x) {
+      const float4 p = __ldg(src + idx[j]);
+      sx += (double)p.x;
+      sy += (double)p.y;
+      sz += (double)p.z;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      sx += __shfl_xor_sync(FULL, sx, o);
+      sy += __shfl_xor_sync(FULL, sy, o);
+      sz += __shfl_xor_sync(FULL, sz, o);
+    }
+    if (lane_id() == 0) {
+      sh[warp_id()][0] = sx;
+      sh[warp_id()][1] = sy;
+      sh[warp_id()][2] = sz;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+      shc[threadIdx.x] = (float)(s / (double)(e - b));
+    }
+    __syncthreads();
+    const float cx = shc[0], cy = shc[1], cz = shc[2];
+    float r = 0.0f;
+    for (int j = b + threadIdx.x; j < e; j += blockDim.x) {
+      const float4 p = __ldg(src + idx[j]);
+      const float d = sqrtf(dist2(p.x, p.y, p.z, cx, cy, cz));  // od.cpp:457-464 arithmetic
+      r = fmaxf(r, d);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, o));
+    if (lane_id() == 0) shr[warp_id()] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float rr = shr[0];
+      for (int w = 1; w < 8; ++w) rr = fmaxf(rr, shr[w]);
+      obstacles[(size_t)f * cap + c] = make_float4(cx, cy, cz, rr);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+void run_grid_sort(const Ctx& c, const float4* in, size_t in_stride, const int* n_in, float cell, MinMax* minmax,
+                   EceFrame* ef, const SortBufs& sort, float4* sorted_pts, int* parent, int* csize) {
+  const int tiles = cdiv(c.cap, CT_TILE);
+  run_minmax(c, in, in_stride, n_in, minmax);
+  k_ece_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(minmax, n_in, cell, ef, c.B);
+  sort_reset_maxkey(c, sort);
+  k_ece_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, ef, sort.key[0], sort.maxkey, parent,
+                                                            csize, c.cap);
+  count_launch(c, 2);
+  radix_sort_batched(c, sort, n_in, true);
+  k_ece_gather<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, sort.val[0], sort.val[1], sort.npass,
+                                                              sorted_pts, c.cap);
+  count_launch(c);
+}
+
+void run_cluster(const Ctx& c, const ClusterArgs& a) {
+  const int tiles = cdiv(c.cap, CT_TILE);
+  const float r2 = (float)((double)a.tol * (double)a.tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
+  run_grid_sort(c, a.in, a.in_stride, a.n_in, a.tol, a.minmax, a.ef, a.sort, a.sorted_pts, a.parent, a.csize);
+  k_ece_union<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass,
+                                                                 a.n_in, a.ef, a.parent, r2, c.cap);
+  k_ece_flatten<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.parent, a.csize, a.n_in, c.cap);
+  count_launch(c, 2);
+  // kept roots, ordered by size descending (stable => smallest index first among equals)
+  cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
+  sort_reset_maxkey(c, a.sort);
+  k_ece_roots<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.n_in, a.min_size, a.max_size, a.roots,
+                                                             a.sort.key[0], a.sort.maxkey, a.n_clusters, a.desc, c.cap,
+                                                             tiles);
+  count_launch(c);
+  radix_sort_batched(c, a.sort, a.n_clusters, true);
+  k_ece_rank<<<c.B, 256, 0, c.stream>>>(a.roots, a.sort.val[0], a.sort.val[1], a.sort.npass, a.csize, a.n_clusters,
+                                        a.rank_of, a.offsets, a.n_cluster_pts, c.cap);
+  // CSR indices: stable sort of the points by cluster rank
+  sort_reset_maxkey(c, a.sort);
+  k_ece_member_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.rank_of, a.n_in, a.n_clusters,
+                                                                   a.min_size, a.max_size, a.sort.key[0], a.sort.maxkey,
+                                                                   c.cap);
+  count_launch(c, 2);
+  radix_sort_batched(c, a.sort, a.n_in, true);
+  k_ece_indices<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.sort.val[0], a.sort.val[1], a.sort.npass,
+                                                                   a.n_cluster_pts, a.indices, c.cap);
+  count_launch(c);
+}
+
+void run_centroid_radius(const Ctx& c, const ClusterArgs& a) {
+  k_centroid_radius<<<dim3(64, c.B), 256, 0, c.stream>>>(a.in, a.in_stride, a.offsets, a.indices, a.n_clusters,
+                                                         a.obstacles, c.cap);
+  count_launch(c);
+}
+
+}  // namespace pcop

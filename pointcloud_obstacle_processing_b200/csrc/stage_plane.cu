@@ -1,0 +1,627 @@
+// RANSAC plane-removal loop (reference: segment_plane_and_extract_indices od.cpp:342-428 ->
+// pcl::SACSegmentation<SACMODEL_PERPENDICULAR_PLANE, SAC_RANSAC> + pcl::ExtractIndices,
+// SURVEY 8a-4).
+//
+// PCL draws samples sequentially but the draws never depend on the scores, so per pass and per
+// frame: (1) one warp replays boost::mt19937(12345) + the persistent index shuffle sparsely and
+// emits all <= 51 hypotheses; (2) one sweep over the points scores every hypothesis (warp
+// ballots -> integer counts); (3) one thread replays PCL's adaptive-k loop over the counts;
+// (4) the nine inlier moments are accumulated in double in the canonical tree order;
+// (5) one thread runs PCL's closed-form eigen33 and validates the refined model; (6) a stable
+// compaction removes the refined inliers; (7) the while(size > 0.3*nr) rule is evaluated per
+// frame.  Frames of a wave run their passes in lock-step; finished frames idle.
+#include "det_math.cuh"
+#include "internal.cuh"
+#include "primitives.cuh"
+
+namespace pcop {
+
+namespace {
+
+constexpr int MAP_CAP = RNG_TABLE + 8;
+constexpr double kHalfPi = 1.57079632679489661923;
+
+__device__ __forceinline__ const float4* cur_cloud(const PlaneFrame& P, const float4* in, size_t in_stride,
+                                                   float4* const* buf, int f, int cap) {
+  return (P.cur < 0) ? (in + (size_t)f * in_stride) : (buf[P.cur] + (size_t)f * cap);
+}
+
+struct BufPair {
+  float4* p[2];
+  int* s[2];
+};
+
+__device__ bool model_valid(const PlaneConst& pc, const float4 co) {
+  if (!(pc.eps_angle > 0.0)) return true;
+  if (pc.eps_angle >= kHalfPi) return true;
+  const double nx = co.x, ny = co.y, nz = co.z;
+  const double dot = dadd(dadd(dmul(nx, pc.axis[0]), dmul(ny, pc.axis[1])), dmul(nz, pc.axis[2]));
+  const double nn = __dsqrt_rn(dadd(dadd(dmul(nx, nx), dmul(ny, ny)), dmul(nz, nz)));
+  const double na = __dsqrt_rn(dadd(dadd(dmul(pc.axis[0], pc.axis[0]), dmul(pc.axis[1], pc.axis[1])),
+                                    dmul(pc.axis[2], pc.axis[2])));
+  const double cosang = ddiv(fabs(dot), dmul(nn, na));
+  return !(cosang < pc.cos_eps);
+}
+
+__device__ __forceinline__ bool collinear_ratio_test(const float4 p0, const float4 p1, const float4 p2) {
+  const float ax = fdiv(fsub(p1.x, p0.x), fsub(p2.x, p0.x));
+  const float ay = fdiv(fsub(p1.y, p0.y), fsub(p2.y, p0.y));
+  const float az = fdiv(fsub(p1.z, p0.z), fsub(p2.z, p0.z));
+  return (ax == ay) && (az == ay);
+}
+
+__device__ float4 compute_model(const float4 p0, const float4 p1, const float4 p2) {
+  const float ax = fsub(p1.x, p0.x), ay = fsub(p1.y, p0.y), az = fsub(p1.z, p0.z);
+  const float bx = fsub(p2.x, p0.x), by = fsub(p2.y, p0.y), bz = fsub(p2.z, p0.z);
+  float nx = fsub(fmul(ay, bz), fmul(az, by));
+  float ny = fsub(fmul(az, bx), fmul(ax, bz));
+  float nz = fsub(fmul(ax, by), fmul(ay, bx));
+  const float norm = __fsqrt_rn(fadd(fadd(fmul(nx, nx), fmul(ny, ny)), fmul(nz, nz)));
+  nx = fdiv(nx, norm);
+  ny = fdiv(ny, norm);
+  nz = fdiv(nz, norm);
+  const float d = -fadd(fadd(fmul(nx, p0.x), fmul(ny, p0.y)), fmul(nz, p0.z));
+  return make_float4(nx, ny, nz, d);
+}
+
+__global__ void k_plane_init(PlaneFrame* __restrict__ pf, const int* __restrict__ n_in, double keep_fraction,
+                             int* __restrict__ n_active, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  PlaneFrame& P = pf[f];
+  const int n = n_in[f];
+  P.cur = -1;
+  P.nr_points = n;
+  P.n = n;
+  P.n_passes = 0;
+  P.n_hyp = 0;
+  P.gen_end = 0;
+  P.best = -1;
+  P.model_ok = 0;
+  P.n_inliers_last = 0;
+  P.coeff_sel = make_float4(0.f, 0.f, 0.f, 0.f);
+  P.coeff_ref = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < PCOP_MAX_PLANE_PASSES_RECORDED; ++k) {
+    P.pass_points[k] = 0;
+    P.pass_inliers[k] = 0;
+    P.pass_coeff[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  P.active = ((double)n > dmul(keep_fraction, (double)n)) ? 1 : 0;  // od.cpp:379
+  if (P.active) atomicAdd(n_active, 1);
+}
+
+// one warp per frame: hypothesis generation (getSamples/drawIndexSample/isSampleGood/
+// computeModelCoefficients).  shuffled_indices_ is simulated sparsely: positions 0..2 live in
+// registers, every other touched position in a (pos,val) list searched by the 32 lanes.
+__global__ void __launch_bounds__(32)
+    k_plane_gen(PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp,
+                const int* __restrict__ rng, PlaneConst pc, uint32_t* __restrict__ warnings, int cap) {
+  const int f = blockIdx.x;
+  PlaneFrame& P = pf[f];
+  if (!P.active) return;
+  const int lane = threadIdx.x;
+  __shared__ int mpos[MAP_CAP];
+  __shared__ int mval[MAP_CAP];
+  const int n = P.n;
+  const float4* pts = cur_cloud(P, in, in_stride, bp.p, f, cap);
+  int ne = 0;
+  int s[3] = {0, 1, 2};
+  int t = 0;
+  int nh = 0;
+  int gen_end = 0;
+  if (n < 3) {
+    gen_end = 1;  // getSamples: fewer points than the sample size -> empty selection
+  } else {
+    while (nh <= pc.max_iterations && nh < MAX_HYP) {
+      bool good = false;
+      float4 p0, p1, p2;
+      for (int check = 0; check < 1000; ++check) {
+        if (t + 3 > RNG_TABLE) {
+          gen_end = 2;
+          break;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int r = rng[t++];
+          const int j = i + (int)((unsigned)r % (unsigned)(n - i));
+          const int vi = s[i];
+          if (j < 3) {
+            // j >= i always; swap two register slots
+            const int vj = (j == 0) ? s[0] : ((j == 1) ? s[1] : s[2]);
+            if (j == 0) s[0] = vi;
+            else if (j == 1) s[1] = vi;
+            else s[2] = vi;
+            s[i] = vj;
+          } else {
+            int found = -1;
+            for (int e = lane; e < ne; e += 32)
+              if (mpos[e] == j) found = e;
+            const unsigned b = __ballot_sync(FULL, found >= 0);
+            int vj = j;
+            if (b) {
+              const int idx = __shfl_sync(FULL, found, __ffs(b) - 1);
+              vj = mval[idx];
+              __syncwarp();
+              if (lane == 0) mval[idx] = vi;
+            } else {
+              if (lane == 0) {
+                mpos[ne] = j;
+                mval[ne] = vi;
+              }
+              ++ne;
+            }
+            __syncwarp();
+            s[i] = vj;
+          }
+        }
+        p0 = pts[s[0]];
+        p1 = pts[s[1]];
+        p2 = pts[s[2]];
+        if (!collinear_ratio_test(p0, p1, p2)) {  // isSampleGood
+          good = true;
+          break;
+        }
+      }
+      if (!good) {
+        if (!gen_end) gen_end = 1;
+        break;
+      }
+      // computeModelCoefficients repeats the same collinearity test, so it cannot fail here
+      const float4 co = compute_model(p0, p1, p2);
+      if (lane == 0) {
+        P.hyp[nh] = co;
+        P.hyp_valid[nh] = model_valid(pc, co) ? 1 : 0;
+      }
+      ++nh;
+    }
+  }
+  if (lane == 0) {
+    P.n_hyp = nh;
+    P.gen_end = gen_end;
+    if (gen_end == 2) atomicOr(&warnings[f], (uint32_t)PCOP_WARN_RNG_TABLE_EXHAUSTED);
+  }
+  for (int h = lane; h < MAX_HYP; h += 32) P.counts[h] = 0;
+}
+
+// countWithinDistance for every hypothesis in one sweep
+__global__ void __launch_bounds__(CT_THREADS)
+    k_plane_score(PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp, float thr,
+                  int cap) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  PlaneFrame& P = pf[f];
+  if (!P.active) return;
+  const int n = P.n;
+  if (tile * CT_TILE >= n) return;
+  const int nh = P.n_hyp;
+  if (nh == 0) return;
+  __shared__ float4 hyp[MAX_HYP];
+  __shared__ int cnt[MAX_HYP];
+  if (threadIdx.x < MAX_HYP) {
+    hyp[threadIdx.x] = (threadIdx.x < nh) ? P.hyp[threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+    cnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  const float4* pts = cur_cloud(P, in, in_stride, bp.p, f, cap);
+  float4 p[CT_ITEMS];
+  bool valid[CT_ITEMS];
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int i = ct_index(tile, k);
+    valid[k] = i < n;
+    p[k] = valid[k] ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int lane = lane_id();
+  int acc[MAX_HYP / 32];
+#pragma unroll
+  for (int hh = 0; hh < MAX_HYP / 32; ++hh) acc[hh] = 0;
+#pragma unroll
+  for (int hh = 0; hh < MAX_HYP / 32; ++hh) {
+    for (int hl = 0; hl < 32; ++hl) {
+      const int h = hh * 32 + hl;
+      if (h >= nh) break;
+      const float4 co = hyp[h];
+      int c = 0;
+#pragma unroll
+      for (int k = 0; k < CT_ITEMS; ++k)
+        c += __popc(__ballot_sync(FULL, valid[k] && plane_dist(co, p[k].x, p[k].y, p[k].z) < thr));
+      if (lane == hl) acc[hh] += c;
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < MAX_HYP / 32; ++hh)
+    if (acc[hh]) atomicAdd(&cnt[hh * 32 + lane], acc[hh]);
+  __syncthreads();
+  if (threadIdx.x < nh && cnt[threadIdx.x]) atomicAdd(&P.counts[threadIdx.x], cnt[threadIdx.x]);
+}
+
+// RandomSampleConsensus::computeModel's loop, replayed over the precomputed counts
+__global__ void k_plane_select(PlaneFrame* __restrict__ pf, PlaneConst pc, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  PlaneFrame& P = pf[f];
+  if (!P.active) return;
+  const int nh = P.n_hyp;
+  const double log_probability = det_log(dsub(1.0, pc.probability));
+  const double one_over_indices = ddiv(1.0, (double)P.n);
+  const double eps = 2.220446049250313e-16;
+  int best = -2147483647;
+  int sel = -1;
+  double k = 1.0;
+  for (int h = 0; h < nh; ++h) {
+    if (!((double)h < k)) break;
+    const int c = P.hyp_valid[h] ? P.counts[h] : 0;
+    if (c > best) {
+      best = c;
+      sel = h;
+      const double w = dmul((double)best, one_over_indices);
+      double p_no = dsub(1.0, dmul(dmul(w, w), w));
+      p_no = (eps < p_no) ? p_no : eps;
+      p_no = (p_no < dsub(1.0, eps)) ? p_no : dsub(1.0, eps);
+      k = ddiv(log_probability, det_log(p_no));
+    }
+    if (h + 1 > pc.max_iterations) break;
+  }
+  P.best = sel;
+  P.model_ok = (sel >= 0 && P.hyp_valid[sel]) ? 1 : 0;
+  P.coeff_sel = (sel >= 0) ? P.hyp[sel] : make_float4(0.f, 0.f, 0.f, 0.f);
+  P.coeff_ref = P.coeff_sel;
+}
+
+// nine moments + count of the RANSAC inliers, canonical tree order, one 2048-point chunk per block
+__global__ void __launch_bounds__(256)
+    k_plane_moments(const PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp,
+                    float thr, double* __restrict__ partial, int chunks, int cap) {
+  const int f = blockIdx.y, chunk = blockIdx.x;
+  const PlaneFrame& P = pf[f];
+  if (!P.active) return;
+  const int n = P.n;
+  if (chunk * TS_CHUNK >= n) return;
+  const float4* pts = cur_cloud(P, in, in_stride, bp.p, f, cap);
+  const float4 co = P.coeff_sel;
+  const bool ok = P.model_ok != 0;
+  double a[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a[k] = 0.0;
+  int cnt = 0;
+#pragma unroll
+  for (int r = 0; r < TS_CHUNK / 256; ++r) {
+    const int i = chunk * TS_CHUNK + r * 256 + threadIdx.x;
+    double e[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) e[k] = 0.0;
+    if (i < n) {
+      const float4 p = __ldg(pts + i);
+      if (ok && plane_dist(co, p.x, p.y, p.z) < thr) {
+        const double x = p.x, y = p.y, z = p.z;
+        e[0] = dmul(x, x);
+        e[1] = dmul(x, y);
+        e[2] = dmul(x, z);
+        e[3] = dmul(y, y);
+        e[4] = dmul(y, z);
+        e[5] = dmul(z, z);
+        e[6] = x;
+        e[7] = y;
+        e[8] = z;
+        ++cnt;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] = dadd(a[k], e[k]);
+  }
+  __shared__ double sh[8][9];
+  __shared__ int shc[8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a[k] = tree_butterfly(a[k]);
+  cnt = __reduce_add_sync(FULL, cnt);
+  if (lane_id() == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sh[warp_id()][k] = a[k];
+    shc[warp_id()] = cnt;
+  }
+  __syncthreads();
+  double* out = partial + ((size_t)f * chunks + chunk) * 10;
+  if (threadIdx.x < 9) {
+    double s = sh[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) s = dadd(s, sh[w][threadIdx.x]);
+    out[threadIdx.x] = s;
+  } else if (threadIdx.x == 9) {
+    int c = 0;
+    for (int w = 0; w < 8; ++w) c += shc[w];
+    out[9] = (double)c;
+  }
+}
+
+__device__ void compute_roots2(double b, double c, double* r) {
+  r[0] = 0.0;
+  double d = dsub(dmul(b, b), dmul(4.0, c));
+  if (d < 0.0) d = 0.0;
+  const double sd = __dsqrt_rn(d);
+  r[2] = dmul(0.5, dadd(b, sd));
+  r[1] = dmul(0.5, dsub(b, sd));
+}
+
+__device__ void compute_roots(const double* m, double* r) {
+  const double m00 = m[0], m01 = m[1], m02 = m[2], m11 = m[4], m12 = m[5], m22 = m[8];
+  double c0 = dmul(dmul(m00, m11), m22);
+  c0 = dadd(c0, dmul(dmul(dmul(2.0, m01), m02), m12));
+  c0 = dsub(c0, dmul(dmul(m00, m12), m12));
+  c0 = dsub(c0, dmul(dmul(m11, m02), m02));
+  c0 = dsub(c0, dmul(dmul(m22, m01), m01));
+  double c1 = dsub(dmul(m00, m11), dmul(m01, m01));
+  c1 = dadd(c1, dmul(m00, m22));
+  c1 = dsub(c1, dmul(m02, m02));
+  c1 = dadd(c1, dmul(m11, m22));
+  c1 = dsub(c1, dmul(m12, m12));
+  const double c2 = dadd(dadd(m00, m11), m22);
+  if (fabs(c0) < 2.220446049250313e-16) {
+    compute_roots2(c2, c1, r);
+    return;
+  }
+  const double s_inv3 = ddiv(1.0, 3.0);
+  const double s_sqrt3 = __dsqrt_rn(3.0);
+  const double c2_over_3 = dmul(c2, s_inv3);
+  double a_over_3 = dmul(dsub(c1, dmul(c2, c2_over_3)), s_inv3);
+  if (a_over_3 > 0.0) a_over_3 = 0.0;
+  const double half_b =
+      dmul(0.5, dadd(c0, dmul(c2_over_3, dsub(dmul(dmul(2.0, c2_over_3), c2_over_3), c1))));
+  double q = dadd(dmul(half_b, half_b), dmul(dmul(a_over_3, a_over_3), a_over_3));
+  if (q > 0.0) q = 0.0;
+  const double rho = __dsqrt_rn(-a_over_3);
+  const double theta = dmul(det_atan2_ypos(__dsqrt_rn(-q), half_b), s_inv3);
+  const double cos_theta = det_cos(theta);
+  const double sin_theta = det_sin(theta);
+  r[0] = dadd(c2_over_3, dmul(dmul(2.0, rho), cos_theta));
+  r[1] = dsub(c2_over_3, dmul(rho, dadd(cos_theta, dmul(s_sqrt3, sin_theta))));
+  r[2] = dsub(c2_over_3, dmul(rho, dsub(cos_theta, dmul(s_sqrt3, sin_theta))));
+  double t;
+  if (r[0] >= r[1]) {
+    t = r[0];
+    r[0] = r[1];
+    r[1] = t;
+  }
+  if (r[1] >= r[2]) {
+    t = r[1];
+    r[1] = r[2];
+    r[2] = t;
+    if (r[0] >= r[1]) {
+      t = r[0];
+      r[0] = r[1];
+      r[1] = t;
+    }
+  }
+  if (r[0] <= 0.0) compute_roots2(c2, c1, r);
+}
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o) {
+  o[0] = dsub(dmul(a[1], b[2]), dmul(a[2], b[1]));
+  o[1] = dsub(dmul(a[2], b[0]), dmul(a[0], b[2]));
+  o[2] = dsub(dmul(a[0], b[1]), dmul(a[1], b[0]));
+}
+
+__device__ void eigen33_smallest(const double* mat, double* evec) {
+  double scale = 0.0;
+  for (int i = 0; i < 9; ++i) scale = fabs(mat[i]) > scale ? fabs(mat[i]) : scale;
+  if (scale <= 2.2250738585072014e-308) scale = 1.0;
+  double sm[9];
+  for (int i = 0; i < 9; ++i) sm[i] = ddiv(mat[i], scale);
+  double r[3];
+  compute_roots(sm, r);
+  sm[0] = dsub(sm[0], r[0]);
+  sm[4] = dsub(sm[4], r[0]);
+  sm[8] = dsub(sm[8], r[0]);
+  double v1[3], v2[3], v3[3];
+  cross3(&sm[0], &sm[3], v1);
+  cross3(&sm[0], &sm[6], v2);
+  cross3(&sm[3], &sm[6], v3);
+  const double l1 = dadd(dadd(dmul(v1[0], v1[0]), dmul(v1[1], v1[1])), dmul(v1[2], v1[2]));
+  const double l2 = dadd(dadd(dmul(v2[0], v2[0]), dmul(v2[1], v2[1])), dmul(v2[2], v2[2]));
+  const double l3 = dadd(dadd(dmul(v3[0], v3[0]), dmul(v3[1], v3[1])), dmul(v3[2], v3[2]));
+  const double* v;
+  double l;
+  if (l1 >= l2 && l1 >= l3) {
+    v = v1;
+    l = l1;
+  } else if (l2 >= l1 && l2 >= l3) {
+    v = v2;
+    l = l2;
+  } else {
+    v = v3;
+    l = l3;
+  }
+  const double s = __dsqrt_rn(l);
+  evec[0] = ddiv(v[0], s);
+  evec[1] = ddiv(v[1], s);
+  evec[2] = ddiv(v[2], s);
+}
+
+// optimizeModelCoefficients: chunk partials summed sequentially, eigen33, validity check
+__global__ void __launch_bounds__(32)
+    k_plane_refine(PlaneFrame* __restrict__ pf, const double* __restrict__ partial, PlaneConst pc, int chunks) {
+  const int f = blockIdx.x;
+  PlaneFrame& P = pf[f];
+  if (!P.active) return;
+  if (!pc.optimize || !P.model_ok) return;  // coeff_ref already = coeff_sel
+  const int lane = threadIdx.x;
+  const int nch = cdiv(P.n, TS_CHUNK);
+  double tot = 0.0;
+  if (lane < 10) {
+    const double* src = partial + (size_t)f * chunks * 10 + lane;
+    for (int c = 0; c < nch; ++c) tot = dadd(tot, src[(size_t)c * 10]);
+  }
+  double a[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a[k] = __shfl_sync(FULL, tot, k);
+  const double cntd = __shfl_sync(FULL, tot, 9);
+  if (lane != 0) return;
+  if (cntd < 4.0) return;  // fewer than 4 inliers: keep the RANSAC model
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a[k] = ddiv(a[k], cntd);
+  double cov[9];
+  cov[0] = dsub(a[0], dmul(a[6], a[6]));
+  cov[1] = dsub(a[1], dmul(a[6], a[7]));
+  cov[2] = dsub(a[2], dmul(a[6], a[8]));
+  cov[4] = dsub(a[3], dmul(a[7], a[7]));
+  cov[5] = dsub(a[4], dmul(a[7], a[8]));
+  cov[8] = dsub(a[5], dmul(a[8], a[8]));
+  cov[3] = cov[1];
+  cov[6] = cov[2];
+  cov[7] = cov[5];
+  double vec[3];
+  eigen33_smallest(cov, vec);
+  float4 o;
+  o.x = (float)vec[0];
+  o.y = (float)vec[1];
+  o.z = (float)vec[2];
+  const float cx = (float)a[6], cy = (float)a[7], cz = (float)a[8];
+  o.w = -fadd(fadd(fmul(o.x, cx), fmul(o.y, cy)), fmul(o.z, cz));
+  if (model_valid(pc, o)) P.coeff_ref = o;
+}
+
+// ExtractIndices(negative) with the refined model: stable compaction of the outliers into the
+// other ping-pong buffer; the inlier list falls out of the same scan (slot = i - kept_before_i)
+__global__ void __launch_bounds__(CT_THREADS)
+    k_plane_extract(const PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp,
+                    float thr, int* __restrict__ inlier_idx, int* __restrict__ n_tmp, unsigned* __restrict__ desc, int cap,
+                    int tiles) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const PlaneFrame& P = pf[f];
+  if (!P.active) return;
+  const int n = P.n;
+  if (tile * CT_TILE >= n) {
+    if (tile == 0 && threadIdx.x == 0) n_tmp[f] = 0;
+    return;
+  }
+  __shared__ CompactSmem sm;
+  const float4* pts = cur_cloud(P, in, in_stride, bp.p, f, cap);
+  const int* srcidx = (P.cur < 0) ? nullptr : (bp.s[P.cur] + (size_t)f * cap);
+  const int dst = (P.cur < 0) ? 0 : (1 - P.cur);
+  float4* dpts = bp.p[dst] + (size_t)f * cap;
+  int* dsrc = bp.s[dst] + (size_t)f * cap;
+  const float4 co = P.coeff_ref;
+  const bool ok = P.model_ok != 0;
+  float4 p[CT_ITEMS];
+  bool keep[CT_ITEMS], valid[CT_ITEMS];
+  unsigned pos[CT_ITEMS];
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int i = ct_index(tile, k);
+    valid[k] = i < n;
+    keep[k] = false;
+    if (valid[k]) {
+      p[k] = __ldg(pts + i);
+      const bool inl = ok && plane_dist(co, p[k].x, p[k].y, p[k].z) < thr;
+      keep[k] = !inl;
+    }
+  }
+  const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm);
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    if (!valid[k]) continue;
+    const int i = ct_index(tile, k);
+    if (keep[k]) {
+      dpts[pos[k]] = p[k];
+      dsrc[pos[k]] = srcidx ? srcidx[i] : i;
+    } else {
+      inlier_idx[(size_t)f * cap + (i - (int)pos[k])] = i;
+    }
+  }
+  if ((tile + 1) * CT_TILE >= n && threadIdx.x == 0) n_tmp[f] = (int)incl_total;
+}
+
+// od.cpp:379-399 bookkeeping after one pass
+__global__ void k_plane_update(PlaneFrame* __restrict__ pf, const int* __restrict__ n_tmp, double keep_fraction,
+                               int* __restrict__ n_active, uint32_t* __restrict__ warnings, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  PlaneFrame& P = pf[f];
+  if (!P.active) return;
+  const int remaining = n_tmp[f];
+  const int inliers = P.n - remaining;
+  P.n_inliers_last = inliers;
+  if (inliers == 0) {  // od.cpp:383-387: "Couldn't estimate a planar model", break
+    P.active = 0;
+    atomicOr(&warnings[f], (uint32_t)PCOP_WARN_PLANE_BREAK);
+    return;
+  }
+  if (P.n_passes < PCOP_MAX_PLANE_PASSES_RECORDED) {
+    P.pass_points[P.n_passes] = P.n;
+    P.pass_inliers[P.n_passes] = inliers;
+    P.pass_coeff[P.n_passes] = P.coeff_ref;
+  }
+  P.n_passes += 1;
+  P.cur = (P.cur < 0) ? 0 : (1 - P.cur);  // planar_cloud.swap(cloud_f)
+  P.n = remaining;
+  P.active = ((double)remaining > dmul(keep_fraction, (double)P.nr_points)) ? 1 : 0;
+  if (P.active) atomicAdd(n_active, 1);
+}
+
+// copy what is left (planar_cloud_y, od.cpp:765) into the stage output
+__global__ void __launch_bounds__(CT_THREADS)
+    k_plane_finalize(const PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp,
+                     float4* __restrict__ out, int* __restrict__ out_src, int* __restrict__ n_out, int cap) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const PlaneFrame& P = pf[f];
+  const int n = P.n;
+  if (tile == 0 && threadIdx.x == 0) n_out[f] = n;
+  if (tile * CT_TILE >= n) return;
+  const float4* pts = cur_cloud(P, in, in_stride, bp.p, f, cap);
+  const int* srcidx = (P.cur < 0) ? nullptr : (bp.s[P.cur] + (size_t)f * cap);
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int i = ct_index(tile, k);
+    if (i < n) {
+      out[(size_t)f * cap + i] = __ldg(pts + i);
+      out_src[(size_t)f * cap + i] = srcidx ? srcidx[i] : i;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
+  const int tiles = cdiv(c.cap, CT_TILE);
+  const int chunks = cdiv(c.cap, TS_CHUNK);
+  BufPair bp;
+  bp.p[0] = a.buf[0];
+  bp.p[1] = a.buf[1];
+  bp.s[0] = a.src[0];
+  bp.s[1] = a.src[1];
+  cudaError_t e;
+  cudaMemsetAsync(a.n_active, 0, sizeof(int), c.stream);
+  k_plane_init<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_in, a.pc.keep_fraction, a.n_active, c.B);
+  count_launch(c);
+  cudaMemcpyAsync(a.h_n_active, a.n_active, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+  if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return e;
+  while (*a.h_n_active > 0) {
+    k_plane_gen<<<c.B, 32, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.rng, a.pc, a.warnings, c.cap);
+    k_plane_score<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap);
+    k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B);
+    k_plane_moments<<<dim3(chunks, c.B), 256, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.partial, chunks,
+                                                             c.cap);
+    k_plane_refine<<<c.B, 32, 0, c.stream>>>(a.pf, a.partial, a.pc, chunks);
+    cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
+    k_plane_extract<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx,
+                                                                   a.n_tmp, a.desc, c.cap, tiles);
+    cudaMemsetAsync(a.n_active, 0, sizeof(int), c.stream);
+    k_plane_update<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_tmp, a.pc.keep_fraction, a.n_active, a.warnings, c.B);
+    count_launch(c, 7);
+    cudaMemcpyAsync(a.h_n_active, a.n_active, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+    if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return e;
+  }
+  return cudaGetLastError();
+}
+
+// exposed to the API translation unit
+void run_plane_finalize(const Ctx& c, const PlaneArgs& a, float4* out, int* out_src) {
+  const int tiles = cdiv(c.cap, CT_TILE);
+  BufPair bp;
+  bp.p[0] = a.buf[0];
+  bp.p[1] = a.buf[1];
+  bp.s[0] = a.src[0];
+  bp.s[1] = a.src[1];
+  k_plane_finalize<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, out, out_src, a.n_out,
+                                                                  c.cap);
+  count_launch(c);
+}
+
+}  // namespace pcop
