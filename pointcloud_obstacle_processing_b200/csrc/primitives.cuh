@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned lookback_warp(unsigned* desc_frame, int tile
       while ((d >> 30) == 0u) d = ld_volatile_u32(desc_frame + idx);
     }
     const unsigned is_prefix = __ballot_sync(FULL, (d >> 30) == 2u);
-    const int first = __ffs(is_prefix) - 1;  // nearest tile that already knows its inclusive prefix
+    const int first = is_prefix ? (__ffs(is_prefix) - 1) : 31;  // nearest tile that already knows its inclusive prefix
     unsigned v = (lane <= first) ? (d & LB_VALUE) : 0u;
     v = __reduce_add_sync(FULL, v);
     exclusive += v;

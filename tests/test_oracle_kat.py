@@ -1,0 +1,372 @@
+"""CPU tests of the oracle: known-answer vectors pinned in SURVEY.md 8c (computed independently of this repo:
+std::mt19937 stream, float bit patterns), independent numpy / scipy restatements, and O(n^2) brute force.
+The reference ships no tests or golden vectors, so these are the strongest pins available ("parity unpinned")."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pointcloud_obstacle_processing_b200 import synth
+from pointcloud_obstacle_processing_b200._ctypes_abi import (WARN_PLANE_BREAK, WARN_SOR_TOO_FEW_POINTS,
+                                                            WARN_VOXEL_OVERFLOW_FALLBACK)
+
+
+def f32bits(x):
+    return int(np.float32(x).view(np.uint32))
+
+
+def cloud_of(xyz):
+    xyz = np.asarray(xyz, np.float32).reshape(-1, 3)
+    return np.concatenate([xyz, np.ones((len(xyz), 1), np.float32)], axis=1)
+
+
+# ---- RNG / sampling known answers ---------------------------------
+def test_mt19937_stream_kat():
+    raw, rnd = O.rng_raw(12345, 6)
+    assert raw.tolist() == [3992670690, 3823185381, 1358822685, 561383553, 789925284, 170765737]
+    assert rnd.tolist() == [1996335345, 1911592690, 679411342, 280691776, 394962642, 85382868]
+
+
+def test_mt19937_matches_numpy_generator():
+    # numpy's legacy MT19937 seeded by init_genrand(seed) produces the same raw stream
+    rs = np.random.RandomState(12345)
+    ref = rs.randint(0, 2**32, size=2000, dtype=np.uint64).astype(np.uint32)
+    raw, _ = O.rng_raw(12345, 2000)
+    assert np.array_equal(raw, ref)
+
+
+@pytest.mark.parametrize("n,expect", [
+    (1000, [[345, 197, 888], [776, 197, 976], [855, 614, 458]]),
+    (30000, [[15345, 26412, 16640], [11776, 25808, 8562], [29855, 17240, 1496]]),
+    (120000, [[15345, 8621, 102666], [11776, 45934, 64292], [89855, 92869, 532]]),
+])
+def test_draw_index_sample_kat(n, expect):
+    assert O.draw_samples(12345, n, 3).tolist() == expect
+
+
+# ---- float bit patterns -----------------------------------------
+@pytest.mark.parametrize("tol,bits", [(0.4, 0x3E23D70B), (0.05, 0x3B23D70B), (0.3, 0x3DB851EC)])
+def test_radius2_bits(tol, bits):
+    assert f32bits(O.lib().pcop_oracle_radius2(np.float32(tol))) == bits
+
+
+@pytest.mark.parametrize("leaf,bits", [(0.015, 0x42855556), (0.1, 0x41200000), (0.02, 0x42480000)])
+def test_inverse_leaf_bits(leaf, bits):
+    assert f32bits(O.lib().pcop_oracle_inverse_leaf(np.float32(leaf))) == bits
+
+
+# ---- deterministic elementary functions ---------------------------------------------------
+def test_det_math_accuracy():
+    L = O.lib()
+    rng = np.random.default_rng(1)
+    for x in np.concatenate([rng.uniform(1e-12, 1.0, 500), rng.uniform(1.0, 1e6, 200), [0.01, 0.5, 1.0, 2.0]]):
+        assert abs(L.pcop_oracle_det_log(x) - math.log(x)) <= 4e-16 * max(1.0, abs(math.log(x)))
+    for t in rng.uniform(0, math.pi / 3, 500):
+        assert abs(L.pcop_oracle_det_sin(t) - math.sin(t)) < 3e-16
+        assert abs(L.pcop_oracle_det_cos(t) - math.cos(t)) < 3e-16
+    for y, x in zip(rng.uniform(0, 10, 500), rng.uniform(-10, 10, 500)):
+        assert abs(L.pcop_oracle_det_atan2_ypos(y, x) - math.atan2(y, x)) < 1e-15
+
+
+def test_tree_sum_matches_fsum_and_is_chunked():
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 31, 256, 2047, 2048, 2049, 10000):
+        v = rng.normal(size=n) * 1e3
+        s = O.tree_sum(v)
+        assert abs(s - math.fsum(v)) <= 1e-9 * max(1.0, np.abs(v).sum())
+    # shape check: lanes of one chunk are added in xor-butterfly order, chunks sequentially
+    v = np.zeros(4096)
+    v[0], v[16], v[2048] = 1.0, 2.0 ** -53, 1.0
+    assert O.tree_sum(v) == 2.0  # (1 + 2^-53) rounds to 1 inside the chunk; an exact sum would give 2 + 2^-53 -> 2.0 too
+    w = np.full(2048, 0.1)
+    lane = 0.0
+    for _ in range(8):
+        lane += 0.1
+    part = lane
+    for _ in range(5):
+        part = part + part
+    expect = part
+    for _ in range(7):
+        expect += part
+    assert O.tree_sum(w) == expect
+
+
+def test_eigen33_against_numpy():
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        a = rng.normal(size=(3, 3)) * rng.uniform(0.01, 10)
+        m = a @ a.T + np.diag(rng.uniform(1e-6, 1e-3, 3))
+        ev, vec = O.eigen33_smallest(m.reshape(-1))
+        w, v = np.linalg.eigh(m)
+        assert abs(ev - w[0]) <= 1e-9 * w[2]
+        if w[1] - w[0] > 1e-6 * w[2]:
+            assert abs(abs(vec @ v[:, 0]) - 1.0) < 1e-6
+
+
+# ---- crop (od.cpp:195-215) -----------------------------------------------------------------
+def test_crop_literal_predicate():
+    p = synth.params(1)
+    nan = np.nan
+    pts = cloud_of([
+        [0.0, 0.0, -0.5],      # inclusive lower bounds: kept
+        [4.5, 3.78, 0.25],     # inclusive upper bounds: kept
+        [4.5000005, 1.0, 0.0], # just outside x
+        [nan, 1.0, 0.0],       # NaN x: dropped
+        [1.0, nan, 0.0],       # NaN y with valid x: kept (quirk: only x is NaN-tested)
+        [1.0, 1.0, nan],       # NaN z with valid x: kept
+        [1.0, -0.0001, 0.0],   # below y_min
+        [2.0, 2.0, 0.3],       # above z_max
+    ])
+    out, kept = O.crop(p, pts)
+    assert kept.tolist() == [0, 1, 4, 5]
+    assert np.array_equal(out.view(np.uint32), pts[kept].view(np.uint32))
+    out, kept = O.crop(p, np.zeros((0, 4), np.float32))
+    assert len(kept) == 0
+
+
+def test_crop_matches_numpy_on_synthetic():
+    p = synth.params(1)
+    c = synth.frame(1, 3)
+    x, y, z = c[:, 0], c[:, 1], c[:, 2]
+    with np.errstate(invalid="ignore"):
+        drop = np.isnan(x) | (x < p.x_min) | (x > p.x_max) | (z < p.z_min) | (z > p.z_max) | (y < p.y_min) | (y > p.y_max)
+    _, kept = O.crop(p, c)
+    assert np.array_equal(kept, np.nonzero(~drop)[0])
+    assert 0.4 * len(c) < len(kept)
+
+
+# ---- VoxelGrid -------------------------------------------------------------------------------
+def numpy_voxel_keys(p, c):
+    inv = np.float32(1.0) / np.float32(p.downsample_size)
+    mn = c[:, :3].min(axis=0)
+    mx = c[:, :3].max(axis=0)
+    min_b = np.floor(mn * inv).astype(np.int32)
+    max_b = np.floor(mx * inv).astype(np.int32)
+    div = (max_b - min_b + 1).astype(np.int64)
+    ijk = (np.floor(c[:, :3] * inv) - min_b.astype(np.float32)).astype(np.int32).astype(np.int64)
+    return (ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]).astype(np.uint32), div
+
+
+def test_voxel_extents_params_yaml():
+    # the params.yaml crop box spans 301 x 253 x 51 voxels of 0.015 m
+    p = synth.params(1)
+    corners = cloud_of([[p.x_min, p.y_min, p.z_min], [p.x_max, p.y_max, p.z_max]])
+    keys = O.voxel_keys(p, corners)
+    _, div = numpy_voxel_keys(p, corners)
+    assert div.tolist() == [301, 253, 51]
+    assert keys.tolist() == [0, 300 + 252 * 301 + 50 * 301 * 253]
+
+
+@pytest.mark.parametrize("config", [1, 2, 3])
+def test_voxel_against_numpy(config):
+    p = synth.params(config)
+    c, _ = O.crop(p, synth.frame(config, 1))
+    keys_np, _ = numpy_voxel_keys(p, c)
+    assert np.array_equal(O.voxel_keys(p, c), keys_np)
+    out, keys, w = O.voxel(p, c)
+    assert w == 0
+    uk, inverse, counts = np.unique(keys_np, return_inverse=True, return_counts=True)
+    assert np.array_equal(keys, uk)  # ascending key order
+    sums = np.zeros((len(uk), 3), np.float64)
+    np.add.at(sums, inverse, c[:, :3].astype(np.float64))
+    cen = sums / counts[:, None]
+    np.testing.assert_allclose(out[:, :3], cen, rtol=1e-5, atol=1e-6)
+    assert np.all(out[:, 3] == 1.0)
+    # bit-exact check of the sequential float sum on the most populated voxels
+    order = np.argsort(-counts)[:50]
+    for v in order:
+        s = np.zeros(3, np.float32)
+        for i in np.nonzero(keys_np == uk[v])[0]:
+            s = (s + c[i, :3]).astype(np.float32)
+        assert np.array_equal((s / np.float32(counts[v])).view(np.uint32), out[v, :3].view(np.uint32))
+
+
+def test_voxel_overflow_fallback_and_empty():
+    p = synth.params(1)
+    p.downsample_size = 1e-4
+    c = cloud_of([[0, 0, 0], [100, 100, 100], [5, 5, 5]])
+    out, keys, w = O.voxel(p, c)
+    assert w == WARN_VOXEL_OVERFLOW_FALLBACK
+    assert np.array_equal(out.view(np.uint32), c.view(np.uint32))
+    out, keys, w = O.voxel(p, np.zeros((0, 4), np.float32))
+    assert len(out) == 0 and w == 0
+
+
+# ---- StatisticalOutlierRemoval -------------------------------------------------------------------
+def test_sor_kdtree_equals_bruteforce_and_scipy():
+    from scipy.spatial import cKDTree
+    p = synth.params(1)
+    rng = np.random.default_rng(5)
+    c = cloud_of(np.concatenate([rng.normal(size=(1500, 3)) * 0.1, rng.uniform(-2, 2, size=(60, 3))]))
+    out, kept, w, dist, thr = O.sor(p, c)
+    assert w == 0
+    assert np.array_equal(dist.view(np.uint32), O.sor_distances_bruteforce(c, 15).view(np.uint32))
+    d, _ = cKDTree(c[:, :3].astype(np.float64)).query(c[:, :3].astype(np.float64), k=16)
+    np.testing.assert_allclose(dist, d[:, 1:].mean(axis=1), rtol=2e-5)
+    mean, std = dist.astype(np.float64).mean(), dist.astype(np.float64).std(ddof=1)
+    assert abs(thr - (mean + 4.0 * std)) < 1e-6 * thr  # PCL's sq_sum uses float products: loose
+    assert np.array_equal(kept, np.nonzero(~(dist.astype(np.float64) > thr))[0])
+    assert 0 < len(c) - len(kept) < 60
+
+
+def test_sor_too_few_points_passthrough():
+    p = synth.params(1)
+    c = cloud_of(np.random.default_rng(6).normal(size=(15, 3)))
+    out, kept, w, _, _ = O.sor(p, c)
+    assert w == WARN_SOR_TOO_FEW_POINTS and kept.tolist() == list(range(15))
+    out, kept, w, _, _ = O.sor(p, np.zeros((0, 4), np.float32))
+    assert w == 0 and len(kept) == 0
+
+
+# ---- RANSAC plane loop -----------------------------------------------------------------------------
+def plane_scene(rng, n_plane=4000, n_out=800, noise=0.005):
+    xy = rng.uniform(-2, 2, size=(n_plane, 2))
+    z = 0.1 * xy[:, 0] - 0.05 * xy[:, 1] + 0.3 + rng.normal(size=n_plane) * noise
+    plane = np.column_stack([xy, z])
+    outl = rng.uniform(-2, 2, size=(n_out, 3)) + [0, 0, 1.5]
+    pts = np.concatenate([plane, outl])
+    rng.shuffle(pts)
+    return cloud_of(pts)
+
+
+def test_segment_recovers_plane():
+    p = synth.params(1)
+    c = plane_scene(np.random.default_rng(7))
+    s = O.segment_once(p, c)
+    assert s["ok"]
+    n = np.array([0.1, -0.05, -1.0])
+    n /= np.linalg.norm(n)
+    got = s["refined_coeff"][:3].astype(np.float64)
+    assert abs(abs(got @ n) - 1.0) < 1e-4
+    assert abs(abs(s["refined_coeff"][3]) - 0.3 / np.linalg.norm([0.1, -0.05, -1.0])) < 2e-3
+    assert s["n_refined_inliers"] >= 3990
+    # independent check of the refinement: numpy eigh of the inlier covariance
+    d = np.abs(c[:, :3].astype(np.float64) @ s["ransac_coeff"][:3].astype(np.float64) + float(s["ransac_coeff"][3]))
+    inl = c[d < float(np.float32(p.plane_segment_dist_thres)) - 1e-6, :3].astype(np.float64)
+    w, v = np.linalg.eigh(np.cov(inl.T, bias=True))
+    assert abs(abs(v[:, 0] @ got) - 1.0) < 1e-6
+
+
+def test_ransac_first_hypothesis_uses_kat_sample():
+    # with probability 0.99 and a 100 % inlier cloud RANSAC stops after the first sample (k < 1 after it)
+    p = synth.params(1)
+    p.optimize_coefficients = 0
+    rng = np.random.default_rng(8)
+    xy = rng.uniform(-1, 1, size=(1000, 2))
+    c = cloud_of(np.column_stack([xy, np.zeros(1000)]))
+    s = O.segment_once(p, c)
+    assert s["iterations"] == 1 and s["n_ransac_inliers"] == 1000
+    i0, i1, i2 = 345, 197, 888  # SURVEY 8a-4.3, n = 1000
+    nrm = np.cross(c[i1, :3] - c[i0, :3], c[i2, :3] - c[i0, :3]).astype(np.float64)
+    nrm /= np.linalg.norm(nrm)
+    np.testing.assert_allclose(s["ransac_coeff"][:3], nrm, atol=1e-6)
+
+
+def test_plane_loop_rule_and_break():
+    p = synth.params(1)
+    c = plane_scene(np.random.default_rng(9), n_plane=3000, n_out=2000)
+    o = O.plane(p, c)
+    assert o["n_passes"] >= 1
+    assert o["pass_points"][0] == len(c)
+    rem = len(c)
+    for k in range(o["n_passes"]):
+        assert rem > 0.3 * len(c)        # od.cpp:379: the pass only ran because > 30 % was left
+        assert o["pass_points"][k] == rem
+        rem -= o["pass_inliers"][k]
+    assert rem == len(o["remaining"]) and (rem <= 0.3 * len(c) or o["warnings"] & WARN_PLANE_BREAK)
+    assert np.array_equal(o["remaining"].view(np.uint32), c[o["src"]].view(np.uint32))
+    assert np.all(np.diff(o["src"]) > 0)  # ExtractIndices keeps order
+    # fewer than 3 points: segment() fails, loop breaks (od.cpp:383-387)
+    o = O.plane(p, c[:2])
+    assert o["n_passes"] == 0 and o["warnings"] & WARN_PLANE_BREAK and len(o["remaining"]) == 2
+    o = O.plane(p, c[:0])
+    assert o["n_passes"] == 0 and o["warnings"] == 0
+
+
+# ---- Euclidean clustering --------------------------------------------------------------------------------
+def random_cluster_scene(rng, n):
+    centers = rng.uniform(-3, 3, size=(12, 3))
+    pts = centers[rng.integers(0, 12, n)] + rng.normal(size=(n, 3)) * 0.15
+    pts = np.concatenate([pts, rng.uniform(-4, 4, size=(n // 10, 3))])
+    return cloud_of(pts)
+
+
+@pytest.mark.parametrize("seed,tol", [(10, 0.05), (11, 0.1), (12, 0.2), (13, 0.4)])
+def test_cluster_kdtree_equals_bruteforce(seed, tol):
+    p = synth.params(1)
+    p.euc_cluster_tolerance = tol
+    p.euc_min_cluster_size = 3
+    p.euc_max_cluster_size = 700
+    c = random_cluster_scene(np.random.default_rng(seed), 1500)
+    o1, i1 = O.cluster(p, c)
+    o2, i2 = O.cluster_bruteforce(p, c)
+    assert np.array_equal(o1, o2) and np.array_equal(i1, i2)
+    sizes = np.diff(o1)
+    assert np.all(sizes[:-1] >= sizes[1:]) and np.all(sizes >= 3) and np.all(sizes <= 700)
+    for k in range(len(sizes)):  # indices ascending inside a cluster; ties ordered by smallest index
+        seg = i1[o1[k]:o1[k + 1]]
+        assert np.all(np.diff(seg) > 0)
+        if k and sizes[k] == sizes[k - 1]:
+            assert i1[o1[k - 1]] < seg[0]
+
+
+def test_cluster_against_scipy_components():
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    p = synth.params(1)
+    p.euc_cluster_tolerance = 0.12
+    p.euc_min_cluster_size = 1
+    p.euc_max_cluster_size = 10**6
+    c = random_cluster_scene(np.random.default_rng(14), 3000)
+    offs, idx = O.cluster(p, c)
+    xyz = c[:, :3].astype(np.float64)
+    pairs = cKDTree(xyz).sparse_distance_matrix(cKDTree(xyz), 0.12 * (1 - 1e-6), output_type="coo_matrix")
+    ncomp, lab = connected_components(pairs, directed=False)
+    assert ncomp == len(offs) - 1
+    for k in range(len(offs) - 1):
+        assert len(set(lab[idx[offs[k]:offs[k + 1]]])) == 1
+    assert offs[-1] == len(c)
+
+
+def test_cluster_oversize_dropped_whole():
+    p = synth.params(1)
+    p.euc_cluster_tolerance = 0.1
+    p.euc_min_cluster_size = 2
+    p.euc_max_cluster_size = 10
+    line = np.column_stack([np.arange(30) * 0.05, np.zeros(30), np.zeros(30)])   # one 30-point chain: dropped
+    pair = np.array([[10, 0, 0], [10.05, 0, 0]])                                 # kept
+    single = np.array([[20, 0, 0]])                                              # below min: dropped
+    offs, idx = O.cluster(p, cloud_of(np.concatenate([line, pair, single])))
+    assert offs.tolist() == [0, 2] and idx.tolist() == [30, 31]
+
+
+def test_centroid_radius_against_numpy():
+    p = synth.params(2)
+    o = O.process(p, synth.frame(2, 0))
+    assert o.n_clusters > 5
+    for k in range(o.n_clusters):
+        m = o.remaining_cloud[o.cluster_indices[o.cluster_offsets[k]:o.cluster_offsets[k + 1]], :3].astype(np.float64)
+        cen = m.mean(axis=0)
+        np.testing.assert_allclose(o.obstacles[k, :3], cen, rtol=1e-6, atol=1e-6)
+        assert abs(o.obstacles[k, 3] - np.sqrt(((m - cen) ** 2).sum(axis=1)).max()) < 1e-5
+
+
+# ---- whole pipeline: stage chaining ------------------------------------------------------------------------
+@pytest.mark.parametrize("config", [1, 2, 3])
+def test_pipeline_equals_chained_stages(config):
+    p = synth.params(config)
+    c = synth.frame(config, 2)
+    o = O.process(p, c)
+    a, kept = O.crop(p, c)
+    assert np.array_equal(kept, o.crop_kept_idx)
+    b, keys, _ = O.voxel(p, a)
+    assert np.array_equal(keys, o.voxel_keys)
+    if p.enable_sor:
+        b, sk, _, _, _ = O.sor(p, b)
+        assert np.array_equal(sk, o.sor_kept_idx)
+    pl = O.plane(p, b)
+    assert np.array_equal(pl["remaining"].view(np.uint32), o.remaining_cloud.view(np.uint32))
+    offs, idx = O.cluster(p, pl["remaining"])
+    assert np.array_equal(offs, o.cluster_offsets) and np.array_equal(idx, o.cluster_indices)
+    assert o.n_clusters >= 3
