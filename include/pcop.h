@@ -200,6 +200,16 @@ int pcop_stage_times_us(const pcop_handle* h, float us[PCOP_N_STAGES]);
 int64_t pcop_last_launch_count(const pcop_handle* h);
 /* Algorithmic bytes of the last call, from its counts. */
 double pcop_last_algorithmic_bytes(const pcop_handle* h);
+/* Keys moved by radix-sort passes during the last call (each is 8 B read + 8 B written). */
+int64_t pcop_last_sort_pass_keys(const pcop_handle* h);
+
+/*
+ * Optional per-kernel timing (CUDA events around every launch, on the handle's stream).  Totals
+ * accumulate over calls from the moment timing is enabled; enabling again resets them.
+ */
+int pcop_enable_kernel_timing(pcop_handle* h, int enable);
+int pcop_kernel_timing_count(const pcop_handle* h);
+int pcop_kernel_timing_get(const pcop_handle* h, int i, const char** name, double* total_us, int64_t* launches);
 
 /*
  * Stage-isolated entry points, one per reference wrapper, so a host can swap

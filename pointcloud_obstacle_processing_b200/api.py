@@ -29,7 +29,8 @@ EXPORTS = [
     "pcop_params_init_params_yaml", "pcop_create", "pcop_destroy", "pcop_set_params", "pcop_process",
     "pcop_process_batch", "pcop_last_elapsed_us", "pcop_stage_times_us", "pcop_last_launch_count",
     "pcop_last_algorithmic_bytes", "pcop_crop", "pcop_voxel", "pcop_sor", "pcop_plane", "pcop_cluster",
-    "pcop_centroid_radius",
+    "pcop_centroid_radius", "pcop_enable_kernel_timing", "pcop_kernel_timing_count", "pcop_kernel_timing_get",
+    "pcop_last_sort_pass_keys",
 ]
 
 
@@ -68,6 +69,12 @@ def load_library():
     L.pcop_last_launch_count.argtypes = [vp]
     L.pcop_last_algorithmic_bytes.restype = C.c_double
     L.pcop_last_algorithmic_bytes.argtypes = [vp]
+    L.pcop_last_sort_pass_keys.restype = C.c_int64
+    L.pcop_last_sort_pass_keys.argtypes = [vp]
+    L.pcop_enable_kernel_timing.argtypes = [vp, C.c_int]
+    L.pcop_kernel_timing_count.argtypes = [vp]
+    L.pcop_kernel_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int64)]
     L.pcop_crop.argtypes = [vp, vp, i32, vp, vp, pi32]
     L.pcop_voxel.argtypes = [vp, vp, i32, vp, vp, pi32, pu32]
     L.pcop_sor.argtypes = [vp, vp, i32, vp, vp, pi32, pu32]
@@ -172,6 +179,23 @@ class ObstacleProcessor:
     @property
     def last_algorithmic_bytes(self) -> float:
         return float(self._lib.pcop_last_algorithmic_bytes(self._h))
+
+    @property
+    def last_sort_pass_keys(self) -> int:
+        return int(self._lib.pcop_last_sort_pass_keys(self._h))
+
+    def enable_kernel_timing(self, enable=True):
+        """CUDA-event pairs around every kernel launch; totals accumulate until enabled again."""
+        self._check(self._lib.pcop_enable_kernel_timing(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """{kernel name: (total device us, launches)} since timing was enabled."""
+        out = {}
+        for i in range(self._lib.pcop_kernel_timing_count(self._h)):
+            name, us, n = C.c_char_p(), C.c_double(), C.c_int64()
+            self._check(self._lib.pcop_kernel_timing_get(self._h, i, C.byref(name), C.byref(us), C.byref(n)))
+            out[name.value.decode()] = (us.value, n.value)
+        return out
 
     def stage_times_us(self):
         us = (C.c_float * len(abi.STAGE_NAMES))()

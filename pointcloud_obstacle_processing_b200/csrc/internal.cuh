@@ -9,14 +9,53 @@ namespace pcop {
 // records the error text in the handle (and the thread's global error slot); returns PCOP_ERR_CUDA
 int fail_cuda(pcop_handle* h, cudaError_t e, const char* expr, const char* file, int line);
 
+// Optional per-kernel timing: CUDA event pairs recorded on the launching stream around every
+// kernel launch of a call, resolved after the call's final synchronisation (bench.py's live
+// roofline measurement).  Disabled => zero overhead beyond one branch per launch.
+struct KernelTimers {
+  static constexpr int MAX_SLOTS = 8192;
+  static constexpr int MAX_NAMES = 64;
+  bool enabled = false;
+  cudaEvent_t* ev = nullptr;  // [2*MAX_SLOTS], created lazily
+  int used = 0;
+  const char* slot_name[MAX_SLOTS];
+  // accumulated per kernel name
+  int n_names = 0;
+  const char* names[MAX_NAMES];
+  double total_us[MAX_NAMES];
+  long long launches[MAX_NAMES];
+};
+
 struct Ctx {
   cudaStream_t stream;
   int B;    // frames in the wave
   int cap;  // per-frame capacity (points)
   int64_t* launches;
+  KernelTimers* kt;
 };
 
 inline void count_launch(const Ctx& c, int n = 1) { *c.launches += n; }
+
+struct KScope {
+  const Ctx& c;
+  int slot;
+  KScope(const Ctx& cc, const char* name) : c(cc), slot(-1) {
+    KernelTimers* k = c.kt;
+    if (k && k->enabled && k->ev && k->used < KernelTimers::MAX_SLOTS) {
+      slot = k->used++;
+      k->slot_name[slot] = name;
+      cudaEventRecord(k->ev[2 * slot], c.stream);
+    }
+  }
+  ~KScope() {
+    if (slot >= 0) cudaEventRecord(c.kt->ev[2 * slot + 1], c.stream);
+  }
+};
+#define KL(ctx, name, ...)          \
+  do {                              \
+    ::pcop::KScope _ks(ctx, name);  \
+    __VA_ARGS__;                    \
+  } while (0)
 
 // ---- batched stable LSD radix sort of (key32, val32) pairs ---------------------
 struct SortBufs {
@@ -26,6 +65,7 @@ struct SortBufs {
   uint32_t* desc;    // [RS_MAX_PASSES][B][tiles][RS_BINS] look-back descriptors
   uint32_t* maxkey;  // [B]  written (atomicMax) by the kernel that produced the keys
   int* npass;        // [B]  passes actually needed for this frame (>= 1)
+  unsigned long long* stats;  // [1] keys moved by all sort passes of the call (accounting only)
 };
 size_t sort_desc_bytes(int B, int cap);
 // Sorts frame f's `count[f]` pairs that sit in key[0]/val[0] (val[0] is ignored and taken as

@@ -115,6 +115,8 @@ struct pcop_handle {
   PlaneRecord* h_prec = nullptr;
   PackMeta* h_meta = nullptr;
   int* h_n_in = nullptr;  // staging for the per-frame input sizes
+  unsigned long long* h_stats = nullptr;
+  unsigned long long sort_pass_keys = 0;
   unsigned char* h_pack = nullptr;
   size_t h_pack_cap = 0;
 
@@ -126,6 +128,7 @@ struct pcop_handle {
   float last_elapsed_us = 0.f;
   int64_t launches = 0;
   double alg_bytes = 0.0;
+  KernelTimers kt;
 
   int* cnt(int row) { return d_counts + (size_t)row * maxB; }
 };
@@ -373,7 +376,35 @@ struct StageTimer {
   ~StageTimer() { cudaEventRecord(h->ev_stage[stage][1], h->stream); }
 };
 
-Ctx make_ctx(pcop_handle* h, int B) { return Ctx{h->stream, B, h->cap, &h->launches}; }
+void resolve_kernel_timers(pcop_handle* h) {
+  KernelTimers& k = h->kt;
+  for (int sl = 0; sl < k.used; ++sl) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, k.ev[2 * sl], k.ev[2 * sl + 1]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    int id = -1;
+    for (int i = 0; i < k.n_names; ++i)
+      if (k.names[i] == k.slot_name[sl] || strcmp(k.names[i], k.slot_name[sl]) == 0) {
+        id = i;
+        break;
+      }
+    if (id < 0 && k.n_names < KernelTimers::MAX_NAMES) {
+      id = k.n_names++;
+      k.names[id] = k.slot_name[sl];
+      k.total_us[id] = 0.0;
+      k.launches[id] = 0;
+    }
+    if (id >= 0) {
+      k.total_us[id] += (double)ms * 1000.0;
+      k.launches[id] += 1;
+    }
+  }
+  k.used = 0;
+}
+
+Ctx make_ctx(pcop_handle* h, int B) { return Ctx{h->stream, B, h->cap, &h->launches, &h->kt}; }
 
 PlaneConst make_plane_const(const pcop_params& p) {
   PlaneConst pc;
@@ -513,7 +544,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride) {
   const pcop_params& p = h->params;
   Ctx c = make_ctx(h, B);
   const int tiles = cdiv(h->cap, CT_TILE);
-  k_zero_u32<<<cdiv(B, 256), 256, 0, h->stream>>>(h->d_warnings, B);
+  KL(c, "k_zero_u32", k_zero_u32<<<cdiv(B, 256), 256, 0, h->stream>>>(h->d_warnings, B));
   count_launch(c);
 
   const float4* cur = in;
@@ -530,7 +561,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride) {
       cur_n = h->cnt(CNT_CROP);
       have_minmax = true;
     } else {
-      k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_CROP), B);
+      KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_CROP), B));
       count_launch(c);
     }
   }
@@ -543,7 +574,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride) {
       cur_stride = h->cap;
       cur_n = h->cnt(CNT_VOX);
     } else {
-      k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_VOX), B);
+      KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_VOX), B));
       count_launch(c);
     }
   }
@@ -555,7 +586,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride) {
       cur_stride = h->cap;
       cur_n = h->cnt(CNT_SOR);
     } else {
-      k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_SOR), B);
+      KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_SOR), B));
       count_launch(c);
     }
   }
@@ -567,8 +598,8 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride) {
       if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
       run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
     } else {
-      k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_REM), B);
-      k_copy_cloud<<<dim3(tiles, B), CT_THREADS, 0, h->stream>>>(cur, cur_stride, cur_n, h->d_rem, h->d_rem_src, h->cap);
+      KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_REM), B));
+      KL(c, "k_copy_cloud", k_copy_cloud<<<dim3(tiles, B), CT_THREADS, 0, h->stream>>>(cur, cur_stride, cur_n, h->d_rem, h->d_rem_src, h->cap));
       count_launch(c, 2);
     }
   }
@@ -597,9 +628,9 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   pcop_frame_result* out = out_all + w0;
   Ctx c = make_ctx(h, B);
   StageTimer t(h, PCOP_STAGE_D2H);
-  k_plane_record<<<cdiv(B, 128), 128, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS),
-                                                      h->cnt(CNT_CLUS1), h->params.enable_plane ? 1 : 0, B);
-  k_pack_scan<<<1, 320, 0, h->stream>>>(h->d_counts, h->maxB, B, mask, h->d_pack_off, h->d_meta);
+  KL(c, "k_plane_record", k_plane_record<<<cdiv(B, 128), 128, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS),
+                                                      h->cnt(CNT_CLUS1), h->params.enable_plane ? 1 : 0, B));
+  KL(c, "k_pack_scan", k_pack_scan<<<1, 320, 0, h->stream>>>(h->d_counts, h->maxB, B, mask, h->d_pack_off, h->d_meta));
   count_launch(c, 2);
   const void* srcs[PK_N] = {h->d_crop_kept, h->d_vox_keys, h->d_vox,     h->d_sor_kept, h->d_inliers,
                             h->d_rem,       h->d_rem_src,  h->d_offsets, h->d_indices,  h->d_obst};
@@ -611,10 +642,10 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
     const int* cnt = h->cnt(kPkCount[k]);
     const int* off = h->d_pack_off + (size_t)k * h->maxB;
     if (kPkElem[k] == 16)
-      k_pack<float4><<<dim3(gx, B), 256, 0, h->stream>>>((const float4*)srcs[k], strides[k], cnt, off, h->d_meta, k,
-                                                         h->d_pack);
+      KL(c, "k_pack", k_pack<float4><<<dim3(gx, B), 256, 0, h->stream>>>((const float4*)srcs[k], strides[k], cnt, off, h->d_meta, k,
+                                                         h->d_pack));
     else
-      k_pack<int><<<dim3(gx, B), 256, 0, h->stream>>>((const int*)srcs[k], strides[k], cnt, off, h->d_meta, k, h->d_pack);
+      KL(c, "k_pack", k_pack<int><<<dim3(gx, B), 256, 0, h->stream>>>((const int*)srcs[k], strides[k], cnt, off, h->d_meta, k, h->d_pack));
     count_launch(c);
   }
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int) * CNT_ROWS * h->maxB, cudaMemcpyDeviceToHost,
@@ -704,6 +735,9 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   TRY(ensure_pack_capacity(h, mask));
   h->launches = 0;
   h->alg_bytes = 0.0;
+  h->kt.used = 0;
+  h->sort_pass_keys = 0;
+  PCOP_CUDA_TRY(cudaMemsetAsync(h->sort.stats, 0, sizeof(unsigned long long), h->stream));
   for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] = 0.f;
   const bool on_device = is_device_pointer(xyzw);
   size_t h_pack_used = 0;
@@ -747,12 +781,15 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, h->ev_stage[s][0], h->ev_stage[s][1]) == cudaSuccess) h->stage_us[s] += ms * 1000.f;
     }
+    resolve_kernel_timers(h);
   }
+  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_stats, h->sort.stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[1], h->stream));
   PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_call[1]));
   float ms = 0.f;
   PCOP_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]));
   h->last_elapsed_us = ms * 1000.f;
+  h->sort_pass_keys = *h->h_stats;
   // the host pack buffer is final now: turn the stored offsets into pointers
   for (size_t fx : fixups) {
     const void** slot = (const void**)((unsigned char*)out + fx);
@@ -932,6 +969,8 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   }
   A(dalloc(h, &h->sort.maxkey, B));
   A(dalloc(h, &h->sort.npass, B));
+  A(dalloc(h, &h->sort.stats, 1));
+  A(halloc(h, &h->h_stats, 1));
   A(dalloc(h, &h->d_desc, (size_t)B * tiles));
   A(dalloc(h, &h->d_counts, (size_t)CNT_ROWS * B));
   A(dalloc(h, &h->d_warnings, B));
@@ -983,6 +1022,10 @@ void pcop_destroy(pcop_handle* h) {
   for (void* p : h->host_allocs) cudaFreeHost(p);
   if (h->d_pack) cudaFree(h->d_pack);
   if (h->h_pack) cudaFreeHost(h->h_pack);
+  if (h->kt.ev) {
+    for (int i = 0; i < 2 * KernelTimers::MAX_SLOTS; ++i) cudaEventDestroy(h->kt.ev[i]);
+    delete[] h->kt.ev;
+  }
   for (int i = 0; i < 2; ++i)
     if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
   for (int s = 0; s < PCOP_N_STAGES; ++s)
@@ -1015,6 +1058,29 @@ int pcop_process_batch(pcop_handle* h, const float* xyzw, size_t frame_stride_po
   return process_impl(h, xyzw, frame_stride_points, n, batch, out);
 }
 
+int pcop_enable_kernel_timing(pcop_handle* h, int enable) {
+  if (!h) return PCOP_ERR_BAD_PARAM;
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  if (enable && !h->kt.ev) {
+    h->kt.ev = new cudaEvent_t[2 * KernelTimers::MAX_SLOTS];
+    for (int i = 0; i < 2 * KernelTimers::MAX_SLOTS; ++i) PCOP_CUDA_TRY(cudaEventCreate(&h->kt.ev[i]));
+  }
+  h->kt.enabled = enable != 0;
+  h->kt.used = 0;
+  h->kt.n_names = 0;
+  return PCOP_OK;
+}
+
+int pcop_kernel_timing_count(const pcop_handle* h) { return h ? h->kt.n_names : 0; }
+
+int pcop_kernel_timing_get(const pcop_handle* h, int i, const char** name, double* total_us, int64_t* launches) {
+  if (!h || i < 0 || i >= h->kt.n_names) return PCOP_ERR_BAD_PARAM;
+  if (name) *name = h->kt.names[i];
+  if (total_us) *total_us = h->kt.total_us[i];
+  if (launches) *launches = h->kt.launches[i];
+  return PCOP_OK;
+}
+
 float pcop_last_elapsed_us(const pcop_handle* h) { return h ? h->last_elapsed_us : 0.f; }
 int pcop_stage_times_us(const pcop_handle* h, float us[PCOP_N_STAGES]) {
   if (!h || !us) return PCOP_ERR_BAD_PARAM;
@@ -1023,6 +1089,7 @@ int pcop_stage_times_us(const pcop_handle* h, float us[PCOP_N_STAGES]) {
 }
 int64_t pcop_last_launch_count(const pcop_handle* h) { return h ? h->launches : 0; }
 double pcop_last_algorithmic_bytes(const pcop_handle* h) { return h ? h->alg_bytes : 0.0; }
+int64_t pcop_last_sort_pass_keys(const pcop_handle* h) { return h ? (int64_t)h->sort_pass_keys : 0; }
 
 // ---- stage-isolated entry points -------------------------------------------------------
 int pcop_crop(pcop_handle* h, const float* xyzw, int32_t n, float* out_xyzw, int32_t* kept_idx, int32_t* m) {
@@ -1079,7 +1146,7 @@ int pcop_plane(pcop_handle* h, const float* xyzw, int32_t s, float* remaining_xy
   cudaError_t e = run_plane(c, a);
   if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
   run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
-  k_plane_record<<<1, 32, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS), h->cnt(CNT_CLUS1), 1, 1);
+  KL(c, "k_plane_record", k_plane_record<<<1, 32, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS), h->cnt(CNT_CLUS1), 1, 1));
   TRY(fetch_count(h, CNT_REM, p));
   TRY(fetch_warnings(h, warnings));
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_prec, h->d_prec, sizeof(PlaneRecord), cudaMemcpyDeviceToHost, h->stream));

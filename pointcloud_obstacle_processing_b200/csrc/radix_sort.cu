@@ -95,13 +95,14 @@ struct PassSmem {
 __global__ void __launch_bounds__(RS_THREADS)
     k_sort_pass(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, const int* __restrict__ count, const int* __restrict__ npass,
                 const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ desc, int pass, int cap, int tiles,
-                int iota_vals) {
+                int iota_vals, unsigned long long* __restrict__ stats) {
   const int f = blockIdx.y;
   const int n = count[f];
   const int tile = blockIdx.x;
   const int tbase = tile * RS_TILE;
   if (tbase >= n) return;
   if (pass >= npass[f]) return;
+  if (tile == 0 && threadIdx.x == 0 && stats) atomicAdd(stats, (unsigned long long)n);  // keys moved by sort passes
   __shared__ PassSmem sm;
   const int lane = lane_id(), warp = warp_id();
   const int shift = pass * RS_RADIX_BITS;
@@ -214,20 +215,20 @@ size_t sort_desc_bytes(int B, int cap) {
 }
 
 void sort_reset_maxkey(const Ctx& c, const SortBufs& s) {
-  k_sort_reset<<<cdiv(c.B, 256), 256, 0, c.stream>>>(s.maxkey, c.B);
+  KL(c, "k_sort_reset", k_sort_reset<<<cdiv(c.B, 256), 256, 0, c.stream>>>(s.maxkey, c.B));
   count_launch(c);
 }
 
 void radix_sort_batched(const Ctx& c, const SortBufs& s, const int* count, bool iota_vals) {
   const int tiles = cdiv(c.cap, RS_TILE);
   cudaMemsetAsync(s.desc, 0, sort_desc_bytes(c.B, c.cap), c.stream);
-  k_sort_setup<<<c.B, 256, 0, c.stream>>>(s.maxkey, s.npass, s.hist, c.B);
-  k_sort_hist<<<dim3(tiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], count, s.npass, s.hist, c.cap);
-  k_sort_scan<<<dim3(RS_MAX_PASSES, c.B), RS_BINS, 0, c.stream>>>(s.hist, s.npass);
+  KL(c, "k_sort_setup", k_sort_setup<<<c.B, 256, 0, c.stream>>>(s.maxkey, s.npass, s.hist, c.B));
+  KL(c, "k_sort_hist", k_sort_hist<<<dim3(tiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], count, s.npass, s.hist, c.cap));
+  KL(c, "k_sort_scan", k_sort_scan<<<dim3(RS_MAX_PASSES, c.B), RS_BINS, 0, c.stream>>>(s.hist, s.npass));
   count_launch(c, 3);
   for (int p = 0; p < RS_MAX_PASSES; ++p) {
-    k_sort_pass<<<dim3(tiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.key[1], s.val[1], count, s.npass,
-                                                               s.hist, s.desc, p, c.cap, tiles, iota_vals ? 1 : 0);
+    KL(c, "k_sort_pass", k_sort_pass<<<dim3(tiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.key[1], s.val[1], count, s.npass,
+                                                               s.hist, s.desc, p, c.cap, tiles, iota_vals ? 1 : 0, s.stats));
     count_launch(c);
   }
 }

@@ -389,14 +389,14 @@ void run_grid_sort(const Ctx& c, const float4* in, size_t in_stride, const int* 
                    EceFrame* ef, const SortBufs& sort, float4* sorted_pts, int* parent, int* csize) {
   const int tiles = cdiv(c.cap, CT_TILE);
   run_minmax(c, in, in_stride, n_in, minmax);
-  k_ece_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(minmax, n_in, cell, ef, c.B);
+  KL(c, "k_ece_setup", k_ece_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(minmax, n_in, cell, ef, c.B));
   sort_reset_maxkey(c, sort);
-  k_ece_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, ef, sort.key[0], sort.maxkey, parent,
-                                                            csize, c.cap);
+  KL(c, "k_ece_keys", k_ece_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, ef, sort.key[0], sort.maxkey, parent,
+                                                            csize, c.cap));
   count_launch(c, 2);
   radix_sort_batched(c, sort, n_in, true);
-  k_ece_gather<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, sort.val[0], sort.val[1], sort.npass,
-                                                              sorted_pts, c.cap);
+  KL(c, "k_ece_gather", k_ece_gather<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, sort.val[0], sort.val[1], sort.npass,
+                                                              sorted_pts, c.cap));
   count_launch(c);
 }
 
@@ -404,35 +404,35 @@ void run_cluster(const Ctx& c, const ClusterArgs& a) {
   const int tiles = cdiv(c.cap, CT_TILE);
   const float r2 = (float)((double)a.tol * (double)a.tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
   run_grid_sort(c, a.in, a.in_stride, a.n_in, a.tol, a.minmax, a.ef, a.sort, a.sorted_pts, a.parent, a.csize);
-  k_ece_union<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass,
-                                                                 a.n_in, a.ef, a.parent, r2, c.cap);
-  k_ece_flatten<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.parent, a.csize, a.n_in, c.cap);
+  KL(c, "k_ece_union", k_ece_union<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass,
+                                                                 a.n_in, a.ef, a.parent, r2, c.cap));
+  KL(c, "k_ece_flatten", k_ece_flatten<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.parent, a.csize, a.n_in, c.cap));
   count_launch(c, 2);
   // kept roots, ordered by size descending (stable => smallest index first among equals)
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
   sort_reset_maxkey(c, a.sort);
-  k_ece_roots<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.n_in, a.min_size, a.max_size, a.roots,
+  KL(c, "k_ece_roots", k_ece_roots<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.n_in, a.min_size, a.max_size, a.roots,
                                                              a.sort.key[0], a.sort.maxkey, a.n_clusters, a.desc, c.cap,
-                                                             tiles);
+                                                             tiles));
   count_launch(c);
   radix_sort_batched(c, a.sort, a.n_clusters, true);
-  k_ece_rank<<<c.B, 256, 0, c.stream>>>(a.roots, a.sort.val[0], a.sort.val[1], a.sort.npass, a.csize, a.n_clusters,
-                                        a.rank_of, a.offsets, a.n_cluster_pts, c.cap);
+  KL(c, "k_ece_rank", k_ece_rank<<<c.B, 256, 0, c.stream>>>(a.roots, a.sort.val[0], a.sort.val[1], a.sort.npass, a.csize, a.n_clusters,
+                                        a.rank_of, a.offsets, a.n_cluster_pts, c.cap));
   // CSR indices: stable sort of the points by cluster rank
   sort_reset_maxkey(c, a.sort);
-  k_ece_member_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.rank_of, a.n_in, a.n_clusters,
+  KL(c, "k_ece_member_keys", k_ece_member_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.rank_of, a.n_in, a.n_clusters,
                                                                    a.min_size, a.max_size, a.sort.key[0], a.sort.maxkey,
-                                                                   c.cap);
+                                                                   c.cap));
   count_launch(c, 2);
   radix_sort_batched(c, a.sort, a.n_in, true);
-  k_ece_indices<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.sort.val[0], a.sort.val[1], a.sort.npass,
-                                                                   a.n_cluster_pts, a.indices, c.cap);
+  KL(c, "k_ece_indices", k_ece_indices<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.sort.val[0], a.sort.val[1], a.sort.npass,
+                                                                   a.n_cluster_pts, a.indices, c.cap));
   count_launch(c);
 }
 
 void run_centroid_radius(const Ctx& c, const ClusterArgs& a) {
-  k_centroid_radius<<<dim3(64, c.B), 256, 0, c.stream>>>(a.in, a.in_stride, a.offsets, a.indices, a.n_clusters,
-                                                         a.obstacles, c.cap);
+  KL(c, "k_centroid_radius", k_centroid_radius<<<dim3(64, c.B), 256, 0, c.stream>>>(a.in, a.in_stride, a.offsets, a.indices, a.n_clusters,
+                                                         a.obstacles, c.cap));
   count_launch(c);
 }
 

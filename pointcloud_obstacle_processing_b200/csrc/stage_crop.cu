@@ -137,17 +137,17 @@ __global__ void __launch_bounds__(CT_THREADS)
 void run_crop(const Ctx& c, const CropArgs& a) {
   const int tiles = cdiv(c.cap, CT_TILE);
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
-  k_minmax_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, c.B);
-  k_crop<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.out, a.kept_idx, a.n_out, a.minmax,
+  KL(c, "k_minmax_init", k_minmax_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, c.B));
+  KL(c, "k_crop", k_crop<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.out, a.kept_idx, a.n_out, a.minmax,
                                                         a.desc, c.cap, tiles, a.lim[0], a.lim[1], a.lim[2], a.lim[3],
-                                                        a.lim[4], a.lim[5]);
+                                                        a.lim[4], a.lim[5]));
   count_launch(c, 2);
 }
 
 void run_minmax(const Ctx& c, const float4* pts, size_t stride, const int* n, MinMax* minmax) {
   const int tiles = cdiv(c.cap, CT_TILE);
-  k_minmax_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(minmax, c.B);
-  k_minmax<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(pts, stride, n, minmax);
+  KL(c, "k_minmax_init", k_minmax_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(minmax, c.B));
+  KL(c, "k_minmax", k_minmax<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(pts, stride, n, minmax));
   count_launch(c, 2);
 }
 

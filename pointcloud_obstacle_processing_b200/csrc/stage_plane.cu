@@ -588,22 +588,22 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
   bp.s[1] = a.src[1];
   cudaError_t e;
   cudaMemsetAsync(a.n_active, 0, sizeof(int), c.stream);
-  k_plane_init<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_in, a.pc.keep_fraction, a.n_active, c.B);
+  KL(c, "k_plane_init", k_plane_init<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_in, a.pc.keep_fraction, a.n_active, c.B));
   count_launch(c);
   cudaMemcpyAsync(a.h_n_active, a.n_active, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
   if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return e;
   while (*a.h_n_active > 0) {
-    k_plane_gen<<<c.B, 32, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.rng, a.pc, a.warnings, c.cap);
-    k_plane_score<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap);
-    k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B);
-    k_plane_moments<<<dim3(chunks, c.B), 256, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.partial, chunks,
-                                                             c.cap);
-    k_plane_refine<<<c.B, 32, 0, c.stream>>>(a.pf, a.partial, a.pc, chunks);
+    KL(c, "k_plane_gen", k_plane_gen<<<c.B, 32, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.rng, a.pc, a.warnings, c.cap));
+    KL(c, "k_plane_score", k_plane_score<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap));
+    KL(c, "k_plane_select", k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B));
+    KL(c, "k_plane_moments", k_plane_moments<<<dim3(chunks, c.B), 256, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.partial, chunks,
+                                                             c.cap));
+    KL(c, "k_plane_refine", k_plane_refine<<<c.B, 32, 0, c.stream>>>(a.pf, a.partial, a.pc, chunks));
     cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
-    k_plane_extract<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx,
-                                                                   a.n_tmp, a.desc, c.cap, tiles);
+    KL(c, "k_plane_extract", k_plane_extract<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx,
+                                                                   a.n_tmp, a.desc, c.cap, tiles));
     cudaMemsetAsync(a.n_active, 0, sizeof(int), c.stream);
-    k_plane_update<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_tmp, a.pc.keep_fraction, a.n_active, a.warnings, c.B);
+    KL(c, "k_plane_update", k_plane_update<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_tmp, a.pc.keep_fraction, a.n_active, a.warnings, c.B));
     count_launch(c, 7);
     cudaMemcpyAsync(a.h_n_active, a.n_active, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
     if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return e;
@@ -619,8 +619,8 @@ void run_plane_finalize(const Ctx& c, const PlaneArgs& a, float4* out, int* out_
   bp.p[1] = a.buf[1];
   bp.s[0] = a.src[0];
   bp.s[1] = a.src[1];
-  k_plane_finalize<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, out, out_src, a.n_out,
-                                                                  c.cap);
+  KL(c, "k_plane_finalize", k_plane_finalize<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, out, out_src, a.n_out,
+                                                                  c.cap));
   count_launch(c);
 }
 

@@ -142,18 +142,18 @@ __global__ void __launch_bounds__(256)
 
 void run_voxel(const Ctx& c, const VoxelArgs& a) {
   const int tiles = cdiv(c.cap, CT_TILE);
-  k_voxel_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.minmax, a.n_in, a.leaf, a.vf, a.warnings, c.B);
+  KL(c, "k_voxel_setup", k_voxel_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.minmax, a.n_in, a.leaf, a.vf, a.warnings, c.B));
   sort_reset_maxkey(c, a.sort);
-  k_voxel_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.vf, a.sort.key[0],
-                                                              a.sort.maxkey, c.cap);
+  KL(c, "k_voxel_keys", k_voxel_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.vf, a.sort.key[0],
+                                                              a.sort.maxkey, c.cap));
   count_launch(c, 2);
   radix_sort_batched(c, a.sort, a.n_in, /*iota_vals=*/true);
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
-  k_voxel_heads<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.sort.key[0], a.sort.key[1], a.sort.npass, a.n_in, a.vf,
-                                                               a.run_start, a.n_out, a.desc, c.cap, tiles);
-  k_voxel_centroid<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(
+  KL(c, "k_voxel_heads", k_voxel_heads<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.sort.key[0], a.sort.key[1], a.sort.npass, a.n_in, a.vf,
+                                                               a.run_start, a.n_out, a.desc, c.cap, tiles));
+  KL(c, "k_voxel_centroid", k_voxel_centroid<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(
       a.in, a.in_stride, a.n_in, a.sort.key[0], a.sort.key[1], a.sort.val[0], a.sort.val[1], a.sort.npass, a.vf,
-      a.run_start, a.n_out, a.out, a.out_keys, c.cap);
+      a.run_start, a.n_out, a.out, a.out_keys, c.cap));
   count_launch(c, 2);
 }
 
