@@ -23,6 +23,8 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int CT_THREADS = 256;  // stream-compaction / per-point kernels
 constexpr int CT_ITEMS = 4;
 constexpr int CT_TILE = CT_THREADS * CT_ITEMS;  // 1024 points
+constexpr int BT_ITEMS = 16;                     // big-tile compactions (crop, voxel heads, plane extract)
+constexpr int BT_TILE = CT_THREADS * BT_ITEMS;   // 4096 points
 constexpr int RS_THREADS = 256;  // radix sort
 constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys
@@ -93,6 +95,7 @@ struct EceFrame {
   float mn[3];
   float inv[3];
   int dim[3];
+  int mode;  // 0: clique cells (edge < tol/sqrt(3)), union-find over cells; 1: cells >= tol, per-point neighbour scan
 };
 
 struct PlaneFrame {  // state of the plane loop of one frame
@@ -105,6 +108,7 @@ struct PlaneFrame {  // state of the plane loop of one frame
   int gen_end;       // generator stopped early: 0 no, 1 empty sample / skip limit, 2 rng table exhausted
   int best;          // selected hypothesis or -1
   int model_ok;      // selected + valid
+  int need_more;     // the adaptive-k replay ran past the hypotheses scored so far
   int n_inliers_last;
   float4 coeff_sel;  // RANSAC winner
   float4 coeff_ref;  // after refinement

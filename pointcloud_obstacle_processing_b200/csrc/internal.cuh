@@ -29,9 +29,10 @@ struct KernelTimers {
 struct Ctx {
   cudaStream_t stream;
   int B;    // frames in the wave
-  int cap;  // per-frame capacity (points)
+  int cap;  // per-frame capacity (points) = stride of every frame-strided buffer
   int64_t* launches;
   KernelTimers* kt;
+  int grid_cap;  // points per frame the launch grids must cover (<= cap; the host lowers it when it knows a bound)
 };
 
 inline void count_launch(const Ctx& c, int n = 1) { *c.launches += n; }
@@ -88,8 +89,9 @@ struct CropArgs {
 };
 void run_crop(const Ctx& c, const CropArgs& a);
 
-// min/max of an arbitrary frame-strided cloud (used when crop is disabled and by ECE)
-void run_minmax(const Ctx& c, const float4* pts, size_t stride, const int* n, MinMax* minmax);
+// min/max of an arbitrary frame-strided cloud (used when crop is disabled and by the search grids);
+// finite_only skips +-inf as well as NaN (the search grids must only span finite points)
+void run_minmax(const Ctx& c, const float4* pts, size_t stride, const int* n, MinMax* minmax, bool finite_only = false);
 
 struct VoxelArgs {
   const float4* in;  // [B*stride]
@@ -111,8 +113,11 @@ void run_voxel(const Ctx& c, const VoxelArgs& a);
 // Uniform grid over a frame-strided cloud: cell >= `cell`*(1+2^-8) per axis (<= 1024 cells per axis),
 // points radix-sorted by cell key; sorted_pts[j] = {x,y,z, original index}.  parent/csize (optional)
 // are initialised for the union-find.  Sorted keys: sort.key[sort.npass[f]&1].
+// clique != 0 (ECE): cell edge = cell*0.5728 (< cell/sqrt(3)) so that all points of a cell are within `cell` of each
+// other, per-frame fallback to mode 1 when that needs more than 1024 cells on an axis; points with a non-finite
+// coordinate get a private key >= 2^30.
 void run_grid_sort(const Ctx& c, const float4* in, size_t in_stride, const int* n_in, float cell, MinMax* minmax,
-                   EceFrame* ef, const SortBufs& sort, float4* sorted_pts, int* parent, int* csize);
+                   EceFrame* ef, const SortBufs& sort, float4* sorted_pts, int* parent, int* csize, int clique = 0);
 
 struct SorArgs {
   const float4* in;
@@ -174,6 +179,9 @@ struct ClusterArgs {
   int* csize;          // [B*cap]
   int* roots;          // [B*cap]
   int* rank_of;        // [B*cap]
+  int* cell_start;     // [B*cap] first sorted position of each occupied cell
+  uint32_t* cell_key;  // [B*cap] key of each occupied cell
+  int* n_cells;        // [B]
   unsigned* desc;
   int* offsets;  // [B*(cap+1)]
   int* indices;  // [B*cap]

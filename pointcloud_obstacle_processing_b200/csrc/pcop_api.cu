@@ -30,6 +30,7 @@ enum {  // rows of the per-frame count table (device: d_counts[row*maxB + f])
   CNT_TMP,
   CNT_NINL,   // inliers of the last segment() call
   CNT_CLUS1,  // C + 1 (CSR offsets length)
+  CNT_CELLS,  // occupied clique cells (ECE scratch)
   CNT_ROWS
 };
 
@@ -86,7 +87,8 @@ struct pcop_handle {
          *d_rem = nullptr, *d_sorted = nullptr, *d_obst = nullptr;
   int *d_crop_kept = nullptr, *d_run_start = nullptr, *d_sor_kept = nullptr, *d_psrc[2] = {nullptr, nullptr},
       *d_rem_src = nullptr, *d_inliers = nullptr, *d_parent = nullptr, *d_csize = nullptr, *d_roots = nullptr,
-      *d_rank = nullptr, *d_indices = nullptr, *d_offsets = nullptr;
+      *d_rank = nullptr, *d_indices = nullptr, *d_offsets = nullptr, *d_cell_start = nullptr;
+  uint32_t* d_cell_key = nullptr;
   uint32_t* d_vox_keys = nullptr;
   float* d_sor_dist = nullptr;
   SortBufs sort{};
@@ -404,7 +406,9 @@ void resolve_kernel_timers(pcop_handle* h) {
   k.used = 0;
 }
 
-Ctx make_ctx(pcop_handle* h, int B) { return Ctx{h->stream, B, h->cap, &h->launches, &h->kt}; }
+Ctx make_ctx(pcop_handle* h, int B, int grid_cap = -1) {
+  return Ctx{h->stream, B, h->cap, &h->launches, &h->kt, (grid_cap > 0 && grid_cap < h->cap) ? grid_cap : h->cap};
+}
 
 PlaneConst make_plane_const(const pcop_params& p) {
   PlaneConst pc;
@@ -459,6 +463,9 @@ ClusterArgs make_cluster_args(pcop_handle* h, const float4* in, size_t stride, c
   a.csize = h->d_csize;
   a.roots = h->d_roots;
   a.rank_of = h->d_rank;
+  a.cell_start = h->d_cell_start;
+  a.cell_key = h->d_cell_key;
+  a.n_cells = h->cnt(CNT_CELLS);
   a.desc = h->d_desc;
   a.offsets = h->d_offsets;
   a.indices = h->d_indices;
@@ -540,9 +547,9 @@ bool is_device_pointer(const void* p) {
 }
 
 // All stages of one wave.  `in`/`stride` already on the device; counts row CNT_IN already set.
-int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride) {
+int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int max_n) {
   const pcop_params& p = h->params;
-  Ctx c = make_ctx(h, B);
+  Ctx c = make_ctx(h, B, max_n);  // no stage ever holds more points per frame than the largest input frame
   const int tiles = cdiv(h->cap, CT_TILE);
   KL(c, "k_zero_u32", k_zero_u32<<<cdiv(B, 256), 256, 0, h->stream>>>(h->d_warnings, B));
   count_launch(c);
@@ -596,10 +603,11 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride) {
       PlaneArgs a = make_plane_args(h, cur, cur_stride, cur_n);
       cudaError_t e = run_plane(c, a);
       if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
+      c.grid_cap = std::max(1, std::min(c.grid_cap, h->h_n_active[1]));  // largest remaining cloud of the wave
       run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
     } else {
       KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_REM), B));
-      KL(c, "k_copy_cloud", k_copy_cloud<<<dim3(tiles, B), CT_THREADS, 0, h->stream>>>(cur, cur_stride, cur_n, h->d_rem, h->d_rem_src, h->cap));
+      KL(c, "k_copy_cloud", k_copy_cloud<<<dim3(cdiv(c.grid_cap, CT_TILE), B), CT_THREADS, 0, h->stream>>>(cur, cur_stride, cur_n, h->d_rem, h->d_rem_src, h->cap));
       count_launch(c, 2);
     }
   }
@@ -773,7 +781,9 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
         stride = h->cap;
       }
     }
-    TRY(run_wave_stages(h, B, in, stride));
+    int max_n = 1;
+    for (int f = 0; f < B; ++f) max_n = std::max(max_n, (int)n[w0 + f]);
+    TRY(run_wave_stages(h, B, in, stride, max_n));
     TRY(collect_wave(h, B, mask, &h_pack_used, out, w0, &fixups));
     PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (int s = 0; s < PCOP_N_STAGES; ++s) {
@@ -954,6 +964,8 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   A(dalloc(h, &h->d_roots, BC));
   A(dalloc(h, &h->d_rank, BC));
   A(dalloc(h, &h->d_indices, BC));
+  A(dalloc(h, &h->d_cell_start, BC));
+  A(dalloc(h, &h->d_cell_key, BC));
   A(dalloc(h, &h->d_offsets, BC + B));
   A(dalloc(h, &h->d_vox_keys, BC));
   A(dalloc(h, &h->d_sor_dist, BC));
@@ -1095,7 +1107,7 @@ int64_t pcop_last_sort_pass_keys(const pcop_handle* h) { return h ? (int64_t)h->
 int pcop_crop(pcop_handle* h, const float* xyzw, int32_t n, float* out_xyzw, int32_t* kept_idx, int32_t* m) {
   if (!h || !xyzw || !m) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
   TRY(upload_single(h, xyzw, n, CNT_IN));
-  Ctx c = make_ctx(h, 1);
+  Ctx c = make_ctx(h, 1, n);
   run_crop(c, make_crop_args(h, h->d_in, h->cap, h->cnt(CNT_IN)));
   TRY(fetch_count(h, CNT_CROP, m));
   TRY(download(h, out_xyzw, h->d_crop, (size_t)*m * 16));
@@ -1109,7 +1121,7 @@ int pcop_voxel(pcop_handle* h, const float* xyzw, int32_t m, float* out_xyzw, ui
   if (!h || !xyzw || !v) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
   if (!(h->params.downsample_size > 0.0f)) return fail(h, PCOP_ERR_BAD_PARAM, "downsample_size must be > 0");
   TRY(upload_single(h, xyzw, m, CNT_CROP));
-  Ctx c = make_ctx(h, 1);
+  Ctx c = make_ctx(h, 1, m);
   run_minmax(c, h->d_in, h->cap, h->cnt(CNT_CROP), h->d_minmax);
   run_voxel(c, make_voxel_args(h, h->d_in, h->cap, h->cnt(CNT_CROP)));
   TRY(fetch_count(h, CNT_VOX, v));
@@ -1126,7 +1138,7 @@ int pcop_sor(pcop_handle* h, const float* xyzw, int32_t v, float* out_xyzw, int3
   if (h->params.statistical_outlier_meanK < 1 || h->params.statistical_outlier_meanK > 63)
     return fail(h, PCOP_ERR_BAD_PARAM, "statistical_outlier_meanK must be in [1, 63]");
   TRY(upload_single(h, xyzw, v, CNT_VOX));
-  Ctx c = make_ctx(h, 1);
+  Ctx c = make_ctx(h, 1, v);
   run_sor(c, make_sor_args(h, h->d_in, h->cap, h->cnt(CNT_VOX)));
   TRY(fetch_count(h, CNT_SOR, s));
   TRY(fetch_warnings(h, warnings));
@@ -1141,7 +1153,7 @@ int pcop_plane(pcop_handle* h, const float* xyzw, int32_t s, float* remaining_xy
                float* last_coeff, int32_t* inlier_idx, int32_t* n_inliers, uint32_t* warnings) {
   if (!h || !xyzw || !p) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
   TRY(upload_single(h, xyzw, s, CNT_SOR));
-  Ctx c = make_ctx(h, 1);
+  Ctx c = make_ctx(h, 1, s);
   PlaneArgs a = make_plane_args(h, h->d_in, h->cap, h->cnt(CNT_SOR));
   cudaError_t e = run_plane(c, a);
   if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
@@ -1170,7 +1182,7 @@ int pcop_cluster(pcop_handle* h, const float* xyzw, int32_t p, int32_t* cluster_
   if (!h || !xyzw || !c_out || !l_out) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
   if (!(h->params.euc_cluster_tolerance > 0.0f)) return fail(h, PCOP_ERR_BAD_PARAM, "euc_cluster_tolerance must be > 0");
   TRY(upload_single(h, xyzw, p, CNT_REM));
-  Ctx c = make_ctx(h, 1);
+  Ctx c = make_ctx(h, 1, p);
   run_cluster(c, make_cluster_args(h, h->d_in, h->cap, h->cnt(CNT_REM)));
   TRY(fetch_count(h, CNT_CLUS, c_out));
   TRY(fetch_count(h, CNT_CLPTS, l_out));
@@ -1192,7 +1204,7 @@ int pcop_centroid_radius(pcop_handle* h, const float* xyzw, int32_t p, const int
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->cnt(CNT_CLUS), h->h_n_in + 1, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_offsets, cluster_offsets, (size_t)(c_in + 1) * 4, cudaMemcpyDefault, h->stream));
   if (l > 0) PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_indices, cluster_indices, (size_t)l * 4, cudaMemcpyDefault, h->stream));
-  Ctx c = make_ctx(h, 1);
+  Ctx c = make_ctx(h, 1, p);
   run_centroid_radius(c, make_cluster_args(h, h->d_in, h->cap, h->cnt(CNT_REM)));
   TRY(download(h, obstacles, h->d_obst, (size_t)c_in * 16));
   PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));

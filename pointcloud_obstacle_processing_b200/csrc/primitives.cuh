@@ -107,6 +107,44 @@ __device__ __forceinline__ unsigned tile_compact_positions(const bool (&keep)[CT
   return sm.tile_excl + sm.tile_total;
 }
 
+// Big-tile variant for the bandwidth-heavy compactions: ITEMS (<= 32) items per thread, keep flags as a
+// bit mask, so a thread keeps no payload in registers across the look-back wait (payload is re-read from
+// L1/L2 afterwards).  Tile = 256*ITEMS elements, warp-striped: item k of lane l of warp w is tile element
+// w*32*ITEMS + k*32 + l.  Returns the inclusive kept total up to this tile; wbase = frame-wide output slot
+// of the warp's first kept item.  The caller then walks its rows:
+//   m = __ballot_sync(FULL, keepmask >> k & 1); pos = wbase + popc(m & lanemask_lt()); wbase += popc(m);
+template <int ITEMS>
+__device__ __forceinline__ int bt_index(int tile, int k) {
+  return tile * (CT_THREADS * ITEMS) + warp_id() * (32 * ITEMS) + k * 32 + lane_id();
+}
+template <int ITEMS>
+__device__ __forceinline__ unsigned big_tile_scan(unsigned keepmask, unsigned* desc_frame, int tile, CompactSmem& sm,
+                                                  unsigned& wbase) {
+  const int lane = lane_id(), warp = warp_id();
+  unsigned wtotal = __reduce_add_sync(FULL, (unsigned)__popc(keepmask));
+  if (lane == 0) sm.warp_total[warp] = wtotal;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned t = (lane < CT_THREADS / 32) ? sm.warp_total[lane] : 0u;
+    unsigned incl = t;
+#pragma unroll
+    for (int o = 1; o < CT_THREADS / 32; o <<= 1) {
+      const unsigned up = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const unsigned tile_total = __shfl_sync(FULL, incl, CT_THREADS / 32 - 1);
+    const unsigned excl = lookback_warp(desc_frame, tile, tile_total);
+    if (lane < CT_THREADS / 32) sm.warp_total[lane] = excl + incl - t;
+    if (lane == 0) {
+      sm.tile_excl = excl;
+      sm.tile_total = tile_total;
+    }
+  }
+  __syncthreads();
+  wbase = sm.warp_total[warp];
+  return sm.tile_excl + sm.tile_total;
+}
+
 // element index (inside the frame) of item k of this thread in tile `tile`
 __device__ __forceinline__ int ct_index(int tile, int k) {
   return tile * CT_TILE + warp_id() * (32 * CT_ITEMS) + k * 32 + lane_id();

@@ -220,15 +220,15 @@ void sort_reset_maxkey(const Ctx& c, const SortBufs& s) {
 }
 
 void radix_sort_batched(const Ctx& c, const SortBufs& s, const int* count, bool iota_vals) {
-  const int tiles = cdiv(c.cap, RS_TILE);
-  cudaMemsetAsync(s.desc, 0, sort_desc_bytes(c.B, c.cap), c.stream);
+  const int gtiles = cdiv(c.grid_cap, RS_TILE);
+  cudaMemsetAsync(s.desc, 0, sort_desc_bytes(c.B, c.grid_cap), c.stream);  // stride = launched tiles
   KL(c, "k_sort_setup", k_sort_setup<<<c.B, 256, 0, c.stream>>>(s.maxkey, s.npass, s.hist, c.B));
-  KL(c, "k_sort_hist", k_sort_hist<<<dim3(tiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], count, s.npass, s.hist, c.cap));
+  KL(c, "k_sort_hist", k_sort_hist<<<dim3(gtiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], count, s.npass, s.hist, c.cap));
   KL(c, "k_sort_scan", k_sort_scan<<<dim3(RS_MAX_PASSES, c.B), RS_BINS, 0, c.stream>>>(s.hist, s.npass));
   count_launch(c, 3);
   for (int p = 0; p < RS_MAX_PASSES; ++p) {
-    KL(c, "k_sort_pass", k_sort_pass<<<dim3(tiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.key[1], s.val[1], count, s.npass,
-                                                               s.hist, s.desc, p, c.cap, tiles, iota_vals ? 1 : 0, s.stats));
+    KL(c, "k_sort_pass", k_sort_pass<<<dim3(gtiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.key[1], s.val[1], count, s.npass,
+                                                               s.hist, s.desc, p, c.cap, gtiles, iota_vals ? 1 : 0, s.stats));
     count_launch(c);
   }
 }

@@ -17,26 +17,40 @@ namespace {
 
 constexpr int ECE_MAX_DIM = 1024;  // cells per axis (30-bit keys)
 
-__global__ void k_ece_setup(const MinMax* __restrict__ minmax, const int* __restrict__ n_in, float tol,
+// Grid guarantees (DESIGN.md "search grid"), with s = fl(fl(x - mn) * inv) and at most 1024 cells per axis:
+//  mode 1: cell >= tol*(1+2^-8)  =>  d2 < r2 implies the cell coordinates differ by at most 1 per axis;
+//  mode 0: cell  = tol*0.5728 (< tol/sqrt(3) * (1 - 2^-7))  =>  all points of one cell are mutually within tol
+//          (a clique), and d2 < r2 implies the cell coordinates differ by at most 2 per axis.
+__global__ void k_ece_setup(const MinMax* __restrict__ minmax, const int* __restrict__ n_in, float tol, int clique,
                             EceFrame* __restrict__ ef, int B) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= B) return;
   EceFrame e;
-  const float cell_min = tol * 1.00390625f;  // tolerance * (1 + 2^-8): see DESIGN.md "grid guarantee"
+  float mn[3], ext[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    float mn = ord2f(minmax[f].mn[a]);
+    mn[a] = ord2f(minmax[f].mn[a]);
     float mx = ord2f(minmax[f].mx[a]);
-    if (n_in[f] <= 0 || !(mx >= mn)) {
-      mn = 0.0f;
+    if (n_in[f] <= 0 || !(mx >= mn[a])) {
+      mn[a] = 0.0f;
       mx = 0.0f;
     }
-    const float ext = mx - mn;
-    float cell = fmaxf(cell_min, ext / (float)(ECE_MAX_DIM - 1));
+    ext[a] = mx - mn[a];
+  }
+  const float fine = tol * 0.5728f;
+  e.mode = 1;
+  if (clique && fine > 0.0f) {
+    const float lim = fine * (float)(ECE_MAX_DIM - 2);
+    if (ext[0] < lim && ext[1] < lim && ext[2] < lim) e.mode = 0;
+  }
+  const float cell_min = (e.mode == 0) ? fine : tol * 1.00390625f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float cell = (e.mode == 0) ? cell_min : fmaxf(cell_min, ext[a] / (float)(ECE_MAX_DIM - 1));
     if (!(cell > 0.0f) || !(cell < 3.0e38f)) cell = 1.0f;
-    e.mn[a] = mn;
+    e.mn[a] = mn[a];
     e.inv[a] = 1.0f / cell;
-    int d = (int)floorf(ext * e.inv[a]) + 1;
+    int d = (int)floorf(ext[a] * e.inv[a]) + 1;
     e.dim[a] = min(max(d, 1), ECE_MAX_DIM);
   }
   ef[f] = e;
@@ -66,7 +80,10 @@ __global__ void __launch_bounds__(CT_THREADS)
       const int cx = cell_coord(p.x, e.mn[0], e.inv[0], e.dim[0]);
       const int cy = cell_coord(p.y, e.mn[1], e.inv[1], e.dim[1]);
       const int cz = cell_coord(p.z, e.mn[2], e.inv[2], e.dim[2]);
-      const uint32_t key = (uint32_t)cx + (uint32_t)e.dim[0] * ((uint32_t)cy + (uint32_t)e.dim[1] * (uint32_t)cz);
+      uint32_t key = (uint32_t)cx + (uint32_t)e.dim[0] * ((uint32_t)cy + (uint32_t)e.dim[1] * (uint32_t)cz);
+      // clique mode: a point with a non-finite coordinate is within tol of nothing; give it a private cell
+      if (e.mode == 0 && !(fabsf(p.x) <= 3.0e38f && fabsf(p.y) <= 3.0e38f && fabsf(p.z) <= 3.0e38f))
+        key = 0x40000000u | (uint32_t)i;
       keys[(size_t)f * cap + i] = key;
       if (parent) {
         parent[(size_t)f * cap + i] = i;
@@ -147,6 +164,7 @@ __global__ void __launch_bounds__(256)
   const int n = n_in[f];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  if (ef[f].mode != 1) return;
   const uint32_t* ks = ((npass[f] & 1) ? key1 : key0) + (size_t)f * cap;
   const float4* sp = sorted_pts + (size_t)f * cap;
   int* par = parent + (size_t)f * cap;
@@ -179,6 +197,161 @@ __global__ void __launch_bounds__(256)
     for (int q = lower_bound_u32(ks, n, lo_key); q < n && ks[q] <= hi_key; ++q) {
       const float4 o = sp[q];
       if (dist2(p.x, p.y, p.z, o.x, o.y, o.z) < r2) uf_union(par, pi, (int)__float_as_uint(o.w));
+    }
+  }
+}
+
+// clique mode: first sorted position + key of every occupied cell (stable compaction of the run heads)
+__global__ void __launch_bounds__(CT_THREADS)
+    k_ece_cell_heads(const uint32_t* __restrict__ key0, const uint32_t* __restrict__ key1, const int* __restrict__ npass,
+                     const int* __restrict__ n_in, const EceFrame* __restrict__ ef,
+                     const float4* __restrict__ sorted_pts, int* __restrict__ cell_start, uint32_t* __restrict__ cell_key,
+                     int* __restrict__ cell_rep, int* __restrict__ n_cells, unsigned* __restrict__ desc, int cap,
+                     int tiles) {
+  const int f = blockIdx.y, tile = blockIdx.x;
+  const int n = n_in[f];
+  if (tile * CT_TILE >= n || ef[f].mode != 0) {
+    if (tile == 0 && threadIdx.x == 0) n_cells[f] = 0;
+    return;
+  }
+  __shared__ CompactSmem sm;
+  const uint32_t* ks = ((npass[f] & 1) ? key1 : key0) + (size_t)f * cap;
+  bool keep[CT_ITEMS];
+  unsigned pos[CT_ITEMS];
+  uint32_t kk[CT_ITEMS];
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int j = ct_index(tile, k);
+    keep[k] = false;
+    kk[k] = 0;
+    if (j < n) {
+      kk[k] = ks[j];
+      keep[k] = j == 0 || kk[k] != ks[j - 1];
+    }
+  }
+  const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm);
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k)
+    if (keep[k]) {
+      cell_start[(size_t)f * cap + pos[k]] = ct_index(tile, k);
+      cell_key[(size_t)f * cap + pos[k]] = kk[k];
+      // representative = first sorted point of the cell = its smallest original index (stable sort)
+      cell_rep[(size_t)f * cap + pos[k]] = (int)__float_as_uint(sorted_pts[(size_t)f * cap + ct_index(tile, k)].w);
+    }
+  if ((tile + 1) * CT_TILE >= n && threadIdx.x == 0) n_cells[f] = (int)incl_total;
+}
+
+// clique mode: one warp per occupied cell A.  The cell's representative is its first sorted point, which (stable
+// sort) is its smallest original index; the other points are hung under it.  A is merged with each of the 62
+// "forward" cells B within 2 cells per axis as soon as ONE pair (a in A, b in B) passes the exact predicate; pairs
+// are only tested while A and B are still in different sets.  Lanes 0..12 each locate the candidate cells of one
+// forward row (binary search in the sorted cell-key list) in parallel; the warp then walks the found cells.
+__global__ void __launch_bounds__(256)
+    k_ece_cell_union(const float4* __restrict__ sorted_pts, const int* __restrict__ cell_start,
+                     const uint32_t* __restrict__ cell_key, const int* __restrict__ cell_rep,
+                     const int* __restrict__ n_cells, const int* __restrict__ n_in, const EceFrame* __restrict__ ef,
+                     int* __restrict__ parent, float r2, int cap) {
+  const int f = blockIdx.y;
+  const int nc = n_cells[f];
+  const int warps_per_frame = gridDim.x * (blockDim.x >> 5);
+  const int lane = lane_id();
+  int c = blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (c >= nc) return;
+  const int n = n_in[f];
+  const EceFrame e = ef[f];
+  const float4* sp = sorted_pts + (size_t)f * cap;
+  const int* cs = cell_start + (size_t)f * cap;
+  const uint32_t* ck = cell_key + (size_t)f * cap;
+  const int* crep = cell_rep + (size_t)f * cap;
+  int* par = parent + (size_t)f * cap;
+  const uint32_t dimx = (uint32_t)e.dim[0], dimy = (uint32_t)e.dim[1];
+  for (; c < nc; c += warps_per_frame) {
+    const int j0 = cs[c];
+    const int j1 = (c + 1 < nc) ? cs[c + 1] : n;
+    const uint32_t keyA = ck[c];
+    const int repA = crep[c];
+    for (int j = j0 + 1 + lane; j < j1; j += 32) par[(int)__float_as_uint(sp[j].w)] = repA;
+    if (keyA >= 0x40000000u) continue;  // private cell of a non-finite point
+    const int cx = (int)(keyA % dimx);
+    const int cy = (int)((keyA / dimx) % dimy);
+    const int cz = (int)(keyA / (dimx * dimy));
+    const int x_lo = max(cx - 2, 0), x_hi = min(cx + 2, e.dim[0] - 1);
+    // lane r < 13: first candidate cell and number of candidate cells (<= 5) of forward row r.
+    // row 0 = own row (cells x+1, x+2 follow A directly); r = 1,2: dz = 0, dy = 1,2;
+    // r = 3..12: dz = 1 + (r-3)/5, dy = (r-3)%5 - 2
+    int my_start = nc, my_cnt = 0;
+    if (lane < 13) {
+      uint32_t hi_key = 0;
+      bool ok = true;
+      if (lane == 0) {
+        my_start = c + 1;
+        hi_key = keyA - (uint32_t)cx + (uint32_t)x_hi;
+      } else {
+        const int dz = (lane < 3) ? 0 : 1 + (lane - 3) / 5;
+        const int dy = (lane < 3) ? lane : (lane - 3) % 5 - 2;
+        const int yy = cy + dy, zz = cz + dz;
+        ok = !(yy < 0 || yy >= e.dim[1] || zz >= e.dim[2]);
+        if (ok) {
+          const uint32_t row = dimx * ((uint32_t)yy + dimy * (uint32_t)zz);
+          const uint32_t lo_key = row + (uint32_t)x_lo;
+          hi_key = row + (uint32_t)x_hi;
+          int lo = c + 1, hi = nc;  // forward rows have larger keys than A
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ck[mid] < lo_key) lo = mid + 1;
+            else hi = mid;
+          }
+          my_start = lo;
+        }
+      }
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int cb = my_start + k;
+          const uint32_t kb = (cb < nc) ? ck[cb] : 0xffffffffu;
+          if (kb <= hi_key) my_cnt = k + 1;  // keys ascend, so the matches are a prefix
+        }
+      }
+    }
+    // spread the candidate cells (<= 62) over the lanes: lane q handles candidate q, q + 32
+    int excl = my_cnt;  // inclusive scan over lanes (rows), then made exclusive
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const int up = __shfl_up_sync(FULL, excl, o);
+      if (lane >= o) excl += up;
+    }
+    const int total_cand = __shfl_sync(FULL, excl, 12);
+    excl -= my_cnt;
+    for (int q0 = 0; q0 < total_cand; q0 += 32) {
+      const int q = q0 + lane;
+      int cb = -1;
+#pragma unroll
+      for (int r = 0; r < 13; ++r) {
+        const int e_r = __shfl_sync(FULL, excl, r);
+        const int c_r = __shfl_sync(FULL, my_cnt, r);
+        const int s_r = __shfl_sync(FULL, my_start, r);
+        if (q >= e_r && q < e_r + c_r) cb = s_r + (q - e_r);
+      }
+      if (cb >= 0) {
+        const int repB = crep[cb];
+        if (uf_find(par, repA) != uf_find(par, repB)) {
+          const int jb0 = cs[cb];
+          const int jb1 = (cb + 1 < nc) ? cs[cb + 1] : n;
+          bool hit = false;
+          for (int a = j0; a < j1 && !hit; ++a) {
+            const float4 pa = sp[a];
+            for (int b = jb0; b < jb1; ++b) {
+              const float4 pb = sp[b];
+              if (dist2(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z) < r2) {
+                hit = true;
+                break;
+              }
+            }
+          }
+          if (hit) uf_union(par, repA, repB);
+        }
+      }
+      __syncwarp();
     }
   }
 }
@@ -386,32 +559,43 @@ __global__ void __launch_bounds__(256)
 }  // namespace
 
 void run_grid_sort(const Ctx& c, const float4* in, size_t in_stride, const int* n_in, float cell, MinMax* minmax,
-                   EceFrame* ef, const SortBufs& sort, float4* sorted_pts, int* parent, int* csize) {
-  const int tiles = cdiv(c.cap, CT_TILE);
-  run_minmax(c, in, in_stride, n_in, minmax);
-  KL(c, "k_ece_setup", k_ece_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(minmax, n_in, cell, ef, c.B));
+                   EceFrame* ef, const SortBufs& sort, float4* sorted_pts, int* parent, int* csize, int clique) {
+  const int tiles = cdiv(c.cap, CT_TILE);        // descriptor stride
+  const int gtiles = cdiv(c.grid_cap, CT_TILE);  // blocks actually launched per frame
+  run_minmax(c, in, in_stride, n_in, minmax, /*finite_only=*/true);
+  KL(c, "k_ece_setup", k_ece_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(minmax, n_in, cell, clique, ef, c.B));
   sort_reset_maxkey(c, sort);
-  KL(c, "k_ece_keys", k_ece_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, ef, sort.key[0], sort.maxkey, parent,
+  KL(c, "k_ece_keys", k_ece_keys<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, ef, sort.key[0], sort.maxkey, parent,
                                                             csize, c.cap));
   count_launch(c, 2);
   radix_sort_batched(c, sort, n_in, true);
-  KL(c, "k_ece_gather", k_ece_gather<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, sort.val[0], sort.val[1], sort.npass,
+  KL(c, "k_ece_gather", k_ece_gather<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(in, in_stride, n_in, sort.val[0], sort.val[1], sort.npass,
                                                               sorted_pts, c.cap));
   count_launch(c);
 }
 
 void run_cluster(const Ctx& c, const ClusterArgs& a) {
-  const int tiles = cdiv(c.cap, CT_TILE);
+  const int tiles = cdiv(c.cap, CT_TILE);        // descriptor stride
+  const int gtiles = cdiv(c.grid_cap, CT_TILE);  // blocks actually launched per frame
   const float r2 = (float)((double)a.tol * (double)a.tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
-  run_grid_sort(c, a.in, a.in_stride, a.n_in, a.tol, a.minmax, a.ef, a.sort, a.sorted_pts, a.parent, a.csize);
-  KL(c, "k_ece_union", k_ece_union<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass,
+  run_grid_sort(c, a.in, a.in_stride, a.n_in, a.tol, a.minmax, a.ef, a.sort, a.sorted_pts, a.parent, a.csize, /*clique=*/1);
+  // frames in clique mode: union-find over cells
+  cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
+  KL(c, "k_ece_cell_heads", k_ece_cell_heads<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(
+      a.sort.key[0], a.sort.key[1], a.sort.npass, a.n_in, a.ef, a.sorted_pts, a.cell_start, a.cell_key,
+      /*cell_rep (scratch, reused for the root list afterwards)=*/a.roots, a.n_cells, a.desc, c.cap, tiles));
+  KL(c, "k_ece_cell_union", k_ece_cell_union<<<dim3(max(1, min(cdiv(c.grid_cap, 16), 512)), c.B), 256, 0, c.stream>>>(
+      a.sorted_pts, a.cell_start, a.cell_key, a.roots, a.n_cells, a.n_in, a.ef, a.parent, r2, c.cap));
+  count_launch(c, 2);
+  // frames whose extent does not fit 1024 clique cells per axis: per-point neighbour scan
+  KL(c, "k_ece_union", k_ece_union<<<dim3(cdiv(c.grid_cap, 256), c.B), 256, 0, c.stream>>>(a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass,
                                                                  a.n_in, a.ef, a.parent, r2, c.cap));
-  KL(c, "k_ece_flatten", k_ece_flatten<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.parent, a.csize, a.n_in, c.cap));
+  KL(c, "k_ece_flatten", k_ece_flatten<<<dim3(cdiv(c.grid_cap, 256), c.B), 256, 0, c.stream>>>(a.parent, a.csize, a.n_in, c.cap));
   count_launch(c, 2);
   // kept roots, ordered by size descending (stable => smallest index first among equals)
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
   sort_reset_maxkey(c, a.sort);
-  KL(c, "k_ece_roots", k_ece_roots<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.n_in, a.min_size, a.max_size, a.roots,
+  KL(c, "k_ece_roots", k_ece_roots<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.n_in, a.min_size, a.max_size, a.roots,
                                                              a.sort.key[0], a.sort.maxkey, a.n_clusters, a.desc, c.cap,
                                                              tiles));
   count_launch(c);
@@ -420,12 +604,12 @@ void run_cluster(const Ctx& c, const ClusterArgs& a) {
                                         a.rank_of, a.offsets, a.n_cluster_pts, c.cap));
   // CSR indices: stable sort of the points by cluster rank
   sort_reset_maxkey(c, a.sort);
-  KL(c, "k_ece_member_keys", k_ece_member_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.rank_of, a.n_in, a.n_clusters,
+  KL(c, "k_ece_member_keys", k_ece_member_keys<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.parent, a.csize, a.rank_of, a.n_in, a.n_clusters,
                                                                    a.min_size, a.max_size, a.sort.key[0], a.sort.maxkey,
                                                                    c.cap));
   count_launch(c, 2);
   radix_sort_batched(c, a.sort, a.n_in, true);
-  KL(c, "k_ece_indices", k_ece_indices<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(a.sort.val[0], a.sort.val[1], a.sort.npass,
+  KL(c, "k_ece_indices", k_ece_indices<<<dim3(cdiv(c.grid_cap, 256), c.B), 256, 0, c.stream>>>(a.sort.val[0], a.sort.val[1], a.sort.npass,
                                                                    a.n_cluster_pts, a.indices, c.cap));
   count_launch(c);
 }

@@ -76,47 +76,55 @@ __global__ void __launch_bounds__(CT_THREADS)
            int cap, int tiles, float x_min, float x_max, float y_min, float y_max, float z_min, float z_max) {
   const int f = blockIdx.y, tile = blockIdx.x;
   const int n = n_in[f];
-  if (tile * CT_TILE >= n) {
+  if (tile * BT_TILE >= n) {
     if (tile == 0 && threadIdx.x == 0) n_out[f] = 0;
     return;
   }
   __shared__ CompactSmem sm;
   __shared__ float shmm[CT_THREADS / 32][6];
   const float4* src = in + (size_t)f * in_stride;
-  float4 p[CT_ITEMS];
-  bool keep[CT_ITEMS];
-  unsigned pos[CT_ITEMS];
+  unsigned keepmask = 0u;
   MinMaxAcc acc;
   acc.init();
+  // pass 1: 16 independent 16-byte loads per thread, predicate only; nothing is held across the look-back
 #pragma unroll
-  for (int k = 0; k < CT_ITEMS; ++k) {
-    const int i = ct_index(tile, k);
-    keep[k] = false;
+  for (int k = 0; k < BT_ITEMS; ++k) {
+    const int i = bt_index<BT_ITEMS>(tile, k);
     if (i < n) {
-      p[k] = __ldg(src + i);
+      const float4 p = __ldg(src + i);
       // od.cpp:197-199, literal: drop iff isnan(x) || x<x_min || x>x_max || z<z_min || z>z_max || y<y_min || y>y_max
-      const bool drop = (p[k].x != p[k].x) || p[k].x < x_min || p[k].x > x_max || p[k].z < z_min || p[k].z > z_max ||
-                        p[k].y < y_min || p[k].y > y_max;
-      keep[k] = !drop;
-      if (keep[k]) acc.add(p[k]);
+      const bool drop = (p.x != p.x) || p.x < x_min || p.x > x_max || p.z < z_min || p.z > z_max || p.y < y_min ||
+                        p.y > y_max;
+      if (!drop) {
+        keepmask |= 1u << k;
+        acc.add(p);
+      }
     }
   }
-  const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm);
+  unsigned wbase;
+  const unsigned incl_total = big_tile_scan<BT_ITEMS>(keepmask, desc + (size_t)f * tiles, tile, sm, wbase);
   float4* dst = out + (size_t)f * cap;
   int* kdst = kept_idx + (size_t)f * cap;
+  // pass 2: survivors are re-read (L1/L2 hits) and written to their stable slots
 #pragma unroll
-  for (int k = 0; k < CT_ITEMS; ++k) {
-    if (keep[k]) {
-      dst[pos[k]] = p[k];
-      kdst[pos[k]] = ct_index(tile, k);
+  for (int k = 0; k < BT_ITEMS; ++k) {
+    const bool keep = (keepmask >> k) & 1u;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) {
+      const int i = bt_index<BT_ITEMS>(tile, k);
+      const unsigned pos = wbase + __popc(m & lanemask_lt());
+      dst[pos] = __ldg(src + i);
+      kdst[pos] = i;
     }
+    wbase += __popc(m);
   }
-  if ((tile + 1) * CT_TILE >= n && threadIdx.x == 0) n_out[f] = (int)incl_total;
+  if ((tile + 1) * BT_TILE >= n && threadIdx.x == 0) n_out[f] = (int)incl_total;
   acc.commit(minmax + f, shmm);
 }
 
 __global__ void __launch_bounds__(CT_THREADS)
-    k_minmax(const float4* __restrict__ pts, size_t stride, const int* __restrict__ n_in, MinMax* __restrict__ minmax) {
+    k_minmax(const float4* __restrict__ pts, size_t stride, const int* __restrict__ n_in, MinMax* __restrict__ minmax,
+             int finite_only) {
   const int f = blockIdx.y, tile = blockIdx.x;
   const int n = n_in[f];
   if (tile * CT_TILE >= n) return;
@@ -127,7 +135,16 @@ __global__ void __launch_bounds__(CT_THREADS)
 #pragma unroll
   for (int k = 0; k < CT_ITEMS; ++k) {
     const int i = ct_index(tile, k);
-    if (i < n) acc.add(__ldg(src + i));
+    if (i < n) {
+      float4 p = __ldg(src + i);
+      if (finite_only) {  // drop +-inf (NaN is ignored by the compares anyway)
+        const float big = 3.0e38f;
+        if (fabsf(p.x) > big) p.x = __int_as_float(0x7fc00000);
+        if (fabsf(p.y) > big) p.y = __int_as_float(0x7fc00000);
+        if (fabsf(p.z) > big) p.z = __int_as_float(0x7fc00000);
+      }
+      acc.add(p);
+    }
   }
   acc.commit(minmax + f, shmm);
 }
@@ -135,19 +152,20 @@ __global__ void __launch_bounds__(CT_THREADS)
 }  // namespace
 
 void run_crop(const Ctx& c, const CropArgs& a) {
-  const int tiles = cdiv(c.cap, CT_TILE);
+  const int tiles = cdiv(c.cap, BT_TILE);        // descriptor stride
+  const int gtiles = cdiv(c.grid_cap, BT_TILE);  // blocks actually launched per frame
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
   KL(c, "k_minmax_init", k_minmax_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, c.B));
-  KL(c, "k_crop", k_crop<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.out, a.kept_idx, a.n_out, a.minmax,
+  KL(c, "k_crop", k_crop<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.out, a.kept_idx, a.n_out, a.minmax,
                                                         a.desc, c.cap, tiles, a.lim[0], a.lim[1], a.lim[2], a.lim[3],
                                                         a.lim[4], a.lim[5]));
   count_launch(c, 2);
 }
 
-void run_minmax(const Ctx& c, const float4* pts, size_t stride, const int* n, MinMax* minmax) {
-  const int tiles = cdiv(c.cap, CT_TILE);
+void run_minmax(const Ctx& c, const float4* pts, size_t stride, const int* n, MinMax* minmax, bool finite_only) {
+  const int gtiles = cdiv(c.grid_cap, CT_TILE);
   KL(c, "k_minmax_init", k_minmax_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(minmax, c.B));
-  KL(c, "k_minmax", k_minmax<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(pts, stride, n, minmax));
+  KL(c, "k_minmax", k_minmax<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(pts, stride, n, minmax, finite_only ? 1 : 0));
   count_launch(c, 2);
 }
 

@@ -78,6 +78,7 @@ __global__ void k_plane_init(PlaneFrame* __restrict__ pf, const int* __restrict_
   P.gen_end = 0;
   P.best = -1;
   P.model_ok = 0;
+  P.need_more = 0;
   P.n_inliers_last = 0;
   P.coeff_sel = make_float4(0.f, 0.f, 0.f, 0.f);
   P.coeff_ref = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -88,6 +89,7 @@ __global__ void k_plane_init(PlaneFrame* __restrict__ pf, const int* __restrict_
   }
   P.active = ((double)n > dmul(keep_fraction, (double)n)) ? 1 : 0;  // od.cpp:379
   if (P.active) atomicAdd(n_active, 1);
+  atomicMax(n_active + 1, n);  // largest current cloud over the wave (sizes the next launches)
 }
 
 // one warp per frame: hypothesis generation (getSamples/drawIndexSample/isSampleGood/
@@ -186,14 +188,15 @@ __global__ void __launch_bounds__(32)
 // countWithinDistance for every hypothesis in one sweep
 __global__ void __launch_bounds__(CT_THREADS)
     k_plane_score(PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp, float thr,
-                  int cap) {
+                  int cap, int h_begin, int h_end, int second_phase) {
   const int f = blockIdx.y, tile = blockIdx.x;
   PlaneFrame& P = pf[f];
   if (!P.active) return;
+  if (second_phase && !P.need_more) return;
   const int n = P.n;
   if (tile * CT_TILE >= n) return;
-  const int nh = P.n_hyp;
-  if (nh == 0) return;
+  const int nh = min(P.n_hyp, h_end);
+  if (nh <= h_begin) return;
   __shared__ float4 hyp[MAX_HYP];
   __shared__ int cnt[MAX_HYP];
   if (threadIdx.x < MAX_HYP) {
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(CT_THREADS)
     for (int hl = 0; hl < 32; ++hl) {
       const int h = hh * 32 + hl;
       if (h >= nh) break;
+      if (h < h_begin) continue;
       const float4 co = hyp[h];
       int c = 0;
 #pragma unroll
@@ -231,15 +235,19 @@ __global__ void __launch_bounds__(CT_THREADS)
   for (int hh = 0; hh < MAX_HYP / 32; ++hh)
     if (acc[hh]) atomicAdd(&cnt[hh * 32 + lane], acc[hh]);
   __syncthreads();
-  if (threadIdx.x < nh && cnt[threadIdx.x]) atomicAdd(&P.counts[threadIdx.x], cnt[threadIdx.x]);
+  if (threadIdx.x >= h_begin && threadIdx.x < nh && cnt[threadIdx.x]) atomicAdd(&P.counts[threadIdx.x], cnt[threadIdx.x]);
 }
 
 // RandomSampleConsensus::computeModel's loop, replayed over the precomputed counts
-__global__ void k_plane_select(PlaneFrame* __restrict__ pf, PlaneConst pc, int B) {
+// `navail` hypotheses have been scored so far: if the loop asks for a later one the frame is flagged
+// need_more and nothing is decided yet (the remaining hypotheses are scored, then this runs again).
+__global__ void k_plane_select(PlaneFrame* __restrict__ pf, PlaneConst pc, int B, int navail, int second_phase) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= B) return;
   PlaneFrame& P = pf[f];
   if (!P.active) return;
+  if (second_phase && !P.need_more) return;
+  P.need_more = 0;
   const int nh = P.n_hyp;
   const double log_probability = det_log(dsub(1.0, pc.probability));
   const double one_over_indices = ddiv(1.0, (double)P.n);
@@ -249,6 +257,10 @@ __global__ void k_plane_select(PlaneFrame* __restrict__ pf, PlaneConst pc, int B
   double k = 1.0;
   for (int h = 0; h < nh; ++h) {
     if (!((double)h < k)) break;
+    if (h >= navail) {
+      P.need_more = 1;
+      return;
+    }
     const int c = P.hyp_valid[h] ? P.counts[h] : 0;
     if (c > best) {
       best = c;
@@ -487,7 +499,7 @@ __global__ void __launch_bounds__(CT_THREADS)
   const PlaneFrame& P = pf[f];
   if (!P.active) return;
   const int n = P.n;
-  if (tile * CT_TILE >= n) {
+  if (tile * BT_TILE >= n) {
     if (tile == 0 && threadIdx.x == 0) n_tmp[f] = 0;
     return;
   }
@@ -499,33 +511,33 @@ __global__ void __launch_bounds__(CT_THREADS)
   int* dsrc = bp.s[dst] + (size_t)f * cap;
   const float4 co = P.coeff_ref;
   const bool ok = P.model_ok != 0;
-  float4 p[CT_ITEMS];
-  bool keep[CT_ITEMS], valid[CT_ITEMS];
-  unsigned pos[CT_ITEMS];
+  unsigned keepmask = 0u;
 #pragma unroll
-  for (int k = 0; k < CT_ITEMS; ++k) {
-    const int i = ct_index(tile, k);
-    valid[k] = i < n;
-    keep[k] = false;
-    if (valid[k]) {
-      p[k] = __ldg(pts + i);
-      const bool inl = ok && plane_dist(co, p[k].x, p[k].y, p[k].z) < thr;
-      keep[k] = !inl;
+  for (int k = 0; k < BT_ITEMS; ++k) {
+    const int i = bt_index<BT_ITEMS>(tile, k);
+    if (i < n) {
+      const float4 p = __ldg(pts + i);
+      const bool inl = ok && plane_dist(co, p.x, p.y, p.z) < thr;
+      if (!inl) keepmask |= 1u << k;
     }
   }
-  const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm);
+  unsigned wbase;
+  const unsigned incl_total = big_tile_scan<BT_ITEMS>(keepmask, desc + (size_t)f * tiles, tile, sm, wbase);
 #pragma unroll
-  for (int k = 0; k < CT_ITEMS; ++k) {
-    if (!valid[k]) continue;
-    const int i = ct_index(tile, k);
-    if (keep[k]) {
-      dpts[pos[k]] = p[k];
-      dsrc[pos[k]] = srcidx ? srcidx[i] : i;
-    } else {
-      inlier_idx[(size_t)f * cap + (i - (int)pos[k])] = i;
+  for (int k = 0; k < BT_ITEMS; ++k) {
+    const int i = bt_index<BT_ITEMS>(tile, k);
+    const bool keep = (keepmask >> k) & 1u;
+    const unsigned m = __ballot_sync(FULL, keep);
+    const unsigned pos = wbase + __popc(m & lanemask_lt());
+    if (keep) {
+      dpts[pos] = __ldg(pts + i);
+      dsrc[pos] = srcidx ? srcidx[i] : i;
+    } else if (i < n) {
+      inlier_idx[(size_t)f * cap + (i - (int)pos)] = i;
     }
+    wbase += __popc(m);
   }
-  if ((tile + 1) * CT_TILE >= n && threadIdx.x == 0) n_tmp[f] = (int)incl_total;
+  if ((tile + 1) * BT_TILE >= n && threadIdx.x == 0) n_tmp[f] = (int)incl_total;
 }
 
 // od.cpp:379-399 bookkeeping after one pass
@@ -534,13 +546,17 @@ __global__ void k_plane_update(PlaneFrame* __restrict__ pf, const int* __restric
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= B) return;
   PlaneFrame& P = pf[f];
-  if (!P.active) return;
+  if (!P.active) {
+    atomicMax(n_active + 1, P.n);
+    return;
+  }
   const int remaining = n_tmp[f];
   const int inliers = P.n - remaining;
   P.n_inliers_last = inliers;
   if (inliers == 0) {  // od.cpp:383-387: "Couldn't estimate a planar model", break
     P.active = 0;
     atomicOr(&warnings[f], (uint32_t)PCOP_WARN_PLANE_BREAK);
+    atomicMax(n_active + 1, P.n);
     return;
   }
   if (P.n_passes < PCOP_MAX_PLANE_PASSES_RECORDED) {
@@ -553,6 +569,7 @@ __global__ void k_plane_update(PlaneFrame* __restrict__ pf, const int* __restric
   P.n = remaining;
   P.active = ((double)remaining > dmul(keep_fraction, (double)P.nr_points)) ? 1 : 0;
   if (P.active) atomicAdd(n_active, 1);
+  atomicMax(n_active + 1, P.n);
 }
 
 // copy what is left (planar_cloud_y, od.cpp:765) into the stage output
@@ -579,33 +596,45 @@ __global__ void __launch_bounds__(CT_THREADS)
 }  // namespace
 
 cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
-  const int tiles = cdiv(c.cap, CT_TILE);
+  const int tiles = cdiv(c.cap, CT_TILE);        // descriptor stride
+  const int gtiles = cdiv(c.grid_cap, CT_TILE);  // blocks actually launched per frame
   const int chunks = cdiv(c.cap, TS_CHUNK);
+  const int gchunks = cdiv(c.grid_cap, TS_CHUNK);
   BufPair bp;
   bp.p[0] = a.buf[0];
   bp.p[1] = a.buf[1];
   bp.s[0] = a.src[0];
   bp.s[1] = a.src[1];
   cudaError_t e;
-  cudaMemsetAsync(a.n_active, 0, sizeof(int), c.stream);
+  cudaMemsetAsync(a.n_active, 0, 2 * sizeof(int), c.stream);
   KL(c, "k_plane_init", k_plane_init<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_in, a.pc.keep_fraction, a.n_active, c.B));
   count_launch(c);
-  cudaMemcpyAsync(a.h_n_active, a.n_active, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+  cudaMemcpyAsync(a.h_n_active, a.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
   if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return e;
+  Ctx cc = c;
   while (*a.h_n_active > 0) {
+    cc.grid_cap = max(1, min(c.grid_cap, a.h_n_active[1]));
+    const int gtiles = cdiv(cc.grid_cap, CT_TILE);
+    const int gchunks = cdiv(cc.grid_cap, TS_CHUNK);
     KL(c, "k_plane_gen", k_plane_gen<<<c.B, 32, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.rng, a.pc, a.warnings, c.cap));
-    KL(c, "k_plane_score", k_plane_score<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap));
-    KL(c, "k_plane_select", k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B));
-    KL(c, "k_plane_moments", k_plane_moments<<<dim3(chunks, c.B), 256, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.partial, chunks,
+    // adaptive k usually stops within a few hypotheses: score the first PHASE1, replay, and only score the
+    // rest for the frames whose replay ran past them
+    constexpr int PHASE1 = 8;
+    KL(c, "k_plane_score", k_plane_score<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap, 0, PHASE1, 0));
+    KL(c, "k_plane_select", k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B, PHASE1, 0));
+    KL(c, "k_plane_score", k_plane_score<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap, PHASE1, MAX_HYP, 1));
+    KL(c, "k_plane_select", k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B, MAX_HYP, 1));
+    KL(c, "k_plane_moments", k_plane_moments<<<dim3(gchunks, c.B), 256, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.partial, chunks,
                                                              c.cap));
     KL(c, "k_plane_refine", k_plane_refine<<<c.B, 32, 0, c.stream>>>(a.pf, a.partial, a.pc, chunks));
-    cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
-    KL(c, "k_plane_extract", k_plane_extract<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx,
-                                                                   a.n_tmp, a.desc, c.cap, tiles));
-    cudaMemsetAsync(a.n_active, 0, sizeof(int), c.stream);
+    const int btiles = cdiv(c.cap, BT_TILE), gbtiles = cdiv(cc.grid_cap, BT_TILE);
+    cudaMemsetAsync(a.desc, 0, (size_t)c.B * btiles * sizeof(unsigned), c.stream);
+    KL(c, "k_plane_extract", k_plane_extract<<<dim3(gbtiles, c.B), CT_THREADS, 0, c.stream>>>(
+        a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx, a.n_tmp, a.desc, c.cap, btiles));
+    cudaMemsetAsync(a.n_active, 0, 2 * sizeof(int), c.stream);
     KL(c, "k_plane_update", k_plane_update<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_tmp, a.pc.keep_fraction, a.n_active, a.warnings, c.B));
-    count_launch(c, 7);
-    cudaMemcpyAsync(a.h_n_active, a.n_active, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+    count_launch(c, 9);
+    cudaMemcpyAsync(a.h_n_active, a.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
     if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return e;
   }
   return cudaGetLastError();
@@ -613,13 +642,14 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
 
 // exposed to the API translation unit
 void run_plane_finalize(const Ctx& c, const PlaneArgs& a, float4* out, int* out_src) {
-  const int tiles = cdiv(c.cap, CT_TILE);
+  const int tiles = cdiv(c.cap, CT_TILE);        // descriptor stride
+  const int gtiles = cdiv(c.grid_cap, CT_TILE);  // blocks actually launched per frame
   BufPair bp;
   bp.p[0] = a.buf[0];
   bp.p[1] = a.buf[1];
   bp.s[0] = a.src[0];
   bp.s[1] = a.src[1];
-  KL(c, "k_plane_finalize", k_plane_finalize<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, out, out_src, a.n_out,
+  KL(c, "k_plane_finalize", k_plane_finalize<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, out, out_src, a.n_out,
                                                                   c.cap));
   count_launch(c);
 }

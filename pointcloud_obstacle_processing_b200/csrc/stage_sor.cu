@@ -204,17 +204,19 @@ __global__ void __launch_bounds__(CT_THREADS)
 }  // namespace
 
 void run_sor(const Ctx& c, const SorArgs& a) {
-  const int tiles = cdiv(c.cap, CT_TILE);
+  const int tiles = cdiv(c.cap, CT_TILE);        // descriptor stride
+  const int gtiles = cdiv(c.grid_cap, CT_TILE);  // blocks actually launched per frame
   const int chunks = cdiv(c.cap, TS_CHUNK);
+  const int gchunks = cdiv(c.grid_cap, TS_CHUNK);
   KL(c, "k_sor_setup", k_sor_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.n_in, a.meanK, a.thr, a.warnings, c.B));
   count_launch(c);
   run_grid_sort(c, a.in, a.in_stride, a.n_in, a.cell, a.minmax, a.gf, a.sort, a.sorted_pts, nullptr, nullptr);
-  KL(c, "k_sor_knn", k_sor_knn<<<dim3(cdiv(c.cap, 128), c.B), 128, 0, c.stream>>>(a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass,
+  KL(c, "k_sor_knn", k_sor_knn<<<dim3(cdiv(c.grid_cap, 128), c.B), 128, 0, c.stream>>>(a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass,
                                                                a.n_in, a.gf, a.meanK, a.dist, c.cap));
-  KL(c, "k_sor_sums", k_sor_sums<<<dim3(chunks, c.B), 256, 0, c.stream>>>(a.dist, a.n_in, a.meanK, a.partial, chunks, c.cap));
+  KL(c, "k_sor_sums", k_sor_sums<<<dim3(gchunks, c.B), 256, 0, c.stream>>>(a.dist, a.n_in, a.meanK, a.partial, chunks, c.cap));
   KL(c, "k_sor_threshold", k_sor_threshold<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.partial, a.n_in, a.meanK, a.mul, a.thr, chunks, c.B));
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
-  KL(c, "k_sor_filter", k_sor_filter<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.dist, a.thr, a.meanK, a.out,
+  KL(c, "k_sor_filter", k_sor_filter<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.dist, a.thr, a.meanK, a.out,
                                                               a.kept_idx, a.n_out, a.desc, c.cap, tiles));
   count_launch(c, 4);
 }

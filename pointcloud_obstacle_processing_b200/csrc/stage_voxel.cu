@@ -79,27 +79,30 @@ __global__ void __launch_bounds__(CT_THREADS)
                   int* __restrict__ n_out, unsigned* __restrict__ desc, int cap, int tiles) {
   const int f = blockIdx.y, tile = blockIdx.x;
   const int n = n_in[f];
-  if (tile * CT_TILE >= n) {
+  if (tile * BT_TILE >= n) {
     if (tile == 0 && threadIdx.x == 0) n_out[f] = 0;
     return;
   }
   __shared__ CompactSmem sm;
   const uint32_t* ks = ((npass[f] & 1) ? key1 : key0) + (size_t)f * cap;
   const bool all_heads = vf[f].overflow != 0;
-  bool keep[CT_ITEMS];
-  unsigned pos[CT_ITEMS];
+  unsigned keepmask = 0u;
 #pragma unroll
-  for (int k = 0; k < CT_ITEMS; ++k) {
-    const int j = ct_index(tile, k);
-    keep[k] = false;
-    if (j < n) keep[k] = all_heads || j == 0 || ks[j] != ks[j - 1];
+  for (int k = 0; k < BT_ITEMS; ++k) {
+    const int j = bt_index<BT_ITEMS>(tile, k);
+    if (j < n && (all_heads || j == 0 || ks[j] != ks[j - 1])) keepmask |= 1u << k;
   }
-  const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm);
+  unsigned wbase;
+  const unsigned incl_total = big_tile_scan<BT_ITEMS>(keepmask, desc + (size_t)f * tiles, tile, sm, wbase);
   int* rs = run_start + (size_t)f * cap;
 #pragma unroll
-  for (int k = 0; k < CT_ITEMS; ++k)
-    if (keep[k]) rs[pos[k]] = ct_index(tile, k);
-  if ((tile + 1) * CT_TILE >= n && threadIdx.x == 0) n_out[f] = (int)incl_total;
+  for (int k = 0; k < BT_ITEMS; ++k) {
+    const bool keep = (keepmask >> k) & 1u;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) rs[wbase + __popc(m & lanemask_lt())] = bt_index<BT_ITEMS>(tile, k);
+    wbase += __popc(m);
+  }
+  if ((tile + 1) * BT_TILE >= n && threadIdx.x == 0) n_out[f] = (int)incl_total;
 }
 
 __global__ void __launch_bounds__(256)
@@ -141,17 +144,19 @@ __global__ void __launch_bounds__(256)
 }  // namespace
 
 void run_voxel(const Ctx& c, const VoxelArgs& a) {
-  const int tiles = cdiv(c.cap, CT_TILE);
+  const int tiles = cdiv(c.cap, CT_TILE);        // descriptor stride
+  const int gtiles = cdiv(c.grid_cap, CT_TILE);  // blocks actually launched per frame
   KL(c, "k_voxel_setup", k_voxel_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.minmax, a.n_in, a.leaf, a.vf, a.warnings, c.B));
   sort_reset_maxkey(c, a.sort);
-  KL(c, "k_voxel_keys", k_voxel_keys<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.vf, a.sort.key[0],
+  KL(c, "k_voxel_keys", k_voxel_keys<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.in, a.in_stride, a.n_in, a.vf, a.sort.key[0],
                                                               a.sort.maxkey, c.cap));
   count_launch(c, 2);
   radix_sort_batched(c, a.sort, a.n_in, /*iota_vals=*/true);
-  cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
-  KL(c, "k_voxel_heads", k_voxel_heads<<<dim3(tiles, c.B), CT_THREADS, 0, c.stream>>>(a.sort.key[0], a.sort.key[1], a.sort.npass, a.n_in, a.vf,
-                                                               a.run_start, a.n_out, a.desc, c.cap, tiles));
-  KL(c, "k_voxel_centroid", k_voxel_centroid<<<dim3(cdiv(c.cap, 256), c.B), 256, 0, c.stream>>>(
+  const int btiles = cdiv(c.cap, BT_TILE), gbtiles = cdiv(c.grid_cap, BT_TILE);
+  cudaMemsetAsync(a.desc, 0, (size_t)c.B * btiles * sizeof(unsigned), c.stream);
+  KL(c, "k_voxel_heads", k_voxel_heads<<<dim3(gbtiles, c.B), CT_THREADS, 0, c.stream>>>(
+      a.sort.key[0], a.sort.key[1], a.sort.npass, a.n_in, a.vf, a.run_start, a.n_out, a.desc, c.cap, btiles));
+  KL(c, "k_voxel_centroid", k_voxel_centroid<<<dim3(cdiv(c.grid_cap, 256), c.B), 256, 0, c.stream>>>(
       a.in, a.in_stride, a.n_in, a.sort.key[0], a.sort.key[1], a.sort.val[0], a.sort.val[1], a.sort.npass, a.vf,
       a.run_start, a.n_out, a.out, a.out_keys, c.cap));
   count_launch(c, 2);

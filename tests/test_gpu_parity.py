@@ -112,3 +112,61 @@ def test_batch_mixed_sizes():
     for f in range(B):
         o = O.process(p, clouds[f, :counts[f]])
         compare_frames(res[f], o, p, f"frame{f}: ")
+
+
+def _cloud(xyz):
+    xyz = np.asarray(xyz, np.float32).reshape(-1, 3)
+    return np.concatenate([xyz, np.ones((len(xyz), 1), np.float32)], axis=1)
+
+
+def test_cluster_large_extent_falls_back_to_point_scan():
+    """extent / tolerance too large for 1024 clique cells per axis -> per-point neighbour scan path"""
+    p = synth.params(1)
+    p.euc_cluster_tolerance = 0.05
+    p.euc_min_cluster_size = 2
+    p.euc_max_cluster_size = 100000
+    rng = np.random.default_rng(21)
+    blobs = [rng.normal(size=(300, 3)) * 0.05 + c for c in ([0, 0, 0], [90, 5, 1], [-40, 70, 2], [10, -80, 0])]
+    cloud = _cloud(np.concatenate(blobs))
+    with ObstacleProcessor(p, len(cloud)) as op:
+        g_off, g_idx = op.extract_euclidian_clusters(cloud)
+    o_off, o_idx = O.cluster_bruteforce(p, cloud)
+    assert_bits_equal(g_off, o_off, "offsets")
+    assert_bits_equal(g_idx, o_idx, "indices")
+    assert len(o_off) > 4
+
+
+def test_cluster_non_finite_points_are_singletons():
+    p = synth.params(1)
+    p.euc_cluster_tolerance = 0.2
+    p.euc_min_cluster_size = 1
+    p.euc_max_cluster_size = 100000
+    rng = np.random.default_rng(22)
+    pts = rng.normal(size=(500, 3)).astype(np.float32) * 0.3
+    pts[7, 1] = np.nan
+    pts[100, 2] = np.inf
+    pts[101, 0] = -np.inf
+    pts[300] = [np.nan, np.nan, np.nan]
+    cloud = _cloud(pts)
+    with ObstacleProcessor(p, len(cloud)) as op:
+        g_off, g_idx = op.extract_euclidian_clusters(cloud)
+    o_off, o_idx = O.cluster_bruteforce(p, cloud)
+    assert_bits_equal(g_off, o_off, "offsets")
+    assert_bits_equal(g_idx, o_idx, "indices")
+
+
+@pytest.mark.parametrize("seed,tol,n", [(31, 0.05, 4000), (32, 0.11, 4000), (33, 0.3, 2500), (34, 1.0, 1500)])
+def test_cluster_random_against_bruteforce(seed, tol, n):
+    p = synth.params(1)
+    p.euc_cluster_tolerance = tol
+    p.euc_min_cluster_size = 2
+    p.euc_max_cluster_size = 100000
+    rng = np.random.default_rng(seed)
+    centers = rng.uniform(-3, 3, size=(15, 3))
+    pts = centers[rng.integers(0, 15, n)] + rng.normal(size=(n, 3)) * 0.12
+    cloud = _cloud(np.concatenate([pts, rng.uniform(-4, 4, size=(n // 8, 3))]))
+    with ObstacleProcessor(p, len(cloud)) as op:
+        g_off, g_idx = op.extract_euclidian_clusters(cloud)
+    o_off, o_idx = O.cluster_bruteforce(p, cloud)
+    assert_bits_equal(g_off, o_off, "offsets")
+    assert_bits_equal(g_idx, o_idx, "indices")
