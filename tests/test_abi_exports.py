@@ -1,0 +1,78 @@
+"""CPU checks of the drop-in boundary: libpcop.so loads without a GPU, exports every symbol include/pcop.h declares,
+struct layouts match the header, parameter initialisers carry the reference's values, and nothing computes without a
+CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import pointcloud_obstacle_processing_b200 as pkg
+from pointcloud_obstacle_processing_b200 import _ctypes_abi as abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pcop.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcop_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = pkg.load_library()
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in pcop.h but not exported by libpcop.so"
+    assert set(pkg.api.EXPORTS) <= set(names)
+    assert lib.pcop_abi_version() == 1
+
+
+def test_struct_layout_matches_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include "pcop.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(pcop_params),sizeof(pcop_frame_result),offsetof(pcop_params,plane_keep_fraction),'
+                   'offsetof(pcop_frame_result,crop_kept_idx),offsetof(pcop_frame_result,obstacles));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(abi.Params), C.sizeof(abi.FrameResult), abi.Params.plane_keep_fraction.offset,
+                   abi.FrameResult.crop_kept_idx.offset, abi.FrameResult.obstacles.offset]
+
+
+def test_params_yaml_values():
+    p = pkg.params_yaml()  # minibot_cr18/params.yaml:2-31
+    assert (p.x_min, p.x_max, p.y_min, round(p.y_max, 5), p.z_min, p.z_max) == (0.0, 4.5, 0.0, 3.78, -0.5, 0.25)
+    assert round(p.downsample_size, 6) == 0.015 and p.statistical_outlier_meanK == 15
+    assert p.statistical_outlier_stdDevThres == 4.0 and round(p.plane_segment_dist_thres, 6) == 0.04
+    assert p.plane_segment_angle == 20 and round(p.euc_cluster_tolerance, 6) == 0.4
+    assert (p.euc_min_cluster_size, p.euc_max_cluster_size, p.accumulate_count) == (5, 20000, 200)
+    d = pkg.params_code_defaults()  # od.cpp:940-975
+    assert (d.x_min, d.x_max, d.z_min, d.z_max, d.accumulate_count) == (-1.0, 1.0, 0.0, -0.5, 2)
+    assert d.statistical_outlier_stdDevThres == 1.0 and d.plane_keep_fraction == 0.3 and d.ransac_seed == 12345
+    assert list(d.plane_axis) == [0.0, 0.0, 1.0] and d.plane_max_iterations == 50 and d.plane_probability == 0.99
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.PcopError) as e:
+        pkg.ObstacleProcessor(pkg.params_yaml(), 1000)
+    assert e.value.status == abi.ERR_CUDA
+
+
+def test_package_does_not_import_oracle():
+    """the product never includes, imports, links or loads anything under oracle/ (comments may mention it)"""
+    pkg_dir = os.path.join(ROOT, "pointcloud_obstacle_processing_b200")
+    bad = re.compile(r'#include\s*[<"][^>"]*oracle|import\s+oracle|from\s+oracle|oracle_lib|libpcop_oracle|pcop_oracle_\w+\s*\(')
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not bad.search(text), f"{f} uses the oracle"
+    out = subprocess.run(["ldd", pkg.api.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
