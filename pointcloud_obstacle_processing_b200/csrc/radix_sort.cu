@@ -92,10 +92,10 @@ struct PassSmem {
   uint32_t wsum[RS_BINS / 32];
 };
 
-__global__ void __launch_bounds__(RS_THREADS)
-    k_sort_pass(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, const int* __restrict__ count, const int* __restrict__ npass,
-                const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ desc, int pass, int cap, int tiles,
-                int iota_vals, unsigned long long* __restrict__ stats) {
+__global__ void __launch_bounds__(RS_THREADS, 6)
+    k_sort_pass(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, const int* __restrict__ count,
+                const int* __restrict__ npass, const uint32_t* __restrict__ bin_base, uint32_t* __restrict__ desc,
+                int pass, int cap, int tiles, int iota_vals, unsigned long long* __restrict__ stats) {
   const int f = blockIdx.y;
   const int n = count[f];
   const int tile = blockIdx.x;
@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(RS_THREADS)
   if (tbase >= n) return;
   if (pass >= npass[f]) return;
   if (tile == 0 && threadIdx.x == 0 && stats) atomicAdd(stats, (unsigned long long)n);  // keys moved by sort passes
-  __shared__ PassSmem sm;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PassSmem& sm = *reinterpret_cast<PassSmem*>(smem_raw);
   const int lane = lane_id(), warp = warp_id();
   const int shift = pass * RS_RADIX_BITS;
   // buffers of this pass: even passes read buffer 0
@@ -113,38 +114,34 @@ __global__ void __launch_bounds__(RS_THREADS)
   uint32_t* vout = ((pass & 1) ? val_a : val_b) + (size_t)f * cap;
 
   for (int i = threadIdx.x; i < (RS_THREADS / 32) * RS_BINS; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0u;
-  __syncthreads();
 
-  // warp-striped: warp w owns tile elements [w*256, w*256+256); item k of lane l = w*256 + k*32 + l
-  uint32_t key[RS_ITEMS], val[RS_ITEMS];
-  uint32_t rank[RS_ITEMS];
-  bool valid[RS_ITEMS];
+  // warp-striped: warp w owns tile elements [w*32*ITEMS, (w+1)*32*ITEMS); item k of lane l = that base + k*32 + l
+  uint32_t key[RS_ITEMS];
+  unsigned short rank[RS_ITEMS];
+  const int wbase_idx = tbase + warp * (32 * RS_ITEMS) + lane;
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
-    const int i = tbase + warp * (32 * RS_ITEMS) + k * 32 + lane;
-    valid[k] = i < n;
-    key[k] = valid[k] ? kin[i] : 0xffffffffu;
-    val[k] = valid[k] ? ((iota_vals && pass == 0) ? (uint32_t)i : vin[i]) : 0u;
+    const int i = wbase_idx + k * 32;
+    key[k] = (i < n) ? kin[i] : 0xffffffffu;
   }
-  // rank keys inside the warp, digit by digit, rows in order => stable
+  __syncthreads();
+  // rank keys inside the warp, row by row => stable.  One shared atomic per distinct digit of a row (issued by the
+  // lowest lane of the match group); its return value is the group's base, broadcast by shuffle.
+  uint32_t* wh = sm.warp_hist[warp];
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
+    const bool valid = (wbase_idx + k * 32) < n;
     const uint32_t d = (key[k] >> shift) & (RS_BINS - 1);
-    const unsigned vm = __ballot_sync(FULL, valid[k]);
-    unsigned m = __match_any_sync(FULL, valid[k] ? d : (RS_BINS + lane));  // invalid lanes match nobody
-    m &= vm;
+    const unsigned m = __match_any_sync(FULL, valid ? d : (RS_BINS + lane));  // invalid lanes match nobody
+    const int leader = __ffs(m) - 1;
     uint32_t before = 0;
-    if (valid[k]) before = sm.warp_hist[warp][d];
-    __syncwarp();
-    if (valid[k]) {
-      rank[k] = before + __popc(m & lanemask_lt());
-      if ((m & lanemask_lt()) == 0u) sm.warp_hist[warp][d] = before + __popc(m);  // lowest lane of the group
-    }
-    __syncwarp();
+    if (valid && lane == leader) before = atomicAdd(&wh[d], (uint32_t)__popc(m));
+    before = __shfl_sync(FULL, before, leader);
+    rank[k] = (unsigned short)(before + __popc(m & lanemask_lt()));
   }
   __syncthreads();
 
-  // thread d: exclusive scan of digit d over the 8 warps, tile count, look-back
+  // thread d: exclusive scan of digit d over the warps, tile count, look-back
   {
     const int d = threadIdx.x;
     uint32_t run = 0;
@@ -155,6 +152,10 @@ __global__ void __launch_bounds__(RS_THREADS)
       run += c;
     }
     const uint32_t tile_count = run;
+    // publish this tile's digit count as early as possible
+    unsigned* dd = desc + (((size_t)pass * gridDim.y + f) * tiles) * RS_BINS + d;
+    if (tile == 0) st_volatile_u32(dd, LB_PREFIX | tile_count);
+    else st_volatile_u32(dd + (size_t)tile * RS_BINS, LB_AGG | tile_count);
     // tile-local exclusive scan over digits
     uint32_t incl = tile_count;
 #pragma unroll
@@ -167,35 +168,36 @@ __global__ void __launch_bounds__(RS_THREADS)
     uint32_t wb = 0;
     for (int w = 0; w < warp; ++w) wb += sm.wsum[w];
     sm.tile_off[d] = wb + incl - tile_count;
+  }
+  __syncthreads();
 
-    // decoupled look-back for digit d over the earlier tiles of this frame
+  // stage the tile in sorted order (values are only loaded now, straight into shared memory)
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int i = wbase_idx + k * 32;
+    if (i < n) {
+      const uint32_t d = (key[k] >> shift) & (RS_BINS - 1);
+      const uint32_t p = sm.tile_off[d] + sm.warp_hist[warp][d] + rank[k];
+      sm.skey[p] = key[k];
+      sm.sval[p] = (iota_vals && pass == 0) ? (uint32_t)i : vin[i];
+    }
+  }
+  // decoupled look-back for digit d over the earlier tiles of this frame (after the staging loads were issued)
+  {
+    const int d = threadIdx.x;
     unsigned* dd = desc + (((size_t)pass * gridDim.y + f) * tiles) * RS_BINS + d;
     uint32_t excl = 0;
-    if (tile == 0) {
-      st_volatile_u32(dd, LB_PREFIX | tile_count);
-    } else {
-      st_volatile_u32(dd + (size_t)tile * RS_BINS, LB_AGG | tile_count);
+    if (tile > 0) {
       for (int t = tile - 1; t >= 0; --t) {
         unsigned v = ld_volatile_u32(dd + (size_t)t * RS_BINS);
         while ((v >> 30) == 0u) v = ld_volatile_u32(dd + (size_t)t * RS_BINS);
         excl += v & LB_VALUE;
         if ((v >> 30) == 2u) break;
       }
+      const uint32_t tile_count = ((d + 1 < RS_BINS) ? sm.tile_off[d + 1] : (uint32_t)min(RS_TILE, n - tbase)) - sm.tile_off[d];
       st_volatile_u32(dd + (size_t)tile * RS_BINS, LB_PREFIX | (excl + tile_count));
     }
     sm.glob_base[d] = bin_base[((size_t)f * RS_MAX_PASSES + pass) * RS_BINS + d] + excl;
-  }
-  __syncthreads();
-
-  // stage the tile in sorted order
-#pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    if (valid[k]) {
-      const uint32_t d = (key[k] >> shift) & (RS_BINS - 1);
-      const uint32_t p = sm.tile_off[d] + sm.warp_hist[warp][d] + rank[k];
-      sm.skey[p] = key[k];
-      sm.sval[p] = val[k];
-    }
   }
   __syncthreads();
   const int tile_n = min(RS_TILE, n - tbase);
@@ -220,6 +222,8 @@ void sort_reset_maxkey(const Ctx& c, const SortBufs& s) {
 }
 
 void radix_sort_batched(const Ctx& c, const SortBufs& s, const int* count, bool iota_vals) {
+  // dynamic shared memory opt-in (per device, idempotent and cheap)
+  cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem));
   const int gtiles = cdiv(c.grid_cap, RS_TILE);
   cudaMemsetAsync(s.desc, 0, sort_desc_bytes(c.B, c.grid_cap), c.stream);  // stride = launched tiles
   KL(c, "k_sort_setup", k_sort_setup<<<c.B, 256, 0, c.stream>>>(s.maxkey, s.npass, s.hist, c.B));
@@ -227,7 +231,7 @@ void radix_sort_batched(const Ctx& c, const SortBufs& s, const int* count, bool 
   KL(c, "k_sort_scan", k_sort_scan<<<dim3(RS_MAX_PASSES, c.B), RS_BINS, 0, c.stream>>>(s.hist, s.npass));
   count_launch(c, 3);
   for (int p = 0; p < RS_MAX_PASSES; ++p) {
-    KL(c, "k_sort_pass", k_sort_pass<<<dim3(gtiles, c.B), RS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.key[1], s.val[1], count, s.npass,
+    KL(c, "k_sort_pass", k_sort_pass<<<dim3(gtiles, c.B), RS_THREADS, sizeof(PassSmem), c.stream>>>(s.key[0], s.val[0], s.key[1], s.val[1], count, s.npass,
                                                                s.hist, s.desc, p, c.cap, gtiles, iota_vals ? 1 : 0, s.stats));
     count_launch(c);
   }
