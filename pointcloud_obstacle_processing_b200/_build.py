@@ -15,7 +15,7 @@ SYNTH_SRC = os.path.join(HERE, "synth", "synth.cpp")
 SYNTH_LIB = os.path.join(HERE, "synth", "libpcop_synth.so")
 
 CU_SOURCES = ["pcop_api.cu", "radix_sort.cu", "stage_crop.cu", "stage_voxel.cu", "stage_sor.cu", "stage_plane.cu",
-              "stage_cluster.cu"]
+              "stage_cluster.cu", "stage_cluster_small.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",          # no FMA contraction anywhere: float predicates must match the oracle bit for bit
@@ -49,7 +49,8 @@ def build_cuda(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _newer(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            extra = os.environ.get("PCOP_NVCC_EXTRA", "").split()  # e.g. -DPCOP_ECE_DEBUG_CLK for tools/ece_phases.py
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -182,6 +182,7 @@ struct ClusterArgs {
   int* cell_start;     // [B*cap] first sorted position of each occupied cell
   uint32_t* cell_key;  // [B*cap] key of each occupied cell
   int* n_cells;        // [B]
+  int* n_route;        // [B] scratch: per-frame point count as seen by the generic path
   unsigned* desc;
   int* offsets;  // [B*(cap+1)]
   int* indices;  // [B*cap]
@@ -189,7 +190,14 @@ struct ClusterArgs {
   int* n_cluster_pts;
   float4* obstacles;  // [B*cap]
 };
-void run_cluster(const Ctx& c, const ClusterArgs& a);
+// Largest cloud the fused shared-memory clustering kernel takes (stage_cluster_small.cu).
+constexpr int ECE_SMALL_MAX = 9216;
+// ECE_SMALL_MAX, or the value of the environment variable PCOP_ECE_SMALL_MAX clamped to [0, ECE_SMALL_MAX]
+// (0 forces every frame through the generic path; used by the tests to cover both paths)
+int ece_small_limit();
+// returns true when the generic centroid/radius kernel still has to run (some frame may have taken the generic path)
+bool run_cluster(const Ctx& c, const ClusterArgs& a);
+void run_cluster_small(const Ctx& c, const ClusterArgs& a, int small_max);
 void run_centroid_radius(const Ctx& c, const ClusterArgs& a);
 
 }  // namespace pcop

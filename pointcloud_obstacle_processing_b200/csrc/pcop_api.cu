@@ -31,6 +31,7 @@ enum {  // rows of the per-frame count table (device: d_counts[row*maxB + f])
   CNT_NINL,   // inliers of the last segment() call
   CNT_CLUS1,  // C + 1 (CSR offsets length)
   CNT_CELLS,  // occupied clique cells (ECE scratch)
+  CNT_ROUTE,  // point count as seen by the generic clustering path (ECE scratch)
   CNT_ROWS
 };
 
@@ -466,6 +467,7 @@ ClusterArgs make_cluster_args(pcop_handle* h, const float4* in, size_t stride, c
   a.cell_start = h->d_cell_start;
   a.cell_key = h->d_cell_key;
   a.n_cells = h->cnt(CNT_CELLS);
+  a.n_route = h->cnt(CNT_ROUTE);
   a.desc = h->d_desc;
   a.offsets = h->d_offsets;
   a.indices = h->d_indices;
@@ -612,10 +614,11 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
     }
   }
   ClusterArgs ca = make_cluster_args(h, h->d_rem, h->cap, h->cnt(CNT_REM));
+  bool generic_centroid = false;
   {
     StageTimer t(h, PCOP_STAGE_CLUSTER);
     if (p.enable_cluster) {
-      run_cluster(c, ca);
+      generic_centroid = run_cluster(c, ca);  // the fused small-cloud kernel writes the obstacles itself
     } else {
       cudaMemsetAsync(h->cnt(CNT_CLUS), 0, sizeof(int) * B, h->stream);
       cudaMemsetAsync(h->cnt(CNT_CLPTS), 0, sizeof(int) * B, h->stream);
@@ -623,7 +626,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
   }
   {
     StageTimer t(h, PCOP_STAGE_CENTROID);
-    if (p.enable_cluster) run_centroid_radius(c, ca);
+    if (p.enable_cluster && generic_centroid) run_centroid_radius(c, ca);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(h, e, "stage launches", __FILE__, __LINE__);

@@ -8,6 +8,10 @@
 // in an atomic-min union-find whose roots are the smallest original index of each component, so
 // labels are deterministic.  Clusters = connected components, filtered by size, ordered by
 // size descending then smallest index ascending, indices ascending inside a cluster.
+#include <algorithm>
+#include <cstdlib>
+
+#include "ece_common.cuh"
 #include "internal.cuh"
 #include "primitives.cuh"
 
@@ -15,51 +19,17 @@ namespace pcop {
 
 namespace {
 
-constexpr int ECE_MAX_DIM = 1024;  // cells per axis (30-bit keys)
-
-// Grid guarantees (DESIGN.md "search grid"), with s = fl(fl(x - mn) * inv) and at most 1024 cells per axis:
-//  mode 1: cell >= tol*(1+2^-8)  =>  d2 < r2 implies the cell coordinates differ by at most 1 per axis;
-//  mode 0: cell  = tol*0.5728 (< tol/sqrt(3) * (1 - 2^-7))  =>  all points of one cell are mutually within tol
-//          (a clique), and d2 < r2 implies the cell coordinates differ by at most 2 per axis.
 __global__ void k_ece_setup(const MinMax* __restrict__ minmax, const int* __restrict__ n_in, float tol, int clique,
                             EceFrame* __restrict__ ef, int B) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= B) return;
-  EceFrame e;
-  float mn[3], ext[3];
+  float mn[3], mx[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     mn[a] = ord2f(minmax[f].mn[a]);
-    float mx = ord2f(minmax[f].mx[a]);
-    if (n_in[f] <= 0 || !(mx >= mn[a])) {
-      mn[a] = 0.0f;
-      mx = 0.0f;
-    }
-    ext[a] = mx - mn[a];
+    mx[a] = ord2f(minmax[f].mx[a]);
   }
-  const float fine = tol * 0.5728f;
-  e.mode = 1;
-  if (clique && fine > 0.0f) {
-    const float lim = fine * (float)(ECE_MAX_DIM - 2);
-    if (ext[0] < lim && ext[1] < lim && ext[2] < lim) e.mode = 0;
-  }
-  const float cell_min = (e.mode == 0) ? fine : tol * 1.00390625f;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    float cell = (e.mode == 0) ? cell_min : fmaxf(cell_min, ext[a] / (float)(ECE_MAX_DIM - 1));
-    if (!(cell > 0.0f) || !(cell < 3.0e38f)) cell = 1.0f;
-    e.mn[a] = mn[a];
-    e.inv[a] = 1.0f / cell;
-    int d = (int)floorf(ext[a] * e.inv[a]) + 1;
-    e.dim[a] = min(max(d, 1), ECE_MAX_DIM);
-  }
-  ef[f] = e;
-}
-
-__device__ __forceinline__ int cell_coord(float x, float mn, float inv, int dim) {
-  const float s = floorf((x - mn) * inv);
-  int c = (s == s) ? (int)fminf(fmaxf(s, 0.0f), (float)(dim - 1)) : 0;
-  return c;
+  ef[f] = ece_make_frame(mn, mx, n_in[f], tol, clique);
 }
 
 __global__ void __launch_bounds__(CT_THREADS)
@@ -77,13 +47,7 @@ __global__ void __launch_bounds__(CT_THREADS)
     const int i = ct_index(tile, k);
     if (i < n) {
       const float4 p = __ldg(src + i);
-      const int cx = cell_coord(p.x, e.mn[0], e.inv[0], e.dim[0]);
-      const int cy = cell_coord(p.y, e.mn[1], e.inv[1], e.dim[1]);
-      const int cz = cell_coord(p.z, e.mn[2], e.inv[2], e.dim[2]);
-      uint32_t key = (uint32_t)cx + (uint32_t)e.dim[0] * ((uint32_t)cy + (uint32_t)e.dim[1] * (uint32_t)cz);
-      // clique mode: a point with a non-finite coordinate is within tol of nothing; give it a private cell
-      if (e.mode == 0 && !(fabsf(p.x) <= 3.0e38f && fabsf(p.y) <= 3.0e38f && fabsf(p.z) <= 3.0e38f))
-        key = 0x40000000u | (uint32_t)i;
+      const uint32_t key = ece_point_key(p, e, i);
       keys[(size_t)f * cap + i] = key;
       if (parent) {
         parent[(size_t)f * cap + i] = i;
@@ -115,34 +79,6 @@ __global__ void __launch_bounds__(CT_THREADS)
       p.w = __uint_as_float(i);
       sorted_pts[(size_t)f * cap + j] = p;
     }
-  }
-}
-
-__device__ __forceinline__ int uf_find(int* parent, int v) {
-  // path halving with atomicMin: parents only ever decrease, so a stale read is still an ancestor
-  int p = parent[v];
-  while (p != v) {
-    const int gp = parent[p];
-    if (gp != p) atomicMin(&parent[v], gp);
-    v = p;
-    p = gp;
-  }
-  return v;
-}
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
-  while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) {
-      const int t = a;
-      a = b;
-      b = t;
-    }
-    const int old = atomicMin(&parent[a], b);  // hook the larger root under the smaller
-    if (old == a) return;
-    a = old;  // a was no longer a root: merge its (former) parent with b instead
   }
 }
 
@@ -574,7 +510,13 @@ void run_grid_sort(const Ctx& c, const float4* in, size_t in_stride, const int* 
   count_launch(c);
 }
 
-void run_cluster(const Ctx& c, const ClusterArgs& a) {
+// frames the fused shared-memory kernel handles look empty to the generic kernels
+__global__ void k_ece_route(const int* __restrict__ n_in, int* __restrict__ n_generic, int small_max, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < B) n_generic[f] = (n_in[f] > small_max) ? n_in[f] : 0;
+}
+
+static void run_cluster_generic(const Ctx& c, const ClusterArgs& a) {
   const int tiles = cdiv(c.cap, CT_TILE);        // descriptor stride
   const int gtiles = cdiv(c.grid_cap, CT_TILE);  // blocks actually launched per frame
   const float r2 = (float)((double)a.tol * (double)a.tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
@@ -612,6 +554,32 @@ void run_cluster(const Ctx& c, const ClusterArgs& a) {
   KL(c, "k_ece_indices", k_ece_indices<<<dim3(cdiv(c.grid_cap, 256), c.B), 256, 0, c.stream>>>(a.sort.val[0], a.sort.val[1], a.sort.npass,
                                                                    a.n_cluster_pts, a.indices, c.cap));
   count_launch(c);
+}
+
+int ece_small_limit() {
+  const char* s = getenv("PCOP_ECE_SMALL_MAX");
+  if (!s || !*s) return ECE_SMALL_MAX;
+  const long v = strtol(s, nullptr, 10);
+  return (int)std::min<long>(std::max<long>(v, 0), ECE_SMALL_MAX);
+}
+
+// Frames with at most `small_max` points are clustered by the fused shared-memory kernel (which also writes
+// their obstacles); the others by the generic path.  Returns true when some frame may have taken the generic
+// path, i.e. the generic centroid/radius kernel still has to run.
+bool run_cluster(const Ctx& c, const ClusterArgs& a) {
+  const int small_max = ece_small_limit();
+  const bool maybe_big = c.grid_cap > small_max;  // grid_cap bounds every frame's point count
+  if (maybe_big) {
+    ClusterArgs g = a;
+    if (small_max > 0) {
+      KL(c, "k_ece_route", k_ece_route<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.n_in, a.n_route, small_max, c.B));
+      count_launch(c);
+      g.n_in = a.n_route;
+    }
+    run_cluster_generic(c, g);
+  }
+  if (small_max > 0) run_cluster_small(c, a, small_max);
+  return maybe_big;
 }
 
 void run_centroid_radius(const Ctx& c, const ClusterArgs& a) {

@@ -10,6 +10,17 @@ from pointcloud_obstacle_processing_b200 import _ctypes_abi as abi
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["fused", "generic"])
+def ece_path(request, monkeypatch):
+    """Euclidean clustering has two device paths: the fused shared-memory kernel for small clouds and the generic
+    multi-kernel path.  PCOP_ECE_SMALL_MAX=0 forces the generic one (read by the library at every call)."""
+    if request.param == "generic":
+        monkeypatch.setenv("PCOP_ECE_SMALL_MAX", "0")
+    else:
+        monkeypatch.delenv("PCOP_ECE_SMALL_MAX", raising=False)
+    return request.param
+
+
 def all_outputs(p):
     p = p.copy()
     p.outputs = abi.OUT_ALL
@@ -77,7 +88,7 @@ def test_stage_plane(config, frames):
 
 
 @pytest.mark.parametrize("config", [1, 2, 3])
-def test_stage_cluster_and_centroid(config, frames):
+def test_stage_cluster_and_centroid(config, frames, ece_path):
     p = synth.params(config)
     of = O.process(p, frames[config])
     cloud = of.remaining_cloud
@@ -90,7 +101,7 @@ def test_stage_cluster_and_centroid(config, frames):
 
 
 @pytest.mark.parametrize("config", [1, 2, 3, 4])
-def test_pipeline(config, frames):
+def test_pipeline(config, frames, ece_path):
     p = all_outputs(synth.params(config))
     cloud = frames[config] if config in frames else synth.frame(config, 0)
     with ObstacleProcessor(p, len(cloud)) as op:
@@ -100,8 +111,12 @@ def test_pipeline(config, frames):
     assert o.n_clusters > 0
 
 
-def test_batch_mixed_sizes():
-    """frames of different sizes (ragged batch), more frames than one wave"""
+@pytest.mark.parametrize("small_max", [None, 0, 4500])
+def test_batch_mixed_sizes(small_max, monkeypatch):
+    """frames of different sizes (ragged batch), more frames than one wave; small_max = 4500 routes the frames of one
+    wave to different clustering paths"""
+    if small_max is not None:
+        monkeypatch.setenv("PCOP_ECE_SMALL_MAX", str(small_max))
     p = all_outputs(synth.params(2))
     n = synth.points_per_frame(2)
     B = 5
@@ -119,7 +134,7 @@ def _cloud(xyz):
     return np.concatenate([xyz, np.ones((len(xyz), 1), np.float32)], axis=1)
 
 
-def test_cluster_large_extent_falls_back_to_point_scan():
+def test_cluster_large_extent_falls_back_to_point_scan(ece_path):
     """extent / tolerance too large for 1024 clique cells per axis -> per-point neighbour scan path"""
     p = synth.params(1)
     p.euc_cluster_tolerance = 0.05
@@ -136,7 +151,7 @@ def test_cluster_large_extent_falls_back_to_point_scan():
     assert len(o_off) > 4
 
 
-def test_cluster_non_finite_points_are_singletons():
+def test_cluster_non_finite_points_are_singletons(ece_path):
     p = synth.params(1)
     p.euc_cluster_tolerance = 0.2
     p.euc_min_cluster_size = 1
@@ -156,7 +171,7 @@ def test_cluster_non_finite_points_are_singletons():
 
 
 @pytest.mark.parametrize("seed,tol,n", [(31, 0.05, 4000), (32, 0.11, 4000), (33, 0.3, 2500), (34, 1.0, 1500)])
-def test_cluster_random_against_bruteforce(seed, tol, n):
+def test_cluster_random_against_bruteforce(seed, tol, n, ece_path):
     p = synth.params(1)
     p.euc_cluster_tolerance = tol
     p.euc_min_cluster_size = 2
@@ -165,6 +180,45 @@ def test_cluster_random_against_bruteforce(seed, tol, n):
     centers = rng.uniform(-3, 3, size=(15, 3))
     pts = centers[rng.integers(0, 15, n)] + rng.normal(size=(n, 3)) * 0.12
     cloud = _cloud(np.concatenate([pts, rng.uniform(-4, 4, size=(n // 8, 3))]))
+    with ObstacleProcessor(p, len(cloud)) as op:
+        g_off, g_idx = op.extract_euclidian_clusters(cloud)
+    o_off, o_idx = O.cluster_bruteforce(p, cloud)
+    assert_bits_equal(g_off, o_off, "offsets")
+    assert_bits_equal(g_idx, o_idx, "indices")
+
+
+def test_cluster_fused_kernel_capacity_edge(monkeypatch):
+    """clouds just below / above the fused kernel's capacity take different paths and must agree with the oracle"""
+    p = synth.params(1)
+    p.euc_cluster_tolerance = 0.08
+    p.euc_min_cluster_size = 3
+    p.euc_max_cluster_size = 100000
+    rng = np.random.default_rng(41)
+    for n in (9216, 9217):
+        centers = rng.uniform(-5, 5, size=(40, 3))
+        pts = centers[rng.integers(0, 40, n)] + rng.normal(size=(n, 3)) * 0.15
+        cloud = _cloud(pts)
+        with ObstacleProcessor(p, len(cloud)) as op:
+            g_off, g_idx = op.extract_euclidian_clusters(cloud)
+            g_obs = op.centroid_radius(cloud, g_off, g_idx)
+        o_off, o_idx = O.cluster_bruteforce(p, cloud)
+        assert_bits_equal(g_off, o_off, "offsets")
+        assert_bits_equal(g_idx, o_idx, "indices")
+        assert len(o_off) > 10
+
+
+def test_cluster_drops_oversize_and_undersize(ece_path):
+    """components outside [min, max] are dropped whole; ties in size are ordered by smallest index"""
+    p = synth.params(1)
+    p.euc_cluster_tolerance = 0.1
+    p.euc_min_cluster_size = 10
+    p.euc_max_cluster_size = 200
+    rng = np.random.default_rng(42)
+    sizes = [500, 200, 200, 199, 10, 10, 9, 1, 1]
+    blobs = [rng.uniform(-0.2, 0.2, size=(s, 3)) * [1, 1, 0.2] + [3.0 * k, 0, 0] for k, s in enumerate(sizes)]
+    pts = np.concatenate(blobs)
+    pts = pts[rng.permutation(len(pts))]
+    cloud = _cloud(pts)
     with ObstacleProcessor(p, len(cloud)) as op:
         g_off, g_idx = op.extract_euclidian_clusters(cloud)
     o_off, o_idx = O.cluster_bruteforce(p, cloud)
