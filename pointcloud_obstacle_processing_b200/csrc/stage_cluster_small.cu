@@ -7,17 +7,23 @@
 // ordering, CSR indices and the per-cluster centroid + bounding radius -- in one launch:
 //
 //   1. min/max of the finite points -> grid (same rules as the generic path, ece_common.cuh);
-//   2. (cell key, point index) packed in 64 bits, sorted by a normalised bitonic network in shared memory
-//      (index in the low word => stable, a cell's first point is its smallest original index);
-//   3. occupied-cell list + an open-addressing hash table cell key -> cell (replaces the kd-tree / binary search);
-//   4. union-find in shared memory, atomic-min hooking (roots = smallest original index, so labels are
-//      deterministic).  Clique mode: one warp per cell, the 62 forward neighbour cells are looked up by the
-//      lanes in parallel, point pairs are tested with the exact float predicate only until the first hit and
-//      only while the two cells are still in different sets.  Point mode (extent too large for clique cells):
-//      one thread per point scans its forward neighbour cells;
-//   5. sizes, kept roots sorted by (size desc, smallest index asc), CSR offsets, members sorted by
-//      (cluster rank, index) -> cluster_indices;
-//   6. one warp per cluster: centroid (double sums) and max distance (od.cpp:457-464 arithmetic).
+//   2. points grouped by cell WITHOUT a sort: cell keys (10 bits per axis) go into an open-addressing hash table
+//      (atomicCAS), occupied slots get dense cell ids by a block scan, points take a slot inside their cell with
+//      one shared-memory atomicAdd, coordinates are scattered into cell order.  The order of the points inside a
+//      cell depends on the atomics, but nothing observable does: components do not depend on the test order and
+//      every output is ordered by original index afterwards;
+//   3. union-find in shared memory, atomic-min hooking.
+//      Clique mode (cell edge < tol/sqrt(3)): the nodes are the CELLS.  One thread per cell looks up its 62
+//      forward neighbour cells (hash probes only), then walks the cells it found: point pairs are tested with the
+//      exact float predicate only while the two cells are still in different sets and only until the first hit.
+//      Point mode (extent too large for clique cells): the nodes are the points; one thread per point scans the
+//      rest of its cell and the 13 forward neighbour cells;
+//   4. per component: size and smallest original index (shared-memory atomics per node), kept roots ranked by
+//      (size desc, smallest index asc), CSR offsets;
+//   5. cluster_indices: labels by original index, then a block-wide stable multi-way split by cluster rank
+//      (<= ES_SPLIT_MAXC clusters; a bitonic sort of (rank, index) otherwise);
+//   6. member coordinates staged in shared memory; one warp per cluster: centroid (double sums) and bounding radius
+//      (od.cpp:457-464 arithmetic).
 //
 // The result is identical to the generic path (and the oracle): clusters are the connected components of the
 // graph "float ((dx*dx)+(dy*dy))+(dz*dz) < r2", which does not depend on the acceleration structure.
@@ -34,36 +40,46 @@ namespace {
 
 constexpr int ES_THREADS = 1024;
 constexpr int ES_WARPS = ES_THREADS / 32;
+constexpr int ES_MAX = ECE_SMALL_MAX;
+constexpr int ES_IPT = ES_MAX / ES_THREADS;  // points (cells, hash slots / 2) per thread
 constexpr int ES_HASH_BITS = 14;
 constexpr int ES_HASH = 1 << ES_HASH_BITS;
-constexpr int ES_MAX = ECE_SMALL_MAX;
+constexpr int ES_SCAN_MAXC = 128;   // cluster offsets of up to this many clusters are mirrored in shared memory
+constexpr int ES_SPLIT_MAXC = 1024;  // up to this many clusters the members are listed by a block-wide stable split
+constexpr uint32_t ES_EMPTY = 0xffffffffu;
 typedef unsigned long long u64;
 
-// Shared-memory layout (bytes).  Regions are reused between phases:
-//   R1  u64 sortbuf[ES_MAX]        sorts            | float x[ES_MAX], y[ES_MAX] during the union phase
-//   R2  float z[ES_MAX]            union phase      | int csize[ES_MAX] afterwards
-//   R3  int parent[ES_MAX]         union-find over SORTED positions, then labels
-//   R4  u16 idx16[ES_MAX]          original index of each sorted position
-//   R5  u16 cell_start[ES_MAX+8]   first sorted position of each occupied cell   \  afterwards: int minidx[ES_MAX]
-//   R6  u16 hash[ES_HASH]          cell hash table (value = cell + 1, 0 = empty) /  then u16 rank_of[ES_MAX]
-constexpr int ES_R1 = 0;
-constexpr int ES_R2 = ES_R1 + 8 * ES_MAX;
-constexpr int ES_R3 = ES_R2 + 4 * ES_MAX;
-constexpr int ES_R4 = ES_R3 + 4 * ES_MAX;
-constexpr int ES_R5 = ES_R4 + 2 * ES_MAX;
-constexpr int ES_R6 = ES_R5 + 2 * (ES_MAX + 8);
-constexpr int ES_MISC = ES_R6 + 2 * ES_HASH;
+// Shared-memory regions (bytes) and what lives in them per phase:
+//   A  12*ES_MAX  build: u32 tk[ES_HASH] (keys of the hash slots) | union: float x[], y[], z[] in cell order
+//                 after the union: int csize[], int minidx[], u16 lab16[] (by original index), u16 rankc[] (by node)
+//   D  2*ES_HASH  u16 hash[] (cell id + 1 per slot)            \ after the union: u64 sortbuf[ES_MAX]
+//   E  4*ES_MAX   u32 cell_key[] (by cell id)                  /
+//   B  4*ES_MAX   build: int cnt[] (points per cell) | int parent[] (by node)
+//   C  2*ES_MAX   u16 idx16[] (original index of each cell-ordered position)
+//   F  2*ES_MAX+16  u16 node_start[] (first position of each cell; identity in point mode after the union)
+constexpr int ES_A = 0;
+constexpr int ES_D = ES_A + 12 * ES_MAX;
+constexpr int ES_E = ES_D + 2 * ES_HASH;
+constexpr int ES_B = ES_E + 4 * ES_MAX;
+constexpr int ES_C = ES_B + 4 * ES_MAX;
+constexpr int ES_F = ES_C + 2 * ES_MAX;
+constexpr int ES_MISC = ES_F + 2 * ES_MAX + 16;
 struct EceSmallMisc {
   float red[ES_WARPS][6];
   int wscan[ES_WARPS + 1];
   EceFrame ef;
   int n_cells, n_clusters, n_members;
+  int soff[ES_SCAN_MAXC + 1];
+  int fwd[64];  // packed-key offset of forward neighbour q
 };
 constexpr int ES_SMEM_BYTES = ES_MISC + (int)sizeof(EceSmallMisc);
 static_assert(ES_SMEM_BYTES <= 227 * 1024, "fused clustering kernel: shared memory budget");
-static_assert(4 * ES_MAX <= 2 * (ES_MAX + 8) + 2 * ES_HASH, "minidx overlays cell_start + hash");
-static_assert(ES_MAX <= 16383, "positions / indices are packed in 14 bits");
-static_assert(ES_R5 % 4 == 0 && ES_R2 % 16 == 0 && ES_MISC % 8 == 0, "alignment");
+static_assert(4 * ES_HASH <= 12 * ES_MAX, "build-phase key table overlays the coordinates");
+static_assert(2 * ES_HASH + 4 * ES_MAX >= 8 * ES_MAX, "sort buffer overlays hash + cell keys");
+static_assert(ES_MAX <= 8192, "positions / indices / sizes are packed in 13 bits (+1)");
+static_assert(2 * ES_MAX <= ES_HASH, "hash load factor <= 0.5");
+static_assert(2 * ES_WARPS * ES_SPLIT_MAXC <= 8 * ES_MAX, "split offsets overlay sizes + smallest indices");
+static_assert(ES_MISC % 8 == 0 && ES_D % 16 == 0 && ES_B % 16 == 0 && ES_F % 4 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t hi32(u64 v) { return (uint32_t)(v >> 32); }
 __device__ __forceinline__ uint32_t lo32(u64 v) { return (uint32_t)v; }
@@ -140,25 +156,57 @@ __device__ __forceinline__ int block_excl_scan(int v, int* wscan, int& total) {
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key) { return (key * 2654435761u) >> (32 - ES_HASH_BITS); }
 
-struct EceSmallView {
-  const float *x, *y, *z;
-  const unsigned short *idx16, *cell_start, *hash;
-  EceFrame e;
-  __device__ __forceinline__ uint32_t cell_key(int c) const {  // recomputed from the cell's first point
-    const int j = cell_start[c];
-    return ece_point_key(make_float4(x[j], y[j], z[j], 0.f), e, (int)idx16[j]);
+// cell key with 10 bits per axis (the grid has at most 1024 cells per axis); clique mode: a point with a
+// non-finite coordinate is within tol of nothing and gets a private cell (bit 30 set)
+__device__ __forceinline__ uint32_t es_point_key(const float4 p, const EceFrame& e, int i) {
+  const int cx = cell_coord(p.x, e.mn[0], e.inv[0], e.dim[0]);
+  const int cy = cell_coord(p.y, e.mn[1], e.inv[1], e.dim[1]);
+  const int cz = cell_coord(p.z, e.mn[2], e.inv[2], e.dim[2]);
+  uint32_t key = (uint32_t)cx | ((uint32_t)cy << 10) | ((uint32_t)cz << 20);
+  if (e.mode == 0 && !(fabsf(p.x) <= 3.0e38f && fabsf(p.y) <= 3.0e38f && fabsf(p.z) <= 3.0e38f))
+    key = 0x40000000u | (uint32_t)i;
+  return key;
+}
+
+// cell id of `key` or -1
+__device__ __forceinline__ int es_lookup(const unsigned short* hash, const uint32_t* cell_key, uint32_t key) {
+  uint32_t s = hash_slot(key);
+  while (true) {
+    const unsigned v = hash[s];
+    if (v == 0u) return -1;
+    if (cell_key[v - 1] == key) return (int)v - 1;
+    s = (s + 1) & (ES_HASH - 1);
   }
-  // cell index of `key` or -1
-  __device__ __forceinline__ int lookup(uint32_t key) const {
-    uint32_t s = hash_slot(key);
-    while (true) {
-      const unsigned v = hash[s];
-      if (v == 0u) return -1;
-      if (cell_key((int)v - 1) == key) return (int)v - 1;
-      s = (s + 1) & (ES_HASH - 1);
+}
+
+// Union-find on shared memory.  Parents only ever point to smaller node ids and hooks only ever touch roots, so a
+// plain store of an ancestor into a non-root entry (path compression) is safe next to concurrent atomicMin hooks.
+__device__ __forceinline__ int es_find(int* parent, int v) {
+  volatile int* par = parent;
+  while (true) {  // path halving
+    const int p = par[v];
+    if (p == v) return v;
+    const int gp = par[p];
+    if (gp == p) return p;
+    par[v] = gp;
+    v = gp;
+  }
+}
+__device__ __forceinline__ void es_union(int* parent, int a, int b) {
+  while (true) {
+    a = es_find(parent, a);
+    b = es_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      const int t = a;
+      a = b;
+      b = t;
     }
+    const int old = atomicMin(&parent[a], b);  // hook the larger root under the smaller
+    if (old == a) return;
+    a = old;  // a was no longer a root: merge its (former) parent with b instead
   }
-};
+}
 
 // phase timestamps of block 0 (clock64), for tools/ece_phases.py; written only when PCOP_ECE_DEBUG_CLK is defined
 #ifdef PCOP_ECE_DEBUG_CLK
@@ -166,11 +214,24 @@ struct EceSmallView {
   do {                                                                 \
     if (blockIdx.x == 0 && threadIdx.x == 0) g_ece_small_clk[k] = clock64(); \
   } while (0)
+#define ES_CLKW(k)                                                                      \
+  do {                                                                                  \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && c0 == 0) g_ece_small_clk[k] = clock64(); \
+  } while (0)
 #else
+#define ES_CLKW(k) \
+  do {             \
+  } while (0)
 #define ES_CLK(k) \
   do {            \
   } while (0)
 #endif
+
+// forward neighbour q (0..61) of a clique cell: the cells within 2 per axis that follow it in (z, y, x) order:
+// q < 2: (q+1, 0, 0); 2 <= q < 12: dz = 0, dy = 1..2, dx = -2..2; q >= 12: dz = 1..2, dy = -2..2, dx = -2..2
+__host__ __device__ constexpr int es_fwd_dx(int q) { return q < 2 ? q + 1 : (q < 12 ? (q - 2) % 5 - 2 : (q - 12) % 5 - 2); }
+__host__ __device__ constexpr int es_fwd_dy(int q) { return q < 2 ? 0 : (q < 12 ? 1 + (q - 2) / 5 : ((q - 12) % 25) / 5 - 2); }
+__host__ __device__ constexpr int es_fwd_dz(int q) { return q < 12 ? 0 : 1 + (q - 12) / 25; }
 
 __global__ void __launch_bounds__(ES_THREADS, 1)
     k_ece_small(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, float tol, float r2,
@@ -180,17 +241,21 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
   const int n = n_in[f];
   if (n > small_max) return;  // this frame takes the generic path
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* sortbuf = reinterpret_cast<u64*>(smem_raw + ES_R1);
-  float* px = reinterpret_cast<float*>(smem_raw + ES_R1);
+  uint32_t* tk = reinterpret_cast<uint32_t*>(smem_raw + ES_A);
+  float* px = reinterpret_cast<float*>(smem_raw + ES_A);
   float* py = px + ES_MAX;
-  float* pz = reinterpret_cast<float*>(smem_raw + ES_R2);
-  int* csize = reinterpret_cast<int*>(smem_raw + ES_R2);
-  int* parent = reinterpret_cast<int*>(smem_raw + ES_R3);
-  unsigned short* idx16 = reinterpret_cast<unsigned short*>(smem_raw + ES_R4);
-  unsigned short* cell_start = reinterpret_cast<unsigned short*>(smem_raw + ES_R5);
-  unsigned short* hash = reinterpret_cast<unsigned short*>(smem_raw + ES_R6);
-  int* minidx = reinterpret_cast<int*>(smem_raw + ES_R5);
-  unsigned short* rank_of = reinterpret_cast<unsigned short*>(smem_raw + ES_R5);
+  float* pz = py + ES_MAX;
+  int* csize = reinterpret_cast<int*>(smem_raw + ES_A);
+  int* minidx = csize + ES_MAX;
+  unsigned short* lab16 = reinterpret_cast<unsigned short*>(smem_raw + ES_A + 8 * ES_MAX);
+  unsigned short* rankc = lab16 + ES_MAX;
+  unsigned short* hash = reinterpret_cast<unsigned short*>(smem_raw + ES_D);
+  uint32_t* cell_key = reinterpret_cast<uint32_t*>(smem_raw + ES_E);
+  u64* sortbuf = reinterpret_cast<u64*>(smem_raw + ES_D);
+  int* cnt = reinterpret_cast<int*>(smem_raw + ES_B);
+  int* parent = reinterpret_cast<int*>(smem_raw + ES_B);
+  unsigned short* idx16 = reinterpret_cast<unsigned short*>(smem_raw + ES_C);
+  unsigned short* node_start = reinterpret_cast<unsigned short*>(smem_raw + ES_F);
   EceSmallMisc& sm = *reinterpret_cast<EceSmallMisc*>(smem_raw + ES_MISC);
 
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
@@ -207,6 +272,10 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
     return;
   }
 
+#ifdef PCOP_ECE_DEBUG_CLK
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int k = 10; k < 16; ++k) g_ece_small_clk[k] = 0;
+#endif
   ES_CLK(0);
   // ---- 1. min/max over the finite points, grid ---------------------------------------------------------
   {
@@ -238,6 +307,9 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
         sm.red[warp][3 + a] = mx[a];
       }
     }
+    if (tid < 62) sm.fwd[tid] = es_fwd_dx(tid) + es_fwd_dy(tid) * 1024 + es_fwd_dz(tid) * 1048576;
+    for (int s = tid; s < ES_HASH; s += ES_THREADS) tk[s] = ES_EMPTY;
+    for (int i = tid; i < n; i += ES_THREADS) cnt[i] = 0;
     __syncthreads();
     if (tid == 0) {
       float gmn[3], gmx[3];
@@ -257,237 +329,339 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
   const EceFrame e = sm.ef;
 
   ES_CLK(1);
-  // ---- 2. sort (cell key, index); index in the low word => a cell's points ascend by original index ----------
-  for (int i = tid; i < n; i += ES_THREADS) {
-    const float4 p = __ldg(src + i);
-    sortbuf[i] = ((u64)ece_point_key(p, e, i) << 32) | (u64)(uint32_t)i;
+  // ---- 2. group the points by cell ---------------------------------------------------------------------------
+  // point k of this thread is original index tid + k*ES_THREADS; mine[k] = hash slot, then cell id | slot in cell << 16
+  uint32_t mine[ES_IPT];
+#pragma unroll
+  for (int k = 0; k < ES_IPT; ++k) {
+    const int i = tid + k * ES_THREADS;
+    mine[k] = 0u;
+    if (i < n) {
+      const uint32_t key = es_point_key(__ldg(src + i), e, i);
+      uint32_t s = hash_slot(key);
+      while (true) {
+        const uint32_t old = atomicCAS(&tk[s], ES_EMPTY, key);
+        if (old == ES_EMPTY || old == key) break;
+        s = (s + 1) & (ES_HASH - 1);
+      }
+      mine[k] = s;
+    }
   }
   __syncthreads();
-  bitonic_sort_smem(sortbuf, n);
-
-  ES_CLK(2);
-  // ---- 3. unpack: run heads, original indices, then the coordinates overwrite the sort buffer ----------------
-  const int ipt = cdiv(n, ES_THREADS);  // <= ES_MAX / ES_THREADS
-  {
-    constexpr int IPT_MAX = ES_MAX / ES_THREADS;
-    const int j0 = min(tid * ipt, n), j1 = min(j0 + ipt, n);
-    unsigned short my_idx[IPT_MAX];
-    unsigned headmask = 0u;
-    uint32_t prev = (j0 > 0 && j0 < n) ? hi32(sortbuf[j0 - 1]) : 0xffffffffu;
+  {  // dense cell ids for the occupied slots (any fixed bijection will do: slot t + k*ES_THREADS, thread-major)
+    unsigned occ = 0u;
 #pragma unroll
-    for (int k = 0; k < IPT_MAX; ++k) {
-      const int j = j0 + k;
-      if (j < j1) {
-        const u64 v = sortbuf[j];
-        my_idx[k] = (unsigned short)lo32(v);
-        if (j == 0 || hi32(v) != prev) headmask |= 1u << k;
-        prev = hi32(v);
-      }
-    }
+    for (int k = 0; k < ES_HASH / ES_THREADS; ++k) occ |= (tk[tid + k * ES_THREADS] != ES_EMPTY) ? (1u << k) : 0u;
     int total;
-    int pos = block_excl_scan(__popc(headmask), sm.wscan, total);  // (syncs: every thread has read its entries)
+    int pos = block_excl_scan(__popc(occ), sm.wscan, total);
 #pragma unroll
-    for (int k = 0; k < IPT_MAX; ++k) {
-      const int j = j0 + k;
-      if (j < j1) {
-        const float4 p = __ldg(src + my_idx[k]);
-        px[j] = p.x;
-        py[j] = p.y;
-        pz[j] = p.z;
-        idx16[j] = my_idx[k];
-        parent[j] = j;
-        if ((headmask >> k) & 1u) cell_start[pos++] = (unsigned short)j;
+    for (int k = 0; k < ES_HASH / ES_THREADS; ++k) {
+      const int s = tid + k * ES_THREADS;
+      if ((occ >> k) & 1u) {
+        cell_key[pos] = tk[s];
+        hash[s] = (unsigned short)(pos + 1);
+        ++pos;
+      } else {
+        hash[s] = 0;
       }
     }
-    if (tid == 0) {
-      cell_start[total] = (unsigned short)n;
-      sm.n_cells = total;
-    }
-    for (int i = tid; i < ES_HASH / 2; i += ES_THREADS) reinterpret_cast<unsigned*>(hash)[i] = 0u;
+    if (tid == 0) sm.n_cells = total;
     __syncthreads();
   }
-  ES_CLK(3);
   const int nc = sm.n_cells;
-  EceSmallView view{px, py, pz, idx16, cell_start, hash, e};
-  for (int c = tid; c < nc; c += ES_THREADS) {
-    const uint32_t key = view.cell_key(c);
-    if (key >= 0x40000000u) continue;  // private cell of a non-finite point: never looked up
-    uint32_t s = hash_slot(key);
-    while (atomicCAS(&hash[s], (unsigned short)0, (unsigned short)(c + 1)) != 0) s = (s + 1) & (ES_HASH - 1);
+  ES_CLK(2);
+#pragma unroll
+  for (int k = 0; k < ES_IPT; ++k) {
+    const int i = tid + k * ES_THREADS;
+    if (i < n) {
+      const uint32_t id = (uint32_t)hash[mine[k]] - 1u;
+      const uint32_t r = (uint32_t)atomicAdd(&cnt[id], 1);
+      mine[k] = id | (r << 16);
+    }
   }
   __syncthreads();
+  {  // exclusive scan of the cell counts -> first position of each cell
+    int c0 = min(tid * ES_IPT, nc), c1 = min(c0 + ES_IPT, nc);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += cnt[c];
+    int total;
+    int run = block_excl_scan(sum, sm.wscan, total);
+    for (int c = c0; c < c1; ++c) {
+      node_start[c] = (unsigned short)run;
+      run += cnt[c];
+    }
+    if (tid == 0) node_start[nc] = (unsigned short)n;
+    __syncthreads();  // (cnt and tk are dead from here on)
+  }
+#pragma unroll
+  for (int k = 0; k < ES_IPT; ++k) {
+    const int i = tid + k * ES_THREADS;
+    if (i < n) {
+      const float4 p = __ldg(src + i);
+      const int j = (int)node_start[mine[k] & 0xffffu] + (int)(mine[k] >> 16);
+      px[j] = p.x;
+      py[j] = p.y;
+      pz[j] = p.z;
+      idx16[j] = (unsigned short)i;
+    }
+  }
+  const int nn = (e.mode == 0) ? nc : n;  // union-find nodes: cells (clique mode) or points
+  for (int v = tid; v < nn; v += ES_THREADS) parent[v] = v;
+  __syncthreads();
 
-  ES_CLK(4);
-  // ---- 4. union-find over sorted positions ------------------------------------------------------------------
+  ES_CLK(3);
+  // ---- 3. union-find ----------------------------------------------------------------------------------------
   const int dimx = e.dim[0], dimy = e.dim[1], dimz = e.dim[2];
   if (e.mode == 0) {
-    for (int c = warp; c < nc; c += ES_WARPS) {
-      const int j0 = cell_start[c], j1 = cell_start[c + 1];
-      for (int j = j0 + 1 + lane; j < j1; j += 32) parent[j] = j0;  // a clique cell is one super-node
-      const uint32_t keyA = view.cell_key(c);
-      if (keyA >= 0x40000000u) continue;
-      const int cx = (int)(keyA % (uint32_t)dimx);
-      const int cy = (int)((keyA / (uint32_t)dimx) % (uint32_t)dimy);
-      const int cz = (int)(keyA / ((uint32_t)dimx * (uint32_t)dimy));
-      // the 62 forward cells within 2 per axis: q < 2: (dx,0,0) = (q+1,0,0); 2 <= q < 12: dz = 0, dy = 1,2;
-      // q >= 12: dz = 1,2, dy = -2..2; dx = -2..2
-      for (int q = lane; q < 62; q += 32) {
-        int dx, dy, dz;
-        if (q < 2) {
-          dx = q + 1;
-          dy = 0;
-          dz = 0;
-        } else if (q < 12) {
-          const int t = q - 2;
-          dz = 0;
-          dy = 1 + t / 5;
-          dx = t % 5 - 2;
-        } else {
-          const int t = q - 12;
-          dz = 1 + t / 25;
-          dy = (t % 25) / 5 - 2;
-          dx = t % 5 - 2;
-        }
-        const int xx = cx + dx, yy = cy + dy, zz = cz + dz;
-        if (xx < 0 || xx >= dimx || yy < 0 || yy >= dimy || zz >= dimz) continue;
-        const uint32_t keyB = (uint32_t)xx + (uint32_t)dimx * ((uint32_t)yy + (uint32_t)dimy * (uint32_t)zz);
-        const int cb = view.lookup(keyB);
-        if (cb < 0) continue;
-        const int jb0 = cell_start[cb], jb1 = cell_start[cb + 1];
-        if (uf_find(parent, j0) == uf_find(parent, jb0)) continue;
-        bool hit = false;
-        for (int a = j0; a < j1 && !hit; ++a) {
-          const float ax = px[a], ay = py[a], az = pz[a];
-          for (int b = jb0; b < jb1; ++b) {
-            if (dist2(ax, ay, az, px[b], py[b], pz[b]) < r2) {
-              hit = true;
-              break;
+    // warp-uniform loops with explicit reconvergence: without it the lanes of a warp drift apart in the
+    // data-dependent loops below and execute them one lane at a time
+    for (int c0 = warp * 32; c0 < nc; c0 += ES_THREADS) {
+      const int c = c0 + lane;
+      const uint32_t keyA = (c < nc) ? cell_key[c] : 0x40000000u;
+      const bool live = !(keyA & 0x40000000u);  // (private cells of non-finite points have no neighbours)
+      const int cx = (int)(keyA & 1023u), cy = (int)((keyA >> 10) & 1023u), cz = (int)((keyA >> 20) & 1023u);
+      // per-axis validity of the offsets -2..2 (bit d+2); inside the grid the packed key of a neighbour is keyA + a
+      // constant (no carries between the 10-bit fields)
+      unsigned xm = 0u, ym = 0u, zm = 0u;
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        xm |= (live && cx + d >= 0 && cx + d < dimx) ? (1u << (d + 2)) : 0u;
+        ym |= (live && cy + d >= 0 && cy + d < dimy) ? (1u << (d + 2)) : 0u;
+        zm |= (live && cz + d >= 0 && cz + d < dimz) ? (1u << (d + 2)) : 0u;
+      }
+      // which of the 62 forward cells exist (enumeration order = ES_FWD)
+      u64 found = 0ull;
+#pragma unroll
+      for (int q = 0; q < 62; ++q) {
+        const int dx = es_fwd_dx(q), dy = es_fwd_dy(q), dz = es_fwd_dz(q);  // compile-time after unrolling
+        const bool ok = ((xm >> (dx + 2)) & (ym >> (dy + 2)) & (zm >> (dz + 2)) & 1u) != 0u;
+        if (ok && es_lookup(hash, cell_key, keyA + (uint32_t)(dx + dy * 1024 + dz * 1048576)) >= 0) found |= 1ull << q;
+        if (q % 5 == 1) __syncwarp();
+      }
+      __syncwarp();
+      ES_CLKW(10);
+      const int j0 = live ? node_start[c] : 0, j1 = live ? node_start[c + 1] : 0;
+      int rc = live ? c : 0;
+      while (__any_sync(FULL, found != 0ull)) {
+        if (found) {
+          const int qq = __ffsll((long long)found) - 1;
+          found &= found - 1ull;
+          const int cb = es_lookup(hash, cell_key, keyA + (uint32_t)sm.fwd[qq]);
+          rc = es_find(parent, rc);
+          if (rc != es_find(parent, cb)) {
+            const int jb0 = node_start[cb], jb1 = node_start[cb + 1];
+            bool hit = false;
+            for (int a = j0; a < j1 && !hit; ++a) {
+              const float ax = px[a], ay = py[a], az = pz[a];
+              for (int b = jb0; b < jb1; ++b) {
+                if (dist2(ax, ay, az, px[b], py[b], pz[b]) < r2) {
+                  hit = true;
+                  break;
+                }
+              }
             }
+            if (hit) es_union(parent, rc, cb);
           }
         }
-        if (hit) uf_union(parent, j0, jb0);
+        __syncwarp();
       }
+      ES_CLKW(11);
     }
   } else {
-    for (int j = tid; j < n; j += ES_THREADS) {
-      const float x = px[j], y = py[j], z = pz[j];
-      const uint32_t key = ece_point_key(make_float4(x, y, z, 0.f), e, (int)idx16[j]);
-      const int cx = (int)(key % (uint32_t)dimx);
-      const int cy = (int)((key / (uint32_t)dimx) % (uint32_t)dimy);
-      const int cz = (int)(key / ((uint32_t)dimx * (uint32_t)dimy));
-      const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, dimx - 1);
-      // the rest of the own cell directly follows j in sorted order
-      {
-        const int c_own = view.lookup(key);
-        const int j_end = cell_start[c_own + 1];
-        for (int q = j + 1; q < j_end; ++q)
-          if (dist2(x, y, z, px[q], py[q], pz[q]) < r2) uf_union(parent, j, q);
+    for (int c = tid; c < nc; c += ES_THREADS) {
+      const uint32_t keyA = cell_key[c];
+      const int cx = (int)(keyA & 1023u), cy = (int)((keyA >> 10) & 1023u), cz = (int)(keyA >> 20);
+      const int j0 = node_start[c], j1 = node_start[c + 1];
+      // inside the cell
+      for (int a = j0; a < j1; ++a) {
+        const float ax = px[a], ay = py[a], az = pz[a];
+        for (int b = a + 1; b < j1; ++b)
+          if (dist2(ax, ay, az, px[b], py[b], pz[b]) < r2) es_union(parent, a, b);
       }
-      // forward cells: (+1,0,0), then the rows (dy,dz) = (+1,0), (-1,+1), (0,+1), (+1,+1) with dx = -1..1
+      // the 13 forward cells: (+1,0,0), then the rows (dy,dz) = (+1,0), (-1,+1), (0,+1), (+1,+1) with dx = -1..1
       for (int r = -1; r < 4; ++r) {
         const int dy = (r <= 0) ? (r + 1) : (r - 2);
         const int dz = (r <= 0) ? 0 : 1;
         const int yy = cy + dy, zz = cz + dz;
         if (yy < 0 || yy >= dimy || zz >= dimz) continue;
-        const int xa = (r < 0) ? cx + 1 : x_lo;
-        for (int xx = xa; xx <= x_hi; ++xx) {
-          const uint32_t keyB = (uint32_t)xx + (uint32_t)dimx * ((uint32_t)yy + (uint32_t)dimy * (uint32_t)zz);
-          const int cb = view.lookup(keyB);
+        for (int xx = (r < 0) ? cx + 1 : cx - 1; xx <= cx + 1; ++xx) {
+          if (xx < 0 || xx >= dimx) continue;
+          const uint32_t keyB = (uint32_t)xx | ((uint32_t)yy << 10) | ((uint32_t)zz << 20);
+          const int cb = es_lookup(hash, cell_key, keyB);
           if (cb < 0) continue;
-          const int jb0 = cell_start[cb], jb1 = cell_start[cb + 1];
-          for (int q = jb0; q < jb1; ++q)
-            if (dist2(x, y, z, px[q], py[q], pz[q]) < r2) uf_union(parent, j, q);
+          const int jb0 = node_start[cb], jb1 = node_start[cb + 1];
+          for (int a = j0; a < j1; ++a) {
+            const float ax = px[a], ay = py[a], az = pz[a];
+            for (int b = jb0; b < jb1; ++b)
+              if (dist2(ax, ay, az, px[b], py[b], pz[b]) < r2) es_union(parent, a, b);
+          }
         }
       }
     }
   }
   __syncthreads();
 
-  ES_CLK(5);
-  // ---- 5. labels, sizes, smallest original index per component, kept roots in canonical order, CSR ----------
-  for (int i = tid; i < n; i += ES_THREADS) {
-    csize[i] = 0;                // (z is dead)
-    minidx[i] = 0x7fffffff;      // (cell_start and the hash table are dead)
+  ES_CLK(4);
+  // ---- 4. sizes, smallest original index per component, kept roots in canonical order, CSR offsets -----------
+  if (e.mode != 0) {  // point mode: from here on every point is its own node
+    for (int j = tid; j <= n; j += ES_THREADS) node_start[j] = (unsigned short)j;
+  }
+  for (int v = tid; v < nn; v += ES_THREADS) {  // (the coordinates are dead)
+    csize[v] = 0;
+    minidx[v] = 0x7fffffff;
   }
   __syncthreads();
-  for (int j = tid; j < n; j += ES_THREADS) {
-    int root = parent[j];
+  for (int v = tid; v < nn; v += ES_THREADS) {
+    int root = v;
     while (true) {
       const int up = parent[root];
       if (up == root) break;
       root = up;
     }
-    parent[j] = root;  // racing readers see either an ancestor or the root
-    atomicAdd(&csize[root], 1);
-    atomicMin(&minidx[root], (int)idx16[j]);
+    const int j0 = node_start[v], j1 = node_start[v + 1];
+    int mi = 0x7fffffff;
+    for (int j = j0; j < j1; ++j) mi = min(mi, (int)idx16[j]);
+    atomicAdd(&csize[root], j1 - j0);
+    atomicMin(&minidx[root], mi);
+    parent[v] = root;  // racing readers see either an ancestor or the root
   }
   __syncthreads();
-  ES_CLK(6);
+  ES_CLK(5);
+  const int npt = cdiv(nn, ES_THREADS);
   {
-    const int i0 = min(tid * ipt, n), i1 = min(i0 + ipt, n);
-    int cnt = 0;
-    for (int j = i0; j < i1; ++j) {
-      const int sz = csize[j];
-      cnt += (parent[j] == j && sz >= min_size && sz <= max_size) ? 1 : 0;
+    const int v0 = min(tid * npt, nn), v1 = min(v0 + npt, nn);
+    int k = 0;
+    for (int v = v0; v < v1; ++v) {
+      const int sz = csize[v];
+      k += (parent[v] == v && sz >= min_size && sz <= max_size) ? 1 : 0;
     }
     int total;
-    int pos = block_excl_scan(cnt, sm.wscan, total);
-    for (int j = i0; j < i1; ++j) {
-      const int sz = csize[j];
-      if (parent[j] == j && sz >= min_size && sz <= max_size)  // size desc, smallest original index asc
-        sortbuf[pos++] = ((u64)(uint32_t)(n - sz) << 32) | ((u64)(uint32_t)minidx[j] << 16) | (u64)(uint32_t)j;
+    int pos = block_excl_scan(k, sm.wscan, total);
+    for (int v = v0; v < v1; ++v) {
+      const int sz = csize[v];
+      if (parent[v] == v && sz >= min_size && sz <= max_size)  // size desc, smallest original index asc
+        sortbuf[pos++] = ((u64)(uint32_t)(n - sz) << 32) | ((u64)(uint32_t)minidx[v] << 16) | (u64)(uint32_t)v;
     }
     if (tid == 0) sm.n_clusters = total;
     __syncthreads();
   }
-  ES_CLK(7);
   const int C = sm.n_clusters;
-  bitonic_sort_smem(sortbuf, C);
-  ES_CLK(8);
+  if (C <= ES_THREADS) {  // rank by counting (keys are distinct: they contain the node id)
+    const u64 mykey = (tid < C) ? sortbuf[tid] : 0ull;
+    int rk = 0;
+    if (tid < C)
+      for (int o = 0; o < C; ++o) rk += (sortbuf[o] < mykey) ? 1 : 0;
+    __syncthreads();
+    if (tid < C) sortbuf[rk] = mykey;
+    __syncthreads();
+  } else {
+    bitonic_sort_smem(sortbuf, C);
+  }
+  ES_CLK(6);
   {
     const int cpt = cdiv(max(C, 1), ES_THREADS);
     const int r0 = min(tid * cpt, C), r1 = min(r0 + cpt, C);
     int sum = 0;
     for (int r = r0; r < r1; ++r) sum += n - (int)hi32(sortbuf[r]);
     int total;
-    int run = block_excl_scan(sum, sm.wscan, total);  // (syncs: minidx is dead from here on)
+    int run = block_excl_scan(sum, sm.wscan, total);
     for (int r = r0; r < r1; ++r) {
       const u64 v = sortbuf[r];
       offs[r] = run;
-      rank_of[lo32(v) & 0xffffu] = (unsigned short)r;
+      if (r < ES_SCAN_MAXC) sm.soff[r] = run;
+      rankc[lo32(v) & 0xffffu] = (unsigned short)r;
       run += n - (int)hi32(v);
     }
     if (tid == 0) {
       offs[C] = total;
+      if (C <= ES_SCAN_MAXC) sm.soff[C] = total;
       sm.n_members = total;
       n_clusters[f] = C;
       n_cluster_pts[f] = total;
     }
     __syncthreads();
   }
-  ES_CLK(9);
   const int L = sm.n_members;
-  for (int j = tid; j < n; j += ES_THREADS) {
-    const int root = parent[j];
+  // ---- 5. labels by original index, cluster_indices, centroids ---------------------------------------------------
+  for (int v = tid; v < nn; v += ES_THREADS) {
+    const int root = parent[v];
     const int sz = csize[root];
-    const bool kept = sz >= min_size && sz <= max_size;
-    sortbuf[j] = kept ? (((u64)rank_of[root] << 32) | (u64)idx16[j]) : ~0ull;
+    const unsigned short lab = (sz >= min_size && sz <= max_size) ? rankc[root] : (unsigned short)0xffffu;
+    const int j0 = node_start[v], j1 = node_start[v + 1];
+    for (int j = j0; j < j1; ++j) lab16[idx16[j]] = lab;
   }
   __syncthreads();
-  ES_CLK(10);
-  bitonic_sort_smem(sortbuf, n);
-  for (int j = tid; j < L; j += ES_THREADS) idx_out[j] = (int)lo32(sortbuf[j]);
-
-  ES_CLK(11);
-  // ---- 6. centroid + bounding radius, one warp per cluster --------------------------------------------------
+  ES_CLK(7);
+  unsigned short* mem16 = idx16;  // member list (the cell-ordered index list is dead)
+  if (C <= ES_SPLIT_MAXC) {
+    // stable multi-way split of the points by cluster rank: warp w owns the index range [w*chunk, (w+1)*chunk);
+    // per-(warp, cluster) counts -> running offsets -> positions (match_any ranks the lanes of one cluster)
+    unsigned short* woff = reinterpret_cast<unsigned short*>(smem_raw + ES_A);  // [ES_WARPS][C]  (sizes are dead)
+    const int chunk = cdiv(cdiv(n, ES_WARPS), 32) * 32;
+    const int i0 = warp * chunk, i1 = min(i0 + chunk, n);
+    for (int k = tid; k < ES_WARPS * C; k += ES_THREADS) woff[k] = 0;
+    __syncthreads();
+    for (int base = i0; base < i1; base += 32) {
+      const int i = base + lane;
+      const unsigned lab = (i < i1) ? (unsigned)lab16[i] : 0xffffu;
+      const unsigned peers = __match_any_sync(FULL, lab);
+      if (lab != 0xffffu && (peers & lanemask_lt()) == 0u) woff[warp * C + lab] += (unsigned short)__popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += ES_THREADS) {
+      int run = (C <= ES_SCAN_MAXC) ? sm.soff[c] : offs[c];
+      for (int w = 0; w < ES_WARPS; ++w) {
+        const int t = woff[w * C + c];
+        woff[w * C + c] = (unsigned short)run;
+        run += t;
+      }
+    }
+    __syncthreads();
+    for (int base = i0; base < i1; base += 32) {
+      const int i = base + lane;
+      const unsigned lab = (i < i1) ? (unsigned)lab16[i] : 0xffffu;
+      const unsigned peers = __match_any_sync(FULL, lab);
+      if (lab != 0xffffu) {
+        const int first = (int)woff[warp * C + lab];
+        const int pos = first + __popc(peers & lanemask_lt());
+        mem16[pos] = (unsigned short)i;
+        idx_out[pos] = i;
+        __syncwarp(peers);
+        if ((peers & lanemask_lt()) == 0u) woff[warp * C + lab] = (unsigned short)(first + __popc(peers));
+      }
+      __syncwarp();
+    }
+  } else {
+    for (int i = tid; i < n; i += ES_THREADS) {
+      const unsigned short lab = lab16[i];
+      sortbuf[i] = (lab != 0xffffu) ? (((u64)lab << 32) | (u64)(uint32_t)i) : ~0ull;
+    }
+    __syncthreads();
+    bitonic_sort_smem(sortbuf, n);
+    for (int j = tid; j < L; j += ES_THREADS) {
+      const uint32_t i = lo32(sortbuf[j]);
+      mem16[j] = (unsigned short)i;
+      idx_out[j] = (int)i;
+    }
+  }
+  __syncthreads();
+  ES_CLK(8);
+  // ---- 6. member coordinates staged in shared memory (labels, sizes are dead), centroid + radius per cluster -------
+  for (int j = tid; j < L; j += ES_THREADS) {
+    const float4 p = __ldg(src + mem16[j]);
+    px[j] = p.x;
+    py[j] = p.y;
+    pz[j] = p.z;
+  }
+  __syncthreads();
   for (int c = warp; c < C; c += ES_WARPS) {
-    const int b = offs[c], en = offs[c + 1];
+    const int b = (C <= ES_SCAN_MAXC) ? sm.soff[c] : offs[c], en = (C <= ES_SCAN_MAXC) ? sm.soff[c + 1] : offs[c + 1];
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int j = b + lane; j < en; j += 32) {
-      const float4 p = __ldg(src + lo32(sortbuf[j]));
-      sx += (double)p.x;
-      sy += (double)p.y;
-      sz += (double)p.z;
+      sx += (double)px[j];
+      sy += (double)py[j];
+      sz += (double)pz[j];
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
@@ -495,19 +669,16 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
       sy += __shfl_xor_sync(FULL, sy, o);
       sz += __shfl_xor_sync(FULL, sz, o);
     }
-    const double cnt = (double)(en - b);
-    const float cx = (float)(sx / cnt), cy = (float)(sy / cnt), cz = (float)(sz / cnt);
+    const double dn = (double)(en - b);
+    const float cx = (float)(sx / dn), cy = (float)(sy / dn), cz = (float)(sz / dn);
     float r = 0.0f;
-    for (int j = b + lane; j < en; j += 32) {
-      const float4 p = __ldg(src + lo32(sortbuf[j]));
-      r = fmaxf(r, sqrtf(dist2(p.x, p.y, p.z, cx, cy, cz)));  // od.cpp:457-464 arithmetic
-    }
+    for (int j = b + lane; j < en; j += 32)
+      r = fmaxf(r, sqrtf(dist2(px[j], py[j], pz[j], cx, cy, cz)));  // od.cpp:457-464 arithmetic
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, o));
     if (lane == 0) obs[c] = make_float4(cx, cy, cz, r);
   }
-  __syncthreads();
-  ES_CLK(12);
+  ES_CLK(9);
 }
 
 }  // namespace

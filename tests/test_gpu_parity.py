@@ -194,7 +194,7 @@ def test_cluster_fused_kernel_capacity_edge(monkeypatch):
     p.euc_min_cluster_size = 3
     p.euc_max_cluster_size = 100000
     rng = np.random.default_rng(41)
-    for n in (9216, 9217):
+    for n in (8192, 8193):
         centers = rng.uniform(-5, 5, size=(40, 3))
         pts = centers[rng.integers(0, 40, n)] + rng.normal(size=(n, 3)) * 0.15
         cloud = _cloud(pts)
@@ -224,3 +224,28 @@ def test_cluster_drops_oversize_and_undersize(ece_path):
     o_off, o_idx = O.cluster_bruteforce(p, cloud)
     assert_bits_equal(g_off, o_off, "offsets")
     assert_bits_equal(g_idx, o_idx, "indices")
+
+
+@pytest.mark.parametrize("n_groups,per_group", [(40, 20), (300, 12), (1500, 4)])
+def test_cluster_many_small_clusters(n_groups, per_group, ece_path):
+    """cluster counts on both sides of the fused kernel's thresholds (member listing by warp scans up to 128
+    clusters, root ranking by counting up to 1024 clusters, bitonic sorts beyond)"""
+    p = synth.params(1)
+    p.euc_cluster_tolerance = 0.05
+    p.euc_min_cluster_size = 2
+    p.euc_max_cluster_size = 100000
+    rng = np.random.default_rng(50 + n_groups)
+    side = int(np.ceil(np.sqrt(n_groups)))
+    centers = np.array([[0.5 * (g % side), 0.5 * (g // side), 0.0] for g in range(n_groups)])
+    sizes = rng.integers(max(per_group - 3, 1), per_group + 4, n_groups)
+    pts = np.concatenate([centers[g] + rng.uniform(-0.02, 0.02, size=(sizes[g], 3)) for g in range(n_groups)])
+    pts = pts[rng.permutation(len(pts))]
+    cloud = _cloud(pts)
+    with ObstacleProcessor(p, len(cloud)) as op:
+        g_off, g_idx = op.extract_euclidian_clusters(cloud)
+        g_obs = op.centroid_radius(cloud, g_off, g_idx)
+    o_off, o_idx = O.cluster_bruteforce(p, cloud)
+    assert_bits_equal(g_off, o_off, "offsets")
+    assert_bits_equal(g_idx, o_idx, "indices")
+    assert_close(g_obs, O.centroid_radius(cloud, o_off, o_idx), "obstacles")
+    assert len(o_off) - 1 >= n_groups * 0.8

@@ -9,8 +9,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pointcloud_obstacle_processing_b200 import ObstacleProcessor, synth, load_library
 
-NAMES = ["minmax+grid", "keys+sort", "unpack+heads", "hash build", "union", "flatten+sizes", "roots compaction",
-         "roots sort", "rank+offsets", "member keys", "member sort+write", "centroid/radius"]
+NAMES = ["minmax+grid", "hash insert+cell ids", "count+scan+scatter", "union", "sizes+minidx", "roots+rank",
+         "offsets+labels", "member lists", "centroid/radius"]
 p = synth.params(2)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 clouds = synth.frames(2, 0, B)
@@ -24,5 +24,6 @@ with ObstacleProcessor(p, clouds.shape[1], max_batch=B) as op:
     t = list(out)
     print("frame 0: P =", res[0].n_remaining, "C =", res[0].n_clusters)
     for k, name in enumerate(NAMES):
-        print("%-20s %9d cycles" % (name, t[k + 1] - t[k]))
-    print("%-20s %9d cycles" % ("total", t[12] - t[0]))
+        print("%-24s %9d cycles" % (name, t[k + 1] - t[k]))
+    print("%-24s %9d cycles" % ("total", t[len(NAMES)] - t[0]))
+    print("warp 0, first pass: lookups %d cycles, neighbour walk %d cycles" % (t[10] - t[3], t[11] - t[10]))
