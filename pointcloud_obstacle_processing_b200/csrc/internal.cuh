@@ -119,6 +119,36 @@ void run_voxel(const Ctx& c, const VoxelArgs& a);
 void run_grid_sort(const Ctx& c, const float4* in, size_t in_stride, const int* n_in, float cell, MinMax* minmax,
                    EceFrame* ef, const SortBufs& sort, float4* sorted_pts, int* parent, int* csize, int clique = 0);
 
+// ---- fused crop + VoxelGrid fast path (stage_voxel_fused.cu) ----------------------------------------------
+struct VoxFusedPlan {
+  int ok;          // the crop box bounds the voxel grid tightly enough (and PCL's overflow guard cannot fire)
+  float lim[6];    // x_min,x_max,y_min,y_max,z_min,z_max
+  float inv;       // 1 / leaf
+  int b0[3];       // floor(lo_a * inv)
+  uint32_t nx, ny, nz;  // cells of the crop box per axis
+  int bits, npass, digit_bits;
+};
+VoxFusedPlan make_vox_fused_plan(const pcop_params& p);
+size_t vox_fused_hist_elems(int B);
+size_t vox_fused_desc_bytes(int B, int cap);
+struct VoxelFusedArgs {
+  const float4* in;  // wave input (uncropped), frame-strided
+  size_t in_stride;
+  const int* n_in;
+  VoxFusedPlan plan;
+  float leaf;
+  MinMax* minmax;    // [B] min/max of the crop survivors
+  VoxelFrame* vf;    // [B]
+  SortBufs sort;     // hist: vox_fused_hist_elems, desc: vox_fused_desc_bytes
+  unsigned* desc;    // compaction descriptors
+  uint32_t* flags;   // [B] bit 0: the frame needs the generic path (a survivor with a non-finite y or z)
+  int* n_crop;       // [B] out: M
+  float4* out;       // [B*cap] voxel centroids
+  uint32_t* out_keys;
+  int* n_out;        // [B] V
+};
+void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a);
+
 struct SorArgs {
   const float4* in;
   size_t in_stride;

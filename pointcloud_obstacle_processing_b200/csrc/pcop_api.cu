@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cmath>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.cuh"
@@ -70,6 +71,9 @@ struct PackMeta {  // device -> host in one copy
 };
 
 thread_local std::string g_global_error;
+
+constexpr int PCOP_INTERNAL_REDO_GENERIC = 1000;  // collect_wave -> process_waves, never returned to the caller
+constexpr int PCOP_MIN_LANE_WAVE = 8;  // a call is split over the lanes only when every lane gets at least this many frames
 
 }  // namespace
 
@@ -133,6 +137,17 @@ struct pcop_handle {
   double alg_bytes = 0.0;
   KernelTimers kt;
 
+  // lanes: the handle itself is lane 0; a batched call deals its waves round-robin to the lanes, one host thread
+  // and one stream per lane, so one lane's host synchronisations and result copies overlap the other lanes' kernels
+  VoxFusedPlan vplan{};            // fused crop + voxel fast path (ok = 0: not applicable to these parameters)
+  uint32_t* d_vf_flags = nullptr;  // [maxB]
+  uint32_t* h_vf_flags = nullptr;
+  bool force_generic = false;      // set while a wave is redone by the generic path
+  bool wave_used_fused = false;
+  std::vector<pcop_handle*> extra_lanes;
+  std::vector<size_t> fixups;  // result-pointer slots of the running call (byte offsets into the caller's array)
+  cudaEvent_t ev_lane_done = nullptr;
+
   int* cnt(int row) { return d_counts + (size_t)row * maxB; }
 };
 
@@ -175,6 +190,14 @@ void fill_rng_table(uint32_t seed, int* out, int count) {
     y ^= y >> 18;
     out[k] = (int)(y >> 1);
   }
+}
+
+// fused crop + voxel fast path unless PCOP_VOXEL_FUSED=0 (the tests cover both paths)
+VoxFusedPlan make_plan(const pcop_params& p) {
+  VoxFusedPlan pl = make_vox_fused_plan(p);
+  const char* s = getenv("PCOP_VOXEL_FUSED");
+  if (s && s[0] == '0') pl.ok = 0;
+  return pl;
 }
 
 int validate_params(pcop_handle* h, const pcop_params& p) {
@@ -561,30 +584,61 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
   const int* cur_n = h->cnt(CNT_IN);
   bool have_minmax = false;
 
-  {
-    StageTimer t(h, PCOP_STAGE_CROP);
-    if (p.enable_crop) {
-      run_crop(c, make_crop_args(h, cur, cur_stride, cur_n));
-      cur = h->d_crop;
-      cur_stride = h->cap;
-      cur_n = h->cnt(CNT_CROP);
-      have_minmax = true;
-    } else {
-      KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_CROP), B));
-      count_launch(c);
+  const bool fused = h->vplan.ok && !h->force_generic;
+  h->wave_used_fused = fused;
+  if (fused) {
+    // crop + VoxelGrid in one pass over the input (stage_voxel_fused.cu); the cropped cloud itself is only
+    // materialised when it is a requested output
+    {
+      StageTimer t(h, PCOP_STAGE_CROP);
+      if (effective_outputs(p) & PCOP_OUT_CROP) run_crop(c, make_crop_args(h, cur, cur_stride, cur_n));
     }
-  }
-  {
     StageTimer t(h, PCOP_STAGE_VOXEL);
-    if (p.enable_voxel) {
-      if (!have_minmax) run_minmax(c, cur, cur_stride, cur_n, h->d_minmax);
-      run_voxel(c, make_voxel_args(h, cur, cur_stride, cur_n));
-      cur = h->d_vox;
-      cur_stride = h->cap;
-      cur_n = h->cnt(CNT_VOX);
-    } else {
-      KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_VOX), B));
-      count_launch(c);
+    VoxelFusedArgs a{};
+    a.in = cur;
+    a.in_stride = cur_stride;
+    a.n_in = cur_n;
+    a.plan = h->vplan;
+    a.leaf = p.downsample_size;
+    a.minmax = h->d_minmax;
+    a.vf = h->d_vf;
+    a.sort = h->sort;
+    a.desc = h->d_desc;
+    a.flags = h->d_vf_flags;
+    a.n_crop = h->cnt(CNT_CROP);
+    a.out = h->d_vox;
+    a.out_keys = h->d_vox_keys;
+    a.n_out = h->cnt(CNT_VOX);
+    run_voxel_fused(c, a);
+    cur = h->d_vox;
+    cur_stride = h->cap;
+    cur_n = h->cnt(CNT_VOX);
+  } else {
+    {
+      StageTimer t(h, PCOP_STAGE_CROP);
+      if (p.enable_crop) {
+        run_crop(c, make_crop_args(h, cur, cur_stride, cur_n));
+        cur = h->d_crop;
+        cur_stride = h->cap;
+        cur_n = h->cnt(CNT_CROP);
+        have_minmax = true;
+      } else {
+        KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_CROP), B));
+        count_launch(c);
+      }
+    }
+    {
+      StageTimer t(h, PCOP_STAGE_VOXEL);
+      if (p.enable_voxel) {
+        if (!have_minmax) run_minmax(c, cur, cur_stride, cur_n, h->d_minmax);
+        run_voxel(c, make_voxel_args(h, cur, cur_stride, cur_n));
+        cur = h->d_vox;
+        cur_stride = h->cap;
+        cur_n = h->cnt(CNT_VOX);
+      } else {
+        KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_VOX), B));
+        count_launch(c);
+      }
     }
   }
   {
@@ -664,7 +718,12 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_warnings, h->d_warnings, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, h->stream));
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_prec, h->d_prec, sizeof(PlaneRecord) * B, cudaMemcpyDeviceToHost, h->stream));
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_meta, h->d_meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, h->stream));
+  if (h->wave_used_fused)
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_vf_flags, h->d_vf_flags, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, h->stream));
   PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->wave_used_fused)
+    for (int f = 0; f < B; ++f)
+      if (h->h_vf_flags[f]) return PCOP_INTERNAL_REDO_GENERIC;  // the fast voxel path declined a frame of this wave
   const PackMeta meta = *h->h_meta;
   const size_t base_off = (*h_pack_used + 255) & ~(size_t)255;
   TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
@@ -732,31 +791,21 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   return PCOP_OK;
 }
 
-int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n, int32_t batch,
-                 pcop_frame_result* out) {
-  if (!h) return fail(nullptr, PCOP_ERR_BAD_PARAM, "null handle");
-  if (!xyzw || !n || !out || batch < 0) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+// Runs the waves wave_first, wave_first + wave_step, ... of a call on lane h (waves are `wave` frames each).
+// Blocks until the lane's results are in its pinned host buffer; fills out[] (pointers fixed up at the end).
+int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n, int32_t batch,
+                  pcop_frame_result* out, int wave, int wave_first, int wave_step, bool on_device, uint32_t mask) {
   PCOP_CUDA_TRY(cudaSetDevice(h->device));
-  for (int f = 0; f < batch; ++f) {
-    if (n[f] < 0) return fail(h, PCOP_ERR_BAD_PARAM, "negative point count");
-    if (n[f] > h->cap) return fail(h, PCOP_ERR_CAPACITY, "frame has more points than max_points");
-    if ((size_t)n[f] > frame_stride_points && batch > 1) return fail(h, PCOP_ERR_BAD_PARAM, "frame_stride_points < n");
-  }
-  const uint32_t mask = effective_outputs(h->params);
-  TRY(ensure_pack_capacity(h, mask));
   h->launches = 0;
   h->alg_bytes = 0.0;
   h->kt.used = 0;
   h->sort_pass_keys = 0;
   PCOP_CUDA_TRY(cudaMemsetAsync(h->sort.stats, 0, sizeof(unsigned long long), h->stream));
   for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] = 0.f;
-  const bool on_device = is_device_pointer(xyzw);
   size_t h_pack_used = 0;
-  std::vector<size_t> fixups;
-  fixups.reserve((size_t)batch * 6);
-  PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[0], h->stream));
-  for (int w0 = 0; w0 < batch; w0 += h->maxB) {
-    const int B = std::min(h->maxB, batch - w0);
+  h->fixups.clear();
+  for (int w0 = wave_first * wave; w0 < batch; w0 += wave_step * wave) {
+    const int B = std::min(wave, batch - w0);
     for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_used[s] = false;
     const float4* in;
     size_t stride;
@@ -787,7 +836,14 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     int max_n = 1;
     for (int f = 0; f < B; ++f) max_n = std::max(max_n, (int)n[w0 + f]);
     TRY(run_wave_stages(h, B, in, stride, max_n));
-    TRY(collect_wave(h, B, mask, &h_pack_used, out, w0, &fixups));
+    int cst = collect_wave(h, B, mask, &h_pack_used, out, w0, &h->fixups);
+    if (cst == PCOP_INTERNAL_REDO_GENERIC) {
+      h->force_generic = true;
+      cst = run_wave_stages(h, B, in, stride, max_n);
+      h->force_generic = false;
+      if (cst == PCOP_OK) cst = collect_wave(h, B, mask, &h_pack_used, out, w0, &h->fixups);
+    }
+    TRY(cst);
     PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (int s = 0; s < PCOP_N_STAGES; ++s) {
       if (!h->stage_used[s]) continue;
@@ -797,17 +853,97 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     resolve_kernel_timers(h);
   }
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_stats, h->sort.stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaEventRecord(h->ev_lane_done, h->stream));
+  PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_lane_done));
+  h->sort_pass_keys = *h->h_stats;
+  // the host pack buffer is final now: turn the stored offsets into pointers
+  for (size_t fx : h->fixups) {
+    const void** slot = (const void**)((unsigned char*)out + fx);
+    const size_t off = (size_t)(uintptr_t)(*slot) - 1;
+    *slot = h->h_pack + off;
+  }
+  return PCOP_OK;
+}
+
+// add lane `l`'s per-kernel timing table into h's and clear it
+void merge_kernel_timers(pcop_handle* h, pcop_handle* l) {
+  KernelTimers& d = h->kt;
+  KernelTimers& s = l->kt;
+  for (int i = 0; i < s.n_names; ++i) {
+    int id = -1;
+    for (int j = 0; j < d.n_names; ++j)
+      if (d.names[j] == s.names[i] || strcmp(d.names[j], s.names[i]) == 0) {
+        id = j;
+        break;
+      }
+    if (id < 0 && d.n_names < KernelTimers::MAX_NAMES) {
+      id = d.n_names++;
+      d.names[id] = s.names[i];
+      d.total_us[id] = 0.0;
+      d.launches[id] = 0;
+    }
+    if (id >= 0) {
+      d.total_us[id] += s.total_us[i];
+      d.launches[id] += s.launches[i];
+    }
+  }
+  s.n_names = 0;
+}
+
+int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n, int32_t batch,
+                 pcop_frame_result* out) {
+  if (!h) return fail(nullptr, PCOP_ERR_BAD_PARAM, "null handle");
+  if (!xyzw || !n || !out || batch < 0) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  for (int f = 0; f < batch; ++f) {
+    if (n[f] < 0) return fail(h, PCOP_ERR_BAD_PARAM, "negative point count");
+    if (n[f] > h->cap) return fail(h, PCOP_ERR_CAPACITY, "frame has more points than max_points");
+    if ((size_t)n[f] > frame_stride_points && batch > 1) return fail(h, PCOP_ERR_BAD_PARAM, "frame_stride_points < n");
+  }
+  const uint32_t mask = effective_outputs(h->params);
+  const bool on_device = is_device_pointer(xyzw);
+  // lanes used by this call: per-kernel timing needs each kernel alone on the GPU, so it serialises the lanes
+  int n_lanes = 1 + (int)h->extra_lanes.size();
+  if (h->kt.enabled) n_lanes = 1;
+  int wave = h->maxB;
+  if (n_lanes > 1) {
+    wave = std::min(h->maxB, std::max(PCOP_MIN_LANE_WAVE, (batch + n_lanes - 1) / n_lanes));
+    n_lanes = std::min(n_lanes, std::max(1, (batch + wave - 1) / wave));
+  }
+  std::vector<pcop_handle*> lanes(1, h);
+  for (int l = 1; l < n_lanes; ++l) lanes.push_back(h->extra_lanes[l - 1]);
+  for (pcop_handle* l : lanes) {
+    l->params = h->params;
+    l->vplan = h->vplan;
+    TRY(ensure_pack_capacity(l, mask));
+  }
+  PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[0], h->stream));
+  for (int l = 1; l < n_lanes; ++l) PCOP_CUDA_TRY(cudaStreamWaitEvent(lanes[l]->stream, h->ev_call[0], 0));
+  std::vector<int> status(n_lanes, PCOP_OK);
+  std::vector<std::thread> workers;
+  for (int l = 1; l < n_lanes; ++l)
+    workers.emplace_back([&, l]() {
+      status[l] = process_waves(lanes[l], xyzw, frame_stride_points, n, batch, out, wave, l, n_lanes, on_device, mask);
+    });
+  status[0] = process_waves(h, xyzw, frame_stride_points, n, batch, out, wave, 0, n_lanes, on_device, mask);
+  for (std::thread& t : workers) t.join();
+  for (int l = 0; l < n_lanes; ++l)
+    if (status[l] != PCOP_OK) {
+      if (l > 0) h->err = lanes[l]->err;
+      return status[l];
+    }
+  for (int l = 1; l < n_lanes; ++l) PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, lanes[l]->ev_lane_done, 0));
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[1], h->stream));
   PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_call[1]));
   float ms = 0.f;
   PCOP_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]));
   h->last_elapsed_us = ms * 1000.f;
-  h->sort_pass_keys = *h->h_stats;
-  // the host pack buffer is final now: turn the stored offsets into pointers
-  for (size_t fx : fixups) {
-    const void** slot = (const void**)((unsigned char*)out + fx);
-    const size_t off = (size_t)(uintptr_t)(*slot) - 1;
-    *slot = h->h_pack + off;
+  for (int l = 1; l < n_lanes; ++l) {  // per-call accounting is reported on the handle (sums over the lanes)
+    h->launches += lanes[l]->launches;
+    h->alg_bytes += lanes[l]->alg_bytes;
+    h->sort_pass_keys += lanes[l]->sort_pass_keys;
+    for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] += lanes[l]->stage_us[s];
+    merge_kernel_timers(h, lanes[l]);
   }
   return PCOP_OK;
 }
@@ -903,9 +1039,7 @@ void pcop_params_init_params_yaml(pcop_params* p) {
   p->publish_point_clouds = 1;
 }
 
-int pcop_create(const pcop_params* params, int device, size_t max_points, int max_batch, pcop_handle** out) {
-  if (!params || !out || max_points == 0 || max_points > (size_t)(1u << 30) || max_batch < 1)
-    return fail(nullptr, PCOP_ERR_BAD_PARAM, "pcop_create: bad argument");
+static int create_lane(const pcop_params* params, int device, size_t max_points, int max_batch, pcop_handle** out) {
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -920,6 +1054,7 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
     return fail(nullptr, PCOP_ERR_CUDA, "pcop_create: device is not sm_100-class (kernels are built for sm_100a only)");
   pcop_handle* h = new pcop_handle();
   h->params = *params;
+  h->vplan = make_plan(*params);
   h->device = device;
   h->cap = (int)max_points;
   h->maxB = max_batch;
@@ -976,12 +1111,14 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   A(dalloc(h, &h->sort.key[1], BC));
   A(dalloc(h, &h->sort.val[0], BC));
   A(dalloc(h, &h->sort.val[1], BC));
-  A(dalloc(h, &h->sort.hist, (size_t)B * RS_MAX_PASSES * RS_BINS));
+  A(dalloc(h, &h->sort.hist, std::max((size_t)B * RS_MAX_PASSES * RS_BINS, vox_fused_hist_elems(B))));
   {
     unsigned char* d = nullptr;
-    A(dalloc(h, &d, sort_desc_bytes(B, h->cap)));
+    A(dalloc(h, &d, std::max(sort_desc_bytes(B, h->cap), vox_fused_desc_bytes(B, h->cap))));
     h->sort.desc = (uint32_t*)d;
   }
+  A(dalloc(h, &h->d_vf_flags, B));
+  A(halloc(h, &h->h_vf_flags, B));
   A(dalloc(h, &h->sort.maxkey, B));
   A(dalloc(h, &h->sort.npass, B));
   A(dalloc(h, &h->sort.stats, 1));
@@ -1023,14 +1160,43 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
     for (int i = 0; i < 2; ++i)
       if ((e = cudaEventCreate(&h->ev_stage[s][i])) != cudaSuccess)
         return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
+  if ((e = cudaEventCreateWithFlags(&h->ev_lane_done, cudaEventDisableTiming)) != cudaSuccess)
+    return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
   st = ensure_pack_capacity(h, effective_outputs(h->params));
   if (st != PCOP_OK) return bail(st);
   *out = h;
   return PCOP_OK;
 }
 
+int pcop_create(const pcop_params* params, int device, size_t max_points, int max_batch, pcop_handle** out) {
+  if (!params || !out || max_points == 0 || max_points > (size_t)(1u << 30) || max_batch < 1)
+    return fail(nullptr, PCOP_ERR_BAD_PARAM, "pcop_create: bad argument");
+  *out = nullptr;
+  // lanes: max_batch frames are in flight at once, split over the lanes (PCOP_LANES overrides the default of 2)
+  int n_lanes = 2;
+  if (const char* s = getenv("PCOP_LANES")) n_lanes = (int)std::min<long>(std::max<long>(strtol(s, nullptr, 10), 1), 8);
+  n_lanes = std::max(1, std::min(n_lanes, max_batch / PCOP_MIN_LANE_WAVE));
+  const int lane_batch = (max_batch + n_lanes - 1) / n_lanes;
+  pcop_handle* h = nullptr;
+  int st = create_lane(params, device, max_points, lane_batch, &h);
+  if (st != PCOP_OK) return st;
+  for (int l = 1; l < n_lanes; ++l) {
+    pcop_handle* x = nullptr;
+    st = create_lane(params, device, max_points, lane_batch, &x);
+    if (st != PCOP_OK) {
+      pcop_destroy(h);
+      return st;
+    }
+    h->extra_lanes.push_back(x);
+  }
+  *out = h;
+  return PCOP_OK;
+}
+
 void pcop_destroy(pcop_handle* h) {
   if (!h) return;
+  for (pcop_handle* l : h->extra_lanes) pcop_destroy(l);
+  h->extra_lanes.clear();
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->dev_allocs) cudaFree(p);
@@ -1043,6 +1209,7 @@ void pcop_destroy(pcop_handle* h) {
   }
   for (int i = 0; i < 2; ++i)
     if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
+  if (h->ev_lane_done) cudaEventDestroy(h->ev_lane_done);
   for (int s = 0; s < PCOP_N_STAGES; ++s)
     for (int i = 0; i < 2; ++i)
       if (h->ev_stage[s][i]) cudaEventDestroy(h->ev_stage[s][i]);
@@ -1061,6 +1228,14 @@ int pcop_set_params(pcop_handle* h, const pcop_params* params) {
     PCOP_CUDA_TRY(cudaMemcpy(h->d_rng, tbl.data(), sizeof(int) * RNG_TABLE, cudaMemcpyHostToDevice));
   }
   h->params = *params;
+  h->vplan = make_plan(*params);
+  for (pcop_handle* l : h->extra_lanes) {
+    const int ls = pcop_set_params(l, params);
+    if (ls != PCOP_OK) {
+      h->err = l->err;
+      return ls;
+    }
+  }
   return ensure_pack_capacity(h, effective_outputs(h->params));
 }
 

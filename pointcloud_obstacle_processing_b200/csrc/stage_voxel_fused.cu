@@ -1,0 +1,525 @@
+// Fused crop + VoxelGrid fast path (reference: the crop of od.cpp:195-215 followed by downsample_cloud
+// od.cpp:271-296 -> pcl::VoxelGrid::applyFilter).
+//
+// When the crop box is enabled its limits bound the voxel coordinates of every surviving point, so the sort key
+// does not have to wait for the min/max of the cropped cloud: with F_a = (int)floorf(p.a * inv) (PCL's float
+// multiply + floor) the composite key  (F_z - B_z) * ny * nx + (F_y - B_y) * nx + (F_x - B_x),  B_a =
+// (int)floorf(lo_a * inv), orders the points exactly like PCL's  ijk0 + ijk1*div_b0 + ijk2*div_b0*div_b1
+// (both are the lexicographic order of (F_z, F_y, F_x); ijk_a = F_a - min_b_a exactly because all values are
+// integers below 2^24).  That removes the cropped-cloud round trip through HBM:
+//
+//   k_vf_crop_key   one read of the input: crop predicate (literal, od.cpp:197-199), composite key, STABLE compaction
+//                   of (key, original index) pairs (warp ballots + decoupled look-back), min/max of the survivors
+//                   (PCL's key arithmetic and overflow guard need them), all digit histograms of the sort;
+//   k_vf_scan       exclusive scan of the digit histograms;
+//   k_vf_sort_pass  onesweep LSD radix passes with ceil(bits / npass)-bit digits (<= 9 bits: 25-bit keys of the
+//                   HDL-64 configuration take 3 passes instead of 4);
+//   k_vf_reduce     run heads + voxel count + centroids in one kernel: the tile's points are gathered into shared
+//                   memory in sorted order, every run head sums its run sequentially (ascending original index:
+//                   the compaction and the sort are stable) and divides by the float count; PCL's own key of the
+//                   voxel is computed from the head point.
+//
+// The path is taken only if the host can prove PCL's int32 overflow guard cannot fire inside the crop box.  A
+// surviving point with a NaN y or z (kept by the reference's predicate: only x is NaN-tested) would get a key that
+// depends on the cloud's min/max; such a frame raises an internal flag and the whole wave is redone by the generic
+// path (pcop_api.cu), so the result is always the reference's.
+#include <cmath>
+#include <cstdlib>
+
+#include "internal.cuh"
+#include "primitives.cuh"
+
+namespace pcop {
+
+namespace {
+
+constexpr int VF_MAX_BITS = 9;
+constexpr int VF_MAX_PASSES = 6;  // (digit-width experiments: 6 x 5 bits)
+constexpr int VF_MAX_BINS = 1 << VF_MAX_BITS;
+
+struct VfSmemA {
+  CompactSmem cs;
+  float shmm[CT_THREADS / 32][6];
+  uint32_t hist[VF_MAX_PASSES * VF_MAX_BINS];
+};
+
+// compare-based min/max: NaN never updates (oracle voxel_setup)
+struct VfMinMax {
+  float mn[3], mx[3];
+  __device__ void init() {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = 3.402823466e+38f;
+      mx[a] = -3.402823466e+38f;
+    }
+  }
+  __device__ void add(const float4 p) {
+    const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (v[a] < mn[a]) mn[a] = v[a];
+      if (v[a] > mx[a]) mx[a] = v[a];
+    }
+  }
+};
+
+__global__ void k_vf_init(MinMax* mm, uint32_t* __restrict__ flags, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < B) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mm[f].mn[a] = ORD_POS_FLT_MAX;
+      mm[f].mx[a] = ORD_NEG_FLT_MAX;
+    }
+    flags[f] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(CT_THREADS)
+    k_vf_crop_key(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
+                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ n_out,
+                  MinMax* __restrict__ minmax, uint32_t* __restrict__ hist, uint32_t* __restrict__ flags,
+                  unsigned* __restrict__ desc, int cap, int tiles) {
+  const int f = blockIdx.x, tile = blockIdx.y;  // frame-major dispatch: see run_voxel_fused
+  const int n = n_in[f];
+  if (tile * BT_TILE >= n) {
+    if (tile == 0 && threadIdx.x == 0) n_out[f] = 0;
+    return;
+  }
+  __shared__ VfSmemA sm;
+  const int nbins = 1 << pl.digit_bits;
+  for (int i = threadIdx.x; i < pl.npass * nbins; i += CT_THREADS) sm.hist[i] = 0u;
+  __syncthreads();
+  const float4* src = in + (size_t)f * in_stride;
+  unsigned keepmask = 0u;
+  uint32_t key[BT_ITEMS];
+  VfMinMax acc;
+  acc.init();
+  bool odd = false;  // a survivor whose y or z is not finite
+#pragma unroll
+  for (int k = 0; k < BT_ITEMS; ++k) {
+    const int i = bt_index<BT_ITEMS>(tile, k);
+    key[k] = 0u;
+    if (i < n) {
+      const float4 p = __ldg(src + i);
+      // od.cpp:197-199, literal: drop iff isnan(x) || x<x_min || x>x_max || z<z_min || z>z_max || y<y_min || y>y_max
+      const bool drop = (p.x != p.x) || p.x < pl.lim[0] || p.x > pl.lim[1] || p.z < pl.lim[4] || p.z > pl.lim[5] ||
+                        p.y < pl.lim[2] || p.y > pl.lim[3];
+      if (!drop) {
+        keepmask |= 1u << k;
+        acc.add(p);
+        odd = odd || !(fabsf(p.y) <= 3.0e38f) || !(fabsf(p.z) <= 3.0e38f);
+        const int cx = __float2int_rz(floorf(fmul(p.x, pl.inv))) - pl.b0[0];
+        const int cy = __float2int_rz(floorf(fmul(p.y, pl.inv))) - pl.b0[1];
+        const int cz = __float2int_rz(floorf(fmul(p.z, pl.inv))) - pl.b0[2];
+        const uint32_t kk = (uint32_t)cx + pl.nx * ((uint32_t)cy + pl.ny * (uint32_t)cz);
+        key[k] = kk;
+        for (int q = 0; q < pl.npass; ++q) atomicAdd(&sm.hist[q * nbins + ((kk >> (q * pl.digit_bits)) & (nbins - 1))], 1u);
+      }
+    }
+  }
+  if (__any_sync(FULL, odd) && lane_id() == 0) atomicOr(&flags[f], 1u);
+  unsigned wbase;
+  const unsigned incl_total = big_tile_scan<BT_ITEMS>(keepmask, desc + (size_t)f * tiles, tile, sm.cs, wbase);
+  uint32_t* kd = keys + (size_t)f * cap;
+  uint32_t* vd = vals + (size_t)f * cap;
+#pragma unroll
+  for (int k = 0; k < BT_ITEMS; ++k) {
+    const bool keep = (keepmask >> k) & 1u;
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) {
+      const unsigned pos = wbase + __popc(m & lanemask_lt());
+      kd[pos] = key[k];
+      vd[pos] = (uint32_t)bt_index<BT_ITEMS>(tile, k);
+    }
+    wbase += __popc(m);
+  }
+  if ((tile + 1) * BT_TILE >= n && threadIdx.x == 0) n_out[f] = (int)incl_total;
+  // min/max: block reduce + one atomic per axis per block
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      acc.mn[a] = fminf(acc.mn[a], __shfl_xor_sync(FULL, acc.mn[a], o));
+      acc.mx[a] = fmaxf(acc.mx[a], __shfl_xor_sync(FULL, acc.mx[a], o));
+    }
+  }
+  if (lane_id() == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      sm.shmm[warp_id()][a] = acc.mn[a];
+      sm.shmm[warp_id()][3 + a] = acc.mx[a];
+    }
+  }
+  __syncthreads();  // (also: all histogram atomics of the block are done)
+  if (threadIdx.x < 6) {
+    const int a = threadIdx.x;
+    float v = sm.shmm[0][a];
+    for (int w = 1; w < CT_THREADS / 32; ++w) v = (a < 3) ? fminf(v, sm.shmm[w][a]) : fmaxf(v, sm.shmm[w][a]);
+    if (a < 3) atomicMin(&minmax[f].mn[a], f2ord(v));
+    else atomicMax(&minmax[f].mx[a - 3], f2ord(v));
+  }
+  uint32_t* gh = hist + (size_t)f * VF_MAX_PASSES * VF_MAX_BINS;
+  for (int i = threadIdx.x; i < pl.npass * nbins; i += CT_THREADS) {
+    const uint32_t v = sm.hist[i];
+    if (v) atomicAdd(&gh[(i / nbins) * VF_MAX_BINS + (i % nbins)], v);
+  }
+}
+
+// exclusive scan of each (frame, pass) histogram, in place; 512 threads = VF_MAX_BINS
+__global__ void __launch_bounds__(VF_MAX_BINS) k_vf_scan(uint32_t* __restrict__ hist) {
+  const int f = blockIdx.y, p = blockIdx.x;
+  uint32_t* h = hist + ((size_t)f * VF_MAX_PASSES + p) * VF_MAX_BINS;
+  __shared__ uint32_t wsum[VF_MAX_BINS / 32];
+  const uint32_t v = h[threadIdx.x];
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(FULL, incl, o);
+    if (lane_id() >= o) incl += up;
+  }
+  if (lane_id() == 31) wsum[warp_id()] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int w = 0; w < warp_id(); ++w) wbase += wsum[w];
+  h[threadIdx.x] = wbase + incl - v;
+}
+
+template <int BITS>
+struct VfPassSmem {
+  static constexpr int BINS = 1 << BITS;
+  uint32_t warp_hist[RS_THREADS / 32][BINS];  // per-warp digit counts -> exclusive across warps
+  uint32_t tile_off[BINS + 1];                // exclusive scan of the tile histogram
+  uint32_t glob_base[BINS];                   // global output slot of the tile's first key of each digit
+  uint32_t skey[RS_TILE];
+  uint32_t sval[RS_TILE];
+  uint32_t wsum[RS_THREADS / 32];
+};
+
+// One LSD pass over 2048-key tiles; same scheme as radix_sort.cu's k_sort_pass (warp match_any multi-split ranks,
+// per-digit decoupled look-back over the tiles of the frame, tile staged in shared memory in sorted order,
+// coalesced run writes), digit width as a template parameter, pass count uniform over the frames.
+template <int BITS>
+__global__ void __launch_bounds__(RS_THREADS, 5)
+    k_vf_sort_pass(const uint32_t* __restrict__ key_in, const uint32_t* __restrict__ val_in, uint32_t* __restrict__ key_out,
+                   uint32_t* __restrict__ val_out, const int* __restrict__ count, const uint32_t* __restrict__ bin_base,
+                   uint32_t* __restrict__ desc, int pass, int shift, int cap, int tiles,
+                   unsigned long long* __restrict__ stats) {
+  constexpr int BINS = 1 << BITS;
+  constexpr int BPT = (BINS + RS_THREADS - 1) / RS_THREADS;  // bins per thread in the per-digit steps
+  const int f = blockIdx.x;
+  const int n = count[f];
+  const int tile = blockIdx.y;
+  const int tbase = tile * RS_TILE;
+  if (tbase >= n) return;
+  if (tile == 0 && threadIdx.x == 0 && stats) atomicAdd(stats, (unsigned long long)n);  // keys moved by sort passes
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  VfPassSmem<BITS>& sm = *reinterpret_cast<VfPassSmem<BITS>*>(smem_raw);
+  const int lane = lane_id(), warp = warp_id();
+  const uint32_t* kin = key_in + (size_t)f * cap;
+  const uint32_t* vin = val_in + (size_t)f * cap;
+  uint32_t* kout = key_out + (size_t)f * cap;
+  uint32_t* vout = val_out + (size_t)f * cap;
+
+  for (int i = threadIdx.x; i < (RS_THREADS / 32) * BINS; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0u;
+
+  uint32_t key[RS_ITEMS];
+  unsigned short rank[RS_ITEMS];
+  const int wbase_idx = tbase + warp * (32 * RS_ITEMS) + lane;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int i = wbase_idx + k * 32;
+    key[k] = (i < n) ? kin[i] : 0xffffffffu;
+  }
+  __syncthreads();
+  uint32_t* wh = sm.warp_hist[warp];
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const bool valid = (wbase_idx + k * 32) < n;
+    const uint32_t d = (key[k] >> shift) & (BINS - 1);
+    const unsigned m = __match_any_sync(FULL, valid ? d : (BINS + lane));  // invalid lanes match nobody
+    const int leader = __ffs(m) - 1;
+    uint32_t before = 0;
+    if (valid && lane == leader) before = atomicAdd(&wh[d], (uint32_t)__popc(m));
+    before = __shfl_sync(FULL, before, leader);
+    rank[k] = (unsigned short)(before + __popc(m & lanemask_lt()));
+  }
+  __syncthreads();
+
+  unsigned* dd_frame = desc + (((size_t)pass * gridDim.x + f) * tiles) * BINS;
+  // per digit: exclusive scan over the warps, tile count, early publish
+  uint32_t tile_count[BPT];
+  {
+    uint32_t thread_sum = 0;
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) {
+      const int d = threadIdx.x * BPT + b;  // consecutive digits per thread => the tile scan is a plain thread scan
+      uint32_t run = 0;
+      if (d < BINS) {
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) {
+          const uint32_t c = sm.warp_hist[w][d];
+          sm.warp_hist[w][d] = run;
+          run += c;
+        }
+        if (tile == 0) st_volatile_u32(dd_frame + d, LB_PREFIX | run);
+        else st_volatile_u32(dd_frame + (size_t)tile * BINS + d, LB_AGG | run);
+      }
+      tile_count[b] = run;
+      thread_sum += run;
+    }
+    uint32_t incl = thread_sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) sm.wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wb = 0;
+    for (int w = 0; w < warp; ++w) wb += sm.wsum[w];
+    uint32_t run = wb + incl - thread_sum;
+#pragma unroll
+    for (int b = 0; b < BPT; ++b) {
+      const int d = threadIdx.x * BPT + b;
+      if (d < BINS) sm.tile_off[d] = run;
+      run += tile_count[b];
+    }
+    if (threadIdx.x == RS_THREADS - 1) sm.tile_off[BINS] = run;
+  }
+  __syncthreads();
+
+  // stage the tile in sorted order (values are only loaded now, straight into shared memory)
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const int i = wbase_idx + k * 32;
+    if (i < n) {
+      const uint32_t d = (key[k] >> shift) & (BINS - 1);
+      const uint32_t p = sm.tile_off[d] + sm.warp_hist[warp][d] + rank[k];
+      sm.skey[p] = key[k];
+      sm.sval[p] = vin[i];
+    }
+  }
+  // decoupled look-back per digit over the earlier tiles of this frame
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) {
+    const int d = threadIdx.x * BPT + b;
+    if (d < BINS) {
+      uint32_t excl = 0;
+      if (tile > 0) {
+        unsigned* dd = dd_frame + d;
+        for (int t = tile - 1; t >= 0; --t) {
+          unsigned v = ld_volatile_u32(dd + (size_t)t * BINS);
+          while ((v >> 30) == 0u) v = ld_volatile_u32(dd + (size_t)t * BINS);
+          excl += v & LB_VALUE;
+          if ((v >> 30) == 2u) break;
+        }
+        st_volatile_u32(dd + (size_t)tile * BINS, LB_PREFIX | (excl + tile_count[b]));
+      }
+      sm.glob_base[d] = bin_base[((size_t)f * VF_MAX_PASSES + pass) * VF_MAX_BINS + d] + excl;
+    }
+  }
+  __syncthreads();
+  const int tile_n = min(RS_TILE, n - tbase);
+  for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+    const uint32_t kk = sm.skey[i];
+    const uint32_t d = (kk >> shift) & (BINS - 1);
+    const uint32_t g = sm.glob_base[d] + ((uint32_t)i - sm.tile_off[d]);
+    kout[g] = kk;
+    vout[g] = sm.sval[i];
+  }
+}
+
+// PCL's voxel frame from the min/max of the survivors (same arithmetic as stage_voxel.cu's k_voxel_setup; the host
+// has proven that the overflow guard cannot fire)
+__global__ void k_vf_setup(const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  VoxelFrame v;
+  v.inv = fdiv(1.0f, leaf);
+  unsigned div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float mn = ord2f(minmax[f].mn[a]), mx = ord2f(minmax[f].mx[a]);
+    v.min_b[a] = cvt_f2i(floorf(fmul(mn, v.inv)));
+    const int max_b = cvt_f2i(floorf(fmul(mx, v.inv)));
+    div_b[a] = (unsigned)max_b - (unsigned)v.min_b[a] + 1u;
+  }
+  v.overflow = 0;
+  v.mul1 = div_b[0];
+  v.mul2 = div_b[0] * div_b[1];
+  vf[f] = v;
+}
+
+struct VfSmemR {
+  CompactSmem cs;
+  uint32_t skey[CT_TILE + 1];  // [0] = key before the tile
+  float sx[CT_TILE], sy[CT_TILE], sz[CT_TILE];
+};
+
+__global__ void __launch_bounds__(CT_THREADS)
+    k_vf_reduce(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_sorted,
+                const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const VoxelFrame* __restrict__ vf,
+                float4* __restrict__ out, uint32_t* __restrict__ out_keys, int* __restrict__ n_out,
+                unsigned* __restrict__ desc, int cap, int tiles) {
+  const int f = blockIdx.x, tile = blockIdx.y;
+  const int m = n_sorted[f];
+  const int tbase = tile * CT_TILE;
+  if (tbase >= m) {
+    if (tile == 0 && threadIdx.x == 0) n_out[f] = 0;
+    return;
+  }
+  __shared__ VfSmemR sm;
+  const uint32_t* ks = keys + (size_t)f * cap;
+  const uint32_t* vs = vals + (size_t)f * cap;
+  const float4* src = in + (size_t)f * in_stride;
+  const int tile_n = min(CT_TILE, m - tbase);
+  // sorted (key, index) of the tile; the points gathered into shared memory in sorted order
+  for (int t = threadIdx.x; t < tile_n; t += CT_THREADS) {
+    sm.skey[t + 1] = ks[tbase + t];
+    const float4 p = __ldg(src + vs[tbase + t]);
+    sm.sx[t] = p.x;
+    sm.sy[t] = p.y;
+    sm.sz[t] = p.z;
+  }
+  if (threadIdx.x == 0) sm.skey[0] = (tbase > 0) ? ks[tbase - 1] : 0u;
+  __syncthreads();
+  bool keep[CT_ITEMS];
+  unsigned pos[CT_ITEMS];
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int t = warp_id() * (32 * CT_ITEMS) + k * 32 + lane_id();
+    keep[k] = t < tile_n && (tbase + t == 0 || sm.skey[t + 1] != sm.skey[t]);
+  }
+  const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm.cs);
+  const VoxelFrame v = vf[f];
+  const float fb0 = (float)v.min_b[0], fb1 = (float)v.min_b[1], fb2 = (float)v.min_b[2];
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    if (!keep[k]) continue;
+    const int t0 = warp_id() * (32 * CT_ITEMS) + k * 32 + lane_id();
+    const uint32_t kk = sm.skey[t0 + 1];
+    const float hx = sm.sx[t0], hy = sm.sy[t0], hz = sm.sz[t0];
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    int t = t0;
+    do {  // the run inside the tile
+      ax = fadd(ax, sm.sx[t]);
+      ay = fadd(ay, sm.sy[t]);
+      az = fadd(az, sm.sz[t]);
+      ++t;
+    } while (t < tile_n && sm.skey[t + 1] == kk);
+    int cnt = t - t0;
+    if (t == tile_n) {  // ... and its tail in the following tiles
+      for (int j = tbase + tile_n; j < m && ks[j] == kk; ++j) {
+        const float4 p = __ldg(src + vs[j]);
+        ax = fadd(ax, p.x);
+        ay = fadd(ay, p.y);
+        az = fadd(az, p.z);
+        ++cnt;
+      }
+    }
+    const float c = (float)cnt;
+    out[(size_t)f * cap + pos[k]] = make_float4(fdiv(ax, c), fdiv(ay, c), fdiv(az, c), 1.0f);
+    // PCL's key of this voxel, from its first point (voxel_grid.hpp: ijk = floor(p*inv) - min_b)
+    const int i0 = cvt_f2i(fsub(floorf(fmul(hx, v.inv)), fb0));
+    const int i1 = cvt_f2i(fsub(floorf(fmul(hy, v.inv)), fb1));
+    const int i2 = cvt_f2i(fsub(floorf(fmul(hz, v.inv)), fb2));
+    out_keys[(size_t)f * cap + pos[k]] = (uint32_t)i0 + (uint32_t)i1 * v.mul1 + (uint32_t)i2 * v.mul2;
+  }
+  if (tbase + CT_TILE >= m && threadIdx.x == 0) n_out[f] = (int)incl_total;
+}
+
+template <int BITS>
+void launch_pass(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
+  cudaFuncSetAttribute(k_vf_sort_pass<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VfPassSmem<BITS>));
+  const int src = pass & 1;
+  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
+      a.sort.key[src], a.sort.val[src], a.sort.key[src ^ 1], a.sort.val[src ^ 1], a.n_crop, a.sort.hist, a.sort.desc, pass,
+      shift, c.cap, gtiles, a.sort.stats));
+  count_launch(c);
+}
+
+}  // namespace
+
+VoxFusedPlan make_vox_fused_plan(const pcop_params& p) {
+  VoxFusedPlan pl{};
+  pl.ok = 0;
+  if (!p.enable_crop || !p.enable_voxel || !(p.downsample_size > 0.0f)) return pl;
+  const float lim[6] = {p.x_min, p.x_max, p.y_min, p.y_max, p.z_min, p.z_max};
+  const float inv = 1.0f / p.downsample_size;  // IEEE division, same value as the device's __fdiv_rn
+  long long cells[3];
+  for (int a = 0; a < 3; ++a) {
+    const float lo = lim[2 * a], hi = lim[2 * a + 1];
+    if (!(std::fabs(lo) <= 3.0e38f) || !(std::fabs(hi) <= 3.0e38f) || !(hi >= lo)) return pl;
+    const float flo = std::floor(lo * inv), fhi = std::floor(hi * inv);
+    if (!(std::fabs(flo) < 8388608.0f) || !(std::fabs(fhi) < 8388608.0f)) return pl;  // exact integer floats only
+    pl.b0[a] = (int)flo;
+    cells[a] = (long long)fhi - (long long)flo + 1;
+    pl.lim[2 * a] = lo;
+    pl.lim[2 * a + 1] = hi;
+  }
+  // PCL's guard: dx*dy*dz > INT32_MAX with d_a = int64((max_a - min_a) * inv) + 1 <= cells_a + 1 inside the box
+  const long double prod = (long double)(cells[0] + 1) * (long double)(cells[1] + 1) * (long double)(cells[2] + 1);
+  if (prod > 2147483647.0L) return pl;
+  pl.inv = inv;
+  pl.nx = (uint32_t)cells[0];
+  pl.ny = (uint32_t)cells[1];
+  pl.nz = (uint32_t)cells[2];
+  const unsigned long long total = (unsigned long long)cells[0] * cells[1] * cells[2];
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) < total) ++bits;
+  pl.bits = bits;
+  int max_digit = VF_MAX_BITS;
+  if (const char* s = getenv("PCOP_VF_BITS")) max_digit = std::min(VF_MAX_BITS, std::max(4, atoi(s)));  // tuning knob
+  pl.npass = (bits + max_digit - 1) / max_digit;
+  if (pl.npass > VF_MAX_PASSES) return pl;
+  pl.digit_bits = std::max(4, (bits + pl.npass - 1) / pl.npass);
+  pl.ok = 1;
+  return pl;
+}
+
+size_t vox_fused_hist_elems(int B) { return (size_t)B * VF_MAX_PASSES * VF_MAX_BINS; }
+size_t vox_fused_desc_bytes(int B, int cap) {
+  return (size_t)VF_MAX_PASSES * B * cdiv(cap, RS_TILE) * VF_MAX_BINS * sizeof(uint32_t);
+}
+
+// Launch geometry of the look-back kernels: blockIdx.x = frame, blockIdx.y = tile.  Blocks are dispatched x-fastest, so
+// tile t of every frame is in flight before any tile t+1: when a tile looks back, its predecessors in the SAME frame
+// were dispatched a whole row of frames earlier and have usually published their inclusive prefix already (look-back
+// depth ~ resident blocks / frames instead of ~ all tiles of the frame).  Lower tiles still have lower linear block
+// ids, which is what the look-back's forward-progress argument needs.
+void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
+  const VoxFusedPlan& pl = a.plan;
+  const int nbins = 1 << pl.digit_bits;
+  const int btiles = cdiv(c.cap, BT_TILE), gbtiles = cdiv(c.grid_cap, BT_TILE);
+  const int gtiles = cdiv(c.grid_cap, RS_TILE);
+  cudaMemsetAsync(a.desc, 0, (size_t)c.B * btiles * sizeof(unsigned), c.stream);
+  cudaMemsetAsync(a.sort.hist, 0, vox_fused_hist_elems(c.B) * sizeof(uint32_t), c.stream);
+  cudaMemsetAsync(a.sort.desc, 0, (size_t)pl.npass * c.B * gtiles * nbins * sizeof(uint32_t), c.stream);
+  KL(c, "k_vf_init", k_vf_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, c.B));
+  KL(c, "k_vf_crop_key", k_vf_crop_key<<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
+      a.in, a.in_stride, a.n_in, pl, a.sort.key[0], a.sort.val[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap,
+      btiles));
+  KL(c, "k_vf_scan", k_vf_scan<<<dim3(pl.npass, c.B), VF_MAX_BINS, 0, c.stream>>>(a.sort.hist));
+  KL(c, "k_vf_setup", k_vf_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.minmax, a.leaf, a.vf, c.B));
+  count_launch(c, 4);
+  for (int p = 0; p < pl.npass; ++p) {
+    const int shift = p * pl.digit_bits;
+    switch (pl.digit_bits) {
+      case 9: launch_pass<9>(c, a, p, shift, gtiles); break;
+      case 8: launch_pass<8>(c, a, p, shift, gtiles); break;
+      case 7: launch_pass<7>(c, a, p, shift, gtiles); break;
+      case 6: launch_pass<6>(c, a, p, shift, gtiles); break;
+      case 5: launch_pass<5>(c, a, p, shift, gtiles); break;
+      default: launch_pass<4>(c, a, p, shift, gtiles); break;
+    }
+  }
+  const int fin = pl.npass & 1;
+  const int tiles = cdiv(c.cap, CT_TILE), gt = cdiv(c.grid_cap, CT_TILE);
+  cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
+  KL(c, "k_vf_reduce", k_vf_reduce<<<dim3(c.B, gt), CT_THREADS, 0, c.stream>>>(
+      a.in, a.in_stride, a.n_crop, a.sort.key[fin], a.sort.val[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles));
+  count_launch(c);
+}
+
+}  // namespace pcop

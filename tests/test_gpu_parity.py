@@ -21,6 +21,17 @@ def ece_path(request, monkeypatch):
     return request.param
 
 
+@pytest.fixture(params=["voxfused", "voxgeneric"])
+def vox_path(request, monkeypatch):
+    """crop + VoxelGrid has a fused fast path (one pass over the input, keys relative to the crop box) and the generic
+    two-stage path; PCOP_VOXEL_FUSED=0 (read when the handle is created) forces the generic one."""
+    if request.param == "voxgeneric":
+        monkeypatch.setenv("PCOP_VOXEL_FUSED", "0")
+    else:
+        monkeypatch.delenv("PCOP_VOXEL_FUSED", raising=False)
+    return request.param
+
+
 def all_outputs(p):
     p = p.copy()
     p.outputs = abi.OUT_ALL
@@ -98,6 +109,39 @@ def test_stage_cluster_and_centroid(config, frames, ece_path):
     assert_bits_equal(g_off, of.cluster_offsets, "cluster offsets")
     assert_bits_equal(g_idx, of.cluster_indices, "cluster indices")
     assert_close(g_obs, of.obstacles, "obstacles")
+
+
+@pytest.mark.parametrize("config", [1, 2])
+def test_pipeline_voxel_paths(config, frames, vox_path):
+    """default outputs (no cropped cloud requested: the fused path does not materialise it) and all outputs"""
+    for outputs in (None, abi.OUT_ALL):
+        p = synth.params(config)
+        if outputs is not None:
+            p.outputs = outputs
+        cloud = frames[config]
+        with ObstacleProcessor(p, len(cloud)) as op:
+            g = op.process(cloud)
+        o = O.process(p, cloud)
+        compare_frames(g, o, p, f"config{config}/{vox_path}: ")
+
+
+def test_pipeline_survivor_with_nan_yz_redone_by_generic_path(frames):
+    """the reference's crop only NaN-tests x (od.cpp:197): a survivor with NaN y or z reaches VoxelGrid; the fused
+    fast path declines such a frame and the wave is redone by the generic path"""
+    p = all_outputs(synth.params(2))
+    n = synth.points_per_frame(2)
+    clouds = synth.frames(2, 200, 3).copy()
+    o_plain = O.process(p, clouds[1])
+    keep = np.flatnonzero(np.isin(np.arange(n), o_plain.crop_kept_idx))
+    clouds[1, keep[100], 1] = np.nan
+    clouds[1, keep[5000], 2] = np.nan
+    counts = np.full(3, n, np.int32)
+    with ObstacleProcessor(p, n, max_batch=3) as op:
+        res = op.process_batch(clouds, counts)
+    for f in range(3):
+        o = O.process(p, clouds[f])
+        compare_frames(res[f], o, p, f"frame{f}: ")
+    assert res[1].n_crop == o_plain.n_crop
 
 
 @pytest.mark.parametrize("config", [1, 2, 3, 4])
@@ -249,3 +293,21 @@ def test_cluster_many_small_clusters(n_groups, per_group, ece_path):
     assert_bits_equal(g_idx, o_idx, "indices")
     assert_close(g_obs, O.centroid_radius(cloud, o_off, o_idx), "obstacles")
     assert len(o_off) - 1 >= n_groups * 0.8
+
+
+def test_batch_over_two_lanes():
+    """max_batch = 16 gives two lanes of 8 frames; 20 frames = three waves dealt round-robin to the lanes
+    (one host thread and stream per lane)"""
+    p = all_outputs(synth.params(2))
+    n = synth.points_per_frame(2)
+    B = 20
+    clouds = synth.frames(2, 100, B)
+    counts = np.full(B, n, np.int32)
+    counts[3] = 70000
+    counts[17] = 0
+    with ObstacleProcessor(p, n, max_batch=16) as op:
+        for _ in range(2):  # second call reuses the lanes' buffers
+            res = op.process_batch(clouds, counts)
+    for f in range(B):
+        o = O.process(p, clouds[f, :counts[f]])
+        compare_frames(res[f], o, p, f"frame{f}: ")
