@@ -139,7 +139,8 @@ struct VoxelFusedArgs {
   float leaf;
   MinMax* minmax;    // [B] min/max of the crop survivors
   VoxelFrame* vf;    // [B]
-  SortBufs sort;     // hist: vox_fused_hist_elems, desc: vox_fused_desc_bytes
+  SortBufs sort;     // hist: vox_fused_hist_elems, desc: vox_fused_desc_bytes (key/val arrays unused)
+  unsigned long long* pair[2];  // [B*cap] ping-pong (key << 32) | original index
   unsigned* desc;    // compaction descriptors
   uint32_t* flags;   // [B] bit 0: the frame needs the generic path (a survivor with a non-finite y or z)
   int* n_crop;       // [B] out: M

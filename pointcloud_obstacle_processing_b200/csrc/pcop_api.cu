@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -111,7 +112,10 @@ struct pcop_handle {
   int* d_rng = nullptr;
   int* d_pack_off = nullptr;  // [PK_N][maxB]
   PackMeta* d_meta = nullptr;
-  unsigned char* d_pack = nullptr;
+  unsigned char* d_pack = nullptr;  // two halves of pack_cap bytes: wave k of a call packs into half k & 1
+  cudaStream_t cstream = nullptr;   // result copies (device -> pinned host) run here, beside the next wave's kernels
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  int wave_seq = 0;                 // waves of the running call seen by this lane
   size_t pack_cap = 0;
   uint32_t alloc_outputs = 0;
 
@@ -141,6 +145,7 @@ struct pcop_handle {
   // and one stream per lane, so one lane's host synchronisations and result copies overlap the other lanes' kernels
   VoxFusedPlan vplan{};            // fused crop + voxel fast path (ok = 0: not applicable to these parameters)
   uint32_t* d_vf_flags = nullptr;  // [maxB]
+  unsigned long long* d_vf_pair[2] = {nullptr, nullptr};
   uint32_t* h_vf_flags = nullptr;
   bool force_generic = false;      // set while a wave is redone by the generic path
   bool wave_used_fused = false;
@@ -258,10 +263,11 @@ int halloc(pcop_handle* h, T** p, size_t n) {
 int ensure_pack_capacity(pcop_handle* h, uint32_t mask) {
   const size_t need = pack_capacity_bytes(mask, h->maxB, h->cap);
   if (need <= h->pack_cap) return PCOP_OK;
+  if (h->cstream) cudaStreamSynchronize(h->cstream);
   if (h->d_pack) cudaFree(h->d_pack);  // not tracked in dev_allocs
   h->d_pack = nullptr;
   h->pack_cap = 0;
-  cudaError_t e = cudaMalloc((void**)&h->d_pack, need);
+  cudaError_t e = cudaMalloc((void**)&h->d_pack, 2 * need);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaMalloc(pack)", __FILE__, __LINE__);
   h->pack_cap = need;
   return PCOP_OK;
@@ -274,6 +280,7 @@ int ensure_host_pack(pcop_handle* h, size_t need) {
   unsigned char* q = nullptr;
   cudaError_t e = cudaHostAlloc((void**)&q, ncap, cudaHostAllocDefault);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(pack)", __FILE__, __LINE__);
+  if (h->cstream) cudaStreamSynchronize(h->cstream);  // copies into the old buffer must have landed
   if (h->h_pack) {
     memcpy(q, h->h_pack, h->h_pack_cap);
     cudaFreeHost(h->h_pack);
@@ -381,15 +388,32 @@ __global__ void k_pack_scan(const int* __restrict__ counts, int maxB, int B, uin
   }
 }
 
-template <class T>
+struct PackSrc {
+  const uint32_t* src[PK_N];  // nullptr: not requested
+  unsigned long long frame_stride_words[PK_N];
+  int count_row[PK_N];
+  int words_per_elem[PK_N];
+};
+
+// all requested output arrays of all frames of the wave in one launch: blockIdx.z = array, blockIdx.y = frame;
+// everything is moved as 32-bit words (the 16-byte arrays as uint4)
 __global__ void __launch_bounds__(256)
-    k_pack(const T* __restrict__ src, size_t frame_stride, const int* __restrict__ count, const int* __restrict__ pack_off,
-           const PackMeta* __restrict__ meta, int which, unsigned char* __restrict__ pack) {
-  const int f = blockIdx.y;
-  const int n = count[f];
-  T* dst = reinterpret_cast<T*>(pack + meta->base[which]) + pack_off[f];
-  const T* s = src + (size_t)f * frame_stride;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = s[i];
+    k_pack(PackSrc ps, const int* __restrict__ counts, int maxB, const int* __restrict__ pack_off,
+           const PackMeta* __restrict__ meta, unsigned char* __restrict__ pack) {
+  const int which = blockIdx.z, f = blockIdx.y;
+  const uint32_t* base = ps.src[which];
+  if (!base) return;
+  const int wpe = ps.words_per_elem[which];
+  const int n = counts[(size_t)ps.count_row[which] * maxB + f];
+  const uint32_t* s = base + (size_t)f * ps.frame_stride_words[which];
+  uint32_t* dst = reinterpret_cast<uint32_t*>(pack + meta->base[which]) + (size_t)pack_off[(size_t)which * maxB + f] * wpe;
+  if (wpe == 4) {  // 16-byte elements; bases are 256-byte aligned and offsets are whole elements
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = s[i];
+  }
 }
 
 struct StageTimer {
@@ -603,6 +627,8 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
     a.minmax = h->d_minmax;
     a.vf = h->d_vf;
     a.sort = h->sort;
+    a.pair[0] = h->d_vf_pair[0];
+    a.pair[1] = h->d_vf_pair[1];
     a.desc = h->d_desc;
     a.flags = h->d_vf_flags;
     a.n_crop = h->cnt(CNT_CROP);
@@ -693,6 +719,9 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   pcop_frame_result* out = out_all + w0;
   Ctx c = make_ctx(h, B);
   StageTimer t(h, PCOP_STAGE_D2H);
+  const int half = h->wave_seq & 1;
+  unsigned char* d_pack = h->d_pack + (size_t)half * h->pack_cap;
+  if (h->wave_seq >= 2) PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied[half], 0));  // half is free again
   KL(c, "k_plane_record", k_plane_record<<<cdiv(B, 128), 128, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS),
                                                       h->cnt(CNT_CLUS1), h->params.enable_plane ? 1 : 0, B));
   KL(c, "k_pack_scan", k_pack_scan<<<1, 320, 0, h->stream>>>(h->d_counts, h->maxB, B, mask, h->d_pack_off, h->d_meta));
@@ -701,17 +730,21 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
                             h->d_rem,       h->d_rem_src,  h->d_offsets, h->d_indices,  h->d_obst};
   const size_t strides[PK_N] = {(size_t)h->cap, (size_t)h->cap, (size_t)h->cap,     (size_t)h->cap, (size_t)h->cap,
                                 (size_t)h->cap, (size_t)h->cap, (size_t)h->cap + 1, (size_t)h->cap, (size_t)h->cap};
-  const int gx = std::min(cdiv(h->cap, 256), 64);
-  for (int k = 0; k < PK_N; ++k) {
-    if (!(mask & kPkMask[k])) continue;
-    const int* cnt = h->cnt(kPkCount[k]);
-    const int* off = h->d_pack_off + (size_t)k * h->maxB;
-    if (kPkElem[k] == 16)
-      KL(c, "k_pack", k_pack<float4><<<dim3(gx, B), 256, 0, h->stream>>>((const float4*)srcs[k], strides[k], cnt, off, h->d_meta, k,
-                                                         h->d_pack));
-    else
-      KL(c, "k_pack", k_pack<int><<<dim3(gx, B), 256, 0, h->stream>>>((const int*)srcs[k], strides[k], cnt, off, h->d_meta, k, h->d_pack));
-    count_launch(c);
+  {
+    PackSrc ps{};
+    bool any = false;
+    for (int k = 0; k < PK_N; ++k) {
+      ps.src[k] = (mask & kPkMask[k]) ? (const uint32_t*)srcs[k] : nullptr;
+      ps.frame_stride_words[k] = (unsigned long long)strides[k] * (kPkElem[k] / 4);
+      ps.count_row[k] = kPkCount[k];
+      ps.words_per_elem[k] = kPkElem[k] / 4;
+      any = any || ps.src[k];
+    }
+    if (any) {
+      const int gx = std::max(1, std::min(cdiv(c.grid_cap, 256 * 4), 16));
+      KL(c, "k_pack", k_pack<<<dim3(gx, B, PK_N), 256, 0, h->stream>>>(ps, h->d_counts, h->maxB, h->d_pack_off, h->d_meta, d_pack));
+      count_launch(c);
+    }
   }
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int) * CNT_ROWS * h->maxB, cudaMemcpyDeviceToHost,
                                 h->stream));
@@ -727,10 +760,12 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   const PackMeta meta = *h->h_meta;
   const size_t base_off = (*h_pack_used + 255) & ~(size_t)255;
   TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
-  if (meta.total_bytes) {
-    PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, h->d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->stream));
-  }
-  // the second sync happens in the caller after the stage-timer event is recorded
+  // payload copy on the copy stream (the pack kernels have finished: the stream was just synchronised); the lane's
+  // next wave starts right away and only waits for this copy before it packs into the same half again
+  if (meta.total_bytes)
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->cstream));
+  PCOP_CUDA_TRY(cudaEventRecord(h->ev_copied[half], h->cstream));
+  ++h->wave_seq;
   *h_pack_used = base_off + meta.total_bytes;
 
   size_t run[PK_N] = {0};
@@ -791,10 +826,12 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   return PCOP_OK;
 }
 
-// Runs the waves wave_first, wave_first + wave_step, ... of a call on lane h (waves are `wave` frames each).
+// Runs the given waves of a call on lane h, in order.
 // Blocks until the lane's results are in its pinned host buffer; fills out[] (pointers fixed up at the end).
-int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n, int32_t batch,
-                  pcop_frame_result* out, int wave, int wave_first, int wave_step, bool on_device, uint32_t mask) {
+typedef std::vector<std::pair<int, int>> WaveList;  // (first frame, frames)
+
+int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n,
+                  pcop_frame_result* out, const WaveList& waves, bool on_device, uint32_t mask) {
   PCOP_CUDA_TRY(cudaSetDevice(h->device));
   h->launches = 0;
   h->alg_bytes = 0.0;
@@ -804,8 +841,9 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
   for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] = 0.f;
   size_t h_pack_used = 0;
   h->fixups.clear();
-  for (int w0 = wave_first * wave; w0 < batch; w0 += wave_step * wave) {
-    const int B = std::min(wave, batch - w0);
+  h->wave_seq = 0;
+  for (const std::pair<int, int>& wv : waves) {
+    const int w0 = wv.first, B = wv.second;
     for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_used[s] = false;
     const float4* in;
     size_t stride;
@@ -835,7 +873,10 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
     }
     int max_n = 1;
     for (int f = 0; f < B; ++f) max_n = std::max(max_n, (int)n[w0 + f]);
+    const bool trace = getenv("PCOP_TRACE") != nullptr;
+    const auto tt0 = std::chrono::steady_clock::now();
     TRY(run_wave_stages(h, B, in, stride, max_n));
+    const auto tt1 = std::chrono::steady_clock::now();
     int cst = collect_wave(h, B, mask, &h_pack_used, out, w0, &h->fixups);
     if (cst == PCOP_INTERNAL_REDO_GENERIC) {
       h->force_generic = true;
@@ -845,6 +886,16 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
     }
     TRY(cst);
     PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (trace) {
+      const auto tt2 = std::chrono::steady_clock::now();
+      cudaStreamSynchronize(h->cstream);
+      const auto tt3 = std::chrono::steady_clock::now();
+      auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
+      };
+      fprintf(stderr, "[pcop trace] lane %p wave %d+%d: stages(host, incl. plane syncs) %ld us, collect %ld us, copy tail %ld us\n",
+              (void*)h, w0, B, us(tt0, tt1), us(tt1, tt2), us(tt2, tt3));
+    }
     for (int s = 0; s < PCOP_N_STAGES; ++s) {
       if (!h->stage_used[s]) continue;
       float ms = 0.f;
@@ -853,6 +904,8 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
     resolve_kernel_timers(h);
   }
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_stats, h->sort.stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaEventRecord(h->ev_lane_done, h->cstream));
+  PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_lane_done, 0));  // the lane is done when its last result copy is
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_lane_done, h->stream));
   PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_lane_done));
   h->sort_pass_keys = *h->h_stats;
@@ -905,10 +958,33 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   // lanes used by this call: per-kernel timing needs each kernel alone on the GPU, so it serialises the lanes
   int n_lanes = 1 + (int)h->extra_lanes.size();
   if (h->kt.enabled) n_lanes = 1;
-  int wave = h->maxB;
-  if (n_lanes > 1) {
-    wave = std::min(h->maxB, std::max(PCOP_MIN_LANE_WAVE, (batch + n_lanes - 1) / n_lanes));
-    n_lanes = std::min(n_lanes, std::max(1, (batch + wave - 1) / wave));
+  n_lanes = std::max(1, std::min(n_lanes, batch / PCOP_MIN_LANE_WAVE));
+  // waves per lane (PCOP_WAVES_PER_LANE): larger waves run the kernels more efficiently, more waves overlap a
+  // wave's result copy with the lane's next wave
+  int wpl = 1;
+  if (const char* sv = getenv("PCOP_WAVES_PER_LANE")) wpl = (int)std::min<long>(std::max<long>(strtol(sv, nullptr, 10), 1), 16);
+  std::vector<WaveList> plan(n_lanes);
+  if (n_lanes > 1 && wpl == 1 && batch <= (h->maxB * n_lanes * 4) / 5) {
+    // one wave per lane, of growing size (weights 1 .. 1.5): the lanes share the GPU, finish one after the other,
+    // and every result copy but the last overlaps the kernels of the lanes still running
+    double wsum = 0.0;
+    for (int l = 0; l < n_lanes; ++l) wsum += 1.0 + 0.5 * l / (n_lanes - 1);
+    int w0 = 0;
+    for (int l = 0; l < n_lanes; ++l) {
+      int B = (l + 1 == n_lanes) ? batch - w0 : (int)((1.0 + 0.5 * l / (n_lanes - 1)) / wsum * batch);
+      B = std::min(B, h->maxB);
+      if (B > 0) plan[l].push_back({w0, B});
+      w0 += B;
+    }
+    for (int l = 0; w0 < batch; l = (l + 1) % n_lanes) {  // leftovers (capacity clamps)
+      const int B = std::min(h->maxB, batch - w0);
+      plan[l].push_back({w0, B});
+      w0 += B;
+    }
+  } else {
+    const int wave = std::min(h->maxB, std::max(PCOP_MIN_LANE_WAVE, (batch + n_lanes * wpl - 1) / (n_lanes * wpl)));
+    int l = 0;
+    for (int w0 = 0; w0 < batch; w0 += wave, l = (l + 1) % n_lanes) plan[l].push_back({w0, std::min(wave, batch - w0)});
   }
   std::vector<pcop_handle*> lanes(1, h);
   for (int l = 1; l < n_lanes; ++l) lanes.push_back(h->extra_lanes[l - 1]);
@@ -923,9 +999,9 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   std::vector<std::thread> workers;
   for (int l = 1; l < n_lanes; ++l)
     workers.emplace_back([&, l]() {
-      status[l] = process_waves(lanes[l], xyzw, frame_stride_points, n, batch, out, wave, l, n_lanes, on_device, mask);
+      status[l] = process_waves(lanes[l], xyzw, frame_stride_points, n, out, plan[l], on_device, mask);
     });
-  status[0] = process_waves(h, xyzw, frame_stride_points, n, batch, out, wave, 0, n_lanes, on_device, mask);
+  status[0] = process_waves(h, xyzw, frame_stride_points, n, out, plan[0], on_device, mask);
   for (std::thread& t : workers) t.join();
   for (int l = 0; l < n_lanes; ++l)
     if (status[l] != PCOP_OK) {
@@ -1118,6 +1194,8 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
     h->sort.desc = (uint32_t*)d;
   }
   A(dalloc(h, &h->d_vf_flags, B));
+  A(dalloc(h, &h->d_vf_pair[0], BC));
+  A(dalloc(h, &h->d_vf_pair[1], BC));
   A(halloc(h, &h->h_vf_flags, B));
   A(dalloc(h, &h->sort.maxkey, B));
   A(dalloc(h, &h->sort.npass, B));
@@ -1162,6 +1240,11 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
         return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
   if ((e = cudaEventCreateWithFlags(&h->ev_lane_done, cudaEventDisableTiming)) != cudaSuccess)
     return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
+  if ((e = cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(fail_cuda(h, e, "cudaStreamCreate", __FILE__, __LINE__));
+  for (int i = 0; i < 2; ++i)
+    if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess)
+      return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
   st = ensure_pack_capacity(h, effective_outputs(h->params));
   if (st != PCOP_OK) return bail(st);
   *out = h;
@@ -1176,7 +1259,8 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   int n_lanes = 2;
   if (const char* s = getenv("PCOP_LANES")) n_lanes = (int)std::min<long>(std::max<long>(strtol(s, nullptr, 10), 1), 8);
   n_lanes = std::max(1, std::min(n_lanes, max_batch / PCOP_MIN_LANE_WAVE));
-  const int lane_batch = (max_batch + n_lanes - 1) / n_lanes;
+  // capacity of a lane: 5/4 of an even share, so that one call of max_batch frames can be dealt in uneven waves
+  const int lane_batch = n_lanes == 1 ? max_batch : std::min(max_batch, ((max_batch + n_lanes - 1) / n_lanes * 5 + 3) / 4);
   pcop_handle* h = nullptr;
   int st = create_lane(params, device, max_points, lane_batch, &h);
   if (st != PCOP_OK) return st;
@@ -1199,6 +1283,7 @@ void pcop_destroy(pcop_handle* h) {
   h->extra_lanes.clear();
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->cstream) cudaStreamSynchronize(h->cstream);
   for (void* p : h->dev_allocs) cudaFree(p);
   for (void* p : h->host_allocs) cudaFreeHost(p);
   if (h->d_pack) cudaFree(h->d_pack);
@@ -1210,6 +1295,9 @@ void pcop_destroy(pcop_handle* h) {
   for (int i = 0; i < 2; ++i)
     if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
   if (h->ev_lane_done) cudaEventDestroy(h->ev_lane_done);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+  if (h->cstream) cudaStreamDestroy(h->cstream);
   for (int s = 0; s < PCOP_N_STAGES; ++s)
     for (int i = 0; i < 2; ++i)
       if (h->ev_stage[s][i]) cudaEventDestroy(h->ev_stage[s][i]);

@@ -111,7 +111,80 @@ __global__ void __launch_bounds__(32)
   int t = 0;
   int nh = 0;
   int gen_end = 0;
-  if (n < 3) {
+  // Fast path: the draws never depend on the points unless a sample fails isSampleGood (collinear, rare).  So first
+  // replay the index draws of all hypotheses assuming every first draw is good (no memory traffic), then let the
+  // lanes fetch and fit the hypotheses in parallel; one bad sample sends the frame through the sequential replay
+  // below, which is PCL's loop verbatim.
+  __shared__ int trip[MAX_HYP][3];
+  bool fast_done = false;
+  const int want = min(pc.max_iterations + 1, MAX_HYP);
+  if (n >= 3 && 3 * want <= RNG_TABLE && 3 * want <= MAP_CAP) {
+    __shared__ int srng[3 * MAX_HYP];  // the random numbers of the fast path, fetched by all lanes at once
+    for (int k = lane; k < 3 * want; k += 32) srng[k] = rng[k];
+    __syncwarp();
+    for (int h = 0; h < want; ++h) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int r = srng[t++];
+        const int j = i + (int)((unsigned)r % (unsigned)(n - i));
+        const int vi = s[i];
+        if (j < 3) {
+          const int vj = (j == 0) ? s[0] : ((j == 1) ? s[1] : s[2]);
+          if (j == 0) s[0] = vi;
+          else if (j == 1) s[1] = vi;
+          else s[2] = vi;
+          s[i] = vj;
+        } else {
+          int found = -1;
+          for (int e = lane; e < ne; e += 32)
+            if (mpos[e] == j) found = e;
+          const unsigned b = __ballot_sync(FULL, found >= 0);
+          int vj = j;
+          if (b) {
+            const int idx = __shfl_sync(FULL, found, __ffs(b) - 1);
+            vj = mval[idx];
+            __syncwarp();
+            if (lane == 0) mval[idx] = vi;
+          } else {
+            if (lane == 0) {
+              mpos[ne] = j;
+              mval[ne] = vi;
+            }
+            ++ne;
+          }
+          __syncwarp();
+          s[i] = vj;
+        }
+      }
+      if (lane < 3) trip[h][lane] = (lane == 0) ? s[0] : ((lane == 1) ? s[1] : s[2]);
+    }
+    __syncwarp();
+    bool bad = false;
+    for (int h = lane; h < want; h += 32) {
+      const float4 p0 = pts[trip[h][0]], p1 = pts[trip[h][1]], p2 = pts[trip[h][2]];
+      if (collinear_ratio_test(p0, p1, p2)) {
+        bad = true;
+      } else {
+        const float4 co = compute_model(p0, p1, p2);
+        P.hyp[h] = co;
+        P.hyp_valid[h] = model_valid(pc, co) ? 1 : 0;
+      }
+    }
+    if (!__any_sync(FULL, bad)) {
+      fast_done = true;
+      nh = want;
+    } else {  // restart from PCL's initial state
+      ne = 0;
+      s[0] = 0;
+      s[1] = 1;
+      s[2] = 2;
+      t = 0;
+    }
+    __syncwarp();
+  }
+  if (fast_done) {
+    // nothing left to do
+  } else   if (n < 3) {
     gen_end = 1;  // getSamples: fewer points than the sample size -> empty selection
   } else {
     while (nh <= pc.max_iterations && nh < MAX_HYP) {

@@ -77,7 +77,7 @@ __global__ void k_vf_init(MinMax* mm, uint32_t* __restrict__ flags, int B) {
 
 __global__ void __launch_bounds__(CT_THREADS)
     k_vf_crop_key(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
-                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ n_out,
+                  unsigned long long* __restrict__ pairs, int* __restrict__ n_out,
                   MinMax* __restrict__ minmax, uint32_t* __restrict__ hist, uint32_t* __restrict__ flags,
                   unsigned* __restrict__ desc, int cap, int tiles) {
   const int f = blockIdx.x, tile = blockIdx.y;  // frame-major dispatch: see run_voxel_fused
@@ -121,16 +121,14 @@ __global__ void __launch_bounds__(CT_THREADS)
   if (__any_sync(FULL, odd) && lane_id() == 0) atomicOr(&flags[f], 1u);
   unsigned wbase;
   const unsigned incl_total = big_tile_scan<BT_ITEMS>(keepmask, desc + (size_t)f * tiles, tile, sm.cs, wbase);
-  uint32_t* kd = keys + (size_t)f * cap;
-  uint32_t* vd = vals + (size_t)f * cap;
+  unsigned long long* pd = pairs + (size_t)f * cap;  // (key << 32) | original index
 #pragma unroll
   for (int k = 0; k < BT_ITEMS; ++k) {
     const bool keep = (keepmask >> k) & 1u;
     const unsigned m = __ballot_sync(FULL, keep);
     if (keep) {
       const unsigned pos = wbase + __popc(m & lanemask_lt());
-      kd[pos] = key[k];
-      vd[pos] = (uint32_t)bt_index<BT_ITEMS>(tile, k);
+      pd[pos] = ((unsigned long long)key[k] << 32) | (unsigned long long)(uint32_t)bt_index<BT_ITEMS>(tile, k);
     }
     wbase += __popc(m);
   }
@@ -190,19 +188,21 @@ struct VfPassSmem {
   static constexpr int BINS = 1 << BITS;
   uint32_t warp_hist[RS_THREADS / 32][BINS];  // per-warp digit counts -> exclusive across warps
   uint32_t tile_off[BINS + 1];                // exclusive scan of the tile histogram
-  uint32_t glob_base[BINS];                   // global output slot of the tile's first key of each digit
-  uint32_t skey[RS_TILE];
-  uint32_t sval[RS_TILE];
+  uint32_t glob_base[BINS];                   // global output slot minus staged position, per digit
+  unsigned long long spair[RS_TILE];
   uint32_t wsum[RS_THREADS / 32];
 };
 
 // One LSD pass over 2048-key tiles; same scheme as radix_sort.cu's k_sort_pass (warp match_any multi-split ranks,
 // per-digit decoupled look-back over the tiles of the frame, tile staged in shared memory in sorted order,
 // coalesced run writes), digit width as a template parameter, pass count uniform over the frames.
+#ifndef VF_SORT_MINBLOCKS
+#define VF_SORT_MINBLOCKS 5
+#endif
 template <int BITS>
-__global__ void __launch_bounds__(RS_THREADS, 5)
-    k_vf_sort_pass(const uint32_t* __restrict__ key_in, const uint32_t* __restrict__ val_in, uint32_t* __restrict__ key_out,
-                   uint32_t* __restrict__ val_out, const int* __restrict__ count, const uint32_t* __restrict__ bin_base,
+__global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
+    k_vf_sort_pass(const unsigned long long* __restrict__ pair_in, unsigned long long* __restrict__ pair_out,
+                   const int* __restrict__ count, const uint32_t* __restrict__ bin_base,
                    uint32_t* __restrict__ desc, int pass, int shift, int cap, int tiles,
                    unsigned long long* __restrict__ stats) {
   constexpr int BINS = 1 << BITS;
@@ -216,28 +216,36 @@ __global__ void __launch_bounds__(RS_THREADS, 5)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VfPassSmem<BITS>& sm = *reinterpret_cast<VfPassSmem<BITS>*>(smem_raw);
   const int lane = lane_id(), warp = warp_id();
-  const uint32_t* kin = key_in + (size_t)f * cap;
-  const uint32_t* vin = val_in + (size_t)f * cap;
-  uint32_t* kout = key_out + (size_t)f * cap;
-  uint32_t* vout = val_out + (size_t)f * cap;
+  const unsigned long long* pin = pair_in + (size_t)f * cap;
+  unsigned long long* pout = pair_out + (size_t)f * cap;
 
   for (int i = threadIdx.x; i < (RS_THREADS / 32) * BINS; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0u;
 
-  uint32_t key[RS_ITEMS];
+  unsigned long long pr[RS_ITEMS];  // (key << 32) | index: one 8-byte load / store per element
   unsigned short rank[RS_ITEMS];
   const int wbase_idx = tbase + warp * (32 * RS_ITEMS) + lane;
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     const int i = wbase_idx + k * 32;
-    key[k] = (i < n) ? kin[i] : 0xffffffffu;
+    pr[k] = (i < n) ? pin[i] : ~0ull;
   }
   __syncthreads();
+  // rank keys inside the warp, row by row => stable.  All match masks first (independent, so their latencies
+  // overlap), then one shared atomic per distinct digit of a row (issued by the lowest lane of the match group);
+  // its return value is the group's base, broadcast by shuffle.
   uint32_t* wh = sm.warp_hist[warp];
+  unsigned mm[RS_ITEMS];
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     const bool valid = (wbase_idx + k * 32) < n;
-    const uint32_t d = (key[k] >> shift) & (BINS - 1);
-    const unsigned m = __match_any_sync(FULL, valid ? d : (BINS + lane));  // invalid lanes match nobody
+    const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
+    mm[k] = __match_any_sync(FULL, valid ? d : (BINS + lane));  // invalid lanes match nobody
+  }
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const bool valid = (wbase_idx + k * 32) < n;
+    const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
+    const unsigned m = mm[k];
     const int leader = __ffs(m) - 1;
     uint32_t before = 0;
     if (valid && lane == leader) before = atomicAdd(&wh[d], (uint32_t)__popc(m));
@@ -289,15 +297,14 @@ __global__ void __launch_bounds__(RS_THREADS, 5)
   }
   __syncthreads();
 
-  // stage the tile in sorted order (values are only loaded now, straight into shared memory)
+  // stage the tile in sorted order
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     const int i = wbase_idx + k * 32;
     if (i < n) {
-      const uint32_t d = (key[k] >> shift) & (BINS - 1);
+      const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
       const uint32_t p = sm.tile_off[d] + sm.warp_hist[warp][d] + rank[k];
-      sm.skey[p] = key[k];
-      sm.sval[p] = vin[i];
+      sm.spair[p] = pr[k];
     }
   }
   // decoupled look-back per digit over the earlier tiles of this frame
@@ -316,17 +323,16 @@ __global__ void __launch_bounds__(RS_THREADS, 5)
         }
         st_volatile_u32(dd + (size_t)tile * BINS, LB_PREFIX | (excl + tile_count[b]));
       }
-      sm.glob_base[d] = bin_base[((size_t)f * VF_MAX_PASSES + pass) * VF_MAX_BINS + d] + excl;
+      // (global slot of the digit's first key in this tile) - (its position in the staged tile)
+      sm.glob_base[d] = bin_base[((size_t)f * VF_MAX_PASSES + pass) * VF_MAX_BINS + d] + excl - sm.tile_off[d];
     }
   }
   __syncthreads();
   const int tile_n = min(RS_TILE, n - tbase);
   for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
-    const uint32_t kk = sm.skey[i];
-    const uint32_t d = (kk >> shift) & (BINS - 1);
-    const uint32_t g = sm.glob_base[d] + ((uint32_t)i - sm.tile_off[d]);
-    kout[g] = kk;
-    vout[g] = sm.sval[i];
+    const unsigned long long pp = sm.spair[i];
+    const uint32_t d = ((uint32_t)(pp >> 32) >> shift) & (BINS - 1);
+    pout[sm.glob_base[d] + (uint32_t)i] = pp;
   }
 }
 
@@ -359,7 +365,7 @@ struct VfSmemR {
 
 __global__ void __launch_bounds__(CT_THREADS)
     k_vf_reduce(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_sorted,
-                const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const VoxelFrame* __restrict__ vf,
+                const unsigned long long* __restrict__ pairs, const VoxelFrame* __restrict__ vf,
                 float4* __restrict__ out, uint32_t* __restrict__ out_keys, int* __restrict__ n_out,
                 unsigned* __restrict__ desc, int cap, int tiles) {
   const int f = blockIdx.x, tile = blockIdx.y;
@@ -370,19 +376,19 @@ __global__ void __launch_bounds__(CT_THREADS)
     return;
   }
   __shared__ VfSmemR sm;
-  const uint32_t* ks = keys + (size_t)f * cap;
-  const uint32_t* vs = vals + (size_t)f * cap;
+  const unsigned long long* ps = pairs + (size_t)f * cap;
   const float4* src = in + (size_t)f * in_stride;
   const int tile_n = min(CT_TILE, m - tbase);
   // sorted (key, index) of the tile; the points gathered into shared memory in sorted order
   for (int t = threadIdx.x; t < tile_n; t += CT_THREADS) {
-    sm.skey[t + 1] = ks[tbase + t];
-    const float4 p = __ldg(src + vs[tbase + t]);
+    const unsigned long long pp = ps[tbase + t];
+    sm.skey[t + 1] = (uint32_t)(pp >> 32);
+    const float4 p = __ldg(src + (uint32_t)pp);
     sm.sx[t] = p.x;
     sm.sy[t] = p.y;
     sm.sz[t] = p.z;
   }
-  if (threadIdx.x == 0) sm.skey[0] = (tbase > 0) ? ks[tbase - 1] : 0u;
+  if (threadIdx.x == 0) sm.skey[0] = (tbase > 0) ? (uint32_t)(ps[tbase - 1] >> 32) : 0u;
   __syncthreads();
   bool keep[CT_ITEMS];
   unsigned pos[CT_ITEMS];
@@ -410,8 +416,10 @@ __global__ void __launch_bounds__(CT_THREADS)
     } while (t < tile_n && sm.skey[t + 1] == kk);
     int cnt = t - t0;
     if (t == tile_n) {  // ... and its tail in the following tiles
-      for (int j = tbase + tile_n; j < m && ks[j] == kk; ++j) {
-        const float4 p = __ldg(src + vs[j]);
+      for (int j = tbase + tile_n; j < m; ++j) {
+        const unsigned long long pp = ps[j];
+        if ((uint32_t)(pp >> 32) != kk) break;
+        const float4 p = __ldg(src + (uint32_t)pp);
         ax = fadd(ax, p.x);
         ay = fadd(ay, p.y);
         az = fadd(az, p.z);
@@ -434,8 +442,7 @@ void launch_pass(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int
   cudaFuncSetAttribute(k_vf_sort_pass<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VfPassSmem<BITS>));
   const int src = pass & 1;
   KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
-      a.sort.key[src], a.sort.val[src], a.sort.key[src ^ 1], a.sort.val[src ^ 1], a.n_crop, a.sort.hist, a.sort.desc, pass,
-      shift, c.cap, gtiles, a.sort.stats));
+      a.pair[src], a.pair[src ^ 1], a.n_crop, a.sort.hist, a.sort.desc, pass, shift, c.cap, gtiles, a.sort.stats));
   count_launch(c);
 }
 
@@ -498,8 +505,7 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   cudaMemsetAsync(a.sort.desc, 0, (size_t)pl.npass * c.B * gtiles * nbins * sizeof(uint32_t), c.stream);
   KL(c, "k_vf_init", k_vf_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, c.B));
   KL(c, "k_vf_crop_key", k_vf_crop_key<<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
-      a.in, a.in_stride, a.n_in, pl, a.sort.key[0], a.sort.val[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap,
-      btiles));
+      a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles));
   KL(c, "k_vf_scan", k_vf_scan<<<dim3(pl.npass, c.B), VF_MAX_BINS, 0, c.stream>>>(a.sort.hist));
   KL(c, "k_vf_setup", k_vf_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.minmax, a.leaf, a.vf, c.B));
   count_launch(c, 4);
@@ -518,7 +524,7 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   const int tiles = cdiv(c.cap, CT_TILE), gt = cdiv(c.grid_cap, CT_TILE);
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
   KL(c, "k_vf_reduce", k_vf_reduce<<<dim3(c.B, gt), CT_THREADS, 0, c.stream>>>(
-      a.in, a.in_stride, a.n_crop, a.sort.key[fin], a.sort.val[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles));
+      a.in, a.in_stride, a.n_crop, a.pair[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles));
   count_launch(c);
 }
 

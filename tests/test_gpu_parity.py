@@ -311,3 +311,35 @@ def test_batch_over_two_lanes():
     for f in range(B):
         o = O.process(p, clouds[f, :counts[f]])
         compare_frames(res[f], o, p, f"frame{f}: ")
+
+
+def _compare_plane(p, cloud):
+    with ObstacleProcessor(p, len(cloud)) as op:
+        g = op.segment_plane_and_extract_indices(cloud)
+    o = O.plane(p, cloud)
+    assert g["n_passes"] == o["n_passes"]
+    assert_bits_equal(g["pass_points"], o["pass_points"], "pass_points")
+    assert_bits_equal(g["pass_inliers"], o["pass_inliers"], "pass_inliers")
+    assert_close(g["pass_coeff"], o["pass_coeff"], "pass_coeff")
+    assert_bits_equal(g["inliers"], o["inliers"], "last inliers")
+    assert_bits_equal(g["src"], o["src"], "remaining src idx")
+    assert_bits_equal(g["remaining"], o["remaining"], "remaining cloud")
+    assert g["warnings"] == o["warnings"]
+    return o
+
+
+@pytest.mark.parametrize("frac_line", [0.5, 0.9, 1.0])
+def test_plane_collinear_samples_redrawn(frac_line):
+    """samples that fail isSampleGood are redrawn (consuming random numbers): the hypothesis generator's parallel
+    fast path must hand such frames to the sequential replay; an all-collinear cloud exhausts the 1000 redraws"""
+    p = synth.params(2)
+    rng = np.random.default_rng(61)
+    n = 6000
+    n_line = int(n * frac_line)
+    t = rng.integers(-2000, 2000, n_line).astype(np.float32) / 64.0
+    line = np.stack([t, t, t], axis=1)  # exactly collinear: (p1-p0)/(p2-p0) has equal components
+    rest = np.concatenate([rng.uniform(-30, 30, size=(n - n_line, 2)), rng.normal(size=(n - n_line, 1)) * 0.05], axis=1)
+    pts = np.concatenate([line, rest]).astype(np.float32)
+    pts = pts[rng.permutation(n)]
+    o = _compare_plane(p, _cloud(pts))
+    print("passes", o["n_passes"], "warnings", o["warnings"])
