@@ -259,10 +259,13 @@ def main():
         step_host()
     barrier()
     t1 = time.perf_counter()
+    d2h_exact = 0.0
     for _ in range(args.steps):
         gather_results(step_host())
+        d2h_exact += op.last_d2h_bytes
     barrier()
     wall_e2e = time.perf_counter() - t1
+    d2h_bytes = d2h_exact / args.steps  # counted by the library from the copies it issued
 
     # ---- max over ranks -----------------------------------------------------------------------------
     t = torch.tensor([wall, wall_e2e, dev_us * 1e-6], dtype=torch.float64, device=dev.device)
@@ -316,22 +319,33 @@ def main():
             name, (us, cnt) = top
             per_frame = {k: v / B for k, v in counts_sum.items()}
             N_, M_, V_, P_ = (counts_sum[k] * args.steps for k in ("n_input", "n_crop", "n_voxel", "n_remaining"))
-            alg = {  # algorithmic bytes of ALL launches of that kernel over the timed steps (DESIGN.md "kernels")
-                "k_sort_pass": 16.0 * sort_keys,                 # (key,val) read + written once per pass
+            L_, C_ = (counts_sum[k] * args.steps for k in ("n_cluster_points", "n_clusters"))
+            alg_all = {  # algorithmic bytes of ALL launches of a kernel over the instrumented steps (DESIGN.md "kernels")
+                "k_vf_sort_pass": 16.0 * sort_keys,              # 8-byte (key, index) element read + written once per pass
+                "k_vf_crop_key": 16.0 * N_ + 8.0 * M_,           # input read once, (key, index) of the survivors written
+                "k_vf_reduce": 8.0 * M_ + 16.0 * M_ + 20.0 * V_,  # sorted pairs + point gather in, voxels + keys out
+                "k_sort_pass": 16.0 * sort_keys,
                 "k_crop": 16.0 * N_ + 20.0 * M_,                 # SURVEY 8d crop row
                 "k_voxel_keys": 16.0 * M_ + 4.0 * M_,
-                "k_sort_hist": 4.0 * (sort_keys / 3.0),
                 "k_voxel_centroid": 16.0 * M_ + 8.0 * M_ + 20.0 * V_,
                 "k_plane_score": 16.0 * V_,
                 "k_plane_moments": 16.0 * V_,
                 "k_plane_extract": 16.0 * V_ + 20.0 * P_,
-                "k_ece_union": 20.0 * P_,
-            }.get(name)
+                "k_ece_small": 32.0 * P_ + 8.0 * L_ + 20.0 * C_,  # SURVEY 8d ECE + centroid/radius rows (fused kernel)
+                "k_pack": 2.0 * (20.0 * P_ + 4.0 * L_ + 20.0 * C_),
+            }
+            for k in ktable:
+                if k in alg_all and kernel_times[k][0] > 0:
+                    ktable[k]["achieved_GBps"] = round(alg_all[k] / (kernel_times[k][0] * 1e-6) / 1e9, 1)
+                    ktable[k]["frac_of_hbm_peak"] = round(ktable[k]["achieved_GBps"] / peak, 4)
+            alg = alg_all.get(name)
             if alg is not None and us > 0:
                 ach = alg / (us * 1e-6) / 1e9
                 roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "traffic": None, "peak_source": peak_kind,
                         "launches": cnt, "avg_launch_us": us / cnt,
+                        "timed": "second pass of the same K steps with a CUDA-event pair around every launch on the "
+                                 "library's stream (lanes serialised so that each kernel runs alone)",
                         "algorithmic_bytes_per_launch": alg / cnt,
                         "share_of_kernel_time": us / tot_us}
             else:

@@ -202,6 +202,8 @@ int64_t pcop_last_launch_count(const pcop_handle* h);
 double pcop_last_algorithmic_bytes(const pcop_handle* h);
 /* Keys moved by radix-sort passes during the last call (each is 8 B read + 8 B written). */
 int64_t pcop_last_sort_pass_keys(const pcop_handle* h);
+/* bytes copied device -> host by the last call (results, counts, records; padded rows of the early remaining-cloud copy included) */
+double pcop_last_d2h_bytes(const pcop_handle* h);
 
 /*
  * Optional per-kernel timing (CUDA events around every launch, on the handle's stream).  Totals

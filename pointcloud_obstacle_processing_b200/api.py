@@ -31,6 +31,7 @@ EXPORTS = [
     "pcop_last_algorithmic_bytes", "pcop_crop", "pcop_voxel", "pcop_sor", "pcop_plane", "pcop_cluster",
     "pcop_centroid_radius", "pcop_enable_kernel_timing", "pcop_kernel_timing_count", "pcop_kernel_timing_get",
     "pcop_last_sort_pass_keys",
+    "pcop_last_d2h_bytes",
 ]
 
 
@@ -71,6 +72,8 @@ def load_library():
     L.pcop_last_algorithmic_bytes.argtypes = [vp]
     L.pcop_last_sort_pass_keys.restype = C.c_int64
     L.pcop_last_sort_pass_keys.argtypes = [vp]
+    L.pcop_last_d2h_bytes.restype = C.c_double
+    L.pcop_last_d2h_bytes.argtypes = [vp]
     L.pcop_enable_kernel_timing.argtypes = [vp, C.c_int]
     L.pcop_kernel_timing_count.argtypes = [vp]
     L.pcop_kernel_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
@@ -183,6 +186,10 @@ class ObstacleProcessor:
     @property
     def last_sort_pass_keys(self) -> int:
         return int(self._lib.pcop_last_sort_pass_keys(self._h))
+
+    @property
+    def last_d2h_bytes(self) -> float:
+        return float(self._lib.pcop_last_d2h_bytes(self._h))
 
     def enable_kernel_timing(self, enable=True):
         """CUDA-event pairs around every kernel launch; totals accumulate until enabled again."""

@@ -116,6 +116,20 @@ struct pcop_handle {
   cudaStream_t cstream = nullptr;   // result copies (device -> pinned host) run here, beside the next wave's kernels
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};
   int wave_seq = 0;                 // waves of the running call seen by this lane
+  // early copy of the remaining cloud: it is final once the plane loop ends, so it travels to the host (strided 2-D
+  // copy, rows padded to the wave's largest remaining cloud) while the clustering kernels still run
+  struct PinnedChunk {
+    unsigned char* p;
+    size_t cap;
+  };
+  std::vector<PinnedChunk> rem_chunks;  // one per wave of the running call
+  cudaEvent_t ev_rem_ready = nullptr, ev_rem_copied = nullptr;
+  bool rem_copy_pending = false;
+  bool wave_rem_early = false;
+  int wave_rem_pitch = 0;  // points per row
+  unsigned char* wave_rem_host = nullptr;
+  double d2h_bytes = 0.0;
+  cudaEvent_t trace_origin = nullptr;  // PCOP_TRACE: start event of the running call (on lane 0's stream)
   size_t pack_cap = 0;
   uint32_t alloc_outputs = 0;
 
@@ -233,7 +247,7 @@ size_t pack_capacity_bytes(uint32_t mask, int B, int cap) {
   size_t bytes = 0;
   for (int k = 0; k < PK_N; ++k)
     if (mask & kPkMask[k]) bytes += ((size_t)B * (cap + 1)) * kPkElem[k] + 256;
-  return bytes + 256;
+  return (bytes + 256 + 255) & ~(size_t)255;  // (the second half of the double buffer must stay 256-byte aligned)
 }
 
 template <class T>
@@ -610,6 +624,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
 
   const bool fused = h->vplan.ok && !h->force_generic;
   h->wave_used_fused = fused;
+  h->wave_rem_early = false;
   if (fused) {
     // crop + VoxelGrid in one pass over the input (stage_voxel_fused.cu); the cropped cloud itself is only
     // materialised when it is a requested output
@@ -686,7 +701,38 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
       cudaError_t e = run_plane(c, a);
       if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
       c.grid_cap = std::max(1, std::min(c.grid_cap, h->h_n_active[1]));  // largest remaining cloud of the wave
+      if (h->rem_copy_pending) {  // the previous wave's early copy still reads d_rem
+        cudaStreamWaitEvent(h->stream, h->ev_rem_copied, 0);
+        h->rem_copy_pending = false;
+      }
       run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
+      const size_t pitch = (size_t)c.grid_cap;
+      const size_t need = (size_t)B * pitch * 20;
+      if ((effective_outputs(p) & PCOP_OUT_REMAINING) && B > 1 && need <= ((size_t)256 << 20) && !getenv("PCOP_NO_EARLY_COPY")) {
+        if ((size_t)h->wave_seq >= h->rem_chunks.size()) h->rem_chunks.resize(h->wave_seq + 1, pcop_handle::PinnedChunk{nullptr, 0});
+        pcop_handle::PinnedChunk& ch = h->rem_chunks[h->wave_seq];
+        if (ch.cap < need) {
+          cudaStreamSynchronize(h->cstream);  // (an abandoned copy of a redone wave may still target the old chunk)
+          if (ch.p) cudaFreeHost(ch.p);
+          ch.p = nullptr;
+          ch.cap = 0;
+          const size_t ncap = need + need / 4 + 4096;
+          if (cudaHostAlloc((void**)&ch.p, ncap, cudaHostAllocDefault) != cudaSuccess)
+            return fail_cuda(h, cudaGetLastError(), "cudaHostAlloc(remaining)", __FILE__, __LINE__);
+          ch.cap = ncap;
+        }
+        cudaEventRecord(h->ev_rem_ready, h->stream);
+        cudaStreamWaitEvent(h->cstream, h->ev_rem_ready, 0);
+        cudaMemcpy2DAsync(ch.p, pitch * 16, h->d_rem, (size_t)h->cap * 16, pitch * 16, B, cudaMemcpyDeviceToHost, h->cstream);
+        cudaMemcpy2DAsync(ch.p + (size_t)B * pitch * 16, pitch * 4, h->d_rem_src, (size_t)h->cap * 4, pitch * 4, B,
+                          cudaMemcpyDeviceToHost, h->cstream);
+        cudaEventRecord(h->ev_rem_copied, h->cstream);
+        h->rem_copy_pending = true;
+        h->wave_rem_early = true;
+        h->wave_rem_pitch = (int)pitch;
+        h->wave_rem_host = ch.p;
+        h->d2h_bytes += (double)need;
+      }
     } else {
       KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_REM), B));
       KL(c, "k_copy_cloud", k_copy_cloud<<<dim3(cdiv(c.grid_cap, CT_TILE), B), CT_THREADS, 0, h->stream>>>(cur, cur_stride, cur_n, h->d_rem, h->d_rem_src, h->cap));
@@ -724,6 +770,8 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   if (h->wave_seq >= 2) PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied[half], 0));  // half is free again
   KL(c, "k_plane_record", k_plane_record<<<cdiv(B, 128), 128, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS),
                                                       h->cnt(CNT_CLUS1), h->params.enable_plane ? 1 : 0, B));
+  const uint32_t full_mask = mask;
+  if (h->wave_rem_early) mask &= ~(uint32_t)PCOP_OUT_REMAINING;  // already on its way (run_wave_stages)
   KL(c, "k_pack_scan", k_pack_scan<<<1, 320, 0, h->stream>>>(h->d_counts, h->maxB, B, mask, h->d_pack_off, h->d_meta));
   count_launch(c, 2);
   const void* srcs[PK_N] = {h->d_crop_kept, h->d_vox_keys, h->d_vox,     h->d_sor_kept, h->d_inliers,
@@ -764,6 +812,8 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   // next wave starts right away and only waits for this copy before it packs into the same half again
   if (meta.total_bytes)
     PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->cstream));
+  h->d2h_bytes += (double)meta.total_bytes + (double)(sizeof(int) * CNT_ROWS * h->maxB + sizeof(uint32_t) * B +
+                                                      sizeof(PlaneRecord) * B + sizeof(PackMeta));
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_copied[half], h->cstream));
   ++h->wave_seq;
   *h_pack_used = base_off + meta.total_bytes;
@@ -794,6 +844,11 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
                                 (const void**)&r.plane_inlier_idx, (const void**)&r.remaining_cloud,
                                 (const void**)&r.remaining_src_idx, (const void**)&r.cluster_offsets,
                                 (const void**)&r.cluster_indices,  (const void**)&r.obstacles};
+    if (h->wave_rem_early && (full_mask & PCOP_OUT_REMAINING)) {
+      r.remaining_cloud = reinterpret_cast<const float*>(h->wave_rem_host + (size_t)f * h->wave_rem_pitch * 16);
+      r.remaining_src_idx = reinterpret_cast<const int32_t*>(h->wave_rem_host + (size_t)B * h->wave_rem_pitch * 16 +
+                                                             (size_t)f * h->wave_rem_pitch * 4);
+    }
     for (int k = 0; k < PK_N; ++k) {
       if (!(mask & kPkMask[k])) continue;
       // store the byte offset now; turned into a pointer once the host buffer can no longer move
@@ -835,6 +890,8 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
   PCOP_CUDA_TRY(cudaSetDevice(h->device));
   h->launches = 0;
   h->alg_bytes = 0.0;
+  h->d2h_bytes = 0.0;
+  h->rem_copy_pending = false;
   h->kt.used = 0;
   h->sort_pass_keys = 0;
   PCOP_CUDA_TRY(cudaMemsetAsync(h->sort.stats, 0, sizeof(unsigned long long), h->stream));
@@ -902,6 +959,16 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
       if (cudaEventElapsedTime(&ms, h->ev_stage[s][0], h->ev_stage[s][1]) == cudaSuccess) h->stage_us[s] += ms * 1000.f;
     }
     resolve_kernel_timers(h);
+    if (getenv("PCOP_TRACE")) {
+      fprintf(stderr, "[pcop trace]   lane %p device timeline, us since call start [begin-end]:", (void*)h);
+      for (int s = 0; s < PCOP_N_STAGES; ++s) {
+        float a = 0.f, b = 0.f;
+        if (h->stage_used[s] && h->trace_origin && cudaEventElapsedTime(&a, h->trace_origin, h->ev_stage[s][0]) == cudaSuccess &&
+            cudaEventElapsedTime(&b, h->trace_origin, h->ev_stage[s][1]) == cudaSuccess)
+          fprintf(stderr, " s%d[%.0f-%.0f]", s, a * 1000.f, b * 1000.f);
+      }
+      fprintf(stderr, "\n");
+    }
   }
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_stats, h->sort.stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_lane_done, h->cstream));
@@ -966,7 +1033,8 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   std::vector<WaveList> plan(n_lanes);
   if (n_lanes > 1 && wpl == 1 && batch <= (h->maxB * n_lanes * 4) / 5) {
     // one wave per lane, of growing size (weights 1 .. 1.5): the lanes share the GPU, finish one after the other,
-    // and every result copy but the last overlaps the kernels of the lanes still running
+    // and every result copy but the last overlaps the kernels of the lanes still running.  (Measured on B200, 256
+    // frames, 2 lanes: 2.58 ms per call; even split 2.67 ms; an extra small tail wave 3.0 ms.)
     double wsum = 0.0;
     for (int l = 0; l < n_lanes; ++l) wsum += 1.0 + 0.5 * l / (n_lanes - 1);
     int w0 = 0;
@@ -991,6 +1059,7 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   for (pcop_handle* l : lanes) {
     l->params = h->params;
     l->vplan = h->vplan;
+    l->trace_origin = h->ev_call[0];
     TRY(ensure_pack_capacity(l, mask));
   }
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[0], h->stream));
@@ -1017,6 +1086,7 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   for (int l = 1; l < n_lanes; ++l) {  // per-call accounting is reported on the handle (sums over the lanes)
     h->launches += lanes[l]->launches;
     h->alg_bytes += lanes[l]->alg_bytes;
+    h->d2h_bytes += lanes[l]->d2h_bytes;
     h->sort_pass_keys += lanes[l]->sort_pass_keys;
     for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] += lanes[l]->stage_us[s];
     merge_kernel_timers(h, lanes[l]);
@@ -1245,6 +1315,9 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
   for (int i = 0; i < 2; ++i)
     if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess)
       return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
+  if ((e = cudaEventCreateWithFlags(&h->ev_rem_ready, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_rem_copied, cudaEventDisableTiming)) != cudaSuccess)
+    return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
   st = ensure_pack_capacity(h, effective_outputs(h->params));
   if (st != PCOP_OK) return bail(st);
   *out = h;
@@ -1297,6 +1370,10 @@ void pcop_destroy(pcop_handle* h) {
   if (h->ev_lane_done) cudaEventDestroy(h->ev_lane_done);
   for (int i = 0; i < 2; ++i)
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+  if (h->ev_rem_ready) cudaEventDestroy(h->ev_rem_ready);
+  if (h->ev_rem_copied) cudaEventDestroy(h->ev_rem_copied);
+  for (pcop_handle::PinnedChunk& ch : h->rem_chunks)
+    if (ch.p) cudaFreeHost(ch.p);
   if (h->cstream) cudaStreamDestroy(h->cstream);
   for (int s = 0; s < PCOP_N_STAGES; ++s)
     for (int i = 0; i < 2; ++i)
@@ -1368,6 +1445,7 @@ int pcop_stage_times_us(const pcop_handle* h, float us[PCOP_N_STAGES]) {
 int64_t pcop_last_launch_count(const pcop_handle* h) { return h ? h->launches : 0; }
 double pcop_last_algorithmic_bytes(const pcop_handle* h) { return h ? h->alg_bytes : 0.0; }
 int64_t pcop_last_sort_pass_keys(const pcop_handle* h) { return h ? (int64_t)h->sort_pass_keys : 0; }
+double pcop_last_d2h_bytes(const pcop_handle* h) { return h ? h->d2h_bytes : 0.0; }
 
 // ---- stage-isolated entry points -------------------------------------------------------
 int pcop_crop(pcop_handle* h, const float* xyzw, int32_t n, float* out_xyzw, int32_t* kept_idx, int32_t* m) {

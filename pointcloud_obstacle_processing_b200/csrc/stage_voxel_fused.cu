@@ -380,13 +380,29 @@ __global__ void __launch_bounds__(CT_THREADS)
   const float4* src = in + (size_t)f * in_stride;
   const int tile_n = min(CT_TILE, m - tbase);
   // sorted (key, index) of the tile; the points gathered into shared memory in sorted order
-  for (int t = threadIdx.x; t < tile_n; t += CT_THREADS) {
-    const unsigned long long pp = ps[tbase + t];
-    sm.skey[t + 1] = (uint32_t)(pp >> 32);
-    const float4 p = __ldg(src + (uint32_t)pp);
-    sm.sx[t] = p.x;
-    sm.sy[t] = p.y;
-    sm.sz[t] = p.z;
+  {  // all pair loads, then all gathers, in flight together
+    unsigned long long pp[CT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CT_ITEMS; ++k) {
+      const int t = threadIdx.x + k * CT_THREADS;
+      pp[k] = (t < tile_n) ? ps[tbase + t] : 0ull;
+    }
+    float4 p[CT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CT_ITEMS; ++k) {
+      const int t = threadIdx.x + k * CT_THREADS;
+      p[k] = (t < tile_n) ? __ldg(src + (uint32_t)pp[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < CT_ITEMS; ++k) {
+      const int t = threadIdx.x + k * CT_THREADS;
+      if (t < tile_n) {
+        sm.skey[t + 1] = (uint32_t)(pp[k] >> 32);
+        sm.sx[t] = p[k].x;
+        sm.sy[t] = p[k].y;
+        sm.sz[t] = p[k].z;
+      }
+    }
   }
   if (threadIdx.x == 0) sm.skey[0] = (tbase > 0) ? (uint32_t)(ps[tbase - 1] >> 32) : 0u;
   __syncthreads();
@@ -476,7 +492,9 @@ VoxFusedPlan make_vox_fused_plan(const pcop_params& p) {
   int bits = 1;
   while (bits < 32 && (1ull << bits) < total) ++bits;
   pl.bits = bits;
-  int max_digit = VF_MAX_BITS;
+  // measured on B200: four 7-bit passes over the 25-bit HDL-64 keys beat three 9-bit ones (a pass costs almost the
+  // same for 128..512 bins per key, but the per-tile digit work doubles), so digits are capped at 8 bits by default
+  int max_digit = 8;
   if (const char* s = getenv("PCOP_VF_BITS")) max_digit = std::min(VF_MAX_BITS, std::max(4, atoi(s)));  // tuning knob
   pl.npass = (bits + max_digit - 1) / max_digit;
   if (pl.npass > VF_MAX_PASSES) return pl;
