@@ -202,6 +202,24 @@ int64_t pcop_last_launch_count(const pcop_handle* h);
 double pcop_last_algorithmic_bytes(const pcop_handle* h);
 /* Keys moved by radix-sort passes during the last call (each is 8 B read + 8 B written). */
 int64_t pcop_last_sort_pass_keys(const pcop_handle* h);
+/* ---- accumulator ingest (replaces od.cpp:691-698) --------------------------------------------------
+ * The node transforms every incoming cloud into the world frame (pcl_ros::transformPointCloud, od.cpp:696) and
+ * appends it to passthrough_input_cloud (od.cpp:697) until accumulate_count clouds have arrived; the next callback
+ * runs the pipeline on the accumulated cloud (od.cpp:699 ff).  Here the accumulated cloud lives on the device:
+ *   pcop_accumulate           transform (row-major 4x4 float, NULL = identity; PCL's coefficient formula in float)
+ *                             + append; is_dense = 0 copies points with a non-finite coordinate unchanged (PCL's
+ *                             behaviour for clouds with is_dense == false, e.g. Kinect clouds with NaN holes)
+ *   pcop_accumulated_count    points accumulated so far
+ *   pcop_process_accumulated  pcop_process on the accumulated cloud (never leaves the device), then reset
+ *   pcop_accumulate_reset     drop what was accumulated
+ *   pcop_transform            stage-isolated transform of one cloud (parity tests)
+ * PCOP_ERR_CAPACITY when the accumulated cloud would exceed max_points. */
+int pcop_accumulate(pcop_handle* h, const float* xyzw, int32_t n, const float* transform16, int32_t is_dense, int32_t* total);
+int32_t pcop_accumulated_count(const pcop_handle* h);
+int pcop_process_accumulated(pcop_handle* h, pcop_frame_result* out);
+int pcop_accumulate_reset(pcop_handle* h);
+int pcop_transform(pcop_handle* h, const float* xyzw, int32_t n, const float* transform16, int32_t is_dense, float* out_xyzw);
+
 /* bytes copied device -> host by the last call (results, counts, records; padded rows of the early remaining-cloud copy included) */
 double pcop_last_d2h_bytes(const pcop_handle* h);
 

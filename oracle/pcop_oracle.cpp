@@ -941,6 +941,33 @@ int pcop_oracle_sor_distances_bruteforce(const float* xyzw, int32_t v, int32_t m
   return PCOP_OK;
 }
 
+// pcl_ros::transformPointCloud -> pcl::transformPointCloud(Matrix4f) (od.cpp:696), PCL 1.7/1.8 transforms.hpp:
+// explicit coefficient formula, float, evaluated left to right; non-dense clouds skip non-finite points (the output
+// starts as a copy of the input).
+int pcop_oracle_transform(const float* xyzw, int32_t n, const float* m, int32_t is_dense, float* out) {
+  if (!xyzw || !m || !out || n < 0) return PCOP_ERR_BAD_PARAM;
+  for (int32_t i = 0; i < n; ++i) {
+    const float x = xyzw[4 * i], y = xyzw[4 * i + 1], z = xyzw[4 * i + 2];
+    out[4 * i + 3] = xyzw[4 * i + 3];
+    if (!is_dense && (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z))) {
+      out[4 * i] = x;
+      out[4 * i + 1] = y;
+      out[4 * i + 2] = z;
+      continue;
+    }
+    for (int r = 0; r < 3; ++r) {
+      volatile float a = m[4 * r] * x;  // volatile: one IEEE operation per statement, no contraction, no reassociation
+      volatile float b = m[4 * r + 1] * y;
+      volatile float c = m[4 * r + 2] * z;
+      volatile float s = a + b;
+      s = s + c;
+      s = s + m[4 * r + 3];
+      out[4 * i + r] = s;
+    }
+  }
+  return PCOP_OK;
+}
+
 int pcop_oracle_process(const pcop_params* pr, const float* xyzw, int32_t n, pcop_frame_result* out) {
   std::memset(out, 0, sizeof(*out));
   const P4* in = (const P4*)xyzw;

@@ -39,6 +39,12 @@ int pcop_oracle_cluster(const pcop_params* pr, const float* xyzw, int32_t p, int
 int pcop_oracle_centroid_radius(const float* xyzw, int32_t p, const int32_t* cluster_offsets,
                                 const int32_t* cluster_indices, int32_t c, float* obstacles);
 
+/* Accumulator ingest (od.cpp:691-698): pcl_ros::transformPointCloud of one incoming cloud with a row-major 4x4 float
+ * matrix.  PCL 1.7/1.8 pcl::transformPointCloud(cloud_in, cloud_out, Eigen::Matrix4f) evaluates, in float,
+ *   out.x = m00*x + m01*y + m02*z + m03   (left to right, no FMA), likewise y and z; the 4th float is copied.
+ * is_dense == 0 (Kinect clouds carry NaN holes): points with a non-finite x, y or z are copied unchanged. */
+int pcop_oracle_transform(const float* xyzw, int32_t n, const float* m16, int32_t is_dense, float* out_xyzw);
+
 /* Whole pipeline; result arrays are malloc'ed, release with pcop_oracle_free_result.
  * All PCOP_OUT_* arrays are always filled. */
 int pcop_oracle_process(const pcop_params* pr, const float* xyzw, int32_t n, pcop_frame_result* out);

@@ -32,6 +32,11 @@ EXPORTS = [
     "pcop_centroid_radius", "pcop_enable_kernel_timing", "pcop_kernel_timing_count", "pcop_kernel_timing_get",
     "pcop_last_sort_pass_keys",
     "pcop_last_d2h_bytes",
+    "pcop_accumulate",
+    "pcop_accumulated_count",
+    "pcop_process_accumulated",
+    "pcop_accumulate_reset",
+    "pcop_transform",
 ]
 
 
@@ -74,6 +79,12 @@ def load_library():
     L.pcop_last_sort_pass_keys.argtypes = [vp]
     L.pcop_last_d2h_bytes.restype = C.c_double
     L.pcop_last_d2h_bytes.argtypes = [vp]
+    L.pcop_accumulate.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
+    L.pcop_accumulated_count.argtypes = [vp]
+    L.pcop_accumulated_count.restype = C.c_int32
+    L.pcop_process_accumulated.argtypes = [vp, vp]
+    L.pcop_accumulate_reset.argtypes = [vp]
+    L.pcop_transform.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.pcop_enable_kernel_timing.argtypes = [vp, C.c_int]
     L.pcop_kernel_timing_count.argtypes = [vp]
     L.pcop_kernel_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
@@ -169,6 +180,40 @@ class ObstacleProcessor:
             counts = np.full(clouds.shape[0], clouds.shape[1], np.int32)
         res = self.process_batch_raw(clouds.ctypes.data, clouds.shape[1], counts)
         return [Frame.from_c(r) for r in res]
+
+    # ---- accumulator ingest (od.cpp:691-698) ------------------------------------------
+    def accumulate(self, cloud, transform=None, is_dense=False) -> int:
+        """pcl_ros::transformPointCloud(cloud, world_T_sensor) + `passthrough_input_cloud +=` (od.cpp:696-697), on
+        the device.  transform: 4x4 float (row-major) or None for identity.  Returns the accumulated point count."""
+        cloud = _f32(cloud)
+        t = None if transform is None else np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+        total = C.c_int32()
+        self._check(self._lib.pcop_accumulate(self._h, cloud.ctypes.data_as(C.c_void_p), cloud.shape[0],
+                                              None if t is None else t.ctypes.data_as(C.c_void_p),
+                                              1 if is_dense else 0, C.byref(total)))
+        return total.value
+
+    @property
+    def accumulated_count(self) -> int:
+        return int(self._lib.pcop_accumulated_count(self._h))
+
+    def accumulate_reset(self):
+        self._check(self._lib.pcop_accumulate_reset(self._h))
+
+    def process_accumulated(self) -> Frame:
+        """the pipeline on the accumulated cloud (od.cpp:699 ff); the accumulator is emptied (od.cpp:701)"""
+        r = FrameResult()
+        self._check(self._lib.pcop_process_accumulated(self._h, C.byref(r)))
+        return Frame.from_c(r)
+
+    def transform(self, cloud, transform, is_dense=False):
+        cloud = _f32(cloud)
+        t = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+        out = np.empty((max(cloud.shape[0], 1), 4), np.float32)
+        self._check(self._lib.pcop_transform(self._h, cloud.ctypes.data_as(C.c_void_p), cloud.shape[0],
+                                             t.ctypes.data_as(C.c_void_p), 1 if is_dense else 0,
+                                             out.ctypes.data_as(C.c_void_p)))
+        return out[:cloud.shape[0]].copy()
 
     # ---- timing / accounting of the last call ----------------------------------------
     @property

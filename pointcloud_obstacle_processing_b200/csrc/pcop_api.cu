@@ -129,6 +129,8 @@ struct pcop_handle {
   int wave_rem_pitch = 0;  // points per row
   unsigned char* wave_rem_host = nullptr;
   double d2h_bytes = 0.0;
+  float4* d_acc = nullptr;  // accumulated (world-frame) cloud, od.cpp:697
+  int acc_count = 0;
   cudaEvent_t trace_origin = nullptr;  // PCOP_TRACE: start event of the running call (on lane 0's stream)
   size_t pack_cap = 0;
   uint32_t alloc_outputs = 0;
@@ -313,6 +315,27 @@ __global__ void k_copy_counts(const int* __restrict__ src, int* __restrict__ dst
 __global__ void k_zero_u32(uint32_t* p, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0u;
+}
+
+struct Mat34 {
+  float m[12];  // rows 0..2 of the 4x4
+};
+
+// pcl::transformPointCloud(cloud_in, cloud_out, Eigen::Matrix4f) (via pcl_ros::transformPointCloud, od.cpp:696):
+// out.x = m00*x + m01*y + m02*z + m03 in float, left to right, no FMA; non-dense clouds copy non-finite points
+__global__ void __launch_bounds__(256)
+    k_transform(const float4* __restrict__ in, int n, Mat34 t, int is_dense, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(in + i);
+  float4 o = p;
+  const bool finite = fabsf(p.x) <= 3.402823466e+38f && fabsf(p.y) <= 3.402823466e+38f && fabsf(p.z) <= 3.402823466e+38f;
+  if (is_dense || finite) {
+    o.x = fadd(fadd(fadd(fmul(t.m[0], p.x), fmul(t.m[1], p.y)), fmul(t.m[2], p.z)), t.m[3]);
+    o.y = fadd(fadd(fadd(fmul(t.m[4], p.x), fmul(t.m[5], p.y)), fmul(t.m[6], p.z)), t.m[7]);
+    o.z = fadd(fadd(fadd(fmul(t.m[8], p.x), fmul(t.m[9], p.y)), fmul(t.m[10], p.z)), t.m[11]);
+  }
+  out[i] = o;
 }
 
 // cloud copy for a disabled plane stage: remaining = input, src = identity
@@ -1228,6 +1251,7 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
     if (_s != PCOP_OK) return bail(_s); \
   } while (0)
   A(dalloc(h, &h->d_in, BC));
+  A(dalloc(h, &h->d_acc, (size_t)h->cap));
   A(dalloc(h, &h->d_crop, BC));
   A(dalloc(h, &h->d_vox, BC));
   A(dalloc(h, &h->d_sor, BC));
@@ -1446,6 +1470,64 @@ int64_t pcop_last_launch_count(const pcop_handle* h) { return h ? h->launches : 
 double pcop_last_algorithmic_bytes(const pcop_handle* h) { return h ? h->alg_bytes : 0.0; }
 int64_t pcop_last_sort_pass_keys(const pcop_handle* h) { return h ? (int64_t)h->sort_pass_keys : 0; }
 double pcop_last_d2h_bytes(const pcop_handle* h) { return h ? h->d2h_bytes : 0.0; }
+
+// ---- accumulator ingest (od.cpp:691-698) -------------------------------------------------
+static int transform_into(pcop_handle* h, const float* xyzw, int32_t n, const float* t16, int is_dense, float4* dst) {
+  // staged through d_in (frame 0) when the source is host memory
+  const float4* src = reinterpret_cast<const float4*>(xyzw);
+  if (!is_device_pointer(xyzw)) {
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_in, xyzw, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+    src = h->d_in;
+  }
+  Mat34 t;
+  const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  memcpy(t.m, t16 ? t16 : ident, sizeof(t.m));
+  Ctx c = make_ctx(h, 1, n);
+  KL(c, "k_transform", k_transform<<<cdiv(n, 256), 256, 0, h->stream>>>(src, n, t, is_dense, dst));
+  count_launch(c);
+  return PCOP_OK;
+}
+
+int pcop_accumulate(pcop_handle* h, const float* xyzw, int32_t n, const float* transform16, int32_t is_dense, int32_t* total) {
+  if (!h || (!xyzw && n > 0) || n < 0) return fail(h, PCOP_ERR_BAD_PARAM, "pcop_accumulate: bad argument");
+  if ((long long)h->acc_count + n > h->cap) return fail(h, PCOP_ERR_CAPACITY, "accumulated cloud exceeds max_points");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  if (n > 0) {
+    TRY(transform_into(h, xyzw, n, transform16, is_dense, h->d_acc + h->acc_count));
+    if (!is_device_pointer(xyzw)) PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer
+  }
+  h->acc_count += n;
+  if (total) *total = h->acc_count;
+  return PCOP_OK;
+}
+
+int32_t pcop_accumulated_count(const pcop_handle* h) { return h ? h->acc_count : 0; }
+
+int pcop_accumulate_reset(pcop_handle* h) {
+  if (!h) return PCOP_ERR_BAD_PARAM;
+  h->acc_count = 0;
+  return PCOP_OK;
+}
+
+int pcop_process_accumulated(pcop_handle* h, pcop_frame_result* out) {
+  if (!h || !out) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  const int32_t n = h->acc_count;
+  // od.cpp:701: current_frame_count = 0; the accumulator is consumed by this run
+  const int st = process_impl(h, reinterpret_cast<const float*>(h->d_acc), (size_t)(n > 0 ? n : 1), &n, 1, out);
+  h->acc_count = 0;
+  return st;
+}
+
+int pcop_transform(pcop_handle* h, const float* xyzw, int32_t n, const float* transform16, int32_t is_dense, float* out_xyzw) {
+  if (!h || !xyzw || !out_xyzw || n < 0) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  if (n > h->cap) return fail(h, PCOP_ERR_CAPACITY, "cloud has more points than max_points");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  if (n == 0) return PCOP_OK;
+  TRY(transform_into(h, xyzw, n, transform16, is_dense, h->d_crop));
+  TRY(download(h, out_xyzw, h->d_crop, (size_t)n * 16));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
 
 // ---- stage-isolated entry points -------------------------------------------------------
 int pcop_crop(pcop_handle* h, const float* xyzw, int32_t n, float* out_xyzw, int32_t* kept_idx, int32_t* m) {

@@ -187,3 +187,14 @@ def eigen33_smallest(m):
     vec = np.zeros(3, np.float64)
     lib().pcop_oracle_eigen33_smallest(mp, C.byref(ev), vec.ctypes.data_as(_fp))
     return ev.value, vec
+
+
+def transform(cloud, m, is_dense=False):
+    """pcl_ros::transformPointCloud restatement (od.cpp:696); m: 4x4 float, row-major"""
+    cloud, cp = _c(cloud, np.float32)
+    m = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+    out = np.empty_like(cloud)
+    st = lib().pcop_oracle_transform(cp, cloud.shape[0], m.ctypes.data_as(_fp), 1 if is_dense else 0,
+                                     out.ctypes.data_as(_fp))
+    assert st == 0
+    return out

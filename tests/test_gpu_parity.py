@@ -343,3 +343,50 @@ def test_plane_collinear_samples_redrawn(frac_line):
     pts = pts[rng.permutation(n)]
     o = _compare_plane(p, _cloud(pts))
     print("passes", o["n_passes"], "warnings", o["warnings"])
+
+
+def _rigid(yaw, pitch, roll, t):
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    R = np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                  [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                  [-sp, cp * sr, cp * cr]])
+    m = np.eye(4)
+    m[:3, :3] = R
+    m[:3, 3] = t
+    return m.astype(np.float32)
+
+
+@pytest.mark.parametrize("is_dense", [False, True])
+def test_transform_stage(is_dense, frames):
+    """od.cpp:696 pcl_ros::transformPointCloud: bit-exact against the oracle, NaN holes included"""
+    cloud = frames[3][:50000].copy()  # depth-camera frame: 10 % NaN pixels
+    m = _rigid(0.7, -0.15, 0.05, [0.4, -2.0, 1.3])
+    with ObstacleProcessor(synth.params(3), len(cloud)) as op:
+        g = op.transform(cloud, m, is_dense=is_dense)
+    assert_bits_equal(g, O.transform(cloud, m, is_dense=is_dense), "transformed cloud")
+
+
+def test_accumulate_then_process_matches_oracle_on_concatenated_world_cloud():
+    """od.cpp:691-701: accumulate_count clouds are transformed into the world frame and concatenated, the next callback
+    runs the pipeline on the concatenation and empties the accumulator"""
+    p = all_outputs(synth.params(1))
+    base = synth.frame(1, 0)
+    rng = np.random.default_rng(7)
+    parts, mats = [], []
+    for k in range(4):  # four sensor poses looking at the same arena: world cloud = T_k^-1 applied ... here simply T_k
+        m = _rigid(0.02 * k, 0.01 * k, -0.015 * k, [0.01 * k, -0.02 * k, 0.005 * k])
+        sub = base[rng.permutation(len(base))[:7000]]
+        parts.append(sub)
+        mats.append(m)
+    world = np.concatenate([O.transform(c, m, is_dense=False) for c, m in zip(parts, mats)])
+    with ObstacleProcessor(p, len(world)) as op:
+        for c, m in zip(parts, mats):
+            total = op.accumulate(c, m, is_dense=False)
+        assert total == len(world) == op.accumulated_count
+        g = op.process_accumulated()
+        assert op.accumulated_count == 0
+        with pytest.raises(Exception):
+            op.accumulate(np.zeros((len(world) + 1, 4), np.float32))  # capacity
+    o = O.process(p, world)
+    compare_frames(g, o, p, "accumulated: ")
+    assert o.n_clusters > 0

@@ -370,3 +370,47 @@ def test_pipeline_equals_chained_stages(config):
     offs, idx = O.cluster(p, pl["remaining"])
     assert np.array_equal(offs, o.cluster_offsets) and np.array_equal(idx, o.cluster_indices)
     assert o.n_clusters >= 3
+
+
+def _rigid(yaw, pitch, roll, t):
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    R = np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                  [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                  [-sp, cp * sr, cp * cr]])
+    m = np.eye(4)
+    m[:3, :3] = R
+    m[:3, 3] = t
+    return m.astype(np.float32)
+
+
+def test_transform_matches_pcl_coefficient_formula():
+    """od.cpp:696 pcl_ros::transformPointCloud -> pcl::transformPointCloud(Matrix4f): out.x = m00*x + m01*y + m02*z +
+    m03 in float, left to right; independent numpy float32 restatement, bit for bit"""
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-5, 5, size=(4000, 3)).astype(np.float32)
+    cloud = np.concatenate([pts, np.ones((len(pts), 1), np.float32)], axis=1)
+    m = _rigid(0.3, -0.2, 1.1, [0.5, -1.25, 0.75])
+    out = O.transform(cloud, m, is_dense=True)
+    f = np.float32
+    for r in range(3):
+        ref = (m[r, 0] * pts[:, 0]).astype(f)
+        ref = (ref + (m[r, 1] * pts[:, 1]).astype(f)).astype(f)
+        ref = (ref + (m[r, 2] * pts[:, 2]).astype(f)).astype(f)
+        ref = (ref + m[r, 3]).astype(f)
+        assert np.array_equal(out[:, r].view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(out[:, 3], cloud[:, 3])
+    # identity leaves every bit alone
+    assert np.array_equal(O.transform(cloud, np.eye(4, dtype=np.float32), is_dense=True).view(np.uint32), cloud.view(np.uint32))
+
+
+def test_transform_non_dense_cloud_copies_non_finite_points():
+    """PCL skips points with a non-finite coordinate when cloud.is_dense is false (Kinect clouds), transforms them
+    (-> NaN) when it is true"""
+    cloud = np.array([[1, 2, 3, 1], [np.nan, 2, 3, 1], [1, np.inf, 3, 1], [4, 5, 6, 1]], np.float32)
+    m = _rigid(0.5, 0.1, -0.3, [1, 2, 3])
+    out = O.transform(cloud, m, is_dense=False)
+    assert np.array_equal(out[1].view(np.uint32), cloud[1].view(np.uint32))
+    assert np.array_equal(out[2].view(np.uint32), cloud[2].view(np.uint32))
+    assert not np.array_equal(out[0], cloud[0]) and np.isfinite(out[[0, 3]]).all()
+    dense = O.transform(cloud, m, is_dense=True)
+    assert np.isnan(dense[1, :3]).all() and not np.isfinite(dense[2, :3]).all()
