@@ -220,6 +220,20 @@ int pcop_process_accumulated(pcop_handle* h, pcop_frame_result* out);
 int pcop_accumulate_reset(pcop_handle* h);
 int pcop_transform(pcop_handle* h, const float* xyzw, int32_t n, const float* transform16, int32_t is_dense, float* out_xyzw);
 
+/* ---- PointCloud2 wire ingest (replaces od.cpp:688-689 + 691-698) ------------------------------------
+ * pcl_conversions::toPCL + pcl::fromPCLPointCloud2<PointXYZ> extract the FLOAT32 fields x, y, z of every
+ * point_step-byte record of the message payload (the author's second slowest step, od.cpp:721).  Here the raw
+ * payload is uploaded once and ONE kernel decodes the records, applies the world transform and appends to the
+ * accumulator (the PointXYZ padding float becomes 1.0f, as in a default-constructed pcl::PointXYZ).
+ *   data        sensor_msgs/PointCloud2.data (host or device pointer), n_points = width * height records
+ *   point_step  bytes per record; off_x/off_y/off_z = offsets of the FLOAT32 fields "x", "y", "z"
+ * pcop_pointcloud2_to_xyz is the stage-isolated decode (no transform) for parity tests. */
+int pcop_accumulate_pointcloud2(pcop_handle* h, const unsigned char* data, int32_t n_points, int32_t point_step,
+                                int32_t off_x, int32_t off_y, int32_t off_z, const float* transform16, int32_t is_dense,
+                                int32_t* total);
+int pcop_pointcloud2_to_xyz(pcop_handle* h, const unsigned char* data, int32_t n_points, int32_t point_step, int32_t off_x,
+                            int32_t off_y, int32_t off_z, float* out_xyzw);
+
 /* bytes copied device -> host by the last call (results, counts, records; padded rows of the early remaining-cloud copy included) */
 double pcop_last_d2h_bytes(const pcop_handle* h);
 

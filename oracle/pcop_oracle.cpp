@@ -968,6 +968,23 @@ int pcop_oracle_transform(const float* xyzw, int32_t n, const float* m, int32_t 
   return PCOP_OK;
 }
 
+// pcl::fromPCLPointCloud2<pcl::PointXYZ> (od.cpp:689): per point a memcpy of each mapped field into a
+// default-constructed PointXYZ {0, 0, 0, 1.0f}
+int pcop_oracle_pointcloud2_to_xyz(const unsigned char* data, int32_t n_points, int32_t point_step, int32_t off_x,
+                                   int32_t off_y, int32_t off_z, float* out) {
+  if (!data || !out || n_points < 0 || point_step < 4 || off_x < 0 || off_y < 0 || off_z < 0 || off_x + 4 > point_step ||
+      off_y + 4 > point_step || off_z + 4 > point_step)
+    return PCOP_ERR_BAD_PARAM;
+  for (int32_t i = 0; i < n_points; ++i) {
+    const unsigned char* rec = data + (size_t)i * (size_t)point_step;
+    std::memcpy(out + 4 * (size_t)i + 0, rec + off_x, 4);
+    std::memcpy(out + 4 * (size_t)i + 1, rec + off_y, 4);
+    std::memcpy(out + 4 * (size_t)i + 2, rec + off_z, 4);
+    out[4 * (size_t)i + 3] = 1.0f;
+  }
+  return PCOP_OK;
+}
+
 int pcop_oracle_process(const pcop_params* pr, const float* xyzw, int32_t n, pcop_frame_result* out) {
   std::memset(out, 0, sizeof(*out));
   const P4* in = (const P4*)xyzw;

@@ -45,6 +45,12 @@ int pcop_oracle_centroid_radius(const float* xyzw, int32_t p, const int32_t* clu
  * is_dense == 0 (Kinect clouds carry NaN holes): points with a non-finite x, y or z are copied unchanged. */
 int pcop_oracle_transform(const float* xyzw, int32_t n, const float* m16, int32_t is_dense, float* out_xyzw);
 
+/* Wire ingest (od.cpp:688-689): pcl_conversions::toPCL + pcl::fromPCLPointCloud2<PointXYZ> of a sensor_msgs/PointCloud2
+ * payload: point i's FLOAT32 fields x, y, z sit at data + i*point_step + off_{x,y,z} (little endian); the PointXYZ
+ * padding float is 1.0f (default-constructed point, the field copy does not touch it). */
+int pcop_oracle_pointcloud2_to_xyz(const unsigned char* data, int32_t n_points, int32_t point_step, int32_t off_x,
+                                   int32_t off_y, int32_t off_z, float* out_xyzw);
+
 /* Whole pipeline; result arrays are malloc'ed, release with pcop_oracle_free_result.
  * All PCOP_OUT_* arrays are always filled. */
 int pcop_oracle_process(const pcop_params* pr, const float* xyzw, int32_t n, pcop_frame_result* out);

@@ -37,6 +37,8 @@ EXPORTS = [
     "pcop_process_accumulated",
     "pcop_accumulate_reset",
     "pcop_transform",
+    "pcop_accumulate_pointcloud2",
+    "pcop_pointcloud2_to_xyz",
 ]
 
 
@@ -85,6 +87,8 @@ def load_library():
     L.pcop_process_accumulated.argtypes = [vp, vp]
     L.pcop_accumulate_reset.argtypes = [vp]
     L.pcop_transform.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
+    L.pcop_accumulate_pointcloud2.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp]
+    L.pcop_pointcloud2_to_xyz.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.pcop_enable_kernel_timing.argtypes = [vp, C.c_int]
     L.pcop_kernel_timing_count.argtypes = [vp]
     L.pcop_kernel_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
@@ -192,6 +196,25 @@ class ObstacleProcessor:
                                               None if t is None else t.ctypes.data_as(C.c_void_p),
                                               1 if is_dense else 0, C.byref(total)))
         return total.value
+
+    def accumulate_pointcloud2(self, data, n_points, point_step, off_x, off_y, off_z, transform=None, is_dense=False) -> int:
+        """sensor_msgs/PointCloud2 payload (bytes / uint8 array) -> PointXYZ + world transform + append, one kernel
+        (od.cpp:688-689 + 696-697)"""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        t = None if transform is None else np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+        total = C.c_int32()
+        self._check(self._lib.pcop_accumulate_pointcloud2(self._h, buf.ctypes.data_as(C.c_void_p), n_points, point_step,
+                                                          off_x, off_y, off_z,
+                                                          None if t is None else t.ctypes.data_as(C.c_void_p),
+                                                          1 if is_dense else 0, C.byref(total)))
+        return total.value
+
+    def pointcloud2_to_xyz(self, data, n_points, point_step, off_x, off_y, off_z):
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        out = np.empty((max(n_points, 1), 4), np.float32)
+        self._check(self._lib.pcop_pointcloud2_to_xyz(self._h, buf.ctypes.data_as(C.c_void_p), n_points, point_step, off_x,
+                                                      off_y, off_z, out.ctypes.data_as(C.c_void_p)))
+        return out[:n_points].copy()
 
     @property
     def accumulated_count(self) -> int:

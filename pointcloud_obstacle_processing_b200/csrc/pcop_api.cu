@@ -130,6 +130,8 @@ struct pcop_handle {
   unsigned char* wave_rem_host = nullptr;
   double d2h_bytes = 0.0;
   float4* d_acc = nullptr;  // accumulated (world-frame) cloud, od.cpp:697
+  unsigned char* d_raw = nullptr;  // staging for a raw PointCloud2 payload (grown on demand)
+  size_t raw_cap = 0;
   int acc_count = 0;
   cudaEvent_t trace_origin = nullptr;  // PCOP_TRACE: start event of the running call (on lane 0's stream)
   size_t pack_cap = 0;
@@ -334,6 +336,30 @@ __global__ void __launch_bounds__(256)
     o.x = fadd(fadd(fadd(fmul(t.m[0], p.x), fmul(t.m[1], p.y)), fmul(t.m[2], p.z)), t.m[3]);
     o.y = fadd(fadd(fadd(fmul(t.m[4], p.x), fmul(t.m[5], p.y)), fmul(t.m[6], p.z)), t.m[7]);
     o.z = fadd(fadd(fadd(fmul(t.m[8], p.x), fmul(t.m[9], p.y)), fmul(t.m[10], p.z)), t.m[11]);
+  }
+  out[i] = o;
+}
+
+// sensor_msgs/PointCloud2 payload -> pcl::PointXYZ (od.cpp:688-689) [+ world transform, od.cpp:696] in one pass:
+// record i = data + i*point_step; FLOAT32 x, y, z at the given offsets (any alignment); padding float = 1.0f
+__device__ __forceinline__ float pc2_load_f32(const unsigned char* p) {
+  if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0u) return __ldg(reinterpret_cast<const float*>(p));
+  const uint32_t b = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+  return __uint_as_float(b);
+}
+__global__ void __launch_bounds__(256)
+    k_pc2_ingest(const unsigned char* __restrict__ data, int n, int point_step, int off_x, int off_y, int off_z, Mat34 t,
+                 int apply_transform, int is_dense, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* rec = data + (size_t)i * (size_t)point_step;
+  const float x = pc2_load_f32(rec + off_x), y = pc2_load_f32(rec + off_y), z = pc2_load_f32(rec + off_z);
+  float4 o = make_float4(x, y, z, 1.0f);
+  const bool finite = fabsf(x) <= 3.402823466e+38f && fabsf(y) <= 3.402823466e+38f && fabsf(z) <= 3.402823466e+38f;
+  if (apply_transform && (is_dense || finite)) {
+    o.x = fadd(fadd(fadd(fmul(t.m[0], x), fmul(t.m[1], y)), fmul(t.m[2], z)), t.m[3]);
+    o.y = fadd(fadd(fadd(fmul(t.m[4], x), fmul(t.m[5], y)), fmul(t.m[6], z)), t.m[7]);
+    o.z = fadd(fadd(fadd(fmul(t.m[8], x), fmul(t.m[9], y)), fmul(t.m[10], z)), t.m[11]);
   }
   out[i] = o;
 }
@@ -1384,6 +1410,7 @@ void pcop_destroy(pcop_handle* h) {
   for (void* p : h->dev_allocs) cudaFree(p);
   for (void* p : h->host_allocs) cudaFreeHost(p);
   if (h->d_pack) cudaFree(h->d_pack);
+  if (h->d_raw) cudaFree(h->d_raw);
   if (h->h_pack) cudaFreeHost(h->h_pack);
   if (h->kt.ev) {
     for (int i = 0; i < 2 * KernelTimers::MAX_SLOTS; ++i) cudaEventDestroy(h->kt.ev[i]);
@@ -1525,6 +1552,58 @@ int pcop_transform(pcop_handle* h, const float* xyzw, int32_t n, const float* tr
   if (n == 0) return PCOP_OK;
   TRY(transform_into(h, xyzw, n, transform16, is_dense, h->d_crop));
   TRY(download(h, out_xyzw, h->d_crop, (size_t)n * 16));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+static int pc2_ingest(pcop_handle* h, const unsigned char* data, int32_t n, int32_t point_step, int32_t ox, int32_t oy,
+                      int32_t oz, const float* t16, int is_dense, float4* dst) {
+  if (point_step < 4 || ox < 0 || oy < 0 || oz < 0 || ox + 4 > point_step || oy + 4 > point_step || oz + 4 > point_step)
+    return fail(h, PCOP_ERR_BAD_PARAM, "PointCloud2 field offsets do not fit point_step");
+  const size_t bytes = (size_t)n * (size_t)point_step;
+  const unsigned char* src = data;
+  if (!is_device_pointer(data)) {
+    if (bytes > h->raw_cap) {
+      PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+      if (h->d_raw) cudaFree(h->d_raw);
+      h->d_raw = nullptr;
+      h->raw_cap = 0;
+      PCOP_CUDA_TRY(cudaMalloc((void**)&h->d_raw, bytes + bytes / 4 + 256));
+      h->raw_cap = bytes + bytes / 4 + 256;
+    }
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_raw, data, bytes, cudaMemcpyHostToDevice, h->stream));
+    src = h->d_raw;
+  }
+  Mat34 t;
+  const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  memcpy(t.m, t16 ? t16 : ident, sizeof(t.m));
+  Ctx c = make_ctx(h, 1, n);
+  KL(c, "k_pc2_ingest", k_pc2_ingest<<<cdiv(n, 256), 256, 0, h->stream>>>(src, n, point_step, ox, oy, oz, t, t16 ? 1 : 0, is_dense, dst));
+  count_launch(c);
+  if (src != data) PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer
+  return PCOP_OK;
+}
+
+int pcop_accumulate_pointcloud2(pcop_handle* h, const unsigned char* data, int32_t n_points, int32_t point_step,
+                                int32_t off_x, int32_t off_y, int32_t off_z, const float* transform16, int32_t is_dense,
+                                int32_t* total) {
+  if (!h || (!data && n_points > 0) || n_points < 0) return fail(h, PCOP_ERR_BAD_PARAM, "pcop_accumulate_pointcloud2: bad argument");
+  if ((long long)h->acc_count + n_points > h->cap) return fail(h, PCOP_ERR_CAPACITY, "accumulated cloud exceeds max_points");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  if (n_points > 0) TRY(pc2_ingest(h, data, n_points, point_step, off_x, off_y, off_z, transform16, is_dense, h->d_acc + h->acc_count));
+  h->acc_count += n_points;
+  if (total) *total = h->acc_count;
+  return PCOP_OK;
+}
+
+int pcop_pointcloud2_to_xyz(pcop_handle* h, const unsigned char* data, int32_t n_points, int32_t point_step, int32_t off_x,
+                            int32_t off_y, int32_t off_z, float* out_xyzw) {
+  if (!h || !data || !out_xyzw || n_points < 0) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  if (n_points > h->cap) return fail(h, PCOP_ERR_CAPACITY, "cloud has more points than max_points");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  if (n_points == 0) return PCOP_OK;
+  TRY(pc2_ingest(h, data, n_points, point_step, off_x, off_y, off_z, nullptr, 1, h->d_crop));
+  TRY(download(h, out_xyzw, h->d_crop, (size_t)n_points * 16));
   PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PCOP_OK;
 }

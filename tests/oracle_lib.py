@@ -198,3 +198,13 @@ def transform(cloud, m, is_dense=False):
                                      out.ctypes.data_as(_fp))
     assert st == 0
     return out
+
+
+def pointcloud2_to_xyz(data, n_points, point_step, off_x, off_y, off_z):
+    """pcl::fromPCLPointCloud2<PointXYZ> restatement (od.cpp:689)"""
+    buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data, np.uint8)
+    out = np.empty((max(n_points, 1), 4), np.float32)
+    st = lib().pcop_oracle_pointcloud2_to_xyz(buf.ctypes.data_as(_fp), n_points, point_step, off_x, off_y, off_z,
+                                              out.ctypes.data_as(_fp))
+    assert st == 0, st
+    return out[:n_points].copy()

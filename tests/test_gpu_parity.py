@@ -390,3 +390,35 @@ def test_accumulate_then_process_matches_oracle_on_concatenated_world_cloud():
     o = O.process(p, world)
     compare_frames(g, o, p, "accumulated: ")
     assert o.n_clusters > 0
+
+
+def _make_pointcloud2(xyz, point_step, offs, seed=3):
+    n = len(xyz)
+    rng = np.random.default_rng(seed)
+    buf = rng.integers(0, 256, size=(n, point_step), dtype=np.uint8)
+    for a, off in enumerate(offs):
+        buf[:, off:off + 4] = np.ascontiguousarray(xyz[:, a], np.float32).view(np.uint8).reshape(n, 4)
+    return buf.reshape(-1)
+
+
+@pytest.mark.parametrize("point_step,offs", [(16, (0, 4, 8)), (32, (0, 4, 8)), (22, (1, 9, 14))])
+def test_pointcloud2_ingest(point_step, offs, frames):
+    """od.cpp:688-689 (wire decode) and the fused decode + transform + append (od.cpp:688-697) against the oracle"""
+    cloud = frames[3][:60000]
+    buf = _make_pointcloud2(cloud[:, :3], point_step, offs)
+    m = _rigid(-0.4, 0.2, 0.1, [1.0, 0.5, -0.25])
+    with ObstacleProcessor(synth.params(3), 2 * len(cloud)) as op:
+        g = op.pointcloud2_to_xyz(buf, len(cloud), point_step, *offs)
+        o = O.pointcloud2_to_xyz(buf, len(cloud), point_step, *offs)
+        assert_bits_equal(g, o, "decoded cloud")
+        # fused ingest twice (two callbacks), then the accumulated cloud must be the two transformed clouds in order
+        op.accumulate_pointcloud2(buf, len(cloud), point_step, *offs, transform=m, is_dense=False)
+        total = op.accumulate_pointcloud2(buf, len(cloud), point_step, *offs, transform=None, is_dense=False)
+        assert total == 2 * len(cloud)
+        p = all_outputs(synth.params(3))
+        p.enable_crop = p.enable_voxel = p.enable_sor = p.enable_plane = p.enable_cluster = 0
+        p.outputs = abi.OUT_REMAINING
+        op.set_params(p)
+        acc = op.process_accumulated().remaining_cloud
+    want = np.concatenate([O.transform(o, m, is_dense=False), o])
+    assert_bits_equal(acc, want, "accumulated cloud")

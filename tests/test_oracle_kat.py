@@ -414,3 +414,28 @@ def test_transform_non_dense_cloud_copies_non_finite_points():
     assert not np.array_equal(out[0], cloud[0]) and np.isfinite(out[[0, 3]]).all()
     dense = O.transform(cloud, m, is_dense=True)
     assert np.isnan(dense[1, :3]).all() and not np.isfinite(dense[2, :3]).all()
+
+
+def _make_pointcloud2(xyz, point_step, offs, seed=3):
+    """a sensor_msgs/PointCloud2-like payload: FLOAT32 x, y, z at `offs` inside point_step-byte records, other bytes
+    random (rgb, intensity, padding)"""
+    n = len(xyz)
+    rng = np.random.default_rng(seed)
+    buf = rng.integers(0, 256, size=(n, point_step), dtype=np.uint8)
+    for a, off in enumerate(offs):
+        buf[:, off:off + 4] = np.ascontiguousarray(xyz[:, a], np.float32).view(np.uint8).reshape(n, 4)
+    return buf.reshape(-1)
+
+
+@pytest.mark.parametrize("point_step,offs", [(16, (0, 4, 8)), (32, (0, 4, 8)), (22, (1, 9, 14)), (12, (8, 0, 4))])
+def test_pointcloud2_field_extraction(point_step, offs):
+    """od.cpp:688-689 toPCL + fromPCLPointCloud2<PointXYZ>: strided FLOAT32 field copy, padding float 1.0f, bits kept
+    (NaN payloads included)"""
+    rng = np.random.default_rng(11)
+    xyz = rng.normal(size=(1000, 3)).astype(np.float32)
+    xyz[5] = np.nan
+    xyz[6, 1] = np.inf
+    buf = _make_pointcloud2(xyz, point_step, offs)
+    out = O.pointcloud2_to_xyz(buf, len(xyz), point_step, *offs)
+    assert np.array_equal(out[:, :3].view(np.uint32), xyz.view(np.uint32))
+    assert (out[:, 3] == 1.0).all()
