@@ -5,7 +5,7 @@ A "step" = one pass of the whole hot path (crop -> VoxelGrid -> RANSAC plane loo
 centroid/radius) over one batch of synthetic HDL-64-style 120 000-point frames (BASELINE.json configs[1],
 parameters of SURVEY.md 8d config 2), `--batch` frames per GPU per step.
 
-  value     points/s, whole job, frames already resident in HBM (the batch, 0.49 GB at 256 frames, is larger
+  value     points/s, whole job, frames already resident in HBM (the batch, 1.97 GB at 1024 frames, is larger
             than the 126 MB L2, so every step re-reads its input from HBM; no explicit L2 flush)
   e2e       the same through the C ABI with HOST (pinned) frames: H2D of the frames and D2H of the results
             inside the timed region
@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=1024, help="frames per GPU per step")
     ap.add_argument("--latency-reps", type=int, default=200)
     ap.add_argument("--cpu-sample", type=int, default=128, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-kernel-timing", action="store_true")
@@ -238,6 +238,8 @@ def main():
     wall_instr = None
     if not args.no_kernel_timing:
         op.enable_kernel_timing(True)
+        step_device()  # untimed: the single lane of this pass grows its pinned result buffer once
+        op.enable_kernel_timing(True)  # (re-enabling clears the accumulated totals)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -339,10 +341,21 @@ def main():
                     ktable[k]["achieved_GBps"] = round(alg_all[k] / (kernel_times[k][0] * 1e-6) / 1e9, 1)
                     ktable[k]["frac_of_hbm_peak"] = round(ktable[k]["achieved_GBps"] / peak, 4)
             alg = alg_all.get(name)
+            # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/ncu_full_r01c_summary.csv:
+            # dram__bytes_read.sum + dram__bytes_write.sum at 256 frames per launch), scaled by the units per launch
+            ncu_dram_bytes_per_unit = {
+                "k_vf_sort_pass": ((0.2135e9 + 180.8e6) / 26.35e6, sort_keys),  # per key moved (mean of the 4 passes)
+                "k_vf_reduce": ((1.0807e9 + 276.7e6) / 26.35e6, M_),            # per sorted pair
+                "k_vf_crop_key": ((0.4922e9 + 182.0e6) / 30.72e6, N_),          # per input point
+            }
             if alg is not None and us > 0:
                 ach = alg / (us * 1e-6) / 1e9
+                tr = ncu_dram_bytes_per_unit.get(name)
                 roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": peak_kind,
+                        "frac": ach / peak, "traffic": (tr[0] * tr[1] / cnt) if tr else None,
+                        "traffic_source": "profiles/ncu_full_r01c_summary.csv (ncu --set full, 256 frames per launch), "
+                                          "scaled to this run's units per launch" if tr else None,
+                        "peak_source": peak_kind,
                         "launches": cnt, "avg_launch_us": us / cnt,
                         "timed": "second pass of the same K steps with a CUDA-event pair around every launch on the "
                                  "library's stream (lanes serialised so that each kernel runs alone)",
@@ -364,7 +377,7 @@ def main():
             "frames_per_sec": total_frames / wall,
             "device_ms_per_step": 1000.0 * dev_s / args.steps,
             "instrumented_ms_per_step": 1000.0 * wall_instr / args.steps if wall_instr else None,
-            "lanes": int(os.environ.get("PCOP_LANES", "2")),
+            "lanes": int(os.environ.get("PCOP_LANES", str(min(4, max(2, B // 256))))),
             "e2e": {"value": total_points / wall_e2e, "unit": "points/s", "h2d_bytes_per_step": B * n * 16 + B * 4,
                     "d2h_bytes_per_step": int(d2h_bytes), "frames_per_sec": total_frames / wall_e2e,
                     "ms_per_step": 1000.0 * wall_e2e / args.steps},

@@ -126,6 +126,7 @@ struct pcop_handle {
   cudaEvent_t ev_rem_ready = nullptr, ev_rem_copied = nullptr;
   bool rem_copy_pending = false;
   bool wave_rem_early = false;
+  int call_waves = 1;  // waves of the running call over all lanes
   int wave_rem_pitch = 0;  // points per row
   unsigned char* wave_rem_host = nullptr;
   double d2h_bytes = 0.0;
@@ -757,7 +758,11 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
       run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
       const size_t pitch = (size_t)c.grid_cap;
       const size_t need = (size_t)B * pitch * 20;
-      if ((effective_outputs(p) & PCOP_OUT_REMAINING) && B > 1 && need <= ((size_t)256 << 20) && !getenv("PCOP_NO_EARLY_COPY")) {
+      // Worth it only while the copy engine would otherwise idle: the rows are padded to the wave's largest cloud
+      // (~1.5x the bytes), which costs more than it hides once several waves keep the engine busy anyway (measured:
+      // 256 frames on 1-2 waves: 3.06 -> 2.62 ms and 2.61 -> 2.58 ms; 1024 frames on 4 waves: 8.96 -> 9.85 ms).
+      if ((effective_outputs(p) & PCOP_OUT_REMAINING) && B > 1 && h->call_waves <= 2 && need <= ((size_t)256 << 20) &&
+          !getenv("PCOP_NO_EARLY_COPY")) {
         if ((size_t)h->wave_seq >= h->rem_chunks.size()) h->rem_chunks.resize(h->wave_seq + 1, pcop_handle::PinnedChunk{nullptr, 0});
         pcop_handle::PinnedChunk& ch = h->rem_chunks[h->wave_seq];
         if (ch.cap < need) {
@@ -1105,7 +1110,10 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   }
   std::vector<pcop_handle*> lanes(1, h);
   for (int l = 1; l < n_lanes; ++l) lanes.push_back(h->extra_lanes[l - 1]);
+  int call_waves = 0;
+  for (const WaveList& wl : plan) call_waves += (int)wl.size();
   for (pcop_handle* l : lanes) {
+    l->call_waves = call_waves;
     l->params = h->params;
     l->vplan = h->vplan;
     l->trace_origin = h->ev_call[0];
@@ -1378,8 +1386,9 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   if (!params || !out || max_points == 0 || max_points > (size_t)(1u << 30) || max_batch < 1)
     return fail(nullptr, PCOP_ERR_BAD_PARAM, "pcop_create: bad argument");
   *out = nullptr;
-  // lanes: max_batch frames are in flight at once, split over the lanes (PCOP_LANES overrides the default of 2)
-  int n_lanes = 2;
+  // lanes: max_batch frames are in flight at once, split over the lanes (PCOP_LANES overrides the default: 2 lanes,
+  // one more per 256 frames of max_batch beyond 512, at most 4)
+  int n_lanes = std::min(4, std::max(2, max_batch / 256));
   if (const char* s = getenv("PCOP_LANES")) n_lanes = (int)std::min<long>(std::max<long>(strtol(s, nullptr, 10), 1), 8);
   n_lanes = std::max(1, std::min(n_lanes, max_batch / PCOP_MIN_LANE_WAVE));
   // capacity of a lane: 5/4 of an even share, so that one call of max_batch frames can be dealt in uneven waves
