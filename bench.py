@@ -16,6 +16,7 @@ parameters of SURVEY.md 8d config 2), `--batch` frames per GPU per step.
 cannot be built in this image).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -107,7 +108,7 @@ def oracle_frames_per_sec(params, frames, threads):
     return len(frames) / dt, dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the CPU restatement (oracle port) with all host threads, same metric/config."""
     if rank != 0:
         return
@@ -139,10 +140,18 @@ def run_reference(args, rank, world):
         "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # the contract is ONE JSON line on stdout: everything else that libraries print there (NCCL's version banner,
+    # ...) is sent to stderr; emit() writes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -159,7 +168,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -194,22 +203,48 @@ def main():
     def step_host():
         return op.process_batch_raw(host.data_ptr(), n, counts)
 
+    # ---- final result gather, once per step: per-frame obstacle counts (all-gather), then the obstacle
+    # records padded to the largest rank total (gather to rank 0), over NCCL.  The per-frame fields are read as numpy
+    # views over the ctypes result array; the records of consecutive frames of a wave are adjacent in the library's
+    # pinned result buffer, so they are staged run by run (a handful of memmoves per step).
+    from pointcloud_obstacle_processing_b200._ctypes_abi import FrameResult
+    obs_stage = torch.empty((B * 256, 4), dtype=torch.float32).pin_memory() if world > 1 else None
+    cnt_stage = torch.empty(B + 1, dtype=torch.int32).pin_memory() if world > 1 else None
+    dev_cnt = torch.empty(B + 1, dtype=torch.int32, device=dev.device) if world > 1 else None
+    all_cnt = torch.empty((world, B + 1), dtype=torch.int32, device=dev.device) if world > 1 else None
+    pad_cap = [0, None, None]
+    off_c, off_p, rec = FrameResult.n_clusters.offset, FrameResult.obstacles.offset, C.sizeof(FrameResult)
+
     def gather_results(res):
-        """final result gather: per-frame obstacle counts, then the obstacle records, over NCCL"""
-        if world == 1:
+        if world == 1 or os.environ.get("PCOP_BENCH_NO_GATHER"):
             return
-        c = torch.tensor([r.n_clusters for r in res], dtype=torch.int32, device=dev.device)
-        allc = [torch.empty_like(c) for _ in range(world)]
-        dist.all_gather(allc, c)
-        tot = int(c.sum().item())
-        mx = torch.tensor([tot], dtype=torch.int64, device=dev.device)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        pad = torch.zeros((int(mx.item()), 4), dtype=torch.float32, device=dev.device)
+        raw = np.frombuffer(res, dtype=np.uint8).reshape(len(res), rec)
+        ns = raw[:, off_c:off_c + 4].copy().view(np.int32).ravel()
+        ptrs = raw[:, off_p:off_p + 8].copy().view(np.uint64).ravel()
+        tot = int(ns.sum())
+        cnt_stage[:B].copy_(torch.from_numpy(ns))
+        cnt_stage[B] = tot
+        dev_cnt.copy_(cnt_stage, non_blocking=True)
+        dist.all_gather_into_tensor(all_cnt.view(-1), dev_cnt)
         if tot:
-            obs = np.concatenate([np.ctypeslib.as_array(r.obstacles, shape=(r.n_clusters * 4,)) for r in res
-                                  if r.n_clusters]).reshape(-1, 4)
-            pad[:tot] = torch.from_numpy(obs).to(dev.device)
-        out = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+            live = np.flatnonzero(ns > 0)
+            ends = ptrs[live] + 16 * ns[live].astype(np.uint64)
+            brk = np.flatnonzero(ptrs[live][1:] != ends[:-1]) + 1  # a new run starts where the records are not adjacent
+            starts = np.concatenate([[0], brk])
+            stops = np.concatenate([brk, [len(live)]])
+            o = 0
+            for a, b_ in zip(starts, stops):
+                nrec = int(ns[live[a:b_]].sum())
+                C.memmove(obs_stage.data_ptr() + 16 * o, int(ptrs[live[a]]), 16 * nrec)
+                o += nrec
+        mx = int(all_cnt[:, B].max().item())  # (the one synchronisation of the exchange)
+        if mx > pad_cap[0]:
+            pad_cap[0] = mx + mx // 4
+            pad_cap[1] = torch.zeros((pad_cap[0], 4), dtype=torch.float32, device=dev.device)
+            pad_cap[2] = torch.empty((world, pad_cap[0], 4), dtype=torch.float32, device=dev.device) if rank == 0 else None
+        pad = pad_cap[1][:mx]
+        pad[:tot].copy_(obs_stage[:tot], non_blocking=True)
+        out = list(pad_cap[2][:, :mx].unbind(0)) if rank == 0 else None
         dist.gather(pad, out, dst=0)
 
     # ---- device-resident run ---------------------------------------------------------------------
@@ -385,15 +420,15 @@ def main():
             "clocks": clocks.summary(),
             "roofline": roof,
             "pipeline_roofline": {"algorithmic_bytes_per_frame": alg_bytes / (args.steps * B),
-                                  "achieved_GBps": pipe_gbs, "peak": peak, "frac": pipe_gbs / peak if pipe_gbs else None,
-                                  "what": "sum of SURVEY 8d stage bytes over all frames / elapsed (whole pipeline)"},
+                                  "achieved_GBps": pipe_gbs, "peak": peak * world, "frac": pipe_gbs / (peak * world) if pipe_gbs else None,
+                                  "what": "sum of SURVEY 8d stage bytes over all frames of all GPUs / elapsed (whole pipeline); peak = measured HBM peak x GPUs"},
             "stage_ms_per_step": {k: round(v / args.steps / 1000.0, 3) for k, v in stage_acc.items()},
             "kernels": ktable,
             "counts_per_frame": {k: v / B for k, v in counts_sum.items()},
             "latency": lat,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     op.close()
     if world > 1:
         dist.barrier()
