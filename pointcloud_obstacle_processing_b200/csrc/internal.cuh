@@ -222,7 +222,7 @@ struct ClusterArgs {
   float4* obstacles;  // [B*cap]
 };
 // Largest cloud the fused shared-memory clustering kernel takes (stage_cluster_small.cu).
-constexpr int ECE_SMALL_MAX = 8192;
+constexpr int ECE_SMALL_MAX = 8960;
 // ECE_SMALL_MAX, or the value of the environment variable PCOP_ECE_SMALL_MAX clamped to [0, ECE_SMALL_MAX]
 // (0 forces every frame through the generic path; used by the tests to cover both paths)
 int ece_small_limit();

@@ -41,7 +41,7 @@ namespace {
 constexpr int ES_THREADS = 1024;
 constexpr int ES_WARPS = ES_THREADS / 32;
 constexpr int ES_MAX = ECE_SMALL_MAX;
-constexpr int ES_IPT = ES_MAX / ES_THREADS;  // points (cells, hash slots / 2) per thread
+constexpr int ES_IPT = (ES_MAX + ES_THREADS - 1) / ES_THREADS;  // points (cells) per thread
 constexpr int ES_HASH_BITS = 14;
 constexpr int ES_HASH = 1 << ES_HASH_BITS;
 constexpr int ES_SCAN_MAXC = 128;   // cluster offsets of up to this many clusters are mirrored in shared memory
@@ -50,18 +50,19 @@ constexpr uint32_t ES_EMPTY = 0xffffffffu;
 typedef unsigned long long u64;
 
 // Shared-memory regions (bytes) and what lives in them per phase:
-//   A  12*ES_MAX  build: u32 tk[ES_HASH] (keys of the hash slots) | union: float x[], y[], z[] in cell order
+//   A  12*ES_MAX  build: u32 tk[ES_HASH] (keys of the hash slots), int cnt[ES_MAX] (points per cell) behind it
+//                 union: float x[], y[], z[] in cell order
 //                 after the union: int csize[], int minidx[], u16 lab16[] (by original index), u16 rankc[] (by node)
-//   D  2*ES_HASH  u16 hash[] (cell id + 1 per slot)            \ after the union: u64 sortbuf[ES_MAX]
-//   E  4*ES_MAX   u32 cell_key[] (by cell id)                  /
-//   B  4*ES_MAX   build: int cnt[] (points per cell) | int parent[] (by node)
-//   C  2*ES_MAX   u16 idx16[] (original index of each cell-ordered position)
+//   D  2*ES_HASH  u16 hash[] (cell id + 1 per slot)            \ after the union: u32 rootkey[], u16 rootnode[] (kept
+//   E  4*ES_MAX   u32 cell_key[] (by cell id)                  /  roots), then u32 member sort keys (many clusters)
+//   B  2*ES_MAX   u16 parent[] (by node; nodes < 2^16, atomic-min by 32-bit CAS on the containing word)
+//   C  2*ES_MAX   u16 idx16[] (original index of each cell-ordered position), then the member list
 //   F  2*ES_MAX+16  u16 node_start[] (first position of each cell; identity in point mode after the union)
 constexpr int ES_A = 0;
 constexpr int ES_D = ES_A + 12 * ES_MAX;
 constexpr int ES_E = ES_D + 2 * ES_HASH;
 constexpr int ES_B = ES_E + 4 * ES_MAX;
-constexpr int ES_C = ES_B + 4 * ES_MAX;
+constexpr int ES_C = ES_B + 2 * ES_MAX;
 constexpr int ES_F = ES_C + 2 * ES_MAX;
 constexpr int ES_MISC = ES_F + 2 * ES_MAX + 16;
 struct EceSmallMisc {
@@ -74,19 +75,20 @@ struct EceSmallMisc {
 };
 constexpr int ES_SMEM_BYTES = ES_MISC + (int)sizeof(EceSmallMisc);
 static_assert(ES_SMEM_BYTES <= 227 * 1024, "fused clustering kernel: shared memory budget");
-static_assert(4 * ES_HASH <= 12 * ES_MAX, "build-phase key table overlays the coordinates");
-static_assert(2 * ES_HASH + 4 * ES_MAX >= 8 * ES_MAX, "sort buffer overlays hash + cell keys");
-static_assert(ES_MAX <= 8192, "positions / indices / sizes are packed in 13 bits (+1)");
-static_assert(2 * ES_MAX <= ES_HASH, "hash load factor <= 0.5");
+static_assert(4 * ES_HASH + 4 * ES_MAX <= 12 * ES_MAX, "build-phase key table + cell counts overlay the coordinates");
+static_assert(2 * ES_HASH + 4 * ES_MAX >= 6 * ES_MAX, "kept-root keys + nodes overlay hash + cell keys");
+static_assert(ES_MAX < 16384, "positions / indices / sizes are packed in 14 bits");
+static_assert(ES_MAX * 16 <= ES_HASH * 9, "hash load factor <= 0.5625");
 static_assert(2 * ES_WARPS * ES_SPLIT_MAXC <= 8 * ES_MAX, "split offsets overlay sizes + smallest indices");
-static_assert(ES_MISC % 8 == 0 && ES_D % 16 == 0 && ES_B % 16 == 0 && ES_F % 4 == 0, "alignment");
+static_assert(ES_MISC % 8 == 0 && ES_D % 16 == 0 && ES_B % 16 == 0 && ES_F % 4 == 0 && ES_C % 4 == 0, "alignment");
 
 __device__ __forceinline__ uint32_t hi32(u64 v) { return (uint32_t)(v >> 32); }
 __device__ __forceinline__ uint32_t lo32(u64 v) { return (uint32_t)v; }
 
 // Normalised bitonic network (every comparator puts the smaller element at the lower index), so elements past n
 // behave as +infinity without being stored: a comparator whose upper end is >= n is a no-op.
-__device__ void bitonic_sort_smem(u64* a, int n) {
+template <class T>
+__device__ void bitonic_sort_smem(T* a, int n) {
   if (n <= 1) {
     __syncthreads();
     return;
@@ -101,7 +103,7 @@ __device__ void bitonic_sort_smem(u64* a, int n) {
       const int base = (t - off) << 1;
       const int i = base + off, p = base + k - 1 - off;
       if (p < n) {
-        const u64 x = a[i], y = a[p];
+        const T x = a[i], y = a[p];
         if (x > y) {
           a[i] = y;
           a[p] = x;
@@ -114,7 +116,7 @@ __device__ void bitonic_sort_smem(u64* a, int n) {
         const int off = t & (j - 1);
         const int i = ((t - off) << 1) + off, p = i + j;
         if (p < n) {
-          const u64 x = a[i], y = a[p];
+          const T x = a[i], y = a[p];
           if (x > y) {
             a[i] = y;
             a[p] = x;
@@ -181,18 +183,33 @@ __device__ __forceinline__ int es_lookup(const unsigned short* hash, const uint3
 
 // Union-find on shared memory.  Parents only ever point to smaller node ids and hooks only ever touch roots, so a
 // plain store of an ancestor into a non-root entry (path compression) is safe next to concurrent atomicMin hooks.
-__device__ __forceinline__ int es_find(int* parent, int v) {
-  volatile int* par = parent;
+__device__ __forceinline__ int es_find(unsigned short* parent, int v) {
+  volatile unsigned short* par = parent;
   while (true) {  // path halving
     const int p = par[v];
     if (p == v) return v;
     const int gp = par[p];
     if (gp == p) return p;
-    par[v] = gp;
+    par[v] = (unsigned short)gp;
     v = gp;
   }
 }
-__device__ __forceinline__ void es_union(int* parent, int a, int b) {
+// atomicMin on a 16-bit shared-memory entry: 32-bit CAS on the containing word (a concurrent plain store to the
+// other half makes the CAS fail and retry, so it is never lost); returns the old value
+__device__ __forceinline__ int es_atomic_min16(unsigned short* base, int idx, int val) {
+  unsigned* w = reinterpret_cast<unsigned*>(base + (idx & ~1));
+  const int shift = (idx & 1) * 16;
+  unsigned cur = *reinterpret_cast<volatile unsigned*>(w);
+  while (true) {
+    const int old16 = (int)((cur >> shift) & 0xffffu);
+    if (old16 <= val) return old16;
+    const unsigned nw = (cur & ~(0xffffu << shift)) | ((unsigned)val << shift);
+    const unsigned prev = atomicCAS(w, cur, nw);
+    if (prev == cur) return old16;
+    cur = prev;
+  }
+}
+__device__ __forceinline__ void es_union(unsigned short* parent, int a, int b) {
   while (true) {
     a = es_find(parent, a);
     b = es_find(parent, b);
@@ -202,7 +219,7 @@ __device__ __forceinline__ void es_union(int* parent, int a, int b) {
       a = b;
       b = t;
     }
-    const int old = atomicMin(&parent[a], b);  // hook the larger root under the smaller
+    const int old = es_atomic_min16(parent, a, b);  // hook the larger root under the smaller
     if (old == a) return;
     a = old;  // a was no longer a root: merge its (former) parent with b instead
   }
@@ -251,9 +268,11 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
   unsigned short* rankc = lab16 + ES_MAX;
   unsigned short* hash = reinterpret_cast<unsigned short*>(smem_raw + ES_D);
   uint32_t* cell_key = reinterpret_cast<uint32_t*>(smem_raw + ES_E);
-  u64* sortbuf = reinterpret_cast<u64*>(smem_raw + ES_D);
-  int* cnt = reinterpret_cast<int*>(smem_raw + ES_B);
-  int* parent = reinterpret_cast<int*>(smem_raw + ES_B);
+  uint32_t* rootkey = reinterpret_cast<uint32_t*>(smem_raw + ES_D);  // ((n - size) << 16) | smallest index
+  unsigned short* rootnode = reinterpret_cast<unsigned short*>(smem_raw + ES_D + 4 * ES_MAX);
+  uint32_t* memkey = reinterpret_cast<uint32_t*>(smem_raw + ES_D);   // (rank << 14) | index
+  int* cnt = reinterpret_cast<int*>(smem_raw + ES_A + 4 * ES_HASH);
+  unsigned short* parent = reinterpret_cast<unsigned short*>(smem_raw + ES_B);
   unsigned short* idx16 = reinterpret_cast<unsigned short*>(smem_raw + ES_C);
   unsigned short* node_start = reinterpret_cast<unsigned short*>(smem_raw + ES_F);
   EceSmallMisc& sm = *reinterpret_cast<EceSmallMisc*>(smem_raw + ES_MISC);
@@ -406,7 +425,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
     }
   }
   const int nn = (e.mode == 0) ? nc : n;  // union-find nodes: cells (clique mode) or points
-  for (int v = tid; v < nn; v += ES_THREADS) parent[v] = v;
+  for (int v = tid; v < nn; v += ES_THREADS) parent[v] = (unsigned short)v;
   __syncthreads();
 
   ES_CLK(3);
@@ -523,7 +542,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
     for (int j = j0; j < j1; ++j) mi = min(mi, (int)idx16[j]);
     atomicAdd(&csize[root], j1 - j0);
     atomicMin(&minidx[root], mi);
-    parent[v] = root;  // racing readers see either an ancestor or the root
+    parent[v] = (unsigned short)root;  // racing readers see either an ancestor or the root
   }
   __syncthreads();
   ES_CLK(5);
@@ -533,44 +552,60 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
     int k = 0;
     for (int v = v0; v < v1; ++v) {
       const int sz = csize[v];
-      k += (parent[v] == v && sz >= min_size && sz <= max_size) ? 1 : 0;
+      k += ((int)parent[v] == v && sz >= min_size && sz <= max_size) ? 1 : 0;
     }
     int total;
     int pos = block_excl_scan(k, sm.wscan, total);
     for (int v = v0; v < v1; ++v) {
       const int sz = csize[v];
-      if (parent[v] == v && sz >= min_size && sz <= max_size)  // size desc, smallest original index asc
-        sortbuf[pos++] = ((u64)(uint32_t)(n - sz) << 32) | ((u64)(uint32_t)minidx[v] << 16) | (u64)(uint32_t)v;
+      if ((int)parent[v] == v && sz >= min_size && sz <= max_size) {  // size desc, smallest original index asc
+        rootkey[pos] = ((uint32_t)(n - sz) << 16) | (uint32_t)minidx[v];
+        rootnode[pos] = (unsigned short)v;
+        ++pos;
+      }
     }
     if (tid == 0) sm.n_clusters = total;
     __syncthreads();
   }
   const int C = sm.n_clusters;
-  if (C <= ES_THREADS) {  // rank by counting (keys are distinct: they contain the node id)
-    const u64 mykey = (tid < C) ? sortbuf[tid] : 0ull;
-    int rk = 0;
-    if (tid < C)
-      for (int o = 0; o < C; ++o) rk += (sortbuf[o] < mykey) ? 1 : 0;
+  {  // rank by counting, in place (the keys are distinct: a smallest index belongs to one component)
+    uint32_t mykey[ES_IPT];
+    unsigned short mynode[ES_IPT], myrank[ES_IPT];
+#pragma unroll
+    for (int k = 0; k < ES_IPT; ++k) {
+      const int r = tid + k * ES_THREADS;
+      mykey[k] = (r < C) ? rootkey[r] : 0xffffffffu;
+      mynode[k] = (r < C) ? rootnode[r] : (unsigned short)0;
+      myrank[k] = 0;
+    }
+    for (int o = 0; o < C; ++o) {
+      const uint32_t other = rootkey[o];  // (broadcast)
+#pragma unroll
+      for (int k = 0; k < ES_IPT; ++k) myrank[k] += (other < mykey[k]) ? 1 : 0;
+    }
     __syncthreads();
-    if (tid < C) sortbuf[rk] = mykey;
+#pragma unroll
+    for (int k = 0; k < ES_IPT; ++k) {
+      if (tid + k * ES_THREADS < C) {
+        rootkey[myrank[k]] = mykey[k];
+        rootnode[myrank[k]] = mynode[k];
+      }
+    }
     __syncthreads();
-  } else {
-    bitonic_sort_smem(sortbuf, C);
   }
   ES_CLK(6);
   {
     const int cpt = cdiv(max(C, 1), ES_THREADS);
     const int r0 = min(tid * cpt, C), r1 = min(r0 + cpt, C);
     int sum = 0;
-    for (int r = r0; r < r1; ++r) sum += n - (int)hi32(sortbuf[r]);
+    for (int r = r0; r < r1; ++r) sum += n - (int)(rootkey[r] >> 16);
     int total;
     int run = block_excl_scan(sum, sm.wscan, total);
     for (int r = r0; r < r1; ++r) {
-      const u64 v = sortbuf[r];
       offs[r] = run;
       if (r < ES_SCAN_MAXC) sm.soff[r] = run;
-      rankc[lo32(v) & 0xffffu] = (unsigned short)r;
-      run += n - (int)hi32(v);
+      rankc[rootnode[r]] = (unsigned short)r;
+      run += n - (int)(rootkey[r] >> 16);
     }
     if (tid == 0) {
       offs[C] = total;
@@ -633,14 +668,14 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
       __syncwarp();
     }
   } else {
-    for (int i = tid; i < n; i += ES_THREADS) {
+    for (int i = tid; i < n; i += ES_THREADS) {  // (the kept-root arrays are dead)
       const unsigned short lab = lab16[i];
-      sortbuf[i] = (lab != 0xffffu) ? (((u64)lab << 32) | (u64)(uint32_t)i) : ~0ull;
+      memkey[i] = (lab != 0xffffu) ? (((uint32_t)lab << 14) | (uint32_t)i) : 0xffffffffu;
     }
     __syncthreads();
-    bitonic_sort_smem(sortbuf, n);
+    bitonic_sort_smem(memkey, n);
     for (int j = tid; j < L; j += ES_THREADS) {
-      const uint32_t i = lo32(sortbuf[j]);
+      const uint32_t i = memkey[j] & 0x3fffu;
       mem16[j] = (unsigned short)i;
       idx_out[j] = (int)i;
     }

@@ -238,7 +238,7 @@ def test_cluster_fused_kernel_capacity_edge(monkeypatch):
     p.euc_min_cluster_size = 3
     p.euc_max_cluster_size = 100000
     rng = np.random.default_rng(41)
-    for n in (8192, 8193):
+    for n in (8960, 8961):
         centers = rng.uniform(-5, 5, size=(40, 3))
         pts = centers[rng.integers(0, 40, n)] + rng.normal(size=(n, 3)) * 0.15
         cloud = _cloud(pts)
