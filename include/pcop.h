@@ -234,6 +234,16 @@ int pcop_accumulate_pointcloud2(pcop_handle* h, const unsigned char* data, int32
 int pcop_pointcloud2_to_xyz(pcop_handle* h, const unsigned char* data, int32_t n_points, int32_t point_step, int32_t off_x,
                             int32_t off_y, int32_t off_z, float* out_xyzw);
 
+/* ---- occupancy grid, initial data set (replaces od.cpp:134-157 + 175-269) ---------------------------------
+ * The node's published product starts as a count of the crop survivors per block_size x block_size cell (rows along
+ * -x from x_max, columns along +y from y_min), a per-row integer average and the threshold
+ *   cell = (count < row_average * (1 - dev_percent)) ? 100 : 0        (float compare, od.cpp:258).
+ * pcop_occupancy_dims: width/height as od.cpp:958-959.  pcop_occupancy_grid: xyzw = NULL takes the accumulated cloud
+ * (pcop_accumulate*); grid_data[width*height] int8; counts[width*height] / row_avg[height] int64 are optional.
+ * Hole detection and shadow casting (od.cpp:467-672, 823-852) stay on the host. */
+int pcop_occupancy_dims(const pcop_handle* h, int32_t* width, int32_t* height);
+int pcop_occupancy_grid(pcop_handle* h, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts, int64_t* row_avg);
+
 /* bytes copied device -> host by the last call (results, counts, records; padded rows of the early remaining-cloud copy included) */
 double pcop_last_d2h_bytes(const pcop_handle* h);
 

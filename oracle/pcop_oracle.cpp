@@ -985,6 +985,66 @@ int pcop_oracle_pointcloud2_to_xyz(const unsigned char* data, int32_t n_points, 
   return PCOP_OK;
 }
 
+// od.cpp:958-960: (int)ceil((fabs(lo) + fabs(hi)) / block_size).  ORACLE CHOICE: the unqualified fabs binds to
+// ::fabs(double), so the sum and the division are evaluated in double.
+int pcop_oracle_occupancy_dims(const pcop_params* pr, int32_t* width, int32_t* height) {
+  if (!pr || !width || !height || !(pr->block_size > 0.0f)) return PCOP_ERR_BAD_PARAM;
+  *width = (int32_t)std::ceil((std::fabs((double)pr->y_min) + std::fabs((double)pr->y_max)) / (double)pr->block_size);
+  *height = (int32_t)std::ceil((std::fabs((double)pr->x_min) + std::fabs((double)pr->x_max)) / (double)pr->block_size);
+  return PCOP_OK;
+}
+
+// get_occupancy_grid_x_y (od.cpp:134-150), called as (point.y, point.x, y_min, x_max, block_size) at od.cpp:203
+static void occupancy_xy(float x, float y, float x_min, float y_max, float block_size, int* xc, int* yc) {
+  int x_count = 0, y_count = 0;
+  while (true) {
+    volatile float step = (float)(x_count + 1) * block_size;
+    volatile float edge = x_min + step;
+    if (!(edge < x)) break;
+    x_count++;
+  }
+  while (true) {
+    volatile float step = (float)(y_count + 1) * block_size;
+    volatile float edge = y_max - step;
+    if (!(edge > y)) break;
+    y_count++;
+  }
+  *xc = x_count;
+  *yc = y_count;
+}
+
+int pcop_oracle_occupancy_grid(const pcop_params* pr, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts_out,
+                               int64_t* row_avg_out) {
+  int32_t W = 0, H = 0;
+  if (!xyzw || !grid_data || n < 0 || pcop_oracle_occupancy_dims(pr, &W, &H) != PCOP_OK || W <= 0 || H <= 0) return PCOP_ERR_BAD_PARAM;
+  const long long size = (long long)W * H;
+  std::vector<long long> counts((size_t)size, 0), row_avg((size_t)H, 0);
+  for (int32_t i = 0; i < n; ++i) {  // od.cpp:195-215
+    const float x = xyzw[4 * i], y = xyzw[4 * i + 1], z = xyzw[4 * i + 2];
+    if (std::isnan(x) || x < pr->x_min || x > pr->x_max || z < pr->z_min || z > pr->z_max || y < pr->y_min || y > pr->y_max)
+      continue;
+    int xc, yc;
+    occupancy_xy(y, x, pr->y_min, pr->x_max, pr->block_size, &xc, &yc);
+    const long long index = (long long)yc * W + xc;  // (int arithmetic in the reference; identical in range)
+    if (index >= size) continue;                     // od.cpp:205 "OUT OF BOUNDS INDEX ACCESS"
+    counts[(size_t)index]++;
+  }
+  for (int r = 0; r < H; ++r) {  // od.cpp:226-234
+    long long row = 0;
+    for (int c = 0; c < W; ++c) row += counts[(size_t)r * W + c];
+    row_avg[r] = row / W;
+  }
+  for (long long i = 0; i < size; ++i) {  // od.cpp:241-266
+    const long long avg = row_avg[(size_t)(i / W)];
+    volatile float one_minus = 1.0f - pr->dev_percent;
+    volatile float thr = (float)avg * one_minus;
+    grid_data[i] = ((float)counts[(size_t)i] < thr) ? 100 : 0;
+  }
+  if (counts_out) std::memcpy(counts_out, counts.data(), sizeof(long long) * (size_t)size);
+  if (row_avg_out) std::memcpy(row_avg_out, row_avg.data(), sizeof(long long) * (size_t)H);
+  return PCOP_OK;
+}
+
 int pcop_oracle_process(const pcop_params* pr, const float* xyzw, int32_t n, pcop_frame_result* out) {
   std::memset(out, 0, sizeof(*out));
   const P4* in = (const P4*)xyzw;

@@ -51,6 +51,14 @@ int pcop_oracle_transform(const float* xyzw, int32_t n, const float* m16, int32_
 int pcop_oracle_pointcloud2_to_xyz(const unsigned char* data, int32_t n_points, int32_t point_step, int32_t off_x,
                                    int32_t off_y, int32_t off_z, float* out_xyzw);
 
+/* Initial occupancy-grid data set (od.cpp:134-157, 175-269, sizes od.cpp:958-960), literal: per crop survivor the cell
+ * found by the two while-loops (float arithmetic), int64 counts, per-row integer average, cell = 100 when
+ * (float)count < (float)row_avg * (1.0f - dev_percent), else 0.  width/height as in od.cpp:958-959 (double division).
+ * counts / row_avg may be NULL. */
+int pcop_oracle_occupancy_dims(const pcop_params* pr, int32_t* width, int32_t* height);
+int pcop_oracle_occupancy_grid(const pcop_params* pr, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts,
+                               int64_t* row_avg);
+
 /* Whole pipeline; result arrays are malloc'ed, release with pcop_oracle_free_result.
  * All PCOP_OUT_* arrays are always filled. */
 int pcop_oracle_process(const pcop_params* pr, const float* xyzw, int32_t n, pcop_frame_result* out);

@@ -39,6 +39,8 @@ EXPORTS = [
     "pcop_transform",
     "pcop_accumulate_pointcloud2",
     "pcop_pointcloud2_to_xyz",
+    "pcop_occupancy_dims",
+    "pcop_occupancy_grid",
 ]
 
 
@@ -89,6 +91,8 @@ def load_library():
     L.pcop_transform.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.pcop_accumulate_pointcloud2.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp]
     L.pcop_pointcloud2_to_xyz.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.pcop_occupancy_dims.argtypes = [vp, vp, vp]
+    L.pcop_occupancy_grid.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
     L.pcop_enable_kernel_timing.argtypes = [vp, C.c_int]
     L.pcop_kernel_timing_count.argtypes = [vp]
     L.pcop_kernel_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
@@ -215,6 +219,23 @@ class ObstacleProcessor:
         self._check(self._lib.pcop_pointcloud2_to_xyz(self._h, buf.ctypes.data_as(C.c_void_p), n_points, point_step, off_x,
                                                       off_y, off_z, out.ctypes.data_as(C.c_void_p)))
         return out[:n_points].copy()
+
+    def occupancy_grid(self, cloud=None):
+        """build_initial_occupancy_grid_dataset (od.cpp:175-269) without the crop output: returns (grid int8 [H, W],
+        counts int64 [H, W], row_avg int64 [H]).  cloud=None: the accumulated cloud."""
+        w, h = C.c_int32(), C.c_int32()
+        self._check(self._lib.pcop_occupancy_dims(self._h, C.byref(w), C.byref(h)))
+        grid = np.empty((h.value, w.value), np.int8)
+        counts = np.empty((h.value, w.value), np.int64)
+        avg = np.empty(h.value, np.int64)
+        if cloud is None:
+            ptr, n = None, 0
+        else:
+            cloud = _f32(cloud)
+            ptr, n = cloud.ctypes.data_as(C.c_void_p), cloud.shape[0]
+        self._check(self._lib.pcop_occupancy_grid(self._h, ptr, n, grid.ctypes.data_as(C.c_void_p),
+                                                  counts.ctypes.data_as(C.c_void_p), avg.ctypes.data_as(C.c_void_p)))
+        return grid, counts, avg
 
     @property
     def accumulated_count(self) -> int:

@@ -131,6 +131,8 @@ struct pcop_handle {
   unsigned char* wave_rem_host = nullptr;
   double d2h_bytes = 0.0;
   float4* d_acc = nullptr;  // accumulated (world-frame) cloud, od.cpp:697
+  unsigned char* d_occ = nullptr;  // occupancy grid scratch: int64 counts, int64 row averages, int8 cells
+  size_t occ_cap = 0;
   unsigned char* d_raw = nullptr;  // staging for a raw PointCloud2 payload (grown on demand)
   size_t raw_cap = 0;
   int acc_count = 0;
@@ -363,6 +365,65 @@ __global__ void __launch_bounds__(256)
     o.z = fadd(fadd(fadd(fmul(t.m[8], x), fmul(t.m[9], y)), fmul(t.m[10], z)), t.m[11]);
   }
   out[i] = o;
+}
+
+// ---- occupancy grid, initial data set (od.cpp:134-157, 175-269) ---------------------------------------------------
+// get_occupancy_grid_x_y's while-loops in closed form: the smallest k >= 0 for which the loop condition fails.  The
+// edge value fl(a +- fl((k+1)*bs)) is monotone in k, so a floor estimate followed by a walk of a few steps lands on
+// exactly the k the reference's loop stops at.
+__device__ __forceinline__ int occ_count_up(float x_min, float bs, float x) {  // while (x_min + (k+1)*bs < x) k++
+  if (!(x == x)) return 0;
+  int k = (int)fmaxf(floorf(fdiv(fsub(x, x_min), bs)) - 2.0f, 0.0f);
+  while (k > 0 && !(fadd(x_min, fmul((float)k, bs)) < x)) --k;         // the loop would already have stopped at k-1
+  while (fadd(x_min, fmul((float)(k + 1), bs)) < x) ++k;
+  return k;
+}
+__device__ __forceinline__ int occ_count_down(float y_max, float bs, float y) {  // while (y_max - (k+1)*bs > y) k++
+  if (!(y == y)) return 0;
+  int k = (int)fmaxf(floorf(fdiv(fsub(y_max, y), bs)) - 2.0f, 0.0f);
+  while (k > 0 && !(fsub(y_max, fmul((float)k, bs)) > y)) --k;
+  while (fsub(y_max, fmul((float)(k + 1), bs)) > y) ++k;
+  return k;
+}
+
+__global__ void __launch_bounds__(256)
+    k_occ_count(const float4* __restrict__ in, int n, float x_min, float x_max, float y_min, float y_max, float z_min,
+                float z_max, float bs, int W, long long size, unsigned long long* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(in + i);
+  // od.cpp:197-199, literal
+  if ((p.x != p.x) || p.x < x_min || p.x > x_max || p.z < z_min || p.z > z_max || p.y < y_min || p.y > y_max) return;
+  const int xc = occ_count_up(y_min, bs, p.y);    // od.cpp:203: (x, y, x_min, y_max) := (point.y, point.x, y_min, x_max)
+  const int yc = occ_count_down(x_max, bs, p.x);
+  const long long index = (long long)yc * W + xc;
+  if (index >= size) return;  // od.cpp:205
+  atomicAdd(&counts[index], 1ull);
+}
+
+// one block per row: integer row average (od.cpp:226-234), then the threshold (od.cpp:241-266)
+__global__ void __launch_bounds__(256)
+    k_occ_finish(const unsigned long long* __restrict__ counts, int W, float dev_percent, long long* __restrict__ row_avg,
+                 signed char* __restrict__ grid) {
+  const int r = blockIdx.x;
+  __shared__ unsigned long long part[8];
+  __shared__ long long avg_sh;
+  unsigned long long s = 0;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) s += counts[(size_t)r * W + c];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    avg_sh = (long long)t / (long long)W;
+    row_avg[r] = avg_sh;
+  }
+  __syncthreads();
+  const float thr = fmul((float)avg_sh, fsub(1.0f, dev_percent));
+  for (int c = threadIdx.x; c < W; c += blockDim.x)
+    grid[(size_t)r * W + c] = ((float)(long long)counts[(size_t)r * W + c] < thr) ? 100 : 0;
 }
 
 // cloud copy for a disabled plane stage: remaining = input, src = identity
@@ -1420,6 +1481,7 @@ void pcop_destroy(pcop_handle* h) {
   for (void* p : h->host_allocs) cudaFreeHost(p);
   if (h->d_pack) cudaFree(h->d_pack);
   if (h->d_raw) cudaFree(h->d_raw);
+  if (h->d_occ) cudaFree(h->d_occ);
   if (h->h_pack) cudaFreeHost(h->h_pack);
   if (h->kt.ev) {
     for (int i = 0; i < 2 * KernelTimers::MAX_SLOTS; ++i) cudaEventDestroy(h->kt.ev[i]);
@@ -1575,6 +1637,7 @@ static int pc2_ingest(pcop_handle* h, const unsigned char* data, int32_t n, int3
     if (bytes > h->raw_cap) {
       PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
       if (h->d_raw) cudaFree(h->d_raw);
+  if (h->d_occ) cudaFree(h->d_occ);
       h->d_raw = nullptr;
       h->raw_cap = 0;
       PCOP_CUDA_TRY(cudaMalloc((void**)&h->d_raw, bytes + bytes / 4 + 256));
@@ -1613,6 +1676,60 @@ int pcop_pointcloud2_to_xyz(pcop_handle* h, const unsigned char* data, int32_t n
   if (n_points == 0) return PCOP_OK;
   TRY(pc2_ingest(h, data, n_points, point_step, off_x, off_y, off_z, nullptr, 1, h->d_crop));
   TRY(download(h, out_xyzw, h->d_crop, (size_t)n_points * 16));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+int pcop_occupancy_dims(const pcop_handle* h, int32_t* width, int32_t* height) {
+  if (!h || !width || !height || !(h->params.block_size > 0.0f)) return PCOP_ERR_BAD_PARAM;
+  const pcop_params& p = h->params;  // od.cpp:958-959 (double: the unqualified fabs is ::fabs(double))
+  *width = (int32_t)std::ceil((std::fabs((double)p.y_min) + std::fabs((double)p.y_max)) / (double)p.block_size);
+  *height = (int32_t)std::ceil((std::fabs((double)p.x_min) + std::fabs((double)p.x_max)) / (double)p.block_size);
+  return PCOP_OK;
+}
+
+int pcop_occupancy_grid(pcop_handle* h, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts, int64_t* row_avg) {
+  if (!h || !grid_data || n < 0) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  int32_t W = 0, H = 0;
+  if (pcop_occupancy_dims(h, &W, &H) != PCOP_OK || W <= 0 || H <= 0 || (long long)W * H > (1ll << 26))
+    return fail(h, PCOP_ERR_BAD_PARAM, "occupancy grid: block_size / crop limits give no usable grid");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  const float4* src;
+  if (!xyzw) {  // the accumulated cloud
+    src = h->d_acc;
+    n = h->acc_count;
+  } else {
+    if (n > h->cap) return fail(h, PCOP_ERR_CAPACITY, "cloud has more points than max_points");
+    src = reinterpret_cast<const float4*>(xyzw);
+    if (!is_device_pointer(xyzw)) {
+      if (n > 0) PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_in, xyzw, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+      src = h->d_in;
+    }
+  }
+  const size_t cells = (size_t)W * H;
+  const size_t need = cells * 8 + (size_t)H * 8 + cells;
+  if (need > h->occ_cap) {
+    PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->d_occ) cudaFree(h->d_occ);
+    h->d_occ = nullptr;
+    h->occ_cap = 0;
+    PCOP_CUDA_TRY(cudaMalloc((void**)&h->d_occ, need + 256));
+    h->occ_cap = need;
+  }
+  unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(h->d_occ);
+  long long* d_avg = reinterpret_cast<long long*>(h->d_occ + cells * 8);
+  signed char* d_grid = reinterpret_cast<signed char*>(h->d_occ + cells * 8 + (size_t)H * 8);
+  const pcop_params& p = h->params;
+  Ctx c = make_ctx(h, 1, n);
+  PCOP_CUDA_TRY(cudaMemsetAsync(d_counts, 0, cells * 8, h->stream));
+  if (n > 0)
+    KL(c, "k_occ_count", k_occ_count<<<cdiv(n, 256), 256, 0, h->stream>>>(src, n, p.x_min, p.x_max, p.y_min, p.y_max, p.z_min, p.z_max,
+                                                          p.block_size, W, (long long)cells, d_counts));
+  KL(c, "k_occ_finish", k_occ_finish<<<H, 256, 0, h->stream>>>(d_counts, W, p.dev_percent, d_avg, d_grid));
+  count_launch(c, 2);
+  TRY(download(h, grid_data, d_grid, cells));
+  TRY(download(h, counts, d_counts, cells * 8));
+  TRY(download(h, row_avg, d_avg, (size_t)H * 8));
   PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return PCOP_OK;
 }

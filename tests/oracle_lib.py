@@ -208,3 +208,17 @@ def pointcloud2_to_xyz(data, n_points, point_step, off_x, off_y, off_z):
                                               out.ctypes.data_as(_fp))
     assert st == 0, st
     return out[:n_points].copy()
+
+
+def occupancy_grid(params, cloud):
+    """build_initial_occupancy_grid_dataset restatement (od.cpp:175-269): (grid int8 [H, W], counts, row_avg)"""
+    cloud, cp = _c(cloud, np.float32)
+    w, h = C.c_int32(), C.c_int32()
+    assert lib().pcop_oracle_occupancy_dims(C.byref(params), C.byref(w), C.byref(h)) == 0
+    grid = np.empty((h.value, w.value), np.int8)
+    counts = np.empty((h.value, w.value), np.int64)
+    avg = np.empty(h.value, np.int64)
+    st = lib().pcop_oracle_occupancy_grid(C.byref(params), cp, cloud.shape[0], grid.ctypes.data_as(_fp),
+                                          counts.ctypes.data_as(_fp), avg.ctypes.data_as(_fp))
+    assert st == 0, st
+    return grid, counts, avg

@@ -422,3 +422,22 @@ def test_pointcloud2_ingest(point_step, offs, frames):
         acc = op.process_accumulated().remaining_cloud
     want = np.concatenate([O.transform(o, m, is_dense=False), o])
     assert_bits_equal(acc, want, "accumulated cloud")
+
+
+@pytest.mark.parametrize("config", [1, 2])
+def test_occupancy_grid(config, frames):
+    """od.cpp:175-269 (the occupancy grid's initial data set): counts, row averages and cells, bit-exact"""
+    p = synth.params(config)
+    if config == 2:
+        p.block_size = 0.5
+    cloud = frames[config]
+    with ObstacleProcessor(p, len(cloud)) as op:
+        g_grid, g_counts, g_avg = op.occupancy_grid(cloud)
+        op.accumulate(cloud[:len(cloud) // 2])
+        op.accumulate(cloud[len(cloud) // 2:])
+        a_grid, a_counts, a_avg = op.occupancy_grid(None)  # the accumulated cloud
+    o_grid, o_counts, o_avg = O.occupancy_grid(p, cloud)
+    for g, o, what in ((g_counts, o_counts, "counts"), (g_avg, o_avg, "row averages"), (g_grid, o_grid, "cells"),
+                       (a_counts, o_counts, "counts (accumulated)"), (a_grid, o_grid, "cells (accumulated)")):
+        assert_bits_equal(g, o, what)
+    assert o_counts.sum() > 1000 and (o_grid == 100).any() and (o_grid == 0).any()

@@ -439,3 +439,48 @@ def test_pointcloud2_field_extraction(point_step, offs):
     out = O.pointcloud2_to_xyz(buf, len(xyz), point_step, *offs)
     assert np.array_equal(out[:, :3].view(np.uint32), xyz.view(np.uint32))
     assert (out[:, 3] == 1.0).all()
+
+
+def test_occupancy_grid_dims_params_yaml():
+    """od.cpp:958-959 with params.yaml: 101 x 120 cells (SURVEY 8c known answer)"""
+    import ctypes as C
+    p = synth.params(1)
+    w, h = C.c_int32(), C.c_int32()
+    assert O.lib().pcop_oracle_occupancy_dims(C.byref(p), C.byref(w), C.byref(h)) == 0
+    assert (w.value, h.value) == (101, 120)
+
+
+def test_occupancy_grid_against_literal_python_loops():
+    """od.cpp:134-157 + 175-269 restated independently in Python with numpy float32 scalars (the while-loops as written)"""
+    p = synth.params(1)
+    f = np.float32
+    rng = np.random.default_rng(17)
+    n = 3000
+    pts = np.stack([rng.uniform(-0.2, 4.7, n), rng.uniform(-0.2, 4.0, n), rng.uniform(-0.6, 0.3, n)], 1).astype(f)
+    pts[::97, 0] = np.nan
+    pts[5] = [p.x_max, p.y_max, 0.0]   # corner cases on the box faces
+    pts[6] = [p.x_min, p.y_min, 0.0]
+    cloud = np.concatenate([pts, np.ones((n, 1), f)], 1)
+    grid, counts, avg = O.occupancy_grid(p, cloud)
+    H, W = grid.shape
+    bs, x_min, x_max, y_min, y_max = f(p.block_size), f(p.x_min), f(p.x_max), f(p.y_min), f(p.y_max)
+    ref = np.zeros(H * W, np.int64)
+    for x, y, z in pts:
+        if np.isnan(x) or x < x_min or x > x_max or z < f(p.z_min) or z > f(p.z_max) or y < y_min or y > y_max:
+            continue
+        xc = 0
+        while f(y_min + f(f(xc + 1) * bs)) < y:
+            xc += 1
+        yc = 0
+        while f(x_max - f(f(yc + 1) * bs)) > x:
+            yc += 1
+        idx = yc * W + xc
+        if idx < H * W:
+            ref[idx] += 1
+    assert np.array_equal(counts.ravel(), ref)
+    ravg = ref.reshape(H, W).sum(1) // W
+    assert np.array_equal(avg, ravg)
+    thr = (ravg.astype(f) * f(f(1.0) - f(p.dev_percent))).astype(f)
+    want = np.where(ref.reshape(H, W).astype(f) < thr[:, None], 100, 0).astype(np.int8)
+    assert np.array_equal(grid, want)
+    assert counts.sum() > 1000
