@@ -12,8 +12,9 @@
 //                   of (key, original index) pairs (warp ballots + decoupled look-back), min/max of the survivors
 //                   (PCL's key arithmetic and overflow guard need them), all digit histograms of the sort;
 //   k_vf_scan       exclusive scan of the digit histograms;
-//   k_vf_sort_pass  onesweep LSD radix passes with ceil(bits / npass)-bit digits (<= 9 bits: 25-bit keys of the
-//                   HDL-64 configuration take 3 passes instead of 4);
+//   k_vf_sort_pass  onesweep LSD radix passes with ceil(bits / npass)-bit digits (<= 8 bits by default; 64-bit
+//                   (key, index) elements; warp ranks by MATCH.ANY on the coarse digits, per-bit ballots on the
+//                   high-entropy low digits);
 //   k_vf_reduce     run heads + voxel count + centroids in one kernel: the tile's points are gathered into shared
 //                   memory in sorted order, every run head sums its run sequentially (ascending original index:
 //                   the compaction and the sort are stable) and divides by the float count; PCL's own key of the
@@ -199,7 +200,7 @@ struct VfPassSmem {
 #ifndef VF_SORT_MINBLOCKS
 #define VF_SORT_MINBLOCKS 5
 #endif
-template <int BITS>
+template <int BITS, bool USE_MATCH>
 __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
     k_vf_sort_pass(const unsigned long long* __restrict__ pair_in, unsigned long long* __restrict__ pair_out,
                    const int* __restrict__ count, const uint32_t* __restrict__ bin_base,
@@ -239,7 +240,20 @@ __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
   for (int k = 0; k < RS_ITEMS; ++k) {
     const bool valid = (wbase_idx + k * 32) < n;
     const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
-    mm[k] = __match_any_sync(FULL, valid ? d : (BINS + lane));  // invalid lanes match nobody
+    if (USE_MATCH) {
+      mm[k] = __match_any_sync(FULL, valid ? d : (BINS + lane));  // invalid lanes match nobody
+    } else {
+      // MATCH.ANY runs on the ADU pipe in time proportional to the number of distinct values in the warp (80 % pipe
+      // utilisation on the high-entropy low digits): one ballot per digit bit instead
+      unsigned peers = __ballot_sync(FULL, valid);
+#pragma unroll
+      for (int b = 0; b < BITS; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(FULL, bit);
+        peers &= bit ? bal : ~bal;
+      }
+      mm[k] = valid ? peers : (1u << lane);
+    }
   }
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
@@ -453,13 +467,28 @@ __global__ void __launch_bounds__(CT_THREADS)
   if (tbase + CT_TILE >= m && threadIdx.x == 0) n_out[f] = (int)incl_total;
 }
 
-template <int BITS>
-void launch_pass(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
-  cudaFuncSetAttribute(k_vf_sort_pass<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VfPassSmem<BITS>));
+template <int BITS, bool USE_MATCH>
+void launch_pass_m(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
+  cudaFuncSetAttribute(k_vf_sort_pass<BITS, USE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VfPassSmem<BITS>));
   const int src = pass & 1;
-  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
+  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS, USE_MATCH><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
       a.pair[src], a.pair[src ^ 1], a.n_crop, a.sort.hist, a.sort.desc, pass, shift, c.cap, gtiles, a.sort.stats));
   count_launch(c);
+}
+
+// match_mask bit p set: pass p ranks with MATCH.ANY (few distinct digits per warp), else with per-bit ballots
+template <int BITS>
+void launch_pass(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
+  static const int match_mask = [] {
+    const char* s = getenv("PCOP_VF_MATCH_MASK");
+    return s ? atoi(s) : -1;
+  }();
+  // measured (B200, HDL-64 keys, 4 x 7 bits): MATCH.ANY on the two most significant digits (coarse y / z cells: few
+  // distinct values per warp) and ballots on the others: 1.70 ms per 3 x 256 frames; all MATCH 1.94; all ballots 1.82
+  const bool top = (pass >= a.plan.npass - 2);
+  const bool use_match = (match_mask >= 0) ? ((match_mask >> pass) & 1) : top;
+  if (use_match) launch_pass_m<BITS, true>(c, a, pass, shift, gtiles);
+  else launch_pass_m<BITS, false>(c, a, pass, shift, gtiles);
 }
 
 }  // namespace
