@@ -147,6 +147,7 @@ struct VoxelFusedArgs {
   float4* out;       // [B*cap] voxel centroids
   uint32_t* out_keys;
   int* n_out;        // [B] V
+  int want_keys;     // PCL's voxel keys are an output (PCOP_OUT_VOXEL); otherwise they are not computed
 };
 void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a);
 

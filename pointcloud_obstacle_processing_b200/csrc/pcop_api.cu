@@ -761,6 +761,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
     a.out = h->d_vox;
     a.out_keys = h->d_vox_keys;
     a.n_out = h->cnt(CNT_VOX);
+    a.want_keys = (effective_outputs(p) & PCOP_OUT_VOXEL) ? 1 : 0;
     run_voxel_fused(c, a);
     cur = h->d_vox;
     cur_stride = h->cap;

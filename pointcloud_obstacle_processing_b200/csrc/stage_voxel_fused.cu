@@ -76,6 +76,7 @@ __global__ void k_vf_init(MinMax* mm, uint32_t* __restrict__ flags, int B) {
   }
 }
 
+template <bool NEED_MINMAX>
 __global__ void __launch_bounds__(CT_THREADS)
     k_vf_crop_key(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
                   unsigned long long* __restrict__ pairs, int* __restrict__ n_out,
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(CT_THREADS)
                         p.y < pl.lim[2] || p.y > pl.lim[3];
       if (!drop) {
         keepmask |= 1u << k;
-        acc.add(p);
+        if (NEED_MINMAX) acc.add(p);
         odd = odd || !(fabsf(p.y) <= 3.0e38f) || !(fabsf(p.z) <= 3.0e38f);
         const int cx = __float2int_rz(floorf(fmul(p.x, pl.inv))) - pl.b0[0];
         const int cy = __float2int_rz(floorf(fmul(p.y, pl.inv))) - pl.b0[1];
@@ -134,24 +135,26 @@ __global__ void __launch_bounds__(CT_THREADS)
     wbase += __popc(m);
   }
   if ((tile + 1) * BT_TILE >= n && threadIdx.x == 0) n_out[f] = (int)incl_total;
-  // min/max: block reduce + one atomic per axis per block
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      acc.mn[a] = fminf(acc.mn[a], __shfl_xor_sync(FULL, acc.mn[a], o));
-      acc.mx[a] = fmaxf(acc.mx[a], __shfl_xor_sync(FULL, acc.mx[a], o));
-    }
-  }
-  if (lane_id() == 0) {
+  // min/max (only PCL's own voxel keys need them: PCOP_OUT_VOXEL): block reduce + one atomic per axis per block
+  if (NEED_MINMAX) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      sm.shmm[warp_id()][a] = acc.mn[a];
-      sm.shmm[warp_id()][3 + a] = acc.mx[a];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        acc.mn[a] = fminf(acc.mn[a], __shfl_xor_sync(FULL, acc.mn[a], o));
+        acc.mx[a] = fmaxf(acc.mx[a], __shfl_xor_sync(FULL, acc.mx[a], o));
+      }
+    }
+    if (lane_id() == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        sm.shmm[warp_id()][a] = acc.mn[a];
+        sm.shmm[warp_id()][3 + a] = acc.mx[a];
+      }
     }
   }
   __syncthreads();  // (also: all histogram atomics of the block are done)
-  if (threadIdx.x < 6) {
+  if (NEED_MINMAX && threadIdx.x < 6) {
     const int a = threadIdx.x;
     float v = sm.shmm[0][a];
     for (int w = 1; w < CT_THREADS / 32; ++w) v = (a < 3) ? fminf(v, sm.shmm[w][a]) : fmaxf(v, sm.shmm[w][a]);
@@ -375,8 +378,10 @@ struct VfSmemR {
   CompactSmem cs;
   uint32_t skey[CT_TILE + 1];  // [0] = key before the tile
   float sx[CT_TILE], sy[CT_TILE], sz[CT_TILE];
+  unsigned short head[CT_TILE];  // tile positions of the run heads, dense
 };
 
+template <bool WITH_KEYS>
 __global__ void __launch_bounds__(CT_THREADS)
     k_vf_reduce(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_sorted,
                 const unsigned long long* __restrict__ pairs, const VoxelFrame* __restrict__ vf,
@@ -428,24 +433,27 @@ __global__ void __launch_bounds__(CT_THREADS)
     keep[k] = t < tile_n && (tbase + t == 0 || sm.skey[t + 1] != sm.skey[t]);
   }
   const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm.cs);
+  // dense list of the tile's heads: the per-head work below then runs with every lane busy (half of the sorted
+  // elements are heads; walking them in place left half of each warp idle through four unrolled copies of the loop)
+  const unsigned tile_excl = sm.cs.tile_excl, n_heads = sm.cs.tile_total;
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k)
+    if (keep[k]) sm.head[pos[k] - tile_excl] = (unsigned short)(warp_id() * (32 * CT_ITEMS) + k * 32 + lane_id());
+  __syncthreads();
   const VoxelFrame v = vf[f];
   const float fb0 = (float)v.min_b[0], fb1 = (float)v.min_b[1], fb2 = (float)v.min_b[2];
-#pragma unroll
-  for (int k = 0; k < CT_ITEMS; ++k) {
-    if (!keep[k]) continue;
-    const int t0 = warp_id() * (32 * CT_ITEMS) + k * 32 + lane_id();
+  for (unsigned h = threadIdx.x; h < n_heads; h += CT_THREADS) {
+    const int t0 = sm.head[h];
+    const int t1 = (h + 1 < n_heads) ? (int)sm.head[h + 1] : tile_n;  // the run inside the tile is [t0, t1)
     const uint32_t kk = sm.skey[t0 + 1];
-    const float hx = sm.sx[t0], hy = sm.sy[t0], hz = sm.sz[t0];
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
-    int t = t0;
-    do {  // the run inside the tile
+    for (int t = t0; t < t1; ++t) {
       ax = fadd(ax, sm.sx[t]);
       ay = fadd(ay, sm.sy[t]);
       az = fadd(az, sm.sz[t]);
-      ++t;
-    } while (t < tile_n && sm.skey[t + 1] == kk);
-    int cnt = t - t0;
-    if (t == tile_n) {  // ... and its tail in the following tiles
+    }
+    int cnt = t1 - t0;
+    if (t1 == tile_n) {  // ... and its tail in the following tiles
       for (int j = tbase + tile_n; j < m; ++j) {
         const unsigned long long pp = ps[j];
         if ((uint32_t)(pp >> 32) != kk) break;
@@ -457,12 +465,14 @@ __global__ void __launch_bounds__(CT_THREADS)
       }
     }
     const float c = (float)cnt;
-    out[(size_t)f * cap + pos[k]] = make_float4(fdiv(ax, c), fdiv(ay, c), fdiv(az, c), 1.0f);
-    // PCL's key of this voxel, from its first point (voxel_grid.hpp: ijk = floor(p*inv) - min_b)
-    const int i0 = cvt_f2i(fsub(floorf(fmul(hx, v.inv)), fb0));
-    const int i1 = cvt_f2i(fsub(floorf(fmul(hy, v.inv)), fb1));
-    const int i2 = cvt_f2i(fsub(floorf(fmul(hz, v.inv)), fb2));
-    out_keys[(size_t)f * cap + pos[k]] = (uint32_t)i0 + (uint32_t)i1 * v.mul1 + (uint32_t)i2 * v.mul2;
+    const size_t o = (size_t)f * cap + tile_excl + h;
+    out[o] = make_float4(fdiv(ax, c), fdiv(ay, c), fdiv(az, c), 1.0f);
+    if (WITH_KEYS) {  // PCL's key of this voxel, from its first point (voxel_grid.hpp: ijk = floor(p*inv) - min_b)
+      const int i0 = cvt_f2i(fsub(floorf(fmul(sm.sx[t0], v.inv)), fb0));
+      const int i1 = cvt_f2i(fsub(floorf(fmul(sm.sy[t0], v.inv)), fb1));
+      const int i2 = cvt_f2i(fsub(floorf(fmul(sm.sz[t0], v.inv)), fb2));
+      out_keys[o] = (uint32_t)i0 + (uint32_t)i1 * v.mul1 + (uint32_t)i2 * v.mul2;
+    }
   }
   if (tbase + CT_TILE >= m && threadIdx.x == 0) n_out[f] = (int)incl_total;
 }
@@ -551,8 +561,12 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   cudaMemsetAsync(a.sort.hist, 0, vox_fused_hist_elems(c.B) * sizeof(uint32_t), c.stream);
   cudaMemsetAsync(a.sort.desc, 0, (size_t)pl.npass * c.B * gtiles * nbins * sizeof(uint32_t), c.stream);
   KL(c, "k_vf_init", k_vf_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, c.B));
-  KL(c, "k_vf_crop_key", k_vf_crop_key<<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
-      a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles));
+  if (a.want_keys)
+    KL(c, "k_vf_crop_key", k_vf_crop_key<true><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
+        a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles));
+  else
+    KL(c, "k_vf_crop_key", k_vf_crop_key<false><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
+        a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles));
   KL(c, "k_vf_scan", k_vf_scan<<<dim3(pl.npass, c.B), VF_MAX_BINS, 0, c.stream>>>(a.sort.hist));
   KL(c, "k_vf_setup", k_vf_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.minmax, a.leaf, a.vf, c.B));
   count_launch(c, 4);
@@ -570,8 +584,12 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   const int fin = pl.npass & 1;
   const int tiles = cdiv(c.cap, CT_TILE), gt = cdiv(c.grid_cap, CT_TILE);
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
-  KL(c, "k_vf_reduce", k_vf_reduce<<<dim3(c.B, gt), CT_THREADS, 0, c.stream>>>(
-      a.in, a.in_stride, a.n_crop, a.pair[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles));
+  if (a.want_keys)
+    KL(c, "k_vf_reduce", k_vf_reduce<true><<<dim3(c.B, gt), CT_THREADS, 0, c.stream>>>(
+        a.in, a.in_stride, a.n_crop, a.pair[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles));
+  else
+    KL(c, "k_vf_reduce", k_vf_reduce<false><<<dim3(c.B, gt), CT_THREADS, 0, c.stream>>>(
+        a.in, a.in_stride, a.n_crop, a.pair[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles));
   count_launch(c);
 }
 
