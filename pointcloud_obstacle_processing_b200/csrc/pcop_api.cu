@@ -127,8 +127,11 @@ struct pcop_handle {
   bool rem_copy_pending = false;
   bool wave_rem_early = false;
   int call_waves = 1;  // waves of the running call over all lanes
-  int wave_rem_pitch = 0;  // points per row
+  size_t wave_rem_total = 0;  // points of all remaining clouds of the wave
   unsigned char* wave_rem_host = nullptr;
+  float4* d_rem_pack = nullptr;  // [maxB*cap] staging of the early copy (allocated on first use)
+  int* d_rem_pack_src = nullptr;
+  int* d_rem_off = nullptr;      // [maxB]
   double d2h_bytes = 0.0;
   float4* d_acc = nullptr;  // accumulated (world-frame) cloud, od.cpp:697
   unsigned char* d_occ = nullptr;  // occupancy grid scratch: int64 counts, int64 row averages, int8 cells
@@ -513,6 +516,44 @@ __global__ void k_pack_scan(const int* __restrict__ counts, int maxB, int B, uin
   }
 }
 
+// early result copy: exclusive prefix of the remaining-cloud sizes over the frames of the wave (one block), then the
+// clouds + source indices packed back to back
+__global__ void k_rem_offsets(const int* __restrict__ n_rem, int B, int* __restrict__ off) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int f = base + threadIdx.x;
+    const int v = (f < B) ? n_rem[f] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(FULL, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += up;
+    }
+    __shared__ int wsum[32];
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int wb = carry;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wb += wsum[w];
+    if (f < B) off[f] = wb + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = wb + incl;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256)
+    k_rem_pack(const float4* __restrict__ rem, const int* __restrict__ rem_src, const int* __restrict__ n_rem,
+               const int* __restrict__ off, int cap, float4* __restrict__ out_pts, int* __restrict__ out_src) {
+  const int f = blockIdx.y;
+  const int n = n_rem[f];
+  const size_t o = (size_t)off[f];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    out_pts[o + i] = rem[(size_t)f * cap + i];
+    out_src[o + i] = rem_src[(size_t)f * cap + i];
+  }
+}
+
 struct PackSrc {
   const uint32_t* src[PK_N];  // nullptr: not requested
   unsigned long long frame_stride_words[PK_N];
@@ -818,13 +859,17 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
         h->rem_copy_pending = false;
       }
       run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
-      const size_t pitch = (size_t)c.grid_cap;
-      const size_t need = (size_t)B * pitch * 20;
-      // Worth it only while the copy engine would otherwise idle: the rows are padded to the wave's largest cloud
-      // (~1.5x the bytes), which costs more than it hides once several waves keep the engine busy anyway (measured:
-      // 256 frames on 1-2 waves: 3.06 -> 2.62 ms and 2.61 -> 2.58 ms; 1024 frames on 4 waves: 8.96 -> 9.85 ms).
-      if ((effective_outputs(p) & PCOP_OUT_REMAINING) && B > 1 && h->call_waves <= 2 && need <= ((size_t)256 << 20) &&
-          !getenv("PCOP_NO_EARLY_COPY")) {
+      // Early result copy: the remaining cloud (80 % of the result bytes) is final now; the host knows its total size
+      // from the plane loop's last synchronisation, so it is packed and sent while the clustering kernels run.
+      const size_t total = (size_t)std::max(0, h->h_n_active[2]);
+      const size_t need = total * 20 + 256;
+      if ((effective_outputs(p) & PCOP_OUT_REMAINING) && B > 1 && total > 0 && !getenv("PCOP_NO_EARLY_COPY")) {
+        if (!h->d_rem_pack) {
+          const size_t BC = (size_t)h->maxB * h->cap;
+          if (cudaMalloc((void**)&h->d_rem_pack, BC * 16) != cudaSuccess || cudaMalloc((void**)&h->d_rem_pack_src, BC * 4) != cudaSuccess ||
+              cudaMalloc((void**)&h->d_rem_off, sizeof(int) * h->maxB) != cudaSuccess)
+            return fail_cuda(h, cudaGetLastError(), "cudaMalloc(early copy)", __FILE__, __LINE__);
+        }
         if ((size_t)h->wave_seq >= h->rem_chunks.size()) h->rem_chunks.resize(h->wave_seq + 1, pcop_handle::PinnedChunk{nullptr, 0});
         pcop_handle::PinnedChunk& ch = h->rem_chunks[h->wave_seq];
         if (ch.cap < need) {
@@ -837,17 +882,21 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
             return fail_cuda(h, cudaGetLastError(), "cudaHostAlloc(remaining)", __FILE__, __LINE__);
           ch.cap = ncap;
         }
+        KL(c, "k_rem_offsets", k_rem_offsets<<<1, 1024, 0, h->stream>>>(h->cnt(CNT_REM), B, h->d_rem_off));
+        KL(c, "k_rem_pack", k_rem_pack<<<dim3(std::max(1, std::min(cdiv(c.grid_cap, 256), 8)), B), 256, 0, h->stream>>>(
+            h->d_rem, h->d_rem_src, h->cnt(CNT_REM), h->d_rem_off, h->cap, h->d_rem_pack, h->d_rem_pack_src));
+        count_launch(c, 2);
         cudaEventRecord(h->ev_rem_ready, h->stream);
         cudaStreamWaitEvent(h->cstream, h->ev_rem_ready, 0);
-        cudaMemcpy2DAsync(ch.p, pitch * 16, h->d_rem, (size_t)h->cap * 16, pitch * 16, B, cudaMemcpyDeviceToHost, h->cstream);
-        cudaMemcpy2DAsync(ch.p + (size_t)B * pitch * 16, pitch * 4, h->d_rem_src, (size_t)h->cap * 4, pitch * 4, B,
-                          cudaMemcpyDeviceToHost, h->cstream);
+        const size_t src_off = (total * 16 + 255) & ~(size_t)255;
+        cudaMemcpyAsync(ch.p, h->d_rem_pack, total * 16, cudaMemcpyDeviceToHost, h->cstream);
+        cudaMemcpyAsync(ch.p + src_off, h->d_rem_pack_src, total * 4, cudaMemcpyDeviceToHost, h->cstream);
         cudaEventRecord(h->ev_rem_copied, h->cstream);
         h->rem_copy_pending = true;
         h->wave_rem_early = true;
-        h->wave_rem_pitch = (int)pitch;
+        h->wave_rem_total = total;
         h->wave_rem_host = ch.p;
-        h->d2h_bytes += (double)need;
+        h->d2h_bytes += (double)(total * 20);
       }
     } else {
       KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_REM), B));
@@ -935,6 +984,7 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   *h_pack_used = base_off + meta.total_bytes;
 
   size_t run[PK_N] = {0};
+  size_t rem_run = 0;  // points of the early-copied remaining clouds before frame f
   auto H = [&](int row, int f) { return h->h_counts[(size_t)row * h->maxB + f]; };
   for (int f = 0; f < B; ++f) {
     pcop_frame_result& r = out[f];
@@ -961,9 +1011,10 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
                                 (const void**)&r.remaining_src_idx, (const void**)&r.cluster_offsets,
                                 (const void**)&r.cluster_indices,  (const void**)&r.obstacles};
     if (h->wave_rem_early && (full_mask & PCOP_OUT_REMAINING)) {
-      r.remaining_cloud = reinterpret_cast<const float*>(h->wave_rem_host + (size_t)f * h->wave_rem_pitch * 16);
-      r.remaining_src_idx = reinterpret_cast<const int32_t*>(h->wave_rem_host + (size_t)B * h->wave_rem_pitch * 16 +
-                                                             (size_t)f * h->wave_rem_pitch * 4);
+      const size_t src_off = (h->wave_rem_total * 16 + 255) & ~(size_t)255;
+      r.remaining_cloud = reinterpret_cast<const float*>(h->wave_rem_host + rem_run * 16);
+      r.remaining_src_idx = reinterpret_cast<const int32_t*>(h->wave_rem_host + src_off + rem_run * 4);
+      rem_run += (size_t)r.n_remaining;
     }
     for (int k = 0; k < PK_N; ++k) {
       if (!(mask & kPkMask[k])) continue;
@@ -1482,6 +1533,9 @@ void pcop_destroy(pcop_handle* h) {
   for (void* p : h->host_allocs) cudaFreeHost(p);
   if (h->d_pack) cudaFree(h->d_pack);
   if (h->d_raw) cudaFree(h->d_raw);
+  if (h->d_rem_pack) cudaFree(h->d_rem_pack);
+  if (h->d_rem_pack_src) cudaFree(h->d_rem_pack_src);
+  if (h->d_rem_off) cudaFree(h->d_rem_off);
   if (h->d_occ) cudaFree(h->d_occ);
   if (h->h_pack) cudaFreeHost(h->h_pack);
   if (h->kt.ev) {
@@ -1638,6 +1692,9 @@ static int pc2_ingest(pcop_handle* h, const unsigned char* data, int32_t n, int3
     if (bytes > h->raw_cap) {
       PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
       if (h->d_raw) cudaFree(h->d_raw);
+  if (h->d_rem_pack) cudaFree(h->d_rem_pack);
+  if (h->d_rem_pack_src) cudaFree(h->d_rem_pack_src);
+  if (h->d_rem_off) cudaFree(h->d_rem_off);
   if (h->d_occ) cudaFree(h->d_occ);
       h->d_raw = nullptr;
       h->raw_cap = 0;

@@ -90,6 +90,7 @@ __global__ void k_plane_init(PlaneFrame* __restrict__ pf, const int* __restrict_
   P.active = ((double)n > dmul(keep_fraction, (double)n)) ? 1 : 0;  // od.cpp:379
   if (P.active) atomicAdd(n_active, 1);
   atomicMax(n_active + 1, n);  // largest current cloud over the wave (sizes the next launches)
+  atomicAdd(n_active + 2, n);  // all current clouds together (sizes the early result copy)
 }
 
 // one warp per frame: hypothesis generation (getSamples/drawIndexSample/isSampleGood/
@@ -621,6 +622,7 @@ __global__ void k_plane_update(PlaneFrame* __restrict__ pf, const int* __restric
   PlaneFrame& P = pf[f];
   if (!P.active) {
     atomicMax(n_active + 1, P.n);
+    atomicAdd(n_active + 2, P.n);
     return;
   }
   const int remaining = n_tmp[f];
@@ -630,6 +632,7 @@ __global__ void k_plane_update(PlaneFrame* __restrict__ pf, const int* __restric
     P.active = 0;
     atomicOr(&warnings[f], (uint32_t)PCOP_WARN_PLANE_BREAK);
     atomicMax(n_active + 1, P.n);
+    atomicAdd(n_active + 2, P.n);
     return;
   }
   if (P.n_passes < PCOP_MAX_PLANE_PASSES_RECORDED) {
@@ -643,6 +646,7 @@ __global__ void k_plane_update(PlaneFrame* __restrict__ pf, const int* __restric
   P.active = ((double)remaining > dmul(keep_fraction, (double)P.nr_points)) ? 1 : 0;
   if (P.active) atomicAdd(n_active, 1);
   atomicMax(n_active + 1, P.n);
+  atomicAdd(n_active + 2, P.n);
 }
 
 // copy what is left (planar_cloud_y, od.cpp:765) into the stage output
@@ -679,10 +683,10 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
   bp.s[0] = a.src[0];
   bp.s[1] = a.src[1];
   cudaError_t e;
-  cudaMemsetAsync(a.n_active, 0, 2 * sizeof(int), c.stream);
+  cudaMemsetAsync(a.n_active, 0, 3 * sizeof(int), c.stream);
   KL(c, "k_plane_init", k_plane_init<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_in, a.pc.keep_fraction, a.n_active, c.B));
   count_launch(c);
-  cudaMemcpyAsync(a.h_n_active, a.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+  cudaMemcpyAsync(a.h_n_active, a.n_active, 3 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
   if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return e;
   Ctx cc = c;
   while (*a.h_n_active > 0) {
@@ -704,10 +708,10 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
     cudaMemsetAsync(a.desc, 0, (size_t)c.B * btiles * sizeof(unsigned), c.stream);
     KL(c, "k_plane_extract", k_plane_extract<<<dim3(gbtiles, c.B), CT_THREADS, 0, c.stream>>>(
         a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx, a.n_tmp, a.desc, c.cap, btiles));
-    cudaMemsetAsync(a.n_active, 0, 2 * sizeof(int), c.stream);
+    cudaMemsetAsync(a.n_active, 0, 3 * sizeof(int), c.stream);
     KL(c, "k_plane_update", k_plane_update<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_tmp, a.pc.keep_fraction, a.n_active, a.warnings, c.B));
     count_launch(c, 9);
-    cudaMemcpyAsync(a.h_n_active, a.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+    cudaMemcpyAsync(a.h_n_active, a.n_active, 3 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
     if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) return e;
   }
   return cudaGetLastError();
