@@ -34,6 +34,11 @@ namespace pcop {
 
 namespace {
 
+#ifndef VF_SORT_ITEMS
+#define VF_SORT_ITEMS 16  // 4096-element tiles, 4 blocks per SM: -4.5 % against 2048-element tiles at 5 blocks per SM
+#endif
+constexpr int VF_ITEMS = VF_SORT_ITEMS;         // elements per thread of a sort tile
+constexpr int VF_TILE = RS_THREADS * VF_ITEMS;  // elements per sort tile
 constexpr int VF_MAX_BITS = 9;
 constexpr int VF_MAX_PASSES = 6;  // (digit-width experiments: 6 x 5 bits)
 constexpr int VF_MAX_BINS = 1 << VF_MAX_BITS;
@@ -193,7 +198,7 @@ struct VfPassSmem {
   uint32_t warp_hist[RS_THREADS / 32][BINS];  // per-warp digit counts -> exclusive across warps
   uint32_t tile_off[BINS + 1];                // exclusive scan of the tile histogram
   uint32_t glob_base[BINS];                   // global output slot minus staged position, per digit
-  unsigned long long spair[RS_TILE];
+  unsigned long long spair[VF_TILE];
   uint32_t wsum[RS_THREADS / 32];
 };
 
@@ -201,7 +206,7 @@ struct VfPassSmem {
 // per-digit decoupled look-back over the tiles of the frame, tile staged in shared memory in sorted order,
 // coalesced run writes), digit width as a template parameter, pass count uniform over the frames.
 #ifndef VF_SORT_MINBLOCKS
-#define VF_SORT_MINBLOCKS 5
+#define VF_SORT_MINBLOCKS 4
 #endif
 template <int BITS, bool USE_MATCH>
 __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
   const int f = blockIdx.x;
   const int n = count[f];
   const int tile = blockIdx.y;
-  const int tbase = tile * RS_TILE;
+  const int tbase = tile * VF_TILE;
   if (tbase >= n) return;
   if (tile == 0 && threadIdx.x == 0 && stats) atomicAdd(stats, (unsigned long long)n);  // keys moved by sort passes
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -225,11 +230,11 @@ __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
 
   for (int i = threadIdx.x; i < (RS_THREADS / 32) * BINS; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0u;
 
-  unsigned long long pr[RS_ITEMS];  // (key << 32) | index: one 8-byte load / store per element
-  unsigned short rank[RS_ITEMS];
-  const int wbase_idx = tbase + warp * (32 * RS_ITEMS) + lane;
+  unsigned long long pr[VF_ITEMS];  // (key << 32) | index: one 8-byte load / store per element
+  unsigned short rank[VF_ITEMS];
+  const int wbase_idx = tbase + warp * (32 * VF_ITEMS) + lane;
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
+  for (int k = 0; k < VF_ITEMS; ++k) {
     const int i = wbase_idx + k * 32;
     pr[k] = (i < n) ? pin[i] : ~0ull;
   }
@@ -238,36 +243,41 @@ __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
   // overlap), then one shared atomic per distinct digit of a row (issued by the lowest lane of the match group);
   // its return value is the group's base, broadcast by shuffle.
   uint32_t* wh = sm.warp_hist[warp];
-  unsigned mm[RS_ITEMS];
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    const bool valid = (wbase_idx + k * 32) < n;
-    const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
-    if (USE_MATCH) {
-      mm[k] = __match_any_sync(FULL, valid ? d : (BINS + lane));  // invalid lanes match nobody
-    } else {
-      // MATCH.ANY runs on the ADU pipe in time proportional to the number of distinct values in the warp (80 % pipe
-      // utilisation on the high-entropy low digits): one ballot per digit bit instead
-      unsigned peers = __ballot_sync(FULL, valid);
+  for (int k0 = 0; k0 < VF_ITEMS; k0 += 8) {  // 8 rows at a time: their match masks first, then the atomics
+    unsigned mm[8];
 #pragma unroll
-      for (int b = 0; b < BITS; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const unsigned bal = __ballot_sync(FULL, bit);
-        peers &= bit ? bal : ~bal;
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = k0 + kk;
+      const bool valid = (wbase_idx + k * 32) < n;
+      const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
+      if (USE_MATCH) {
+        mm[kk] = __match_any_sync(FULL, valid ? d : (BINS + lane));  // invalid lanes match nobody
+      } else {
+        // MATCH.ANY runs on the ADU pipe in time proportional to the number of distinct values in the warp (80 %
+        // pipe utilisation on the high-entropy low digits): one ballot per digit bit instead
+        unsigned peers = __ballot_sync(FULL, valid);
+#pragma unroll
+        for (int b = 0; b < BITS; ++b) {
+          const bool bit = (d >> b) & 1u;
+          const unsigned bal = __ballot_sync(FULL, bit);
+          peers &= bit ? bal : ~bal;
+        }
+        mm[kk] = valid ? peers : (1u << lane);
       }
-      mm[k] = valid ? peers : (1u << lane);
     }
-  }
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    const bool valid = (wbase_idx + k * 32) < n;
-    const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
-    const unsigned m = mm[k];
-    const int leader = __ffs(m) - 1;
-    uint32_t before = 0;
-    if (valid && lane == leader) before = atomicAdd(&wh[d], (uint32_t)__popc(m));
-    before = __shfl_sync(FULL, before, leader);
-    rank[k] = (unsigned short)(before + __popc(m & lanemask_lt()));
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = k0 + kk;
+      const bool valid = (wbase_idx + k * 32) < n;
+      const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
+      const unsigned m = mm[kk];
+      const int leader = __ffs(m) - 1;
+      uint32_t before = 0;
+      if (valid && lane == leader) before = atomicAdd(&wh[d], (uint32_t)__popc(m));
+      before = __shfl_sync(FULL, before, leader);
+      rank[k] = (unsigned short)(before + __popc(m & lanemask_lt()));
+    }
   }
   __syncthreads();
 
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
 
   // stage the tile in sorted order
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
+  for (int k = 0; k < VF_ITEMS; ++k) {
     const int i = wbase_idx + k * 32;
     if (i < n) {
       const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
     }
   }
   __syncthreads();
-  const int tile_n = min(RS_TILE, n - tbase);
+  const int tile_n = min(VF_TILE, n - tbase);
   for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
     const unsigned long long pp = sm.spair[i];
     const uint32_t d = ((uint32_t)(pp >> 32) >> shift) & (BINS - 1);
@@ -544,7 +554,7 @@ VoxFusedPlan make_vox_fused_plan(const pcop_params& p) {
 
 size_t vox_fused_hist_elems(int B) { return (size_t)B * VF_MAX_PASSES * VF_MAX_BINS; }
 size_t vox_fused_desc_bytes(int B, int cap) {
-  return (size_t)VF_MAX_PASSES * B * cdiv(cap, RS_TILE) * VF_MAX_BINS * sizeof(uint32_t);
+  return (size_t)VF_MAX_PASSES * B * cdiv(cap, VF_TILE) * VF_MAX_BINS * sizeof(uint32_t);
 }
 
 // Launch geometry of the look-back kernels: blockIdx.x = frame, blockIdx.y = tile.  Blocks are dispatched x-fastest, so
@@ -556,7 +566,7 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   const VoxFusedPlan& pl = a.plan;
   const int nbins = 1 << pl.digit_bits;
   const int btiles = cdiv(c.cap, BT_TILE), gbtiles = cdiv(c.grid_cap, BT_TILE);
-  const int gtiles = cdiv(c.grid_cap, RS_TILE);
+  const int gtiles = cdiv(c.grid_cap, VF_TILE);
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * btiles * sizeof(unsigned), c.stream);
   cudaMemsetAsync(a.sort.hist, 0, vox_fused_hist_elems(c.B) * sizeof(uint32_t), c.stream);
   cudaMemsetAsync(a.sort.desc, 0, (size_t)pl.npass * c.B * gtiles * nbins * sizeof(uint32_t), c.stream);
