@@ -263,12 +263,12 @@ __global__ void __launch_bounds__(32)
 __global__ void __launch_bounds__(CT_THREADS)
     k_plane_score(PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp, float thr,
                   int cap, int h_begin, int h_end, int second_phase) {
-  const int f = blockIdx.y, tile = blockIdx.x;
+  const int f = blockIdx.y;
   PlaneFrame& P = pf[f];
   if (!P.active) return;
   if (second_phase && !P.need_more) return;
   const int n = P.n;
-  if (tile * CT_TILE >= n) return;
+  if (blockIdx.x * CT_TILE >= n) return;
   const int nh = min(P.n_hyp, h_end);
   if (nh <= h_begin) return;
   __shared__ float4 hyp[MAX_HYP];
@@ -279,6 +279,9 @@ __global__ void __launch_bounds__(CT_THREADS)
   }
   __syncthreads();
   const float4* pts = cur_cloud(P, in, in_stride, bp.p, f, cap);
+  const int lane = lane_id();
+  // (the second phase is launched with a few blocks per frame: most frames do not need it)
+  for (int tile = blockIdx.x; tile * CT_TILE < n; tile += gridDim.x) {
   float4 p[CT_ITEMS];
   bool valid[CT_ITEMS];
 #pragma unroll
@@ -287,27 +290,28 @@ __global__ void __launch_bounds__(CT_THREADS)
     valid[k] = i < n;
     p[k] = valid[k] ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const int lane = lane_id();
-  int acc[MAX_HYP / 32];
+  // per-lane counters for 8 hypotheses at a time, one warp reduction per hypothesis and tile (a ballot + popc per
+  // hypothesis and point kept the ADU pipe 63 % busy)
+  for (int h0 = h_begin; h0 < nh; h0 += 8) {
+    int c[8];
 #pragma unroll
-  for (int hh = 0; hh < MAX_HYP / 32; ++hh) acc[hh] = 0;
+    for (int j = 0; j < 8; ++j) {
+      c[j] = 0;
+      if (h0 + j < nh) {
+        const float4 co = hyp[h0 + j];
 #pragma unroll
-  for (int hh = 0; hh < MAX_HYP / 32; ++hh) {
-    for (int hl = 0; hl < 32; ++hl) {
-      const int h = hh * 32 + hl;
-      if (h >= nh) break;
-      if (h < h_begin) continue;
-      const float4 co = hyp[h];
-      int c = 0;
+        for (int k = 0; k < CT_ITEMS; ++k) c[j] += (valid[k] && plane_dist(co, p[k].x, p[k].y, p[k].z) < thr) ? 1 : 0;
+      }
+    }
 #pragma unroll
-      for (int k = 0; k < CT_ITEMS; ++k)
-        c += __popc(__ballot_sync(FULL, valid[k] && plane_dist(co, p[k].x, p[k].y, p[k].z) < thr));
-      if (lane == hl) acc[hh] += c;
+    for (int j = 0; j < 8; ++j) {
+      if (h0 + j < nh) {
+        const int s = __reduce_add_sync(FULL, c[j]);
+        if (lane == 0 && s) atomicAdd(&cnt[h0 + j], s);
+      }
     }
   }
-#pragma unroll
-  for (int hh = 0; hh < MAX_HYP / 32; ++hh)
-    if (acc[hh]) atomicAdd(&cnt[hh * 32 + lane], acc[hh]);
+  }
   __syncthreads();
   if (threadIdx.x >= h_begin && threadIdx.x < nh && cnt[threadIdx.x]) atomicAdd(&P.counts[threadIdx.x], cnt[threadIdx.x]);
 }
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(CT_THREADS)
     k_plane_extract(const PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp,
                     float thr, int* __restrict__ inlier_idx, int* __restrict__ n_tmp, unsigned* __restrict__ desc, int cap,
                     int tiles) {
-  const int f = blockIdx.y, tile = blockIdx.x;
+  const int f = blockIdx.x, tile = blockIdx.y;  // frame-major dispatch (shallow look-back, see stage_voxel_fused.cu)
   const PlaneFrame& P = pf[f];
   if (!P.active) return;
   const int n = P.n;
@@ -699,14 +703,14 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
     constexpr int PHASE1 = 8;
     KL(c, "k_plane_score", k_plane_score<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap, 0, PHASE1, 0));
     KL(c, "k_plane_select", k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B, PHASE1, 0));
-    KL(c, "k_plane_score", k_plane_score<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap, PHASE1, MAX_HYP, 1));
+    KL(c, "k_plane_score", k_plane_score<<<dim3(std::min(gtiles, 8), c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap, PHASE1, MAX_HYP, 1));
     KL(c, "k_plane_select", k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B, MAX_HYP, 1));
     KL(c, "k_plane_moments", k_plane_moments<<<dim3(gchunks, c.B), 256, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.partial, chunks,
                                                              c.cap));
     KL(c, "k_plane_refine", k_plane_refine<<<c.B, 32, 0, c.stream>>>(a.pf, a.partial, a.pc, chunks));
     const int btiles = cdiv(c.cap, BT_TILE), gbtiles = cdiv(cc.grid_cap, BT_TILE);
     cudaMemsetAsync(a.desc, 0, (size_t)c.B * btiles * sizeof(unsigned), c.stream);
-    KL(c, "k_plane_extract", k_plane_extract<<<dim3(gbtiles, c.B), CT_THREADS, 0, c.stream>>>(
+    KL(c, "k_plane_extract", k_plane_extract<<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
         a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx, a.n_tmp, a.desc, c.cap, btiles));
     cudaMemsetAsync(a.n_active, 0, 3 * sizeof(int), c.stream);
     KL(c, "k_plane_update", k_plane_update<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_tmp, a.pc.keep_fraction, a.n_active, a.warnings, c.B));
