@@ -195,7 +195,14 @@ def main():
     synth.frames(CONFIG, rank * B, B, out=host.numpy())
     dev = host.to(f"cuda:{local_rank}", non_blocking=False)
     counts = np.full(B, n, np.int32)
-    op = ObstacleProcessor(params, n, max_batch=B, device=local_rank)
+    from pointcloud_obstacle_processing_b200 import _ctypes_abi as abi
+    # `value`: frames resident in HBM and results LEFT in HBM (outputs | OUT_DEVICE: the result pointers are device
+    # pointers for a GPU-side consumer -- here the NCCL result gather reads them in place); counts, warnings and the
+    # plane record still come back to the host every step.  `value_results_to_host` and `e2e` copy every result
+    # array to pinned host memory.
+    params_dev = params.copy()
+    params_dev.outputs = abi.OUT_DEFAULT | abi.OUT_DEVICE
+    op = ObstacleProcessor(params_dev, n, max_batch=B, device=local_rank)
 
     def step_device():
         return op.process_batch_raw(dev.data_ptr(), n, counts)
@@ -213,6 +220,7 @@ def main():
     dev_cnt = torch.empty(B + 1, dtype=torch.int32, device=dev.device) if world > 1 else None
     all_cnt = torch.empty((world, B + 1), dtype=torch.int32, device=dev.device) if world > 1 else None
     pad_cap = [0, None, None]
+    results_on_device = [True]
     off_c, off_p, rec = FrameResult.n_clusters.offset, FrameResult.obstacles.offset, C.sizeof(FrameResult)
 
     def gather_results(res):
@@ -233,9 +241,12 @@ def main():
             starts = np.concatenate([[0], brk])
             stops = np.concatenate([brk, [len(live)]])
             o = 0
+            runs = []
             for a, b_ in zip(starts, stops):
                 nrec = int(ns[live[a:b_]].sum())
-                C.memmove(obs_stage.data_ptr() + 16 * o, int(ptrs[live[a]]), 16 * nrec)
+                runs.append((o, int(ptrs[live[a]]), nrec))
+                if not results_on_device[0]:
+                    C.memmove(obs_stage.data_ptr() + 16 * o, int(ptrs[live[a]]), 16 * nrec)
                 o += nrec
         mx = int(all_cnt[:, B].max().item())  # (the one synchronisation of the exchange)
         if mx > pad_cap[0]:
@@ -243,7 +254,11 @@ def main():
             pad_cap[1] = torch.zeros((pad_cap[0], 4), dtype=torch.float32, device=dev.device)
             pad_cap[2] = torch.empty((world, pad_cap[0], 4), dtype=torch.float32, device=dev.device) if rank == 0 else None
         pad = pad_cap[1][:mx]
-        pad[:tot].copy_(obs_stage[:tot], non_blocking=True)
+        if results_on_device[0]:
+            for o, src, nrec in (runs if tot else []):  # device -> device, straight out of the library's result buffer
+                op.copy_device(pad.data_ptr() + 16 * o, src, 16 * nrec)
+        else:
+            pad[:tot].copy_(obs_stage[:tot], non_blocking=True)
         out = list(pad_cap[2][:, :mx].unbind(0)) if rank == 0 else None
         dist.gather(pad, out, dst=0)
 
@@ -265,6 +280,18 @@ def main():
             alg_bytes += op.last_algorithmic_bytes
         barrier()
         wall = time.perf_counter() - t0
+    # ---- the same K steps with every result array copied to pinned host memory -----------------------------
+    op.set_params(params)
+    results_on_device[0] = False
+    for _ in range(2):
+        gather_results(step_device())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        gather_results(step_device())
+    barrier()
+    wall_host_results = time.perf_counter() - t0
+    # (the passes below keep the host-result mode: the single lane of the instrumented pass runs four waves)
     # ---- instrumented pass: the same K steps with a CUDA-event pair around every launch on the library's streams.
     # Per-kernel timing needs each kernel alone on the GPU, so the library serialises its lanes here; this pass
     # feeds `roofline`, `kernels` and `stage_ms_per_step` only, never `value`.
@@ -292,6 +319,8 @@ def main():
                     for r in res) + B * 600
 
     # ---- end-to-end run (host frames in, results out) ------------------------------------------------
+    op.set_params(params)
+    results_on_device[0] = False
     for _ in range(2):
         step_host()
     barrier()
@@ -305,10 +334,10 @@ def main():
     d2h_bytes = d2h_exact / args.steps  # counted by the library from the copies it issued
 
     # ---- max over ranks -----------------------------------------------------------------------------
-    t = torch.tensor([wall, wall_e2e, dev_us * 1e-6], dtype=torch.float64, device=dev.device)
+    t = torch.tensor([wall, wall_e2e, dev_us * 1e-6, wall_host_results], dtype=torch.float64, device=dev.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall, wall_e2e, dev_s = [float(x) for x in t.tolist()]
+    wall, wall_e2e, dev_s, wall_host_results = [float(x) for x in t.tolist()]
 
     # ---- single-frame latency (rank 0) -----------------------------------------------------------------
     lat = None
@@ -407,9 +436,15 @@ def main():
             "config": {"workload": "BASELINE configs[1]: HDL-64-style 120k-point frame, crop + 0.1 m voxel + ground-plane "
                                    "RANSAC + Euclidean clustering + centroid/radius (SURVEY 8d config 2 parameters)",
                        "points_per_frame": n, "frames_per_gpu_per_step": B,
+                       "results": "left in HBM (PCOP_OUT_DEVICE; counts and plane records on the host); "
+                                  "value_results_to_host and e2e copy them to pinned host memory",
                        "l2": "no flush: the per-step input batch (%.0f MB) exceeds the 126 MB L2" % (B * n * 16 / 1e6),
                        "parallelism": f"frames sharded over {world} GPU(s), no intra-frame collective"},
             "frames_per_sec": total_frames / wall,
+            "value_results_to_host": {"value": total_points / wall_host_results, "unit": "points/s",
+                                      "ms_per_step": 1000.0 * wall_host_results / args.steps,
+                                      "what": "same K steps, frames resident in HBM, every result array copied to pinned "
+                                              "host memory inside the step"},
             "device_ms_per_step": 1000.0 * dev_s / args.steps,
             "instrumented_ms_per_step": 1000.0 * wall_instr / args.steps if wall_instr else None,
             "lanes": int(os.environ.get("PCOP_LANES", str(min(4, max(2, B // 256))))),

@@ -68,7 +68,12 @@ enum {
   PCOP_OUT_CLUSTERS = 32,  /* cluster_offsets, cluster_indices            */
   PCOP_OUT_OBSTACLES = 64, /* obstacles                                   */
   PCOP_OUT_DEFAULT = 16 | 32 | 64,
-  PCOP_OUT_ALL = 127
+  PCOP_OUT_ALL = 127,
+  /* Modifier: leave the requested arrays in device memory.  The pcop_frame_result pointers are then DEVICE pointers
+   * (valid until the next pcop_process* call on the handle; counts, warnings and the plane record are still host
+   * values) for a consumer that lives on the GPU: the next GPU stage, a peer-to-peer / NCCL transfer, or
+   * pcop_download.  A call may then hold at most 2 waves per lane (batch <= 2 * max_batch), else PCOP_ERR_CAPACITY. */
+  PCOP_OUT_DEVICE = 256
 };
 
 /* stage ids for pcop_stage_times_us */
@@ -243,6 +248,10 @@ int pcop_pointcloud2_to_xyz(pcop_handle* h, const unsigned char* data, int32_t n
  * Hole detection and shadow casting (od.cpp:467-672, 823-852) stay on the host. */
 int pcop_occupancy_dims(const pcop_handle* h, int32_t* width, int32_t* height);
 int pcop_occupancy_grid(pcop_handle* h, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts, int64_t* row_avg);
+
+/* Copies `bytes` from a device result array (PCOP_OUT_DEVICE) to host memory, or device to device when dst is a device
+ * pointer; synchronous. */
+int pcop_download(pcop_handle* h, void* dst, const void* src_device, size_t bytes);
 
 /* bytes copied device -> host by the last call (results, counts, records; padded rows of the early remaining-cloud copy included) */
 double pcop_last_d2h_bytes(const pcop_handle* h);

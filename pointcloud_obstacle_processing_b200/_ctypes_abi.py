@@ -7,6 +7,7 @@ OK, ERR_BAD_PARAM, ERR_CAPACITY, ERR_CUDA, ERR_INTERNAL = 0, 1, 2, 3, 4
 WARN_VOXEL_OVERFLOW_FALLBACK, WARN_SOR_TOO_FEW_POINTS, WARN_PLANE_BREAK, WARN_RNG_TABLE_EXHAUSTED = 1, 2, 4, 8
 OUT_CROP, OUT_VOXEL, OUT_SOR, OUT_PLANE, OUT_REMAINING, OUT_CLUSTERS, OUT_OBSTACLES = 1, 2, 4, 8, 16, 32, 64
 OUT_DEFAULT, OUT_ALL = 16 | 32 | 64, 127
+OUT_DEVICE = 256  # modifier: result arrays stay in device memory (pointers are device pointers)
 STAGE_NAMES = ["h2d", "crop", "voxel", "sor", "plane", "cluster", "centroid", "d2h"]
 
 

@@ -41,6 +41,7 @@ EXPORTS = [
     "pcop_pointcloud2_to_xyz",
     "pcop_occupancy_dims",
     "pcop_occupancy_grid",
+    "pcop_download",
 ]
 
 
@@ -91,6 +92,7 @@ def load_library():
     L.pcop_transform.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.pcop_accumulate_pointcloud2.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp]
     L.pcop_pointcloud2_to_xyz.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.pcop_download.argtypes = [vp, vp, vp, C.c_size_t]
     L.pcop_occupancy_dims.argtypes = [vp, vp, vp]
     L.pcop_occupancy_grid.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
     L.pcop_enable_kernel_timing.argtypes = [vp, C.c_int]
@@ -258,6 +260,20 @@ class ObstacleProcessor:
                                              t.ctypes.data_as(C.c_void_p), 1 if is_dense else 0,
                                              out.ctypes.data_as(C.c_void_p)))
         return out[:cloud.shape[0]].copy()
+
+    def download(self, device_ptr, count, dtype):
+        """copy `count` elements of a device result array (outputs | OUT_DEVICE) to a numpy array"""
+        out = np.empty(count, dtype=dtype)
+        addr = C.cast(device_ptr, C.c_void_p).value if not isinstance(device_ptr, int) else device_ptr
+        if count:
+            self._check(self._lib.pcop_download(self._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(addr), out.nbytes))
+        return out
+
+    def copy_device(self, dst_device_addr: int, src_device_ptr, nbytes: int):
+        """device -> device copy of a result array (e.g. into a torch tensor that NCCL sends on)"""
+        addr = C.cast(src_device_ptr, C.c_void_p).value if not isinstance(src_device_ptr, int) else src_device_ptr
+        if nbytes:
+            self._check(self._lib.pcop_download(self._h, C.c_void_p(dst_device_addr), C.c_void_p(addr), nbytes))
 
     # ---- timing / accounting of the last call ----------------------------------------
     @property

@@ -139,6 +139,7 @@ struct pcop_handle {
   unsigned char* d_raw = nullptr;  // staging for a raw PointCloud2 payload (grown on demand)
   size_t raw_cap = 0;
   int acc_count = 0;
+  cudaEvent_t ev_block = nullptr;  // blocking-sync event for the host waits (nullptr: spin), see stream_wait
   cudaEvent_t trace_origin = nullptr;  // PCOP_TRACE: start event of the running call (on lane 0's stream)
   size_t pack_cap = 0;
   uint32_t alloc_outputs = 0;
@@ -243,7 +244,7 @@ int validate_params(pcop_handle* h, const pcop_params& p) {
 }
 
 uint32_t effective_outputs(const pcop_params& p) {
-  uint32_t m = p.outputs;
+  uint32_t m = p.outputs & (uint32_t)(PCOP_OUT_ALL | PCOP_OUT_DEVICE);
   if (p.publish_point_clouds) m |= PCOP_OUT_ALL;  // od.cpp:945: intermediates wanted
   if (!p.enable_crop) m &= ~(uint32_t)PCOP_OUT_CROP;
   if (!p.enable_voxel) m &= ~(uint32_t)PCOP_OUT_VOXEL;
@@ -621,7 +622,7 @@ void resolve_kernel_timers(pcop_handle* h) {
 }
 
 Ctx make_ctx(pcop_handle* h, int B, int grid_cap = -1) {
-  return Ctx{h->stream, B, h->cap, &h->launches, &h->kt, (grid_cap > 0 && grid_cap < h->cap) ? grid_cap : h->cap};
+  return Ctx{h->stream, B, h->cap, &h->launches, &h->kt, (grid_cap > 0 && grid_cap < h->cap) ? grid_cap : h->cap, h->ev_block};
 }
 
 PlaneConst make_plane_const(const pcop_params& p) {
@@ -863,7 +864,8 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
       // from the plane loop's last synchronisation, so it is packed and sent while the clustering kernels run.
       const size_t total = (size_t)std::max(0, h->h_n_active[2]);
       const size_t need = total * 20 + 256;
-      if ((effective_outputs(p) & PCOP_OUT_REMAINING) && B > 1 && total > 0 && !getenv("PCOP_NO_EARLY_COPY")) {
+      if ((effective_outputs(p) & PCOP_OUT_REMAINING) && !(effective_outputs(p) & PCOP_OUT_DEVICE) && B > 1 && total > 0 &&
+          !getenv("PCOP_NO_EARLY_COPY")) {
         if (!h->d_rem_pack) {
           const size_t BC = (size_t)h->maxB * h->cap;
           if (cudaMalloc((void**)&h->d_rem_pack, BC * 16) != cudaSuccess || cudaMalloc((void**)&h->d_rem_pack_src, BC * 4) != cudaSuccess ||
@@ -966,19 +968,21 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_meta, h->d_meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, h->stream));
   if (h->wave_used_fused)
     PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_vf_flags, h->d_vf_flags, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, h->stream));
-  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  PCOP_CUDA_TRY(stream_wait(h->stream, h->ev_block));
   if (h->wave_used_fused)
     for (int f = 0; f < B; ++f)
       if (h->h_vf_flags[f]) return PCOP_INTERNAL_REDO_GENERIC;  // the fast voxel path declined a frame of this wave
   const PackMeta meta = *h->h_meta;
+  const bool dev_results = (full_mask & PCOP_OUT_DEVICE) != 0;  // the arrays stay in this wave's half of d_pack
+  if (dev_results && h->wave_seq >= 2) return fail(h, PCOP_ERR_CAPACITY, "PCOP_OUT_DEVICE: more than 2 waves per lane in one call");
   const size_t base_off = (*h_pack_used + 255) & ~(size_t)255;
-  TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
+  if (!dev_results) TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
   // payload copy on the copy stream (the pack kernels have finished: the stream was just synchronised); the lane's
   // next wave starts right away and only waits for this copy before it packs into the same half again
-  if (meta.total_bytes)
+  if (meta.total_bytes && !dev_results)
     PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->cstream));
-  h->d2h_bytes += (double)meta.total_bytes + (double)(sizeof(int) * CNT_ROWS * h->maxB + sizeof(uint32_t) * B +
-                                                      sizeof(PlaneRecord) * B + sizeof(PackMeta));
+  h->d2h_bytes += (dev_results ? 0.0 : (double)meta.total_bytes) +
+                  (double)(sizeof(int) * CNT_ROWS * h->maxB + sizeof(uint32_t) * B + sizeof(PlaneRecord) * B + sizeof(PackMeta));
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_copied[half], h->cstream));
   ++h->wave_seq;
   *h_pack_used = base_off + meta.total_bytes;
@@ -1018,10 +1022,14 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
     }
     for (int k = 0; k < PK_N; ++k) {
       if (!(mask & kPkMask[k])) continue;
-      // store the byte offset now; turned into a pointer once the host buffer can no longer move
-      const size_t off = base_off + (size_t)meta.base[k] + run[k] * kPkElem[k];
-      *slots[k] = (const void*)(uintptr_t)(off + 1);  // +1 so that offset 0 is distinguishable from NULL
-      ptr_fixups->push_back((size_t)((const unsigned char*)slots[k] - (const unsigned char*)out_all));
+      if (dev_results) {  // device pointer into this wave's half of the pack buffer (it does not move)
+        *slots[k] = d_pack + (size_t)meta.base[k] + run[k] * kPkElem[k];
+      } else {
+        // store the byte offset now; turned into a pointer once the host buffer can no longer move
+        const size_t off = base_off + (size_t)meta.base[k] + run[k] * kPkElem[k];
+        *slots[k] = (const void*)(uintptr_t)(off + 1);  // +1 so that offset 0 is distinguishable from NULL
+        ptr_fixups->push_back((size_t)((const unsigned char*)slots[k] - (const unsigned char*)out_all));
+      }
       run[k] += (size_t)H(kPkCount[k], f);
     }
     // algorithmic bytes
@@ -1109,7 +1117,7 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
       if (cst == PCOP_OK) cst = collect_wave(h, B, mask, &h_pack_used, out, w0, &h->fixups);
     }
     TRY(cst);
-    PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    PCOP_CUDA_TRY(stream_wait(h->stream, h->ev_block));
     if (trace) {
       const auto tt2 = std::chrono::steady_clock::now();
       cudaStreamSynchronize(h->cstream);
@@ -1141,7 +1149,7 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_lane_done, h->cstream));
   PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_lane_done, 0));  // the lane is done when its last result copy is
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_lane_done, h->stream));
-  PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_lane_done));
+  PCOP_CUDA_TRY(stream_wait(h->stream, h->ev_block));
   h->sort_pass_keys = *h->h_stats;
   // the host pack buffer is final now: turn the stored offsets into pointers
   for (size_t fx : h->fixups) {
@@ -1481,6 +1489,15 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
         return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
   if ((e = cudaEventCreateWithFlags(&h->ev_lane_done, cudaEventDisableTiming)) != cudaSuccess)
     return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
+  {
+    // host waits spin (cudaStreamSynchronize).  PCOP_SYNC=block makes them sleep on a blocking-sync event instead;
+    // measured on B200 boxes it only ever lost: -5 % with one process on 24 cores, 4x slower with 8 processes on 32
+    // cores (58.5 -> 13.6 G points/s), so it stays an opt-in for hosts that cannot spare the cores.
+    bool block = false;
+    if (const char* sv = getenv("PCOP_SYNC")) block = (sv[0] == 'b' || sv[0] == 'B');
+    if (block && (e = cudaEventCreateWithFlags(&h->ev_block, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess)
+      return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
+  }
   if ((e = cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail(fail_cuda(h, e, "cudaStreamCreate", __FILE__, __LINE__));
   for (int i = 0; i < 2; ++i)
@@ -1545,6 +1562,7 @@ void pcop_destroy(pcop_handle* h) {
   for (int i = 0; i < 2; ++i)
     if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
   if (h->ev_lane_done) cudaEventDestroy(h->ev_lane_done);
+  if (h->ev_block) cudaEventDestroy(h->ev_block);
   for (int i = 0; i < 2; ++i)
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
   if (h->ev_rem_ready) cudaEventDestroy(h->ev_rem_ready);
@@ -1621,6 +1639,14 @@ int pcop_stage_times_us(const pcop_handle* h, float us[PCOP_N_STAGES]) {
 }
 int64_t pcop_last_launch_count(const pcop_handle* h) { return h ? h->launches : 0; }
 double pcop_last_algorithmic_bytes(const pcop_handle* h) { return h ? h->alg_bytes : 0.0; }
+int pcop_download(pcop_handle* h, void* dst, const void* src_device, size_t bytes) {
+  if (!h || (bytes && (!dst || !src_device))) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  if (bytes) PCOP_CUDA_TRY(cudaMemcpyAsync(dst, src_device, bytes, cudaMemcpyDefault, h->stream));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
 int64_t pcop_last_sort_pass_keys(const pcop_handle* h) { return h ? (int64_t)h->sort_pass_keys : 0; }
 double pcop_last_d2h_bytes(const pcop_handle* h) { return h ? h->d2h_bytes : 0.0; }
 

@@ -441,3 +441,30 @@ def test_occupancy_grid(config, frames):
                        (a_counts, o_counts, "counts (accumulated)"), (a_grid, o_grid, "cells (accumulated)")):
         assert_bits_equal(g, o, what)
     assert o_counts.sum() > 1000 and (o_grid == 100).any() and (o_grid == 0).any()
+
+
+def test_device_resident_results_match_host_results():
+    """outputs | OUT_DEVICE: the result pointers are device pointers (for a consumer on the GPU); downloaded, every
+    array equals the host-result run; 20 frames on two lanes"""
+    p = synth.params(2)
+    p.outputs = abi.OUT_ALL
+    pd = p.copy()
+    pd.outputs = abi.OUT_ALL | abi.OUT_DEVICE
+    n = synth.points_per_frame(2)
+    B = 20
+    clouds = synth.frames(2, 300, B)
+    counts = np.full(B, n, np.int32)
+    with ObstacleProcessor(p, n, max_batch=16) as op:
+        host = op.process_batch(clouds, counts)
+    with ObstacleProcessor(pd, n, max_batch=16) as op:
+        res = op.process_batch_raw(clouds.ctypes.data, n, counts)
+        for f in range(B):
+            r, hf = res[f], host[f]
+            assert r.n_clusters == hf.n_clusters and r.n_remaining == hf.n_remaining and r.n_voxel == hf.n_voxel
+            assert_bits_equal(op.download(r.remaining_cloud, r.n_remaining * 4, np.float32).reshape(-1, 4), hf.remaining_cloud, "remaining")
+            assert_bits_equal(op.download(r.remaining_src_idx, r.n_remaining, np.int32), hf.remaining_src_idx, "remaining src")
+            assert_bits_equal(op.download(r.cluster_offsets, r.n_clusters + 1, np.int32), hf.cluster_offsets, "offsets")
+            assert_bits_equal(op.download(r.cluster_indices, r.n_cluster_points, np.int32), hf.cluster_indices, "indices")
+            assert_bits_equal(op.download(r.obstacles, r.n_clusters * 4, np.float32).reshape(-1, 4), hf.obstacles, "obstacles")
+            assert_bits_equal(op.download(r.voxel_keys, r.n_voxel, np.uint32), hf.voxel_keys, "voxel keys")
+            assert_bits_equal(op.download(r.crop_kept_idx, r.n_crop, np.int32), hf.crop_kept_idx, "crop kept")
