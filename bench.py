@@ -447,7 +447,7 @@ def main():
                                               "host memory inside the step"},
             "device_ms_per_step": 1000.0 * dev_s / args.steps,
             "instrumented_ms_per_step": 1000.0 * wall_instr / args.steps if wall_instr else None,
-            "lanes": int(os.environ.get("PCOP_LANES", str(min(4, max(2, B // 256))))),
+            "lanes": int(os.environ.get("PCOP_LANES", str(2 if (os.cpu_count() or 1) < 8 * torch.cuda.device_count() else min(4, max(2, B // 256))))),
             "e2e": {"value": total_points / wall_e2e, "unit": "points/s", "h2d_bytes_per_step": B * n * 16 + B * 4,
                     "d2h_bytes_per_step": int(d2h_bytes), "frames_per_sec": total_frames / wall_e2e,
                     "ms_per_step": 1000.0 * wall_e2e / args.steps},

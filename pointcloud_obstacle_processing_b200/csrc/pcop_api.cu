@@ -1519,6 +1519,11 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   // lanes: max_batch frames are in flight at once, split over the lanes (PCOP_LANES overrides the default: 2 lanes,
   // one more per 256 frames of max_batch beyond 512, at most 4)
   int n_lanes = std::min(4, std::max(2, max_batch / 256));
+  {  // every lane is a spinning host thread: two lanes when the box has fewer than 8 hardware threads per GPU
+    int ndev_all = 1;
+    if (cudaGetDeviceCount(&ndev_all) != cudaSuccess || ndev_all < 1) ndev_all = 1;
+    if (std::thread::hardware_concurrency() < 8u * (unsigned)ndev_all) n_lanes = 2;
+  }
   if (const char* s = getenv("PCOP_LANES")) n_lanes = (int)std::min<long>(std::max<long>(strtol(s, nullptr, 10), 1), 8);
   n_lanes = std::max(1, std::min(n_lanes, max_batch / PCOP_MIN_LANE_WAVE));
   // capacity of a lane: 5/4 of an even share, so that one call of max_batch frames can be dealt in uneven waves
