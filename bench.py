@@ -214,26 +214,47 @@ def main():
     # records padded to the largest rank total (gather to rank 0), over NCCL.  The per-frame fields are read as numpy
     # views over the ctypes result array; the records of consecutive frames of a wave are adjacent in the library's
     # pinned result buffer, so they are staged run by run (a handful of memmoves per step).
+    # The exchange is asynchronous and double-buffered: the collectives of step k run on NCCL's stream while step k+1
+    # computes; gather_flush() waits for the outstanding ones before a timed region ends.
     from pointcloud_obstacle_processing_b200._ctypes_abi import FrameResult
-    obs_stage = torch.empty((B * 256, 4), dtype=torch.float32).pin_memory() if world > 1 else None
-    cnt_stage = torch.empty(B + 1, dtype=torch.int32).pin_memory() if world > 1 else None
-    dev_cnt = torch.empty(B + 1, dtype=torch.int32, device=dev.device) if world > 1 else None
-    all_cnt = torch.empty((world, B + 1), dtype=torch.int32, device=dev.device) if world > 1 else None
-    pad_cap = [0, None, None]
+    PADCAP = B * 128  # obstacle records per rank and step (fixed: no size negotiation, no host synchronisation)
+    slots = []
+    if world > 1:
+        for _ in range(2):
+            slots.append({
+                "obs_stage": torch.empty((PADCAP, 4), dtype=torch.float32).pin_memory(),
+                "cnt_stage": torch.empty(B + 1, dtype=torch.int32).pin_memory(),
+                "dev_cnt": torch.empty(B + 1, dtype=torch.int32, device=dev.device),
+                "all_cnt": torch.empty((world, B + 1), dtype=torch.int32, device=dev.device),
+                "pad": torch.zeros((PADCAP, 4), dtype=torch.float32, device=dev.device),
+                "out": torch.empty((world, PADCAP, 4), dtype=torch.float32, device=dev.device) if rank == 0 else None,
+                "work": []})
+    gather_step = [0]
     results_on_device = [True]
     off_c, off_p, rec = FrameResult.n_clusters.offset, FrameResult.obstacles.offset, C.sizeof(FrameResult)
+
+    def gather_flush():
+        for sl in slots:
+            for w in sl["work"]:
+                w.wait()
+            sl["work"] = []
 
     def gather_results(res):
         if world == 1 or os.environ.get("PCOP_BENCH_NO_GATHER"):
             return
+        sl = slots[gather_step[0] & 1]
+        gather_step[0] += 1
+        for w in sl["work"]:  # the slot's buffers are free again once its previous exchange has completed
+            w.wait()
         raw = np.frombuffer(res, dtype=np.uint8).reshape(len(res), rec)
         ns = raw[:, off_c:off_c + 4].copy().view(np.int32).ravel()
         ptrs = raw[:, off_p:off_p + 8].copy().view(np.uint64).ravel()
         tot = int(ns.sum())
-        cnt_stage[:B].copy_(torch.from_numpy(ns))
-        cnt_stage[B] = tot
-        dev_cnt.copy_(cnt_stage, non_blocking=True)
-        dist.all_gather_into_tensor(all_cnt.view(-1), dev_cnt)
+        assert tot <= PADCAP, "more obstacle records than the exchange buffer holds"
+        sl["cnt_stage"][:B].copy_(torch.from_numpy(ns))
+        sl["cnt_stage"][B] = tot
+        sl["dev_cnt"].copy_(sl["cnt_stage"], non_blocking=True)
+        w1 = dist.all_gather_into_tensor(sl["all_cnt"].view(-1), sl["dev_cnt"], async_op=True)
         if tot:
             live = np.flatnonzero(ns > 0)
             ends = ptrs[live] + 16 * ns[live].astype(np.uint64)
@@ -241,26 +262,17 @@ def main():
             starts = np.concatenate([[0], brk])
             stops = np.concatenate([brk, [len(live)]])
             o = 0
-            runs = []
             for a, b_ in zip(starts, stops):
                 nrec = int(ns[live[a:b_]].sum())
-                runs.append((o, int(ptrs[live[a]]), nrec))
-                if not results_on_device[0]:
-                    C.memmove(obs_stage.data_ptr() + 16 * o, int(ptrs[live[a]]), 16 * nrec)
+                if results_on_device[0]:  # device -> device, straight out of the library's result buffer
+                    op.copy_device(sl["pad"].data_ptr() + 16 * o, int(ptrs[live[a]]), 16 * nrec)
+                else:
+                    C.memmove(sl["obs_stage"].data_ptr() + 16 * o, int(ptrs[live[a]]), 16 * nrec)
                 o += nrec
-        mx = int(all_cnt[:, B].max().item())  # (the one synchronisation of the exchange)
-        if mx > pad_cap[0]:
-            pad_cap[0] = mx + mx // 4
-            pad_cap[1] = torch.zeros((pad_cap[0], 4), dtype=torch.float32, device=dev.device)
-            pad_cap[2] = torch.empty((world, pad_cap[0], 4), dtype=torch.float32, device=dev.device) if rank == 0 else None
-        pad = pad_cap[1][:mx]
-        if results_on_device[0]:
-            for o, src, nrec in (runs if tot else []):  # device -> device, straight out of the library's result buffer
-                op.copy_device(pad.data_ptr() + 16 * o, src, 16 * nrec)
-        else:
-            pad[:tot].copy_(obs_stage[:tot], non_blocking=True)
-        out = list(pad_cap[2][:, :mx].unbind(0)) if rank == 0 else None
-        dist.gather(pad, out, dst=0)
+            if not results_on_device[0]:
+                sl["pad"][:tot].copy_(sl["obs_stage"][:tot], non_blocking=True)
+        w2 = dist.gather(sl["pad"], list(sl["out"].unbind(0)) if rank == 0 else None, dst=0, async_op=True)
+        sl["work"] = [w1, w2]
 
     # ---- device-resident run ---------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -278,6 +290,7 @@ def main():
             dev_us += op.last_elapsed_us
             launches += op.last_launch_count
             alg_bytes += op.last_algorithmic_bytes
+        gather_flush()
         barrier()
         wall = time.perf_counter() - t0
     # ---- the same K steps with every result array copied to pinned host memory -----------------------------
@@ -289,6 +302,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         gather_results(step_device())
+    gather_flush()
     barrier()
     wall_host_results = time.perf_counter() - t0
     # (the passes below keep the host-result mode: the single lane of the instrumented pass runs four waves)
@@ -329,6 +343,7 @@ def main():
     for _ in range(args.steps):
         gather_results(step_host())
         d2h_exact += op.last_d2h_bytes
+    gather_flush()
     barrier()
     wall_e2e = time.perf_counter() - t1
     d2h_bytes = d2h_exact / args.steps  # counted by the library from the copies it issued
