@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -139,6 +140,13 @@ struct pcop_handle {
   unsigned char* d_raw = nullptr;  // staging for a raw PointCloud2 payload (grown on demand)
   size_t raw_cap = 0;
   int acc_count = 0;
+  // lane stagger (PCOP_STAGGER=1, experiment): the voxel stages of the lanes of one call run one after the other, so
+  // that a lane's latency-bound plane loop and clustering overlap the next lane's voxel stage
+  cudaEvent_t ev_vox_done = nullptr;
+  std::atomic<long long> vox_gen{0};  // call generation whose first voxel stage has been enqueued (event recorded)
+  pcop_handle* stagger_prev = nullptr;
+  long long call_gen = 0;
+  bool first_wave_of_call = false;
   cudaEvent_t ev_block = nullptr;  // blocking-sync event for the host waits (nullptr: spin), see stream_wait
   cudaEvent_t trace_origin = nullptr;  // PCOP_TRACE: start event of the running call (on lane 0's stream)
   size_t pack_cap = 0;
@@ -836,6 +844,11 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
       }
     }
   }
+  if (h->first_wave_of_call) {  // (see stagger_prev)
+    cudaEventRecord(h->ev_vox_done, h->stream);
+    h->vox_gen.store(h->call_gen, std::memory_order_release);
+    h->first_wave_of_call = false;
+  }
   {
     StageTimer t(h, PCOP_STAGE_SOR);
     if (p.enable_sor) {
@@ -1074,6 +1087,16 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
   size_t h_pack_used = 0;
   h->fixups.clear();
   h->wave_seq = 0;
+  h->first_wave_of_call = true;
+  struct PublishGen {  // never leave the next lane waiting, whatever path this lane exits by
+    pcop_handle* h;
+    ~PublishGen() {
+      if (h->vox_gen.load(std::memory_order_acquire) < h->call_gen) {
+        cudaEventRecord(h->ev_vox_done, h->stream);
+        h->vox_gen.store(h->call_gen, std::memory_order_release);
+      }
+    }
+  } publish_gen{h};
   for (const std::pair<int, int>& wv : waves) {
     const int w0 = wv.first, B = wv.second;
     for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_used[s] = false;
@@ -1107,6 +1130,11 @@ int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points,
     for (int f = 0; f < B; ++f) max_n = std::max(max_n, (int)n[w0 + f]);
     const bool trace = getenv("PCOP_TRACE") != nullptr;
     const auto tt0 = std::chrono::steady_clock::now();
+    if (h->first_wave_of_call && h->stagger_prev) {
+      pcop_handle* pv = h->stagger_prev;
+      while (pv->vox_gen.load(std::memory_order_acquire) < h->call_gen) std::this_thread::yield();
+      PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, pv->ev_vox_done, 0));
+    }
     TRY(run_wave_stages(h, B, in, stride, max_n));
     const auto tt1 = std::chrono::steady_clock::now();
     int cst = collect_wave(h, B, mask, &h_pack_used, out, w0, &h->fixups);
@@ -1210,11 +1238,15 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     // one wave per lane, of growing size (weights 1 .. 1.5): the lanes share the GPU, finish one after the other,
     // and every result copy but the last overlaps the kernels of the lanes still running.  (Measured on B200, 256
     // frames, 2 lanes: 2.58 ms per call; even split 2.67 ms; an extra small tail wave 3.0 ms.)
+    static const double skew = [] {
+      const char* sv = getenv("PCOP_WAVE_SKEW");
+      return sv ? std::min(1.0, std::max(-0.9, atof(sv))) : 0.5;
+    }();
     double wsum = 0.0;
-    for (int l = 0; l < n_lanes; ++l) wsum += 1.0 + 0.5 * l / (n_lanes - 1);
+    for (int l = 0; l < n_lanes; ++l) wsum += 1.0 + skew * l / (n_lanes - 1);
     int w0 = 0;
     for (int l = 0; l < n_lanes; ++l) {
-      int B = (l + 1 == n_lanes) ? batch - w0 : (int)((1.0 + 0.5 * l / (n_lanes - 1)) / wsum * batch);
+      int B = (l + 1 == n_lanes) ? batch - w0 : (int)((1.0 + skew * l / (n_lanes - 1)) / wsum * batch);
       B = std::min(B, h->maxB);
       if (B > 0) plan[l].push_back({w0, B});
       w0 += B;
@@ -1233,6 +1265,17 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   for (int l = 1; l < n_lanes; ++l) lanes.push_back(h->extra_lanes[l - 1]);
   int call_waves = 0;
   for (const WaveList& wl : plan) call_waves += (int)wl.size();
+  // off by default: measured on B200 (1024 frames, 4 lanes) the staggered schedule takes 7.2 ms per call against
+  // 6.3 ms for lanes that run the same stage at the same time (the voxel kernels do not saturate the GPU alone)
+  static const bool stagger = [] {
+    const char* sv = getenv("PCOP_STAGGER");
+    return sv && sv[0] == '1';
+  }();
+  const long long gen = ++h->call_gen;
+  for (int l = 0; l < n_lanes; ++l) {
+    lanes[l]->call_gen = gen;
+    lanes[l]->stagger_prev = (stagger && l > 0) ? lanes[l - 1] : nullptr;
+  }
   for (pcop_handle* l : lanes) {
     l->call_waves = call_waves;
     l->params = h->params;
@@ -1503,6 +1546,8 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
   for (int i = 0; i < 2; ++i)
     if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess)
       return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
+  if ((e = cudaEventCreateWithFlags(&h->ev_vox_done, cudaEventDisableTiming)) != cudaSuccess)
+    return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
   if ((e = cudaEventCreateWithFlags(&h->ev_rem_ready, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->ev_rem_copied, cudaEventDisableTiming)) != cudaSuccess)
     return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
@@ -1568,6 +1613,7 @@ void pcop_destroy(pcop_handle* h) {
     if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
   if (h->ev_lane_done) cudaEventDestroy(h->ev_lane_done);
   if (h->ev_block) cudaEventDestroy(h->ev_block);
+  if (h->ev_vox_done) cudaEventDestroy(h->ev_vox_done);
   for (int i = 0; i < 2; ++i)
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
   if (h->ev_rem_ready) cudaEventDestroy(h->ev_rem_ready);
