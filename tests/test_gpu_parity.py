@@ -468,3 +468,25 @@ def test_device_resident_results_match_host_results():
             assert_bits_equal(op.download(r.obstacles, r.n_clusters * 4, np.float32).reshape(-1, 4), hf.obstacles, "obstacles")
             assert_bits_equal(op.download(r.voxel_keys, r.n_voxel, np.uint32), hf.voxel_keys, "voxel keys")
             assert_bits_equal(op.download(r.crop_kept_idx, r.n_crop, np.int32), hf.crop_kept_idx, "crop kept")
+
+
+def test_batch_from_device_memory_matches_host_input():
+    """pcop_process_batch takes host or device frames (the bench's `value` runs on frames resident in HBM)"""
+    torch = pytest.importorskip("torch")
+    p = synth.params(2)
+    n = synth.points_per_frame(2)
+    B = 12
+    clouds = synth.frames(2, 400, B)
+    counts = np.full(B, n, np.int32)
+    counts[5] = 90000
+    with ObstacleProcessor(p, n, max_batch=16) as op:
+        host = op.process_batch(clouds, counts)
+        dev = torch.from_numpy(clouds).to("cuda:0")
+        res = op.process_batch_raw(dev.data_ptr(), n, counts)
+        from pointcloud_obstacle_processing_b200.result import Frame
+        for f in range(B):
+            g = Frame.from_c(res[f])
+            assert g.n_clusters == host[f].n_clusters and g.n_remaining == host[f].n_remaining
+            assert_bits_equal(g.cluster_indices, host[f].cluster_indices, "indices")
+            assert_bits_equal(g.remaining_cloud, host[f].remaining_cloud, "remaining")
+            assert_bits_equal(g.obstacles, host[f].obstacles, "obstacles")
