@@ -490,3 +490,20 @@ def test_batch_from_device_memory_matches_host_input():
             assert_bits_equal(g.cluster_indices, host[f].cluster_indices, "indices")
             assert_bits_equal(g.remaining_cloud, host[f].remaining_cloud, "remaining")
             assert_bits_equal(g.obstacles, host[f].obstacles, "obstacles")
+
+
+def test_batch_parity_on_64_frames():
+    """BASELINE configs[4] (frame batches): 64 distinct HDL-64 frames through one pcop_process_batch call on two lanes,
+    every frame checked against the oracle (counts, index sets bit-exact, obstacles within 1e-5)"""
+    from concurrent.futures import ThreadPoolExecutor
+    p = synth.params(2)  # default outputs: remaining cloud, clusters, obstacles
+    n = synth.points_per_frame(2)
+    B = 64
+    clouds = synth.frames(2, 1000, B)
+    with ObstacleProcessor(p, n, max_batch=B) as op:
+        res = op.process_batch(clouds)
+    with ThreadPoolExecutor(8) as ex:
+        oracle = list(ex.map(lambda f: O.process(p, clouds[f]), range(B)))
+    for f in range(B):
+        compare_frames(res[f], oracle[f], p, f"frame{f}: ")
+    assert sum(o.n_clusters for o in oracle) > 10 * B
