@@ -152,6 +152,7 @@ struct VoxelFusedArgs {
   unsigned long long* pair[2];  // [B*cap] ping-pong (key << 32) | original index
   unsigned* desc;    // compaction descriptors
   uint32_t* flags;   // [B] bit 0: the frame needs the generic path (a survivor with a non-finite y or z)
+  uint32_t* warnings;  // [B] zeroed by the stage's init kernel when non-null (saves the wave's k_zero_u32 launch)
   int* n_crop;       // [B] out: M
   float4* out;       // [B*cap] voxel centroids
   uint32_t* out_keys;
@@ -186,6 +187,7 @@ struct PlaneArgs {
   const float4* in;  // plane-loop input (S points per frame)
   size_t in_stride;
   const int* n_in;
+  int* n_in_copy;  // optional [B]: the init kernel copies n_in there (the count row of a disabled SOR stage)
   float4* buf[2];  // [B*cap] ping-pong clouds
   int* src[2];     // [B*cap] index into `in` of each remaining point
   int* inlier_idx; // [B*cap] last pass' inliers

@@ -455,10 +455,8 @@ __global__ void __launch_bounds__(CT_THREADS)
   }
 }
 
-__global__ void k_plane_record(const PlaneFrame* __restrict__ pf, PlaneRecord* __restrict__ rec, int* __restrict__ n_inl,
-                               int* __restrict__ n_clus, int* __restrict__ n_clus1, int plane_enabled, int B) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= B) return;
+__device__ void plane_record_one(const PlaneFrame* __restrict__ pf, PlaneRecord* __restrict__ rec, int* __restrict__ n_inl,
+                                 int* __restrict__ n_clus, int* __restrict__ n_clus1, int plane_enabled, int f) {
   PlaneRecord r;
   r.n_passes = 0;
   r.n_inliers_last = 0;
@@ -484,10 +482,22 @@ __global__ void k_plane_record(const PlaneFrame* __restrict__ pf, PlaneRecord* _
   n_clus1[f] = n_clus[f] + 1;
 }
 
+__global__ void k_plane_record(const PlaneFrame* __restrict__ pf, PlaneRecord* __restrict__ rec, int* __restrict__ n_inl,
+                               int* __restrict__ n_clus, int* __restrict__ n_clus1, int plane_enabled, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < B) plane_record_one(pf, rec, n_inl, n_clus, n_clus1, plane_enabled, f);
+}
+
 // exclusive scans over the frames of every requested output's count row + array base offsets
-__global__ void k_pack_scan(const int* __restrict__ counts, int maxB, int B, uint32_t mask, int* __restrict__ pack_off,
-                            PackMeta* __restrict__ meta) {
+// (first the per-frame plane record + the derived count rows CNT_NINL / CNT_CLUS1, which the scans below read)
+__global__ void k_pack_scan(int* __restrict__ counts, int maxB, int B, uint32_t mask, int* __restrict__ pack_off,
+                            PackMeta* __restrict__ meta, const PlaneFrame* __restrict__ pf, PlaneRecord* __restrict__ rec,
+                            int plane_enabled) {
   __shared__ int total[PK_N];
+  for (int f = threadIdx.x; f < B; f += blockDim.x)
+    plane_record_one(pf, rec, counts + (size_t)CNT_NINL * maxB, counts + (size_t)CNT_CLUS * maxB,
+                     counts + (size_t)CNT_CLUS1 * maxB, plane_enabled, f);
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kPkCountD[PK_N] = {CNT_CROP, CNT_VOX, CNT_VOX, CNT_SOR, CNT_NINL, CNT_REM, CNT_REM, CNT_CLUS1, CNT_CLPTS, CNT_CLUS};
   const uint32_t kPkMaskD[PK_N] = {PCOP_OUT_CROP,     PCOP_OUT_VOXEL,     PCOP_OUT_VOXEL,     PCOP_OUT_SOR,
@@ -775,8 +785,11 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
   const pcop_params& p = h->params;
   Ctx c = make_ctx(h, B, max_n);  // no stage ever holds more points per frame than the largest input frame
   const int tiles = cdiv(h->cap, CT_TILE);
-  KL(c, "k_zero_u32", k_zero_u32<<<cdiv(B, 256), 256, 0, h->stream>>>(h->d_warnings, B));
-  count_launch(c);
+  const bool fused_path = h->vplan.ok && !h->force_generic;
+  if (!fused_path || (effective_outputs(p) & PCOP_OUT_CROP)) {  // (the fused voxel path zeroes the warnings itself)
+    KL(c, "k_zero_u32", k_zero_u32<<<cdiv(B, 256), 256, 0, h->stream>>>(h->d_warnings, B));
+    count_launch(c);
+  }
 
   const float4* cur = in;
   size_t cur_stride = stride;
@@ -807,6 +820,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
     a.pair[1] = h->d_vf_pair[1];
     a.desc = h->d_desc;
     a.flags = h->d_vf_flags;
+    a.warnings = (effective_outputs(p) & PCOP_OUT_CROP) ? nullptr : h->d_warnings;  // zeroed by k_vf_init
     a.n_crop = h->cnt(CNT_CROP);
     a.out = h->d_vox;
     a.out_keys = h->d_vox_keys;
@@ -856,7 +870,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
       cur = h->d_sor;
       cur_stride = h->cap;
       cur_n = h->cnt(CNT_SOR);
-    } else {
+    } else if (!p.enable_plane) {  // (with the plane stage on, its init kernel copies the count row)
       KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_SOR), B));
       count_launch(c);
     }
@@ -865,6 +879,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
     StageTimer t(h, PCOP_STAGE_PLANE);
     if (p.enable_plane) {
       PlaneArgs a = make_plane_args(h, cur, cur_stride, cur_n);
+      a.n_in_copy = p.enable_sor ? nullptr : h->cnt(CNT_SOR);
       cudaError_t e = run_plane(c, a);
       if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
       c.grid_cap = std::max(1, std::min(c.grid_cap, h->h_n_active[1]));  // largest remaining cloud of the wave
@@ -948,12 +963,11 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   const int half = h->wave_seq & 1;
   unsigned char* d_pack = h->d_pack + (size_t)half * h->pack_cap;
   if (h->wave_seq >= 2) PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied[half], 0));  // half is free again
-  KL(c, "k_plane_record", k_plane_record<<<cdiv(B, 128), 128, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS),
-                                                      h->cnt(CNT_CLUS1), h->params.enable_plane ? 1 : 0, B));
   const uint32_t full_mask = mask;
   if (h->wave_rem_early) mask &= ~(uint32_t)PCOP_OUT_REMAINING;  // already on its way (run_wave_stages)
-  KL(c, "k_pack_scan", k_pack_scan<<<1, 320, 0, h->stream>>>(h->d_counts, h->maxB, B, mask, h->d_pack_off, h->d_meta));
-  count_launch(c, 2);
+  KL(c, "k_pack_scan", k_pack_scan<<<1, 320, 0, h->stream>>>(h->d_counts, h->maxB, B, mask, h->d_pack_off, h->d_meta, h->d_pf, h->d_prec,
+                                             h->params.enable_plane ? 1 : 0));
+  count_launch(c);
   const void* srcs[PK_N] = {h->d_crop_kept, h->d_vox_keys, h->d_vox,     h->d_sor_kept, h->d_inliers,
                             h->d_rem,       h->d_rem_src,  h->d_offsets, h->d_indices,  h->d_obst};
   const size_t strides[PK_N] = {(size_t)h->cap, (size_t)h->cap, (size_t)h->cap,     (size_t)h->cap, (size_t)h->cap,

@@ -11,6 +11,7 @@
 // compaction removes the refined inliers; (7) the while(size > 0.3*nr) rule is evaluated per
 // frame.  Frames of a wave run their passes in lock-step; finished frames idle.
 #include "det_math.cuh"
+#include <cstdio>
 #include "internal.cuh"
 #include "primitives.cuh"
 
@@ -65,11 +66,12 @@ __device__ float4 compute_model(const float4 p0, const float4 p1, const float4 p
 }
 
 __global__ void k_plane_init(PlaneFrame* __restrict__ pf, const int* __restrict__ n_in, double keep_fraction,
-                             int* __restrict__ n_active, int B) {
+                             int* __restrict__ n_active, int* __restrict__ n_in_copy, int B) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= B) return;
   PlaneFrame& P = pf[f];
   const int n = n_in[f];
+  if (n_in_copy) n_in_copy[f] = n;
   P.cur = -1;
   P.nr_points = n;
   P.n = n;
@@ -119,46 +121,97 @@ __global__ void __launch_bounds__(32)
   __shared__ int trip[MAX_HYP][3];
   bool fast_done = false;
   const int want = min(pc.max_iterations + 1, MAX_HYP);
+#ifdef PCOP_GEN_DEBUG
+  long long gclk[8];
+  gclk[0] = clock64();
+#define GCLK(k) gclk[k] = clock64()
+#else
+#define GCLK(k)
+#endif
   if (n >= 3 && 3 * want <= RNG_TABLE && 3 * want <= MAP_CAP) {
+    // Draw replay in O(1) per draw (no search list).  Step j (i = j % 3) swaps shuf[i] with shuf[q_j],
+    // q_j = i + rnd_j % (n - i).  A_j / T_j = values at positions i / q_j before the step; afterwards position i
+    // holds T_j and position q_j holds A_j, and sample h = (T_3h, T_3h+1, T_3h+2).  The value at a position is what
+    // its latest earlier writer left there: positions 0..2 are rewritten every three steps (so only steps j-1..j-3
+    // matter), a position >= 3 only by an earlier step with the same target (Lq, found by all lanes in parallel).
     __shared__ int srng[3 * MAX_HYP];  // the random numbers of the fast path, fetched by all lanes at once
-    for (int k = lane; k < 3 * want; k += 32) srng[k] = rng[k];
+    __shared__ int sq[3 * MAX_HYP], sA[3 * MAX_HYP], sT[3 * MAX_HYP];
+    __shared__ int sLq[3 * MAX_HYP];
+    const int J = 3 * want;
+    for (int k = lane; k < J; k += 32) {
+      srng[k] = rng[k];
+      const int i = k % 3;
+      sq[k] = i + (int)((unsigned)srng[k] % (unsigned)(n - i));
+    }
     __syncwarp();
-    for (int h = 0; h < want; ++h) {
+    GCLK(1);
+    // Lq[j] = latest k < j with the same target.  Lane l owns the steps k = l, l+32, ... (their targets in registers);
+    // per j one broadcast load, a few register compares and, on the rare match, a warp max.
+    int myq[(3 * MAX_HYP + 31) / 32];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int r = srng[t++];
-        const int j = i + (int)((unsigned)r % (unsigned)(n - i));
-        const int vi = s[i];
-        if (j < 3) {
-          const int vj = (j == 0) ? s[0] : ((j == 1) ? s[1] : s[2]);
-          if (j == 0) s[0] = vi;
-          else if (j == 1) s[1] = vi;
-          else s[2] = vi;
-          s[i] = vj;
-        } else {
-          int found = -1;
-          for (int e = lane; e < ne; e += 32)
-            if (mpos[e] == j) found = e;
-          const unsigned b = __ballot_sync(FULL, found >= 0);
-          int vj = j;
-          if (b) {
-            const int idx = __shfl_sync(FULL, found, __ffs(b) - 1);
-            vj = mval[idx];
-            __syncwarp();
-            if (lane == 0) mval[idx] = vi;
+    for (int c = 0; c < (3 * MAX_HYP + 31) / 32; ++c) myq[c] = (lane + 32 * c < J) ? sq[lane + 32 * c] : -1;
+    for (int j = 0; j < J; ++j) {
+      const int qj = sq[j];
+      int best = -1;
+#pragma unroll
+      for (int c = 0; c < (3 * MAX_HYP + 31) / 32; ++c) {
+        const int k = lane + 32 * c;
+        if (k < j && myq[c] == qj) best = k;
+      }
+      int lq = -1;
+      if (__any_sync(FULL, best >= 0)) lq = __reduce_max_sync(FULL, best);
+      if (lane == 0) sLq[j] = lq;
+    }
+    __syncwarp();
+    GCLK(2);
+    if (lane == 0) {
+      // one hypothesis (three steps, slots 0, 1, 2) per iteration: the six shared-memory loads are issued up front, the
+      // values of the last three steps stay in registers; shared memory is only read again for a repeated target
+      int a1 = 0, a2 = 0, t3 = 0, t2 = 0, t1 = 0;  // A_{j-1}, A_{j-2}, T_{j-3}, T_{j-2}, T_{j-1}
+      int q1 = -1, q2 = -1, q3 = -1;              // q_{j-1}, q_{j-2}, q_{j-3}
+      for (int j0 = 0; j0 < J; j0 += 3) {
+        const int qs[3] = {sq[j0], sq[j0 + 1], sq[j0 + 2]};
+        const int ls[3] = {sLq[j0], sLq[j0 + 1], sLq[j0 + 2]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int j = j0 + i, qj = qs[i], lq = ls[i];
+          int a;
+          if (j >= 1 && q1 == i) a = a1;
+          else if (j >= 2 && q2 == i) a = a2;
+          else if (j >= 3) a = t3;
+          else a = i;
+          int t;
+          if (qj == i) {
+            t = a;
+          } else if (qj < 3) {
+            // position qj in 1..2 (> i): its latest writer among steps j-1, j-2, j-3 (slots i1, i2, i3 = i)
+            t = qj;
+            const int i1 = (i + 2) % 3, i2 = (i + 1) % 3;
+            if (j >= 1 && q1 == qj && i1 != qj) t = a1;
+            else if (j >= 1 && i1 == qj) t = t1;
+            else if (j >= 2 && q2 == qj && i2 != qj) t = a2;
+            else if (j >= 2 && i2 == qj) t = t2;
+            else if (j >= 3 && q3 == qj) t = sA[j - 3];
           } else {
-            if (lane == 0) {
-              mpos[ne] = j;
-              mval[ne] = vi;
-            }
-            ++ne;
+            t = (lq >= 0) ? sA[lq] : qj;
           }
-          __syncwarp();
-          s[i] = vj;
+          sA[j] = a;
+          sT[j] = t;
+          a2 = a1;
+          a1 = a;
+          t3 = t2;
+          t2 = t1;
+          t1 = t;
+          q3 = q2;
+          q2 = q1;
+          q1 = qj;
         }
       }
-      if (lane < 3) trip[h][lane] = (lane == 0) ? s[0] : ((lane == 1) ? s[1] : s[2]);
     }
+    __syncwarp();
+    GCLK(3);
+    for (int k = lane; k < J; k += 32) trip[k / 3][k % 3] = sT[k];
+    t = J;
     __syncwarp();
     bool bad = false;
     for (int h = lane; h < want; h += 32) {
@@ -171,6 +224,12 @@ __global__ void __launch_bounds__(32)
         P.hyp_valid[h] = model_valid(pc, co) ? 1 : 0;
       }
     }
+    GCLK(4);
+#ifdef PCOP_GEN_DEBUG
+    if (f == 0 && lane == 0)
+      printf("gen: rng+q %lld, Lq %lld, replay %lld, fetch+fit %lld cycles, bad=%d n=%d\n", gclk[1] - gclk[0], gclk[2] - gclk[1],
+             gclk[3] - gclk[2], gclk[4] - gclk[3], (int)bad, n);
+#endif
     if (!__any_sync(FULL, bad)) {
       fast_done = true;
       nh = want;
@@ -688,7 +747,7 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
   bp.s[1] = a.src[1];
   cudaError_t e;
   cudaMemsetAsync(a.n_active, 0, 3 * sizeof(int), c.stream);
-  KL(c, "k_plane_init", k_plane_init<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_in, a.pc.keep_fraction, a.n_active, c.B));
+  KL(c, "k_plane_init", k_plane_init<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_in, a.pc.keep_fraction, a.n_active, a.n_in_copy, c.B));
   count_launch(c);
   cudaMemcpyAsync(a.h_n_active, a.n_active, 3 * sizeof(int), cudaMemcpyDeviceToHost, c.stream);
   if ((e = stream_wait(c.stream, c.block_ev)) != cudaSuccess) return e;

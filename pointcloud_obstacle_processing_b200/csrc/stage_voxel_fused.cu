@@ -69,9 +69,10 @@ struct VfMinMax {
   }
 };
 
-__global__ void k_vf_init(MinMax* mm, uint32_t* __restrict__ flags, int B) {
+__global__ void k_vf_init(MinMax* mm, uint32_t* __restrict__ flags, uint32_t* __restrict__ warnings, int B) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f < B) {
+    if (warnings) warnings[f] = 0u;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       mm[f].mn[a] = ORD_POS_FLT_MAX;
@@ -174,8 +175,13 @@ __global__ void __launch_bounds__(CT_THREADS)
 }
 
 // exclusive scan of each (frame, pass) histogram, in place; 512 threads = VF_MAX_BINS
-__global__ void __launch_bounds__(VF_MAX_BINS) k_vf_scan(uint32_t* __restrict__ hist) {
+__device__ void vf_setup_one(const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf, int f);
+
+// (block (0, f) also derives PCL's voxel frame of frame f from the min/max when the keys are an output)
+__global__ void __launch_bounds__(VF_MAX_BINS) k_vf_scan(uint32_t* __restrict__ hist, const MinMax* __restrict__ minmax,
+                                                         float leaf, VoxelFrame* __restrict__ vf, int want_keys) {
   const int f = blockIdx.y, p = blockIdx.x;
+  if (want_keys && p == 0 && threadIdx.x == 0) vf_setup_one(minmax, leaf, vf, f);
   uint32_t* h = hist + ((size_t)f * VF_MAX_PASSES + p) * VF_MAX_BINS;
   __shared__ uint32_t wsum[VF_MAX_BINS / 32];
   const uint32_t v = h[threadIdx.x];
@@ -365,9 +371,7 @@ __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
 
 // PCL's voxel frame from the min/max of the survivors (same arithmetic as stage_voxel.cu's k_voxel_setup; the host
 // has proven that the overflow guard cannot fire)
-__global__ void k_vf_setup(const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf, int B) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= B) return;
+__device__ void vf_setup_one(const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf, int f) {
   VoxelFrame v;
   v.inv = fdiv(1.0f, leaf);
   unsigned div_b[3];
@@ -570,16 +574,15 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * btiles * sizeof(unsigned), c.stream);
   cudaMemsetAsync(a.sort.hist, 0, vox_fused_hist_elems(c.B) * sizeof(uint32_t), c.stream);
   cudaMemsetAsync(a.sort.desc, 0, (size_t)pl.npass * c.B * gtiles * nbins * sizeof(uint32_t), c.stream);
-  KL(c, "k_vf_init", k_vf_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, c.B));
+  KL(c, "k_vf_init", k_vf_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, a.warnings, c.B));
   if (a.want_keys)
     KL(c, "k_vf_crop_key", k_vf_crop_key<true><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
         a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles));
   else
     KL(c, "k_vf_crop_key", k_vf_crop_key<false><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
         a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles));
-  KL(c, "k_vf_scan", k_vf_scan<<<dim3(pl.npass, c.B), VF_MAX_BINS, 0, c.stream>>>(a.sort.hist));
-  KL(c, "k_vf_setup", k_vf_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.minmax, a.leaf, a.vf, c.B));
-  count_launch(c, 4);
+  KL(c, "k_vf_scan", k_vf_scan<<<dim3(pl.npass, c.B), VF_MAX_BINS, 0, c.stream>>>(a.sort.hist, a.minmax, a.leaf, a.vf, a.want_keys));
+  count_launch(c, 3);
   for (int p = 0; p < pl.npass; ++p) {
     const int shift = p * pl.digit_bits;
     switch (pl.digit_bits) {
