@@ -55,7 +55,8 @@ enum {
   PCOP_WARN_VOXEL_OVERFLOW_FALLBACK = 1, /* PCL: "Leaf size is too small": output = input   */
   PCOP_WARN_SOR_TOO_FEW_POINTS = 2,      /* V <= meanK: cloud passed through unchanged      */
   PCOP_WARN_PLANE_BREAK = 4,             /* od.cpp:383-387: no inliers, loop left early     */
-  PCOP_WARN_RNG_TABLE_EXHAUSTED = 8      /* >PCOP rng table draws needed (degenerate cloud) */
+  PCOP_WARN_RNG_TABLE_EXHAUSTED = 8,     /* >PCOP rng table draws needed (degenerate cloud) */
+  PCOP_WARN_SHADOW_DEGENERATE = 16       /* pcop_occupancy_shadows: a shadow fan too long to draw was skipped */
 };
 
 /* which arrays pcop_process* copies back to the host (pcop_params.outputs) */
@@ -245,9 +246,31 @@ int pcop_pointcloud2_to_xyz(pcop_handle* h, const unsigned char* data, int32_t n
  *   cell = (count < row_average * (1 - dev_percent)) ? 100 : 0        (float compare, od.cpp:258).
  * pcop_occupancy_dims: width/height as od.cpp:958-959.  pcop_occupancy_grid: xyzw = NULL takes the accumulated cloud
  * (pcop_accumulate*); grid_data[width*height] int8; counts[width*height] / row_avg[height] int64 are optional.
- * Hole detection and shadow casting (od.cpp:467-672, 823-852) stay on the host. */
+ * Shadow casting and the obstacle marks (od.cpp:466-672, 817-833): pcop_occupancy_shadows below. */
 int pcop_occupancy_dims(const pcop_handle* h, int32_t* width, int32_t* height);
 int pcop_occupancy_grid(pcop_handle* h, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts, int64_t* row_avg);
+
+/* ---- occupancy grid, shadow casting + obstacle marks (replaces od.cpp:466-672 and the loops of od.cpp:817-833) ----
+ * For every cluster of >= 2 points (handle_shadow_casting, od.cpp:572-662): the members go into the sensor frame
+ * (world_to_sensor16 = the "kinect2_link" <- "world" TF lookup of od.cpp:580, row-major 4x4 float, applied with
+ * pcl::transformPointCloud's coefficient formula); the first member with the smallest sensor x starts the shadow, the
+ * largest x and the y range give its height and width; calculate_shadow_cast (od.cpp:539-570) gives the end point,
+ * which goes back to the world frame through sensor_to_world16 (od.cpp:562, 626); a fan of ceil(width / block_size) + 3
+ * lines (traceShadow, od.cpp:466-537) is drawn with cells set to grid_opacity.  Afterwards every remaining point with
+ * a non-NaN x marks its cell 100 (od.cpp:823-833).
+ *   remaining_xyzw / cluster_offsets / cluster_indices   the arrays of a pcop_frame_result (host or device pointers)
+ *   grid_data [height*width]   in/out (host or device pointer): the grid pcop_occupancy_grid produced
+ *   shadow_records [C][6]      optional: start_x, start_y, end_x, end_y of the first line (grid cells, after the
+ *                              half-width shift), lines drawn, skipped flag
+ *   warnings                   optional: PCOP_WARN_SHADOW_DEGENERATE
+ * Where the reference leaves the arithmetic to the platform or runs into undefined behaviour, this library defines:
+ * unqualified fabs / sqrt / asin / tan / ceil are the double overloads (asin, tan: fixed IEEE operation sequences,
+ * < 1e-15 from libm); the cell search of get_occupancy_grid_x_y stops after 2^20 steps; cell indices are 64-bit;
+ * float/double -> int conversions saturate to INT_MIN like cvttss2si / cvttsd2si; a line longer than 65536 pixels or a
+ * fan of more than 65536 lines is skipped (PCOP_WARN_SHADOW_DEGENERATE); the obstacle marks are bounds-checked. */
+int pcop_occupancy_shadows(pcop_handle* h, const float* remaining_xyzw, int32_t n_remaining, const int32_t* cluster_offsets,
+                           const int32_t* cluster_indices, int32_t n_clusters, const float* world_to_sensor16,
+                           const float* sensor_to_world16, int8_t* grid_data, int32_t* shadow_records, uint32_t* warnings);
 
 /* Copies `bytes` from a device result array (PCOP_OUT_DEVICE) to host memory, or device to device when dst is a device
  * pointer; synchronous. */

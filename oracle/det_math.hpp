@@ -20,6 +20,8 @@
 //       Q = Horner of (-1)^j/(2j+1), j=10..0, in u*u; result = ATAN_K[k]+u*Q
 //   det_atan2(y,x), y>=0:     standard octant reduction on det_atan
 //   det_sin/det_cos(x), |x|<=pi/2 (callers use [0, pi/3]): Taylor to x^23 / x^22
+//   det_asin(q):  NaN for NaN or |q|>1; a=|q|; x=sqrt((1-a)*(1+a)); r=det_atan2(a,x); sign of q restored
+//   det_tan(x), |x|<=~pi/2:   det_sin(x)/det_cos(x)
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -85,5 +87,16 @@ inline double det_cos(double x) {
   for (int j = 10; j >= 0; --j) p = INV_FACT[j] - z * p;
   return p;
 }
+
+// asin / tan for the shadow-length formula (od.cpp:543-545)
+inline double det_asin(double q) {
+  if (q != q || std::fabs(q) > 1.0) return std::nan("");
+  const double a = std::fabs(q);
+  const double x = std::sqrt((1.0 - a) * (1.0 + a));
+  const double r = det_atan2_ypos(a, x);
+  return (q < 0.0) ? -r : r;
+}
+
+inline double det_tan(double x) { return det_sin(x) / det_cos(x); }
 
 }  // namespace pcop_oracle

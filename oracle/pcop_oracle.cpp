@@ -1045,6 +1045,204 @@ int pcop_oracle_occupancy_grid(const pcop_params* pr, const float* xyzw, int32_t
   return PCOP_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Shadow casting + obstacle marking on the occupancy grid (od.cpp:466-672, 817-833).
+//
+// ORACLE CHOICES (the reference leaves these to the platform or runs into undefined behaviour):
+//  * unqualified fabs / sqrt / asin / tan / ceil bind to the double overloads of <math.h>; asin and tan are the
+//    deterministic det_asin / det_tan (det_math.hpp, < 1e-15 from libm away from |D| = pi/2);
+//  * the TF lookups (od.cpp:562, 580, 626) are explicit row-major 4x4 float matrices, applied with
+//    pcl::transformPointCloud's coefficient formula (pcop_oracle_transform, dense cloud);
+//  * get_occupancy_grid_x_y's while-loops stop at PCOP_OCC_COUNT_CAP = 2^20 steps (the reference would run on, and
+//    overflow its int counter, for a point that far outside the arena);
+//  * cell indices are formed in 64 bits (reference: int; identical whenever the int does not overflow);
+//  * double -> int and float -> int conversions follow cvttsd2si / cvttss2si (NaN / out of range -> INT_MIN);
+//  * a shadow line of more than PCOP_SHADOW_MAX_LINE = 65536 pixels, or a fan of more than 65536 lines, is not
+//    drawn and raises PCOP_WARN_SHADOW_DEGENERATE (the reference would loop over it for minutes);
+//  * the obstacle marking (od.cpp:823-833) is bounds-checked like the initial data set (od.cpp:205); the reference
+//    writes unchecked.
+namespace {
+constexpr int OCC_COUNT_CAP = 1 << 20;
+constexpr long long SHADOW_MAX_LINE = 65536;
+
+inline int32_t cvt_d2i(double v) {
+  if (v != v || v >= 2147483648.0 || v <= -2147483649.0) return INT32_MIN;
+  return (int32_t)v;
+}
+
+// get_occupancy_grid_x_y (od.cpp:134-150), literal, with the step cap
+static void occupancy_xy_capped(float x, float y, float x_min, float y_max, float block_size, int* xc, int* yc) {
+  int x_count = 0, y_count = 0;
+  while (x_count < OCC_COUNT_CAP) {
+    volatile float step = (float)(x_count + 1) * block_size;
+    volatile float edge = x_min + step;
+    if (!(edge < x)) break;
+    x_count++;
+  }
+  while (y_count < OCC_COUNT_CAP) {
+    volatile float step = (float)(y_count + 1) * block_size;
+    volatile float edge = y_max - step;
+    if (!(edge > y)) break;
+    y_count++;
+  }
+  *xc = x_count;
+  *yc = y_count;
+}
+
+// one point through pcl::transformPointCloud's coefficient formula (row-major 4x4)
+static P4 transform_one(const float* m, const P4& p) {
+  P4 o = p;
+  float* oo = &o.x;
+  for (int r = 0; r < 3; ++r) {
+    volatile float a = m[4 * r] * p.x;
+    volatile float b = m[4 * r + 1] * p.y;
+    volatile float c = m[4 * r + 2] * p.z;
+    volatile float s = a + b;
+    s = s + c;
+    s = s + m[4 * r + 3];
+    oo[r] = s;
+  }
+  return o;
+}
+
+// traceShadow (od.cpp:466-537), literal; returns false when the line is too long to draw
+static bool trace_shadow(float v1x, float v1y, float v2x, float v2y, int8_t* grid, int W, long long size, int8_t opacity) {
+  int x0 = cvt_f2i(v1x), x1 = cvt_f2i(v2x), y0 = cvt_f2i(v1y), y1 = cvt_f2i(v2y);
+  // abs() of the int differences; evaluated in 64 bits (no overflow)
+  const bool steep = std::llabs((long long)y1 - y0) > std::llabs((long long)x1 - x0);
+  if (steep) {
+    std::swap(x0, y0);
+    std::swap(x1, y1);
+  }
+  if (x0 > x1) {
+    std::swap(x0, x1);
+    std::swap(y0, y1);
+  }
+  if ((long long)x1 - x0 + 1 > SHADOW_MAX_LINE) return false;
+  const float dx = (float)(x1 - x0);
+  const float dy = (float)(int32_t)((uint32_t)y1 - (uint32_t)y0);  // int difference, x86 wrap-around
+  volatile float gradient = dy / dx;
+  if (dx == 0.0f) gradient = 1.0f;
+  volatile float intersect_y = (float)y0;
+  for (int x = x0; x <= x1; ++x) {
+    const int fl = cvt_f2i(std::floor(intersect_y));
+    const long long grid_y = steep ? x : fl, grid_x = steep ? fl : x;
+    long long idx = grid_y * W + grid_x;
+    if (idx < size && idx > -1) grid[idx] = opacity;
+    idx += 1;
+    if (idx < size && idx > -1) grid[idx] = opacity;
+    intersect_y = intersect_y + gradient;
+  }
+  return true;
+}
+
+}  // namespace
+
+int pcop_oracle_occupancy_shadows(const pcop_params* pr, const float* remaining_xyzw, int32_t n_remaining,
+                                             const int32_t* cluster_offsets, const int32_t* cluster_indices,
+                                             int32_t n_clusters, const float* world_to_sensor16,
+                                             const float* sensor_to_world16, int8_t* grid_data, int32_t* shadow_records,
+                                             uint32_t* warnings) {
+  int32_t W = 0, H = 0;
+  if (!pr || !grid_data || n_remaining < 0 || n_clusters < 0 || (n_remaining > 0 && !remaining_xyzw) ||
+      (n_clusters > 0 && (!cluster_offsets || !cluster_indices || !world_to_sensor16 || !sensor_to_world16)) ||
+      pcop_oracle_occupancy_dims(pr, &W, &H) != PCOP_OK || W <= 0 || H <= 0)
+    return PCOP_ERR_BAD_PARAM;
+  const long long size = (long long)W * H;
+  const P4* cloud = (const P4*)remaining_xyzw;
+  const float bs = pr->block_size;
+  const int8_t opacity = (int8_t)pr->grid_opacity;  // int stored into a char cell (od.cpp:508)
+  uint32_t warn = 0;
+  for (int32_t c = 0; c < n_clusters; ++c) {  // handle_shadow_casting (od.cpp:572-662), one call per cluster (od.cpp:817-821)
+    int32_t* rec = shadow_records ? shadow_records + 6 * (size_t)c : nullptr;
+    if (rec) std::fill(rec, rec + 6, 0);
+    const int32_t o0 = cluster_offsets[c], o1 = cluster_offsets[c + 1];
+    if (o1 - o0 < 2) continue;  // od.cpp:574
+    // od.cpp:587-609: members into the sensor frame, extrema with strict compares (first occurrence wins)
+    P4 vmin_pt = transform_one(world_to_sensor16, cloud[cluster_indices[o0]]);
+    float vmax = vmin_pt.x, hmin = vmin_pt.y, hmax = vmin_pt.y;
+    for (int32_t j = o0 + 1; j < o1; ++j) {
+      const P4 q = transform_one(world_to_sensor16, cloud[cluster_indices[j]]);
+      if (q.x < vmin_pt.x) vmin_pt = q;
+      if (q.x > vmax) vmax = q.x;
+      if (q.y < hmin) hmin = q.y;
+      if (q.y > hmax) hmax = q.y;
+    }
+    volatile float hdiff = hmax - hmin;
+    const float width = std::fabs(hdiff);  // od.cpp:616
+    // calculate_shadow_cast (od.cpp:539-570)
+    const float a = vmin_pt.z;
+    const float b = std::fabs(vmin_pt.x);
+    volatile float aa = a * a, bb = b * b;
+    volatile float ab = aa + bb;
+    const float cc = (float)std::sqrt((double)ab);
+    const float e = (float)((std::fabs((double)vmax) - std::fabs((double)vmin_pt.x)) + 0.04);
+    volatile float a_over_c = a / cc;
+    const float D = (float)pcop_oracle::det_asin((double)a_over_c);
+    const float d = (float)(pcop_oracle::det_tan((double)D) * (double)e + 0.25);
+    volatile float xx = vmin_pt.x * vmin_pt.x, yy = vmin_pt.y * vmin_pt.y, zz = vmin_pt.z * vmin_pt.z;
+    volatile float s2 = xx + yy;
+    s2 = s2 + zz;
+    const float v_len = (float)std::sqrt((double)s2);
+    P4 end = vmin_pt;
+    {
+      volatile float nx = vmin_pt.x / v_len, ny = vmin_pt.y / v_len, nz = vmin_pt.z / v_len;
+      nx = nx * d;
+      ny = ny * d;
+      nz = nz * d;
+      volatile float ex = nx + vmin_pt.x, ey = ny + vmin_pt.y, ez = nz + vmin_pt.z;
+      end.x = ex;
+      end.y = ey;
+      end.z = ez;
+    }
+    const P4 world_end = transform_one(sensor_to_world16, end);
+    int end_x, end_y, start_x, start_y;
+    occupancy_xy_capped(world_end.y, world_end.x, pr->y_min, pr->x_max, bs, &end_x, &end_y);  // od.cpp:569
+    const P4 world_start = transform_one(sensor_to_world16, vmin_pt);                        // od.cpp:626-634
+    occupancy_xy_capped(world_start.y, world_start.x, pr->y_min, pr->x_max, bs, &start_x, &start_y);
+    // od.cpp:642-643: first += ceil((width / block_size) / 2)   (int += double)
+    volatile float wb = width / bs;
+    volatile float half = wb / 2.0f;
+    const double shift = std::ceil((double)half);
+    start_x = cvt_d2i((double)start_x + shift);
+    end_x = cvt_d2i((double)end_x + shift);
+    // od.cpp:645: for (int i = 0; i < ceil(width / block_size) + 3; i++)
+    const double lim = std::ceil((double)wb) + 3.0;
+    long long n_lines = 0;
+    if (lim == lim && lim > 0.0) n_lines = (lim > 1.0e9) ? 1000000000ll : (long long)std::ceil(lim);
+    bool skipped = false;
+    if (n_lines > SHADOW_MAX_LINE) {
+      skipped = true;
+      n_lines = 0;
+    }
+    if (rec) {
+      rec[0] = start_x;
+      rec[1] = start_y;
+      rec[2] = end_x;
+      rec[3] = end_y;
+    }
+    for (long long i = 0; i < n_lines; ++i) {
+      // Vertex holds floats (od.cpp:127-131); first -= 1 per line (od.cpp:659-660), int wrap-around as on x86
+      const int32_t sx = (int32_t)((uint32_t)start_x - (uint32_t)i), ex = (int32_t)((uint32_t)end_x - (uint32_t)i);
+      if (!trace_shadow((float)sx, (float)start_y, (float)ex, (float)end_y, grid_data, W, size, opacity)) skipped = true;
+    }
+    if (skipped) warn |= PCOP_WARN_SHADOW_DEGENERATE;
+    if (rec) {
+      rec[4] = (int32_t)n_lines;
+      rec[5] = skipped ? 1 : 0;
+    }
+  }
+  for (int32_t i = 0; i < n_remaining; ++i) {  // od.cpp:823-833
+    if (std::isnan(cloud[i].x)) continue;
+    int xc, yc;
+    occupancy_xy_capped(cloud[i].y, cloud[i].x, pr->y_min, pr->x_max, bs, &xc, &yc);
+    const long long idx = (long long)yc * W + xc;
+    if (idx < size) grid_data[idx] = 100;
+  }
+  if (warnings) *warnings = warn;
+  return PCOP_OK;
+}
+
 int pcop_oracle_process(const pcop_params* pr, const float* xyzw, int32_t n, pcop_frame_result* out) {
   std::memset(out, 0, sizeof(*out));
   const P4* in = (const P4*)xyzw;
@@ -1194,6 +1392,8 @@ double pcop_oracle_det_log(double x) { return det_log(x); }
 double pcop_oracle_det_atan2_ypos(double y, double x) { return det_atan2_ypos(y, x); }
 double pcop_oracle_det_sin(double x) { return det_sin(x); }
 double pcop_oracle_det_cos(double x) { return det_cos(x); }
+double pcop_oracle_det_asin(double q) { return pcop_oracle::det_asin(q); }
+double pcop_oracle_det_tan(double x) { return pcop_oracle::det_tan(x); }
 double pcop_oracle_tree_sum(const double* v, int32_t n) { return tree_sum(v, n); }
 void pcop_oracle_eigen33_smallest(const double* m9, double* eval, double* evec3) {
   eigen33_smallest(m9, eval, evec3);

@@ -59,6 +59,20 @@ int pcop_oracle_occupancy_dims(const pcop_params* pr, int32_t* width, int32_t* h
 int pcop_oracle_occupancy_grid(const pcop_params* pr, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts,
                                int64_t* row_avg);
 
+/* Shadow casting + obstacle marking on the grid (od.cpp:466-672, 817-833): per cluster of >= 2 points the members go
+ * into the sensor frame (world_to_sensor16 = the "kinect2_link" <- "world" lookup of od.cpp:580), the point with the
+ * smallest sensor x starts a fan of ceil(width / block_size) + 3 lines (traceShadow, cells set to grid_opacity) towards
+ * the shadow end point (calculate_shadow_cast, back through sensor_to_world16); then every remaining point marks its
+ * cell 100.  grid_data [height*width] is updated in place.  shadow_records (optional, [C][6]) = start_x, start_y,
+ * end_x, end_y (grid cells of the first line, after the half-width shift), lines drawn, skipped flag.  The choices the
+ * reference leaves open are listed beside the code ("ORACLE CHOICES"). */
+int pcop_oracle_occupancy_shadows(const pcop_params* pr, const float* remaining_xyzw, int32_t n_remaining,
+                                  const int32_t* cluster_offsets, const int32_t* cluster_indices, int32_t n_clusters,
+                                  const float* world_to_sensor16, const float* sensor_to_world16, int8_t* grid_data,
+                                  int32_t* shadow_records, uint32_t* warnings);
+double pcop_oracle_det_asin(double q);
+double pcop_oracle_det_tan(double x);
+
 /* Whole pipeline; result arrays are malloc'ed, release with pcop_oracle_free_result.
  * All PCOP_OUT_* arrays are always filled. */
 int pcop_oracle_process(const pcop_params* pr, const float* xyzw, int32_t n, pcop_frame_result* out);

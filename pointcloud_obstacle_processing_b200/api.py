@@ -41,6 +41,7 @@ EXPORTS = [
     "pcop_pointcloud2_to_xyz",
     "pcop_occupancy_dims",
     "pcop_occupancy_grid",
+    "pcop_occupancy_shadows",
     "pcop_download",
 ]
 
@@ -95,6 +96,7 @@ def load_library():
     L.pcop_download.argtypes = [vp, vp, vp, C.c_size_t]
     L.pcop_occupancy_dims.argtypes = [vp, vp, vp]
     L.pcop_occupancy_grid.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
+    L.pcop_occupancy_shadows.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.pcop_enable_kernel_timing.argtypes = [vp, C.c_int]
     L.pcop_kernel_timing_count.argtypes = [vp]
     L.pcop_kernel_timing_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
@@ -238,6 +240,32 @@ class ObstacleProcessor:
         self._check(self._lib.pcop_occupancy_grid(self._h, ptr, n, grid.ctypes.data_as(C.c_void_p),
                                                   counts.ctypes.data_as(C.c_void_p), avg.ctypes.data_as(C.c_void_p)))
         return grid, counts, avg
+
+    def handle_shadow_casting(self, grid, remaining_cloud, cluster_offsets, cluster_indices, world_to_sensor,
+                              sensor_to_world):
+        """handle_shadow_casting for every cluster + the obstacle marks (od.cpp:572-662, 817-833) on `grid`
+        (int8 [H, W], e.g. from occupancy_grid()).  The two 4x4 matrices stand for the TF lookups
+        "kinect2_link" <- "world" (od.cpp:580) and "world" <- "kinect2_link" (od.cpp:562, 626).
+        Returns (grid int8 [H, W], shadow_records int32 [C, 6], warnings)."""
+        w, h = C.c_int32(), C.c_int32()
+        self._check(self._lib.pcop_occupancy_dims(self._h, C.byref(w), C.byref(h)))
+        grid = np.array(grid, dtype=np.int8, order="C", copy=True)
+        if grid.shape != (h.value, w.value):
+            raise ValueError(f"grid must be [{h.value}, {w.value}]")
+        cloud = _f32(remaining_cloud) if len(remaining_cloud) else np.zeros((0, 4), np.float32)
+        off = np.ascontiguousarray(cluster_offsets, np.int32)
+        idx = np.ascontiguousarray(cluster_indices, np.int32)
+        n_clusters = max(len(off) - 1, 0)
+        ws = np.ascontiguousarray(world_to_sensor, np.float32).reshape(16)
+        sw = np.ascontiguousarray(sensor_to_world, np.float32).reshape(16)
+        rec = np.zeros((max(n_clusters, 1), 6), np.int32)
+        warn = C.c_uint32(0)
+        self._check(self._lib.pcop_occupancy_shadows(
+            self._h, cloud.ctypes.data_as(C.c_void_p) if cloud.shape[0] else None, cloud.shape[0],
+            off.ctypes.data_as(C.c_void_p) if n_clusters else None, idx.ctypes.data_as(C.c_void_p) if n_clusters else None,
+            n_clusters, ws.ctypes.data_as(C.c_void_p), sw.ctypes.data_as(C.c_void_p), grid.ctypes.data_as(C.c_void_p),
+            rec.ctypes.data_as(C.c_void_p), C.byref(warn)))
+        return grid, rec[:n_clusters].copy(), warn.value
 
     @property
     def accumulated_count(self) -> int:

@@ -9,6 +9,8 @@
 //                    Q = Horner of (-1)^j/(2j+1), j = 10..0, in u*u;  ATAN_K[k] + u*Q
 //   det_atan2_ypos:  octant reduction on det_atan01, y >= 0
 //   det_sin/det_cos: alternating Taylor series to x^23 / x^22, Horner in x*x
+//   det_asin(q):     NaN for NaN or |q| > 1; a = |q|; x = sqrt((1-a)*(1+a)); det_atan2_ypos(a, x), sign of q restored
+//   det_tan(x):      det_sin(x) / det_cos(x)
 #pragma once
 #include "common.cuh"
 
@@ -86,5 +88,15 @@ __device__ inline double det_cos(double x) {
   for (int j = 10; j >= 0; --j) p = dsub(F[j], dmul(z, p));
   return p;
 }
+
+__device__ inline double det_asin(double q) {
+  if (q != q || fabs(q) > 1.0) return __longlong_as_double(0x7ff8000000000000ll);
+  const double a = fabs(q);
+  const double x = __dsqrt_rn(dmul(dsub(1.0, a), dadd(1.0, a)));
+  const double r = det_atan2_ypos(a, x);
+  return (q < 0.0) ? -r : r;
+}
+
+__device__ inline double det_tan(double x) { return ddiv(det_sin(x), det_cos(x)); }
 
 }  // namespace pcop

@@ -243,4 +243,25 @@ bool run_cluster(const Ctx& c, const ClusterArgs& a);
 void run_cluster_small(const Ctx& c, const ClusterArgs& a, int small_max);
 void run_centroid_radius(const Ctx& c, const ClusterArgs& a);
 
+// ---- occupancy grid: shadow casting + obstacle marking (stage_occupancy.cu; od.cpp:466-672, 817-833) ----------
+struct Mat34 {
+  float m[12];  // rows 0..2 of a row-major 4x4 (pcl::transformPointCloud's coefficient formula)
+};
+struct OccShadowArgs {
+  const float4* cloud;  // [n] remaining cloud (planar_cloud_y, od.cpp:765)
+  int n;
+  const int* offsets;   // [n_clusters + 1] CSR
+  const int* indices;   // [L]
+  int n_clusters;
+  Mat34 world_to_sensor, sensor_to_world;  // the two TF lookups of od.cpp:580 / 562, 626
+  float y_min, x_max, block_size;
+  int W;
+  long long size;       // W * H
+  int opacity;          // grid_opacity
+  signed char* grid;    // [size] in/out
+  int* records;         // [n_clusters][6] or nullptr
+  uint32_t* warnings;   // [1], OR-ed
+};
+void run_occ_shadows(const Ctx& c, const OccShadowArgs& a);
+
 }  // namespace pcop

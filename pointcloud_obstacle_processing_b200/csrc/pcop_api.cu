@@ -137,6 +137,8 @@ struct pcop_handle {
   float4* d_acc = nullptr;  // accumulated (world-frame) cloud, od.cpp:697
   unsigned char* d_occ = nullptr;  // occupancy grid scratch: int64 counts, int64 row averages, int8 cells
   size_t occ_cap = 0;
+  unsigned char* d_shadow = nullptr;  // pcop_occupancy_shadows scratch: grid cells, CSR copy, records, warning word
+  size_t shadow_cap = 0;
   unsigned char* d_raw = nullptr;  // staging for a raw PointCloud2 payload (grown on demand)
   size_t raw_cap = 0;
   int acc_count = 0;
@@ -333,10 +335,6 @@ __global__ void k_zero_u32(uint32_t* p, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0u;
 }
-
-struct Mat34 {
-  float m[12];  // rows 0..2 of the 4x4
-};
 
 // pcl::transformPointCloud(cloud_in, cloud_out, Eigen::Matrix4f) (via pcl_ros::transformPointCloud, od.cpp:696):
 // out.x = m00*x + m01*y + m02*z + m03 in float, left to right, no FMA; non-dense clouds copy non-finite points
@@ -1618,6 +1616,7 @@ void pcop_destroy(pcop_handle* h) {
   if (h->d_rem_pack_src) cudaFree(h->d_rem_pack_src);
   if (h->d_rem_off) cudaFree(h->d_rem_off);
   if (h->d_occ) cudaFree(h->d_occ);
+  if (h->d_shadow) cudaFree(h->d_shadow);
   if (h->h_pack) cudaFreeHost(h->h_pack);
   if (h->kt.ev) {
     for (int i = 0; i < 2 * KernelTimers::MAX_SLOTS; ++i) cudaEventDestroy(h->kt.ev[i]);
@@ -1787,6 +1786,7 @@ static int pc2_ingest(pcop_handle* h, const unsigned char* data, int32_t n, int3
   if (h->d_rem_pack_src) cudaFree(h->d_rem_pack_src);
   if (h->d_rem_off) cudaFree(h->d_rem_off);
   if (h->d_occ) cudaFree(h->d_occ);
+  if (h->d_shadow) cudaFree(h->d_shadow);
       h->d_raw = nullptr;
       h->raw_cap = 0;
       PCOP_CUDA_TRY(cudaMalloc((void**)&h->d_raw, bytes + bytes / 4 + 256));
@@ -1880,6 +1880,100 @@ int pcop_occupancy_grid(pcop_handle* h, const float* xyzw, int32_t n, int8_t* gr
   TRY(download(h, counts, d_counts, cells * 8));
   TRY(download(h, row_avg, d_avg, (size_t)H * 8));
   PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
+// Shadow casting + obstacle marking (od.cpp:466-672, 817-833) on a grid produced by pcop_occupancy_grid
+int pcop_occupancy_shadows(pcop_handle* h, const float* remaining_xyzw, int32_t n_remaining, const int32_t* cluster_offsets,
+                           const int32_t* cluster_indices, int32_t n_clusters, const float* world_to_sensor16,
+                           const float* sensor_to_world16, int8_t* grid_data, int32_t* shadow_records, uint32_t* warnings) {
+  if (!h || !grid_data || n_remaining < 0 || n_clusters < 0 || (n_remaining > 0 && !remaining_xyzw) ||
+      (n_clusters > 0 && (!cluster_offsets || !cluster_indices || !world_to_sensor16 || !sensor_to_world16)))
+    return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  int32_t W = 0, H = 0;
+  if (pcop_occupancy_dims(h, &W, &H) != PCOP_OK || W <= 0 || H <= 0 || (long long)W * H > (1ll << 26))
+    return fail(h, PCOP_ERR_BAD_PARAM, "occupancy grid: block_size / crop limits give no usable grid");
+  if (n_remaining > h->cap) return fail(h, PCOP_ERR_CAPACITY, "cloud has more points than max_points");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  const size_t cells = (size_t)W * H;
+  // the member list's length is the last CSR offset
+  int32_t L = 0;
+  if (n_clusters > 0) {
+    if (is_device_pointer(cluster_offsets)) {
+      PCOP_CUDA_TRY(cudaMemcpyAsync(&L, cluster_offsets + n_clusters, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+      PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    } else {
+      L = cluster_offsets[n_clusters];
+    }
+    if (L < 0 || L > h->cap) return fail(h, PCOP_ERR_BAD_PARAM, "cluster_offsets: last offset out of range");
+  }
+  // scratch: [grid cells][pad][offsets C+1][indices L][records 6C][warnings 1]
+  const size_t off_ints = (cells + 15) & ~(size_t)15;
+  const size_t need = off_ints + ((size_t)n_clusters + 1 + (size_t)L + 6 * (size_t)n_clusters + 1) * sizeof(int32_t);
+  if (need > h->shadow_cap) {
+    PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->d_shadow) cudaFree(h->d_shadow);
+    h->d_shadow = nullptr;
+    h->shadow_cap = 0;
+    PCOP_CUDA_TRY(cudaMalloc((void**)&h->d_shadow, need + 256));
+    h->shadow_cap = need;
+  }
+  int32_t* d_off = reinterpret_cast<int32_t*>(h->d_shadow + off_ints);
+  int32_t* d_idx = d_off + n_clusters + 1;
+  int32_t* d_rec = d_idx + L;
+  uint32_t* d_warn = reinterpret_cast<uint32_t*>(d_rec + 6 * (size_t)n_clusters);
+  pcop::OccShadowArgs a{};
+  a.cloud = reinterpret_cast<const float4*>(remaining_xyzw);
+  if (n_remaining > 0 && !is_device_pointer(remaining_xyzw)) {
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_in, remaining_xyzw, (size_t)n_remaining * 16, cudaMemcpyHostToDevice, h->stream));
+    a.cloud = h->d_in;
+  }
+  a.n = n_remaining;
+  a.offsets = cluster_offsets;
+  a.indices = cluster_indices;
+  if (n_clusters > 0 && !is_device_pointer(cluster_offsets)) {
+    PCOP_CUDA_TRY(cudaMemcpyAsync(d_off, cluster_offsets, ((size_t)n_clusters + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    a.offsets = d_off;
+  }
+  if (n_clusters > 0 && L > 0 && !is_device_pointer(cluster_indices)) {
+    PCOP_CUDA_TRY(cudaMemcpyAsync(d_idx, cluster_indices, (size_t)L * 4, cudaMemcpyHostToDevice, h->stream));
+    a.indices = d_idx;
+  }
+  a.n_clusters = n_clusters;
+  for (int r = 0; r < 12; ++r) {
+    a.world_to_sensor.m[r] = world_to_sensor16 ? world_to_sensor16[r] : ((r % 5 == 0) ? 1.0f : 0.0f);
+    a.sensor_to_world.m[r] = sensor_to_world16 ? sensor_to_world16[r] : ((r % 5 == 0) ? 1.0f : 0.0f);
+  }
+  const pcop_params& p = h->params;
+  a.y_min = p.y_min;
+  a.x_max = p.x_max;
+  a.block_size = p.block_size;
+  a.W = W;
+  a.size = (long long)cells;
+  a.opacity = p.grid_opacity;
+  const bool grid_on_device = is_device_pointer(grid_data);
+  a.grid = reinterpret_cast<signed char*>(grid_data);
+  if (!grid_on_device) {
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_shadow, grid_data, cells, cudaMemcpyHostToDevice, h->stream));
+    a.grid = reinterpret_cast<signed char*>(h->d_shadow);
+  }
+  a.records = shadow_records ? d_rec : nullptr;
+  a.warnings = d_warn;
+  PCOP_CUDA_TRY(cudaMemsetAsync(d_warn, 0, sizeof(uint32_t), h->stream));
+  Ctx c = make_ctx(h, 1, n_remaining);
+  pcop::run_occ_shadows(c, a);
+  PCOP_CUDA_TRY(cudaGetLastError());
+  if (!grid_on_device) TRY(download(h, grid_data, a.grid, cells));
+  if (shadow_records && n_clusters > 0) {
+    if (is_device_pointer(shadow_records))
+      PCOP_CUDA_TRY(cudaMemcpyAsync(shadow_records, d_rec, 6 * (size_t)n_clusters * 4, cudaMemcpyDeviceToDevice, h->stream));
+    else
+      TRY(download(h, shadow_records, d_rec, 6 * (size_t)n_clusters * 4));
+  }
+  uint32_t wv = 0;
+  PCOP_CUDA_TRY(cudaMemcpyAsync(&wv, d_warn, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (warnings) *warnings = wv;
   return PCOP_OK;
 }
 

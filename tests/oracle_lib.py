@@ -222,3 +222,25 @@ def occupancy_grid(params, cloud):
                                           counts.ctypes.data_as(_fp), avg.ctypes.data_as(_fp))
     assert st == 0, st
     return grid, counts, avg
+
+
+def occupancy_shadows(params, grid, remaining, offsets, indices, world_to_sensor, sensor_to_world):
+    """handle_shadow_casting per cluster + obstacle marks (od.cpp:572-662, 817-833): (grid, records [C, 6], warnings)"""
+    grid = np.array(grid, dtype=np.int8, order="C", copy=True)
+    cloud = np.ascontiguousarray(remaining, np.float32).reshape(-1, 4)
+    off = np.ascontiguousarray(offsets, np.int32)
+    idx = np.ascontiguousarray(indices, np.int32)
+    nc = max(len(off) - 1, 0)
+    ws = np.ascontiguousarray(world_to_sensor, np.float32).reshape(16)
+    sw = np.ascontiguousarray(sensor_to_world, np.float32).reshape(16)
+    rec = np.zeros((max(nc, 1), 6), np.int32)
+    warn = C.c_uint32(0)
+    L = lib()
+    L.pcop_oracle_occupancy_shadows.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    st = L.pcop_oracle_occupancy_shadows(C.byref(params), cloud.ctypes.data_as(C.c_void_p), cloud.shape[0],
+                                         off.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), nc,
+                                         ws.ctypes.data_as(C.c_void_p), sw.ctypes.data_as(C.c_void_p),
+                                         grid.ctypes.data_as(C.c_void_p), rec.ctypes.data_as(C.c_void_p), C.byref(warn))
+    assert st == 0, st
+    return grid, rec[:nc].copy(), warn.value

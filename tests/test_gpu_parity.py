@@ -507,3 +507,97 @@ def test_batch_parity_on_64_frames():
     for f in range(B):
         compare_frames(res[f], oracle[f], p, f"frame{f}: ")
     assert sum(o.n_clusters for o in oracle) > 10 * B
+
+
+@pytest.mark.parametrize("seed,opacity", [(1, 0), (2, 50), (3, 77), (4, -5)])
+def test_occupancy_shadows_synthetic(seed, opacity):
+    """od.cpp:466-672, 817-833 on synthetic clusters and an arbitrary sensor pose: start / end cells, line counts and
+    every grid cell bit-exact against the oracle"""
+    from shadow_util import rigid, shadow_scene
+    p = synth.params(1)
+    p.grid_opacity = opacity
+    cloud, offsets, indices = shadow_scene(seed, n_clusters=12, noise=2000)
+    sw, ws = rigid(0.3 * seed, 0.5, 0.1, [5.2, 1.9, 1.1])
+    with ObstacleProcessor(p, len(cloud)) as op:
+        grid0, _, _ = op.occupancy_grid(cloud)
+        g_grid, g_rec, g_warn = op.handle_shadow_casting(grid0, cloud, offsets, indices, ws, sw)
+    o_grid, o_rec, o_warn = O.occupancy_shadows(p, grid0, cloud, offsets, indices, ws, sw)
+    assert_bits_equal(g_rec, o_rec, "shadow records")
+    assert_bits_equal(g_grid, o_grid, "grid cells")
+    assert g_warn == o_warn == 0
+    assert (o_rec[:, 4] > 0).sum() >= 5 and (o_grid == 100).sum() > 500
+
+
+@pytest.mark.parametrize("config", [1, 2])
+def test_occupancy_grid_product_of_a_frame(config, frames):
+    """the node's published product for one frame: initial data set (od.cpp:727), pipeline, shadows + marks
+    (od.cpp:817-833) chained on the device library, against the same chain on the oracle"""
+    from shadow_util import rigid
+    p = synth.params(config)
+    p.grid_opacity = 40
+    if config == 2:
+        p.block_size = 0.25
+    cloud = frames[config]
+    sw, ws = rigid(0.1, 0.45, 0.0, [p.x_max + 0.8, 0.5 * (p.y_min + p.y_max), 1.2])
+    with ObstacleProcessor(p, len(cloud)) as op:
+        grid0, _, _ = op.occupancy_grid(cloud)
+        fr = op.process(cloud)
+        g_grid, g_rec, g_warn = op.handle_shadow_casting(grid0, fr.remaining_cloud, fr.cluster_offsets, fr.cluster_indices,
+                                                         ws, sw)
+    o_grid0, _, _ = O.occupancy_grid(p, cloud)
+    ofr = O.process(p, cloud)
+    o_grid, o_rec, o_warn = O.occupancy_shadows(p, o_grid0, ofr.remaining_cloud, ofr.cluster_offsets, ofr.cluster_indices,
+                                                ws, sw)
+    assert fr.n_clusters == ofr.n_clusters and fr.n_clusters > 0
+    assert_bits_equal(g_rec, o_rec, "shadow records")
+    assert_bits_equal(g_grid, o_grid, "grid cells")
+    assert g_warn == o_warn
+    assert (o_grid == 100).sum() > 0 and (o_rec[:, 4] > 0).any()
+
+
+def test_occupancy_shadows_degenerate_and_device_inputs():
+    """NaN members, the 2^20-step cap of the cell search, a fan too long to draw (warning), no clusters, empty cloud;
+    then the same call with every array resident on the device (PCOP_OUT_DEVICE consumers)"""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    from shadow_util import rigid, shadow_scene
+    p = synth.params(1)
+    p.grid_opacity = 33
+    cloud, offsets, indices = shadow_scene(5)
+    eye = np.eye(4, dtype=np.float32)
+    sw, ws = rigid(0.2, 0.4, 0.0, [5.0, 2.0, 1.0])
+    far_sw, _ = rigid(0.0, 0.0, 0.0, [-3.0e6, 3.0e6, 0.0])
+    bad = cloud.copy()
+    bad[indices[offsets[0]], 1] = np.nan
+    bad[indices[offsets[1] + 1], 0] = np.nan
+    tall = np.array([[1e-6, -1.0, 1.0, 1.0], [0.5, 1.2, 0.2, 1.0], [0.6, 1.1, 0.1, 1.0]], np.float32)
+    cases = [
+        ("no clusters", cloud, np.zeros(1, np.int32), np.zeros(0, np.int32), ws, sw),
+        ("nan members", bad, offsets, indices, ws, sw),
+        ("far pose", cloud, offsets, indices, eye, far_sw),
+        ("fan too long", tall, np.array([0, 3], np.int32), np.arange(3, dtype=np.int32), eye, eye),
+        ("empty cloud", np.zeros((0, 4), np.float32), np.zeros(1, np.int32), np.zeros(0, np.int32), ws, sw),
+    ]
+    with ObstacleProcessor(p, len(cloud)) as op:
+        grid0, _, _ = op.occupancy_grid(cloud)
+        for what, cl, off, idx, m_ws, m_sw in cases:
+            g_grid, g_rec, g_warn = op.handle_shadow_casting(grid0, cl, off, idx, m_ws, m_sw)
+            o_grid, o_rec, o_warn = O.occupancy_shadows(p, grid0, cl, off, idx, m_ws, m_sw)
+            assert_bits_equal(g_rec, o_rec, what + ": shadow records")
+            assert_bits_equal(g_grid, o_grid, what + ": grid cells")
+            assert g_warn == o_warn, what
+            if what == "fan too long":
+                assert g_warn == 16
+        # device-resident inputs and grid
+        d_cloud = torch.from_numpy(cloud).cuda()
+        d_off = torch.from_numpy(offsets).cuda()
+        d_idx = torch.from_numpy(indices).cuda()
+        d_grid = torch.from_numpy(grid0.copy()).cuda()
+        rec = np.zeros((len(offsets) - 1, 6), np.int32)
+        warn = C.c_uint32(0)
+        op._check(op._lib.pcop_occupancy_shadows(op._h, d_cloud.data_ptr(), len(cloud), d_off.data_ptr(), d_idx.data_ptr(),
+                                                 len(offsets) - 1, ws.ctypes.data_as(C.c_void_p), sw.ctypes.data_as(C.c_void_p),
+                                                 d_grid.data_ptr(), rec.ctypes.data_as(C.c_void_p), C.byref(warn)))
+        o_grid, o_rec, _ = O.occupancy_shadows(p, grid0, cloud, offsets, indices, ws, sw)
+        assert_bits_equal(d_grid.cpu().numpy(), o_grid, "device-resident grid")
+        assert_bits_equal(rec, o_rec, "device-resident records")

@@ -484,3 +484,154 @@ def test_occupancy_grid_against_literal_python_loops():
     want = np.where(ref.reshape(H, W).astype(f) < thr[:, None], 100, 0).astype(np.int8)
     assert np.array_equal(grid, want)
     assert counts.sum() > 1000
+
+
+# ---- occupancy grid: shadow casting + obstacle marks (od.cpp:466-672, 817-833) ------------------------------------
+from shadow_util import rigid as rigid_pair, shadow_scene  # noqa: E402
+
+
+def literal_shadows(p, grid, cloud, offsets, indices, ws, sw):
+    """handle_shadow_casting / calculate_shadow_cast / traceShadow / the marking loop restated from od.cpp with numpy
+    float32 scalars and libm's asin / tan (double overloads), independent of oracle/pcop_oracle.cpp"""
+    import math
+    f = np.float32
+    H, W = grid.shape
+    g = grid.copy().ravel()
+    size = H * W
+    bs, y_min, x_max = f(p.block_size), f(p.y_min), f(p.x_max)
+
+    def xf(m, q):
+        return [f(f(f(f(m[r, 0] * q[0]) + f(m[r, 1] * q[1])) + f(m[r, 2] * q[2])) + m[r, 3]) for r in range(3)]
+
+    def grid_xy(x, y, x_mn, y_mx):
+        xc = 0
+        while f(x_mn + f(f(xc + 1) * bs)) < x:
+            xc += 1
+        yc = 0
+        while f(y_mx - f(f(yc + 1) * bs)) > y:
+            yc += 1
+        return xc, yc
+
+    def trace(v1, v2):
+        x0, x1, y0, y1 = int(v1[0]), int(v2[0]), int(v1[1]), int(v2[1])
+        steep = abs(y1 - y0) > abs(x1 - x0)
+        if steep:
+            x0, y0, x1, y1 = y0, x0, y1, x1
+        if x0 > x1:
+            x0, x1, y0, y1 = x1, x0, y1, y0
+        dx, dy = f(x1 - x0), f(y1 - y0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gradient = f(dy / dx)
+        if dx == 0.0:
+            gradient = f(1)
+        iy = f(y0)
+        for x in range(x0, x1 + 1):
+            fl = int(math.floor(iy))
+            idx = x * W + fl if steep else fl * W + x
+            for k in (idx, idx + 1):
+                if -1 < k < size:
+                    g[k] = p.grid_opacity
+            iy = f(iy + gradient)
+
+    records = []
+    for c in range(len(offsets) - 1):
+        mem = indices[offsets[c]:offsets[c + 1]]
+        if len(mem) < 2:
+            records.append([0] * 6)
+            continue
+        tp = [xf(ws, cloud[i]) for i in mem]
+        vmin, vmax, hmin, hmax = tp[0], tp[0][0], tp[0][1], tp[0][1]
+        for q in tp[1:]:
+            if q[0] < vmin[0]:
+                vmin = q
+            if q[0] > vmax:
+                vmax = q[0]
+            if q[1] < hmin:
+                hmin = q[1]
+            if q[1] > hmax:
+                hmax = q[1]
+        width = f(abs(f(hmax - hmin)))
+        a, b = vmin[2], f(abs(vmin[0]))
+        cc = f(math.sqrt(f(f(a * a) + f(b * b))))
+        e = f(abs(float(vmax)) - abs(float(vmin[0])) + 0.04)
+        D = f(math.asin(f(a / cc)))
+        d = f(math.tan(float(D)) * float(e) + 0.25)
+        v_len = f(math.sqrt(f(f(f(vmin[0] * vmin[0]) + f(vmin[1] * vmin[1])) + f(vmin[2] * vmin[2]))))
+        end = [f(f(f(vmin[k] / v_len) * d) + vmin[k]) for k in range(3)]
+        we = xf(sw, end)
+        ex, ey = grid_xy(we[1], we[0], y_min, x_max)
+        wst = xf(sw, vmin)
+        sx, sy = grid_xy(wst[1], wst[0], y_min, x_max)
+        wb = f(width / bs)
+        shift = math.ceil(f(wb / f(2)))
+        sx, ex = int(sx + shift), int(ex + shift)
+        n_lines = int(math.ceil(wb) + 3)
+        records.append([sx, sy, ex, ey, n_lines, 0])
+        for i in range(n_lines):
+            trace((f(sx - i), f(sy)), (f(ex - i), f(ey)))
+    for q in cloud:
+        if np.isnan(q[0]):
+            continue
+        xc, yc = grid_xy(q[1], q[0], y_min, x_max)
+        if yc * W + xc < size:
+            g[yc * W + xc] = 100
+    return g.reshape(H, W), np.array(records, np.int32).reshape(-1, 6)
+
+
+@pytest.mark.parametrize("seed,opacity", [(1, 0), (2, 50), (3, 77)])
+def test_occupancy_shadows_against_literal_python(seed, opacity):
+    """the oracle's shadow casting against an independent literal restatement of od.cpp:466-672, 817-833"""
+    p = synth.params(1)
+    p.grid_opacity = opacity
+    cloud, offsets, indices = shadow_scene(seed)
+    # sensor above and behind the arena, pitched down (any rigid pose will do: the matrices are inputs)
+    sw, ws = rigid_pair(0.3 * seed, 0.5, 0.1, [5.2, 1.9, 1.1])
+    grid0, _, _ = O.occupancy_grid(p, cloud)
+    grid, rec, warn = O.occupancy_shadows(p, grid0, cloud, offsets, indices, ws, sw)
+    want, wrec = literal_shadows(p, grid0, cloud, offsets, indices, ws, sw)
+    assert warn == 0
+    assert np.array_equal(rec, wrec)
+    assert np.array_equal(grid, want)
+    assert (grid == 100).sum() > 100 and (rec[:, 4] > 0).sum() >= 3
+    if opacity:
+        assert (grid == opacity).sum() > 0  # some shadow cells survive the obstacle marks
+
+
+def test_occupancy_shadows_degenerate_inputs():
+    """NaN members, a far-away pose (cell search cap), no clusters: defined results, no hang"""
+    p = synth.params(1)
+    p.grid_opacity = 33
+    cloud, offsets, indices = shadow_scene(5)
+    grid0, _, _ = O.occupancy_grid(p, cloud)
+    sw, ws = rigid_pair(0.2, 0.4, 0.0, [5.0, 2.0, 1.0])
+    g_none, rec, warn = O.occupancy_shadows(p, grid0, cloud, np.zeros(1, np.int32), np.zeros(0, np.int32), ws, sw)
+    assert rec.shape == (0, 6) and warn == 0 and (g_none == 100).sum() > 0 and (g_none == 33).sum() == 0
+    bad = cloud.copy()
+    bad[indices[offsets[0]], 1] = np.nan  # first member of the largest cluster: its NaN y is never replaced (od.cpp:600-609)
+    g_nan, rec_nan, warn = O.occupancy_shadows(p, grid0, bad, offsets, indices, ws, sw)
+    assert rec_nan[0, 4] == 0  # width = NaN -> the line-count comparison is false at once (od.cpp:645)
+    far_sw, _ = rigid_pair(0.0, 0.0, 0.0, [-3.0e6, 3.0e6, 0.0])  # both cell searches run into the 2^20 step cap
+    g_far, rec_far, warn = O.occupancy_shadows(p, grid0, cloud, offsets, indices, np.eye(4, dtype=np.float32), far_sw)
+    assert (rec_far[rec_far[:, 4] > 0, 1] == 1 << 20).all() and (g_far == 33).sum() == 0
+    # a member almost on the sensor's z axis: asin -> pi/2, tan explodes, the end point lands ~1e6 cells away:
+    # the fan is not drawn and the warning is raised
+    eye = np.eye(4, dtype=np.float32)
+    tall = np.array([[1e-6, -1.0, 1.0, 1.0], [0.5, 1.2, 0.2, 1.0], [0.6, 1.1, 0.1, 1.0]], np.float32)
+    g_t, rec_t, warn = O.occupancy_shadows(p, grid0, tall, np.array([0, 3], np.int32), np.arange(3, dtype=np.int32), eye, eye)
+    assert warn == 16 and rec_t[0, 5] == 1 and (g_t == 33).sum() == 0
+
+
+def test_det_asin_tan_against_libm():
+    import ctypes as C
+    import math
+    L = O.lib()
+    for name in ("det_asin", "det_tan"):
+        fn = getattr(L, "pcop_oracle_" + name)
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_double]
+    rng = np.random.default_rng(9)
+    for q in np.concatenate([rng.uniform(-1, 1, 2000), [0.0, 1.0, -1.0, 1e-9, 0.999999, -0.5]]):
+        assert abs(L.pcop_oracle_det_asin(q) - math.asin(q)) <= 4e-16 * max(1.0, abs(math.asin(q)))
+    assert math.isnan(L.pcop_oracle_det_asin(1.0000001)) and math.isnan(L.pcop_oracle_det_asin(float("nan")))
+    for x in np.concatenate([rng.uniform(-1.5, 1.5, 2000), [0.0, 0.7, -1.2]]):
+        assert abs(L.pcop_oracle_det_tan(x) - math.tan(x)) <= 1e-14 * max(1.0, abs(math.tan(x)))
