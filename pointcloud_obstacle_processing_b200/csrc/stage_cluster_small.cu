@@ -244,11 +244,23 @@ __device__ __forceinline__ void es_union(unsigned short* parent, int a, int b) {
   } while (0)
 #endif
 
-// forward neighbour q (0..61) of a clique cell: the cells within 2 per axis that follow it in (z, y, x) order:
-// q < 2: (q+1, 0, 0); 2 <= q < 12: dz = 0, dy = 1..2, dx = -2..2; q >= 12: dz = 1..2, dy = -2..2, dx = -2..2
-__host__ __device__ constexpr int es_fwd_dx(int q) { return q < 2 ? q + 1 : (q < 12 ? (q - 2) % 5 - 2 : (q - 12) % 5 - 2); }
-__host__ __device__ constexpr int es_fwd_dy(int q) { return q < 2 ? 0 : (q < 12 ? 1 + (q - 2) / 5 : ((q - 12) % 25) / 5 - 2); }
-__host__ __device__ constexpr int es_fwd_dz(int q) { return q < 12 ? 0 : 1 + (q - 12) / 25; }
+// The 62 forward neighbours of a clique cell = the cells within 2 per axis that follow it in (z, y, x) order, listed by
+// increasing distance: near cells are the likely links, so once they are merged most of the far cells are already in
+// the same set when their turn comes and their pair tests are skipped.  X(q, dx, dy, dz)
+#define ES_FWD_LIST(X) \
+  X(0, 1, 0, 0) X(1, 0, 1, 0) X(2, 0, 0, 1) X(3, -1, 1, 0) X(4, 1, 1, 0) X(5, 0, -1, 1) \
+  X(6, -1, 0, 1) X(7, 1, 0, 1) X(8, 0, 1, 1) X(9, -1, -1, 1) X(10, 1, -1, 1) X(11, -1, 1, 1) \
+  X(12, 1, 1, 1) X(13, 2, 0, 0) X(14, 0, 2, 0) X(15, 0, 0, 2) X(16, -2, 1, 0) X(17, 2, 1, 0) \
+  X(18, -1, 2, 0) X(19, 1, 2, 0) X(20, 0, -2, 1) X(21, -2, 0, 1) X(22, 2, 0, 1) X(23, 0, 2, 1) \
+  X(24, 0, -1, 2) X(25, -1, 0, 2) X(26, 1, 0, 2) X(27, 0, 1, 2) X(28, -1, -2, 1) X(29, 1, -2, 1) \
+  X(30, -2, -1, 1) X(31, 2, -1, 1) X(32, -2, 1, 1) X(33, 2, 1, 1) X(34, -1, 2, 1) X(35, 1, 2, 1) \
+  X(36, -1, -1, 2) X(37, 1, -1, 2) X(38, -1, 1, 2) X(39, 1, 1, 2) X(40, -2, 2, 0) X(41, 2, 2, 0) \
+  X(42, 0, -2, 2) X(43, -2, 0, 2) X(44, 2, 0, 2) X(45, 0, 2, 2) X(46, -2, -2, 1) X(47, 2, -2, 1) \
+  X(48, -2, 2, 1) X(49, 2, 2, 1) X(50, -1, -2, 2) X(51, 1, -2, 2) X(52, -2, -1, 2) X(53, 2, -1, 2) \
+  X(54, -2, 1, 2) X(55, 2, 1, 2) X(56, -1, 2, 2) X(57, 1, 2, 2) X(58, -2, -2, 2) X(59, 2, -2, 2) \
+  X(60, -2, 2, 2) X(61, 2, 2, 2)
+#define ES_FWD_OFF_ENTRY(q, dx, dy, dz) (dx) + (dy)*1024 + (dz)*1048576,
+__device__ const int ES_FWD_OFF[62] = {ES_FWD_LIST(ES_FWD_OFF_ENTRY)};  // packed-key offset of forward neighbour q
 
 __global__ void __launch_bounds__(ES_THREADS, 1)
     k_ece_small(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, float tol, float r2,
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
         sm.red[warp][3 + a] = mx[a];
       }
     }
-    if (tid < 62) sm.fwd[tid] = es_fwd_dx(tid) + es_fwd_dy(tid) * 1024 + es_fwd_dz(tid) * 1048576;
+    if (tid < 62) sm.fwd[tid] = ES_FWD_OFF[tid];
     for (int s = tid; s < ES_HASH; s += ES_THREADS) tk[s] = ES_EMPTY;
     for (int i = tid; i < n; i += ES_THREADS) cnt[i] = 0;
     __syncthreads();
@@ -448,15 +460,18 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
         ym |= (live && cy + d >= 0 && cy + d < dimy) ? (1u << (d + 2)) : 0u;
         zm |= (live && cz + d >= 0 && cz + d < dimz) ? (1u << (d + 2)) : 0u;
       }
-      // which of the 62 forward cells exist (enumeration order = ES_FWD)
+      // Which of the 62 forward cells may exist: the first probe of every hash lookup, unconditional and independent
+      // (62 loads in flight, no divergence).  The table is < 10 % full, so an empty first slot settles most of them;
+      // a non-empty one is resolved (full lookup) when its turn comes in the walk below.
       u64 found = 0ull;
-#pragma unroll
-      for (int q = 0; q < 62; ++q) {
-        const int dx = es_fwd_dx(q), dy = es_fwd_dy(q), dz = es_fwd_dz(q);  // compile-time after unrolling
-        const bool ok = ((xm >> (dx + 2)) & (ym >> (dy + 2)) & (zm >> (dz + 2)) & 1u) != 0u;
-        if (ok && es_lookup(hash, cell_key, keyA + (uint32_t)(dx + dy * 1024 + dz * 1048576)) >= 0) found |= 1ull << q;
-        if (q % 5 == 1) __syncwarp();
-      }
+#define ES_PROBE(q, dx, dy, dz)                                                                           \
+  {                                                                                                       \
+    const bool ok = ((xm >> ((dx) + 2)) & (ym >> ((dy) + 2)) & (zm >> ((dz) + 2)) & 1u) != 0u;            \
+    const unsigned v = hash[hash_slot(keyA + (uint32_t)((dx) + (dy)*1024 + (dz)*1048576))];               \
+    if (ok && v != 0u) found |= 1ull << (q);                                                              \
+  }
+      ES_FWD_LIST(ES_PROBE)
+#undef ES_PROBE
       __syncwarp();
       ES_CLKW(10);
       const int j0 = live ? node_start[c] : 0, j1 = live ? node_start[c + 1] : 0;
@@ -465,9 +480,9 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
         if (found) {
           const int qq = __ffsll((long long)found) - 1;
           found &= found - 1ull;
-          const int cb = es_lookup(hash, cell_key, keyA + (uint32_t)sm.fwd[qq]);
-          rc = es_find(parent, rc);
-          if (rc != es_find(parent, cb)) {
+          const int cb = es_lookup(hash, cell_key, keyA + (uint32_t)sm.fwd[qq]);  // -1: the slot held another cell
+          if (cb >= 0) rc = es_find(parent, rc);
+          if (cb >= 0 && rc != es_find(parent, cb)) {
             const int jb0 = node_start[cb], jb1 = node_start[cb + 1];
             bool hit = false;
             for (int a = j0; a < j1 && !hit; ++a) {

@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(CT_THREADS)
   __shared__ float4 hyp[MAX_HYP];
   __shared__ int cnt[MAX_HYP];
   if (threadIdx.x < MAX_HYP) {
-    hyp[threadIdx.x] = (threadIdx.x < nh) ? P.hyp[threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // hypotheses past nh are NaN planes: |NaN| < thr is false, so they count nothing and the loops below need no
+    // per-hypothesis guard (a zero plane would count every point)
+    const float qnan = __uint_as_float(0x7fc00000u);
+    hyp[threadIdx.x] = (threadIdx.x < nh) ? P.hyp[threadIdx.x] : make_float4(qnan, qnan, qnan, qnan);
     cnt[threadIdx.x] = 0;
   }
   __syncthreads();
@@ -342,12 +345,11 @@ __global__ void __launch_bounds__(CT_THREADS)
   // (the second phase is launched with a few blocks per frame: most frames do not need it)
   for (int tile = blockIdx.x; tile * CT_TILE < n; tile += gridDim.x) {
   float4 p[CT_ITEMS];
-  bool valid[CT_ITEMS];
 #pragma unroll
-  for (int k = 0; k < CT_ITEMS; ++k) {
+  for (int k = 0; k < CT_ITEMS; ++k) {  // slots past the cloud hold NaN points: never within the threshold
     const int i = ct_index(tile, k);
-    valid[k] = i < n;
-    p[k] = valid[k] ? __ldg(pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float qnan = __uint_as_float(0x7fc00000u);
+    p[k] = (i < n) ? __ldg(pts + i) : make_float4(qnan, qnan, qnan, qnan);
   }
   // per-lane counters for 8 hypotheses at a time, one warp reduction per hypothesis and tile (a ballot + popc per
   // hypothesis and point kept the ADU pipe 63 % busy)
@@ -356,18 +358,14 @@ __global__ void __launch_bounds__(CT_THREADS)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       c[j] = 0;
-      if (h0 + j < nh) {
-        const float4 co = hyp[h0 + j];
+      const float4 co = hyp[h0 + j];  // (MAX_HYP is a multiple of 8)
 #pragma unroll
-        for (int k = 0; k < CT_ITEMS; ++k) c[j] += (valid[k] && plane_dist(co, p[k].x, p[k].y, p[k].z) < thr) ? 1 : 0;
-      }
+      for (int k = 0; k < CT_ITEMS; ++k) c[j] += (plane_dist(co, p[k].x, p[k].y, p[k].z) < thr) ? 1 : 0;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (h0 + j < nh) {
-        const int s = __reduce_add_sync(FULL, c[j]);
-        if (lane == 0 && s) atomicAdd(&cnt[h0 + j], s);
-      }
+      const int s = __reduce_add_sync(FULL, c[j]);
+      if (lane == 0 && s) atomicAdd(&cnt[h0 + j], s);
     }
   }
   }

@@ -265,9 +265,11 @@ __global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
         unsigned peers = __ballot_sync(FULL, valid);
 #pragma unroll
         for (int b = 0; b < BITS; ++b) {
-          const bool bit = (d >> b) & 1u;
-          const unsigned bal = __ballot_sync(FULL, bit);
-          peers &= bit ? bal : ~bal;
+          // s = all ones if bit b of the digit is set, else 0: peers &= (bit ? bal : ~bal) is ONE three-input logic
+          // op, peers & ~(bal ^ s)  (the select form cost a complement + a select + an and per bit)
+          const int s = (int)(d << (31 - b)) >> 31;
+          const unsigned bal = __ballot_sync(FULL, s < 0);
+          peers &= ~(bal ^ (unsigned)s);
         }
         mm[kk] = valid ? peers : (1u << lane);
       }
@@ -400,8 +402,10 @@ __global__ void __launch_bounds__(CT_THREADS)
     k_vf_reduce(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_sorted,
                 const unsigned long long* __restrict__ pairs, const VoxelFrame* __restrict__ vf,
                 float4* __restrict__ out, uint32_t* __restrict__ out_keys, int* __restrict__ n_out,
-                unsigned* __restrict__ desc, int cap, int tiles) {
-  const int f = blockIdx.x, tile = blockIdx.y;
+                unsigned* __restrict__ desc, int cap, int tiles, int frame_contiguous) {
+  // frame_contiguous (experiment, off by default): blockIdx.x = tile, so the tiles of one frame are dispatched
+  // together and the frame's input (1.9 MB) stays in L2 while its points are gathered (see run_voxel_fused)
+  const int f = frame_contiguous ? blockIdx.y : blockIdx.x, tile = frame_contiguous ? blockIdx.x : blockIdx.y;
   const int m = n_sorted[f];
   const int tbase = tile * CT_TILE;
   if (tbase >= m) {
@@ -412,30 +416,25 @@ __global__ void __launch_bounds__(CT_THREADS)
   const unsigned long long* ps = pairs + (size_t)f * cap;
   const float4* src = in + (size_t)f * in_stride;
   const int tile_n = min(CT_TILE, m - tbase);
-  // sorted (key, index) of the tile; the points gathered into shared memory in sorted order
-  {  // all pair loads, then all gathers, in flight together
-    unsigned long long pp[CT_ITEMS];
+  // sorted (key, index) of the tile; the points are gathered into shared memory in sorted order.  The run heads (and
+  // with them the tile's aggregate for the look-back) depend on the keys only, so the gathers are issued first and
+  // stay in flight while the heads are ranked and the tile waits for its predecessors.
+  unsigned long long pp[CT_ITEMS];
 #pragma unroll
-    for (int k = 0; k < CT_ITEMS; ++k) {
-      const int t = threadIdx.x + k * CT_THREADS;
-      pp[k] = (t < tile_n) ? ps[tbase + t] : 0ull;
-    }
-    float4 p[CT_ITEMS];
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int t = threadIdx.x + k * CT_THREADS;
+    pp[k] = (t < tile_n) ? ps[tbase + t] : 0ull;
+  }
+  float4 p[CT_ITEMS];
 #pragma unroll
-    for (int k = 0; k < CT_ITEMS; ++k) {
-      const int t = threadIdx.x + k * CT_THREADS;
-      p[k] = (t < tile_n) ? __ldg(src + (uint32_t)pp[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int t = threadIdx.x + k * CT_THREADS;
+    p[k] = (t < tile_n) ? __ldg(src + (uint32_t)pp[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 #pragma unroll
-    for (int k = 0; k < CT_ITEMS; ++k) {
-      const int t = threadIdx.x + k * CT_THREADS;
-      if (t < tile_n) {
-        sm.skey[t + 1] = (uint32_t)(pp[k] >> 32);
-        sm.sx[t] = p[k].x;
-        sm.sy[t] = p[k].y;
-        sm.sz[t] = p[k].z;
-      }
-    }
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int t = threadIdx.x + k * CT_THREADS;
+    if (t < tile_n) sm.skey[t + 1] = (uint32_t)(pp[k] >> 32);
   }
   if (threadIdx.x == 0) sm.skey[0] = (tbase > 0) ? (uint32_t)(ps[tbase - 1] >> 32) : 0u;
   __syncthreads();
@@ -447,6 +446,15 @@ __global__ void __launch_bounds__(CT_THREADS)
     keep[k] = t < tile_n && (tbase + t == 0 || sm.skey[t + 1] != sm.skey[t]);
   }
   const unsigned incl_total = tile_compact_positions(keep, pos, desc + (size_t)f * tiles, tile, sm.cs);
+#pragma unroll
+  for (int k = 0; k < CT_ITEMS; ++k) {
+    const int t = threadIdx.x + k * CT_THREADS;
+    if (t < tile_n) {
+      sm.sx[t] = p[k].x;
+      sm.sy[t] = p[k].y;
+      sm.sz[t] = p[k].z;
+    }
+  }
   // dense list of the tile's heads: the per-head work below then runs with every lane busy (half of the sorted
   // elements are heads; walking them in place left half of each warp idle through four unrolled copies of the loop)
   const unsigned tile_excl = sm.cs.tile_excl, n_heads = sm.cs.tile_total;
@@ -597,12 +605,21 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   const int fin = pl.npass & 1;
   const int tiles = cdiv(c.cap, CT_TILE), gt = cdiv(c.grid_cap, CT_TILE);
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
+  static const int contiguous = [] {
+    // measured (B200, 4 x 256 HDL-64 frames): dispatching a frame's tiles together (so that its input stays in L2
+    // for the gathers) is slower than frame-major dispatch, 1.56 vs 1.13 ms per step, even with the aggregates
+    // published before the gathers: the look-back chain inside a frame costs more than the second DRAM fetch of a
+    // sector.  Kept as an experiment knob.
+    const char* s = getenv("PCOP_VF_REDUCE_CONTIGUOUS");
+    return s ? atoi(s) : 0;
+  }();
+  const dim3 rgrid = contiguous ? dim3(gt, c.B) : dim3(c.B, gt);
   if (a.want_keys)
-    KL(c, "k_vf_reduce", k_vf_reduce<true><<<dim3(c.B, gt), CT_THREADS, 0, c.stream>>>(
-        a.in, a.in_stride, a.n_crop, a.pair[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles));
+    KL(c, "k_vf_reduce", k_vf_reduce<true><<<rgrid, CT_THREADS, 0, c.stream>>>(
+        a.in, a.in_stride, a.n_crop, a.pair[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles, contiguous));
   else
-    KL(c, "k_vf_reduce", k_vf_reduce<false><<<dim3(c.B, gt), CT_THREADS, 0, c.stream>>>(
-        a.in, a.in_stride, a.n_crop, a.pair[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles));
+    KL(c, "k_vf_reduce", k_vf_reduce<false><<<rgrid, CT_THREADS, 0, c.stream>>>(
+        a.in, a.in_stride, a.n_crop, a.pair[fin], a.vf, a.out, a.out_keys, a.n_out, a.desc, c.cap, tiles, contiguous));
   count_launch(c);
 }
 
