@@ -476,6 +476,22 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
       ES_CLKW(10);
       const int j0 = live ? node_start[c] : 0, j1 = live ? node_start[c + 1] : 0;
       int rc = live ? c : 0;
+      // bounding box of the cell's own points: a point b of another cell whose box distance exceeds r2 cannot pass the
+      // exact predicate against any of them, so two cells that are NOT linked cost |B| box tests instead of |A| x |B|
+      // exact tests.  The pre-test is exact, not approximate: lo <= a <= hi per axis and rounding is monotonic, so
+      // fl(lo - b) or fl(b - hi) never exceeds |fl(a - b)|, and the squares are summed in dist2's order without FMA,
+      // hence box_d2 <= dist2(a, b) in float for every a of the cell (the 1e-4 margin is slack on top of that)
+      float lox = 3.402823466e+38f, loy = 3.402823466e+38f, loz = 3.402823466e+38f;
+      float hix = -3.402823466e+38f, hiy = -3.402823466e+38f, hiz = -3.402823466e+38f;
+      for (int a = j0; a < j1; ++a) {
+        lox = fminf(lox, px[a]);
+        hix = fmaxf(hix, px[a]);
+        loy = fminf(loy, py[a]);
+        hiy = fmaxf(hiy, py[a]);
+        loz = fminf(loz, pz[a]);
+        hiz = fmaxf(hiz, pz[a]);
+      }
+      const float r2m = r2 * 1.0001f;
       while (__any_sync(FULL, found != 0ull)) {
         if (found) {
           const int qq = __ffsll((long long)found) - 1;
@@ -485,10 +501,13 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
           if (cb >= 0 && rc != es_find(parent, cb)) {
             const int jb0 = node_start[cb], jb1 = node_start[cb + 1];
             bool hit = false;
-            for (int a = j0; a < j1 && !hit; ++a) {
-              const float ax = px[a], ay = py[a], az = pz[a];
-              for (int b = jb0; b < jb1; ++b) {
-                if (dist2(ax, ay, az, px[b], py[b], pz[b]) < r2) {
+            for (int b = jb0; b < jb1 && !hit; ++b) {
+              const float bx = px[b], by = py[b], bz = pz[b];
+              const float ex = fmaxf(fmaxf(lox - bx, bx - hix), 0.0f), ey = fmaxf(fmaxf(loy - by, by - hiy), 0.0f),
+                          ez = fmaxf(fmaxf(loz - bz, bz - hiz), 0.0f);
+              if (ex * ex + ey * ey + ez * ez > r2m) continue;
+              for (int a = j0; a < j1; ++a) {
+                if (dist2(px[a], py[a], pz[a], bx, by, bz) < r2) {
                   hit = true;
                   break;
                 }
