@@ -1257,8 +1257,15 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     double wsum = 0.0;
     for (int l = 0; l < n_lanes; ++l) wsum += 1.0 + skew * l / (n_lanes - 1);
     int w0 = 0;
+    std::vector<int> forced;  // PCOP_WAVE_SIZES=a,b,c,...: explicit wave sizes (experiments)
+    if (const char* sv = getenv("PCOP_WAVE_SIZES"))
+      for (const char* q = sv; *q;) {
+        forced.push_back((int)strtol(q, const_cast<char**>(&q), 10));
+        if (*q == ',') ++q;
+      }
     for (int l = 0; l < n_lanes; ++l) {
       int B = (l + 1 == n_lanes) ? batch - w0 : (int)((1.0 + skew * l / (n_lanes - 1)) / wsum * batch);
+      if ((int)forced.size() == n_lanes && l + 1 < n_lanes) B = std::min(std::max(forced[l], 1), batch - w0);
       B = std::min(B, h->maxB);
       if (B > 0) plan[l].push_back({w0, B});
       w0 += B;

@@ -601,3 +601,40 @@ def test_occupancy_shadows_degenerate_and_device_inputs():
         o_grid, o_rec, _ = O.occupancy_shadows(p, grid0, cloud, offsets, indices, ws, sw)
         assert_bits_equal(d_grid.cpu().numpy(), o_grid, "device-resident grid")
         assert_bits_equal(rec, o_rec, "device-resident records")
+
+
+def test_bench_size_batch_is_position_independent():
+    """BASELINE configs[4] at the bench's call size: 1024 frames in ONE pcop_process_batch call (4 lanes, uneven waves,
+    early remaining-cloud copy).  The batch is 24 distinct frames laid out in a pseudo-random order; every copy must
+    give exactly the arrays its source frame gives in a 24-frame call (itself checked against the oracle): a frame's
+    result may not depend on its position, its wave, its lane or its neighbours."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    p = synth.params(2)  # default outputs: remaining cloud + source indices, clusters, obstacles
+    n = synth.points_per_frame(2)
+    D, B = 24, 1024
+    src = synth.frames(2, 2000, D)
+
+    def digest(fr):
+        parts = [np.int32([fr.n_crop, fr.n_voxel, fr.n_remaining, fr.n_clusters, fr.n_cluster_points, fr.warnings]),
+                 fr.remaining_cloud, fr.remaining_src_idx, fr.cluster_offsets, fr.cluster_indices, fr.obstacles]
+        crc = 0
+        for a in parts:
+            crc = zlib.crc32(np.ascontiguousarray(a).tobytes(), crc)
+        return crc
+
+    with ObstacleProcessor(p, n, max_batch=D) as op:
+        small = op.process_batch(src)
+    with ThreadPoolExecutor(8) as ex:
+        oracle = list(ex.map(lambda f: O.process(p, src[f]), range(D)))
+    for f in range(D):
+        compare_frames(small[f], oracle[f], p, f"source frame {f}: ")
+    want = [digest(fr) for fr in small]
+    order = np.random.default_rng(77).integers(0, D, B)
+    batch = np.ascontiguousarray(src[order])
+    with ObstacleProcessor(p, n, max_batch=B) as op:
+        for rep in range(2):  # the second call reuses every lane's buffers
+            res = op.process_batch(batch)
+            got = [digest(fr) for fr in res]
+            bad = [f for f in range(B) if got[f] != want[order[f]]]
+            assert not bad, f"call {rep}: {len(bad)} of {B} frames differ from their source frame, first {bad[:5]}"
