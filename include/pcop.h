@@ -12,6 +12,9 @@
  *   msg/PointWithRad.msg:1-4, msg/PointIndicesArray.msg:1 (dead call od.cpp:806-814)
  *                                                                                 -> pcop_centroid_radius
  *   the whole stage sequence of cloud_cb (od.cpp:699-927)                         -> pcop_process / pcop_process_batch
+ *   od.cpp:688-698  PointCloud2 decode + world transform + accumulate             -> pcop_accumulate_pointcloud2 / pcop_accumulate
+ *   od.cpp:727  build_initial_occupancy_grid_dataset  (grid part od.cpp:134-157, 184-269) -> pcop_occupancy_grid
+ *   od.cpp:817-833  handle_shadow_casting per cluster (od.cpp:466-672) + obstacle marks   -> pcop_occupancy_shadows
  *
  * Plain C: POD structs, raw pointers and sizes, integer status codes.  No C++
  * exceptions, PCL, ROS or torch types cross this boundary.
