@@ -415,7 +415,8 @@ __global__ void k_plane_select(PlaneFrame* __restrict__ pf, PlaneConst pc, int B
 }
 
 // nine moments + count of the RANSAC inliers, canonical tree order, one 2048-point chunk per block
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
     k_plane_moments(const PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp,
                     float thr, double* __restrict__ partial, int chunks, int cap) {
   const int f = blockIdx.y, chunk = blockIdx.x;
@@ -626,7 +627,8 @@ __global__ void __launch_bounds__(32)
 
 // ExtractIndices(negative) with the refined model: stable compaction of the outliers into the
 // other ping-pong buffer; the inlier list falls out of the same scan (slot = i - kept_before_i)
-__global__ void __launch_bounds__(CT_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(CT_THREADS, MINB)
     k_plane_extract(const PlaneFrame* __restrict__ pf, const float4* __restrict__ in, size_t in_stride, BufPair bp,
                     float thr, int* __restrict__ inlier_idx, int* __restrict__ n_tmp, unsigned* __restrict__ desc, int cap,
                     int tiles) {
@@ -762,13 +764,35 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
     KL(c, "k_plane_select", k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B, PHASE1, 0));
     KL(c, "k_plane_score", k_plane_score<<<dim3(std::min(gtiles, 8), c.B), CT_THREADS, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, c.cap, PHASE1, MAX_HYP, 1));
     KL(c, "k_plane_select", k_plane_select<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.pc, c.B, MAX_HYP, 1));
-    KL(c, "k_plane_moments", k_plane_moments<<<dim3(gchunks, c.B), 256, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, a.pc.thr, a.partial, chunks,
-                                                             c.cap));
+    static const int mom_minb = [] {
+      const char* s = getenv("PCOP_PLANE_MOMENTS_MINB");
+      return s ? atoi(s) : 4;
+    }();
+    // measured on B200 (5 x 1024 HDL-64 frames): k_plane_extract at 4 / 6 / 8 blocks per SM (52 / 38 / 32 registers)
+    // 1.85 / 1.41 / 1.33 ms; k_plane_moments at 4 / 5 / 6 blocks (57 / 48 / 40 registers, spills from 5) 1.62 / 1.61 /
+    // 2.06 ms
+    static const int ext_minb = [] {
+      const char* s = getenv("PCOP_PLANE_EXTRACT_MINB");
+      return s ? atoi(s) : 8;
+    }();
+#define MOM_LAUNCH(MINB)                                                                                              \
+  KL(c, "k_plane_moments", k_plane_moments<MINB><<<dim3(gchunks, c.B), 256, 0, c.stream>>>(a.pf, a.in, a.in_stride, bp, \
+                                                                                           a.pc.thr, a.partial, chunks, c.cap))
+    if (mom_minb == 5) MOM_LAUNCH(5);
+    else if (mom_minb == 6) MOM_LAUNCH(6);
+    else if (mom_minb == 8) MOM_LAUNCH(8);
+    else MOM_LAUNCH(4);
+#undef MOM_LAUNCH
     KL(c, "k_plane_refine", k_plane_refine<<<c.B, 32, 0, c.stream>>>(a.pf, a.partial, a.pc, chunks));
     const int btiles = cdiv(c.cap, BT_TILE), gbtiles = cdiv(cc.grid_cap, BT_TILE);
     cudaMemsetAsync(a.desc, 0, (size_t)c.B * btiles * sizeof(unsigned), c.stream);
-    KL(c, "k_plane_extract", k_plane_extract<<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
-        a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx, a.n_tmp, a.desc, c.cap, btiles));
+#define EXT_LAUNCH(MINB)                                                                          \
+  KL(c, "k_plane_extract", k_plane_extract<MINB><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>( \
+      a.pf, a.in, a.in_stride, bp, a.pc.thr, a.inlier_idx, a.n_tmp, a.desc, c.cap, btiles))
+    if (ext_minb == 6) EXT_LAUNCH(6);
+    else if (ext_minb == 4) EXT_LAUNCH(4);
+    else EXT_LAUNCH(8);
+#undef EXT_LAUNCH
     cudaMemsetAsync(a.n_active, 0, 3 * sizeof(int), c.stream);
     KL(c, "k_plane_update", k_plane_update<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.pf, a.n_tmp, a.pc.keep_fraction, a.n_active, a.warnings, c.B));
     count_launch(c, 9);

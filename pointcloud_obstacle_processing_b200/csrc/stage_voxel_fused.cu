@@ -82,8 +82,8 @@ __global__ void k_vf_init(MinMax* mm, uint32_t* __restrict__ flags, uint32_t* __
   }
 }
 
-template <bool NEED_MINMAX>
-__global__ void __launch_bounds__(CT_THREADS)
+template <bool NEED_MINMAX, int MINB>
+__global__ void __launch_bounds__(CT_THREADS, MINB)
     k_vf_crop_key(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
                   unsigned long long* __restrict__ pairs, int* __restrict__ n_out,
                   MinMax* __restrict__ minmax, uint32_t* __restrict__ hist, uint32_t* __restrict__ flags,
@@ -214,8 +214,8 @@ struct VfPassSmem {
 #ifndef VF_SORT_MINBLOCKS
 #define VF_SORT_MINBLOCKS 4
 #endif
-template <int BITS, bool USE_MATCH>
-__global__ void __launch_bounds__(RS_THREADS, VF_SORT_MINBLOCKS)
+template <int BITS, bool USE_MATCH, int MINB = VF_SORT_MINBLOCKS>
+__global__ void __launch_bounds__(RS_THREADS, MINB)
     k_vf_sort_pass(const unsigned long long* __restrict__ pair_in, unsigned long long* __restrict__ pair_out,
                    const int* __restrict__ count, const uint32_t* __restrict__ bin_base,
                    uint32_t* __restrict__ desc, int pass, int shift, int cap, int tiles,
@@ -499,13 +499,27 @@ __global__ void __launch_bounds__(CT_THREADS)
   if (tbase + CT_TILE >= m && threadIdx.x == 0) n_out[f] = (int)incl_total;
 }
 
-template <int BITS, bool USE_MATCH>
-void launch_pass_m(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
-  cudaFuncSetAttribute(k_vf_sort_pass<BITS, USE_MATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VfPassSmem<BITS>));
+template <int BITS, bool USE_MATCH, int MINB>
+void launch_pass_b(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
+  cudaFuncSetAttribute(k_vf_sort_pass<BITS, USE_MATCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VfPassSmem<BITS>));
   const int src = pass & 1;
-  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS, USE_MATCH><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
+  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS, USE_MATCH, MINB><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
       a.pair[src], a.pair[src ^ 1], a.n_crop, a.sort.hist, a.sort.desc, pass, shift, c.cap, gtiles, a.sort.stats));
   count_launch(c);
+}
+template <int BITS, bool USE_MATCH>
+void launch_pass_m(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
+  // blocks per SM the register allocation aims at (experiment knob).  Measured on B200 (5 x 1024 HDL-64 frames, all
+  // four passes): 3 blocks (80 registers) 10.42 ms, 4 blocks (64 registers, default) 10.71 ms and the same step time,
+  // 5 blocks (48 registers + spills) 12.09 ms, 6 blocks 13.14 ms
+  static const int minb = [] {
+    const char* s = getenv(USE_MATCH ? "PCOP_VF_SORT_MINB_MATCH" : "PCOP_VF_SORT_MINB_BALLOT");
+    return s ? atoi(s) : VF_SORT_MINBLOCKS;
+  }();
+  if (BITS == 7 && minb == 5) launch_pass_b<7, USE_MATCH, 5>(c, a, pass, shift, gtiles);
+  else if (BITS == 7 && minb == 6) launch_pass_b<7, USE_MATCH, 6>(c, a, pass, shift, gtiles);
+  else if (BITS == 7 && minb == 3) launch_pass_b<7, USE_MATCH, 3>(c, a, pass, shift, gtiles);
+  else launch_pass_b<BITS, USE_MATCH, VF_SORT_MINBLOCKS>(c, a, pass, shift, gtiles);
 }
 
 // match_mask bit p set: pass p ranks with MATCH.ANY (few distinct digits per warp), else with per-bit ballots
@@ -583,12 +597,23 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   cudaMemsetAsync(a.sort.hist, 0, vox_fused_hist_elems(c.B) * sizeof(uint32_t), c.stream);
   cudaMemsetAsync(a.sort.desc, 0, (size_t)pl.npass * c.B * gtiles * nbins * sizeof(uint32_t), c.stream);
   KL(c, "k_vf_init", k_vf_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, a.warnings, c.B));
-  if (a.want_keys)
-    KL(c, "k_vf_crop_key", k_vf_crop_key<true><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
-        a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles));
-  else
-    KL(c, "k_vf_crop_key", k_vf_crop_key<false><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(
-        a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles));
+  // Blocks per SM the register allocation aims at.  Measured on B200 (5 x 1024 HDL-64 frames): 4 blocks (64
+  // registers, all 16 loads of a thread in flight) 4.58 ms, 5 blocks (46 registers) 3.97 ms, 6 blocks (32 registers)
+  // 3.18 ms, 8 blocks 3.26 ms: the kernel is latency-bound (look-back wait, histogram flush), so resident warps beat
+  // loads in flight per thread.
+  static const int crop_minb = [] {
+    const char* s = getenv("PCOP_VF_CROP_MINB");
+    return s ? atoi(s) : 6;
+  }();
+#define VF_CROP_LAUNCH(KEYS, MINB)                                                                              \
+  KL(c, "k_vf_crop_key", k_vf_crop_key<KEYS, MINB><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(            \
+      a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles))
+  if (a.want_keys) VF_CROP_LAUNCH(true, 6);
+  else if (crop_minb == 4) VF_CROP_LAUNCH(false, 4);
+  else if (crop_minb == 5) VF_CROP_LAUNCH(false, 5);
+  else if (crop_minb == 8) VF_CROP_LAUNCH(false, 8);
+  else VF_CROP_LAUNCH(false, 6);
+#undef VF_CROP_LAUNCH
   KL(c, "k_vf_scan", k_vf_scan<<<dim3(pl.npass, c.B), VF_MAX_BINS, 0, c.stream>>>(a.sort.hist, a.minmax, a.leaf, a.vf, a.want_keys));
   count_launch(c, 3);
   for (int p = 0; p < pl.npass; ++p) {
