@@ -29,8 +29,9 @@ def assert_close(a, b, what, rel=REL_TOL):
     if a.size == 0:
         return
     scale = np.maximum(np.abs(a), np.abs(b))
-    err = np.abs(a - b)
-    ok = (err <= rel * np.maximum(scale, 1e-30)) | (np.isnan(a) & np.isnan(b))
+    with np.errstate(invalid="ignore"):
+        err = np.abs(a - b)  # (inf - inf = NaN: equal infinities are caught by a == b)
+        ok = (a == b) | (np.isfinite(a) & np.isfinite(b) & (err <= rel * np.maximum(scale, 1e-30))) | (np.isnan(a) & np.isnan(b))
     if not ok.all():
         bad = np.argwhere(~ok)
         raise AssertionError(f"{what}: {len(bad)} elements beyond rel {rel}, first {bad[0].tolist()}: "
