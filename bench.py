@@ -420,19 +420,19 @@ def main():
                     ktable[k]["achieved_GBps"] = round(alg_all[k] / (kernel_times[k][0] * 1e-6) / 1e9, 1)
                     ktable[k]["frac_of_hbm_peak"] = round(ktable[k]["achieved_GBps"] / peak, 4)
             alg = alg_all.get(name)
-            # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/ncu_full_r01e_summary.csv:
+            # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/ncu_full_r01f_summary.csv:
             # dram__bytes_read.sum + dram__bytes_write.sum at 256 frames per launch), scaled by the units per launch
             ncu_dram_bytes_per_unit = {
-                "k_vf_sort_pass": ((0.2129e9 + 182.7e6) / 26.35e6, sort_keys),  # per key moved (mean of the 4 passes)
-                "k_vf_reduce": ((1.0781e9 + 207.7e6) / 26.35e6, M_),            # per sorted pair
-                "k_vf_crop_key": ((0.4921e9 + 181.8e6) / 30.72e6, N_),          # per input point
+                "k_vf_sort_pass": ((0.2129e9 + 182.2e6) / 26.35e6, sort_keys),  # per key moved (mean of the 4 passes)
+                "k_vf_reduce": ((1.0779e9 + 207.2e6) / 26.35e6, M_),            # per sorted pair
+                "k_vf_crop_key": ((0.4921e9 + 177.0e6) / 30.72e6, N_),          # per input point
             }
             if alg is not None and us > 0:
                 ach = alg / (us * 1e-6) / 1e9
                 tr = ncu_dram_bytes_per_unit.get(name)
                 roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                         "frac": ach / peak, "traffic": (tr[0] * tr[1] / cnt) if tr else None,
-                        "traffic_source": "profiles/ncu_full_r01e_summary.csv (ncu --set full, 256 frames per launch), "
+                        "traffic_source": "profiles/ncu_full_r01f_summary.csv (ncu --set full, 256 frames per launch), "
                                           "scaled to this run's units per launch" if tr else None,
                         "peak_source": peak_kind,
                         "launches": cnt, "avg_launch_us": us / cnt,
