@@ -214,7 +214,10 @@ struct VfPassSmem {
 #ifndef VF_SORT_MINBLOCKS
 #define VF_SORT_MINBLOCKS 4
 #endif
-template <int BITS, bool USE_MATCH, int MINB = VF_SORT_MINBLOCKS>
+// REREAD (experiment, off by default, not yet measured): rank on the key halves only and fetch the 8-byte elements
+// again (L1 / L2) when the tile is staged, as the big-tile compactions do with their payload: 16 registers instead of
+// 32 for the elements, no spills at 4 blocks per SM, 48 registers at 5.
+template <int BITS, bool USE_MATCH, int MINB = VF_SORT_MINBLOCKS, bool REREAD = false>
 __global__ void __launch_bounds__(RS_THREADS, MINB)
     k_vf_sort_pass(const unsigned long long* __restrict__ pair_in, unsigned long long* __restrict__ pair_out,
                    const int* __restrict__ count, const uint32_t* __restrict__ bin_base,
@@ -236,14 +239,20 @@ __global__ void __launch_bounds__(RS_THREADS, MINB)
 
   for (int i = threadIdx.x; i < (RS_THREADS / 32) * BINS; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0u;
 
-  unsigned long long pr[VF_ITEMS];  // (key << 32) | index: one 8-byte load / store per element
+  unsigned long long pr[REREAD ? 1 : VF_ITEMS];  // (key << 32) | index: one 8-byte load / store per element
+  uint32_t keyhalf[REREAD ? VF_ITEMS : 1];
   unsigned short rank[VF_ITEMS];
   const int wbase_idx = tbase + warp * (32 * VF_ITEMS) + lane;
 #pragma unroll
   for (int k = 0; k < VF_ITEMS; ++k) {
     const int i = wbase_idx + k * 32;
-    pr[k] = (i < n) ? pin[i] : ~0ull;
+    if constexpr (REREAD) keyhalf[k] = (i < n) ? reinterpret_cast<const uint32_t*>(pin)[2 * (size_t)i + 1] : ~0u;
+    else pr[k] = (i < n) ? pin[i] : ~0ull;
   }
+  auto key_of = [&](int k) -> uint32_t {
+    if constexpr (REREAD) return keyhalf[k];
+    else return (uint32_t)(pr[k] >> 32);
+  };
   __syncthreads();
   // rank keys inside the warp, row by row => stable.  All match masks first (independent, so their latencies
   // overlap), then one shared atomic per distinct digit of a row (issued by the lowest lane of the match group);
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB)
     for (int kk = 0; kk < 8; ++kk) {
       const int k = k0 + kk;
       const bool valid = (wbase_idx + k * 32) < n;
-      const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
+      const uint32_t d = (key_of(k) >> shift) & (BINS - 1);
       if (USE_MATCH) {
         mm[kk] = __match_any_sync(FULL, valid ? d : (BINS + lane));  // invalid lanes match nobody
       } else {
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB)
     for (int kk = 0; kk < 8; ++kk) {
       const int k = k0 + kk;
       const bool valid = (wbase_idx + k * 32) < n;
-      const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
+      const uint32_t d = (key_of(k) >> shift) & (BINS - 1);
       const unsigned m = mm[kk];
       const int leader = __ffs(m) - 1;
       uint32_t before = 0;
@@ -337,9 +346,10 @@ __global__ void __launch_bounds__(RS_THREADS, MINB)
   for (int k = 0; k < VF_ITEMS; ++k) {
     const int i = wbase_idx + k * 32;
     if (i < n) {
-      const uint32_t d = ((uint32_t)(pr[k] >> 32) >> shift) & (BINS - 1);
+      const uint32_t d = (key_of(k) >> shift) & (BINS - 1);
       const uint32_t p = sm.tile_off[d] + sm.warp_hist[warp][d] + rank[k];
-      sm.spair[p] = pr[k];
+      if constexpr (REREAD) sm.spair[p] = pin[i];
+      else sm.spair[p] = pr[k];
     }
   }
   // decoupled look-back per digit over the earlier tiles of this frame
@@ -499,11 +509,12 @@ __global__ void __launch_bounds__(CT_THREADS)
   if (tbase + CT_TILE >= m && threadIdx.x == 0) n_out[f] = (int)incl_total;
 }
 
-template <int BITS, bool USE_MATCH, int MINB>
+template <int BITS, bool USE_MATCH, int MINB, bool REREAD = false>
 void launch_pass_b(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
-  cudaFuncSetAttribute(k_vf_sort_pass<BITS, USE_MATCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VfPassSmem<BITS>));
+  cudaFuncSetAttribute(k_vf_sort_pass<BITS, USE_MATCH, MINB, REREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(VfPassSmem<BITS>));
   const int src = pass & 1;
-  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS, USE_MATCH, MINB><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
+  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS, USE_MATCH, MINB, REREAD><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
       a.pair[src], a.pair[src ^ 1], a.n_crop, a.sort.hist, a.sort.desc, pass, shift, c.cap, gtiles, a.sort.stats));
   count_launch(c);
 }
@@ -516,7 +527,14 @@ void launch_pass_m(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, i
     const char* s = getenv(USE_MATCH ? "PCOP_VF_SORT_MINB_MATCH" : "PCOP_VF_SORT_MINB_BALLOT");
     return s ? atoi(s) : VF_SORT_MINBLOCKS;
   }();
-  if (BITS == 7 && minb == 5) launch_pass_b<7, USE_MATCH, 5>(c, a, pass, shift, gtiles);
+  static const int reread = [] {
+    const char* s = getenv("PCOP_VF_SORT_REREAD");
+    return s ? atoi(s) : 0;
+  }();
+  if (BITS == 7 && reread && minb == 5) launch_pass_b<7, USE_MATCH, 5, true>(c, a, pass, shift, gtiles);
+  else if (BITS == 7 && reread && minb == 6) launch_pass_b<7, USE_MATCH, 6, true>(c, a, pass, shift, gtiles);
+  else if (BITS == 7 && reread) launch_pass_b<7, USE_MATCH, 4, true>(c, a, pass, shift, gtiles);
+  else if (BITS == 7 && minb == 5) launch_pass_b<7, USE_MATCH, 5>(c, a, pass, shift, gtiles);
   else if (BITS == 7 && minb == 6) launch_pass_b<7, USE_MATCH, 6>(c, a, pass, shift, gtiles);
   else if (BITS == 7 && minb == 3) launch_pass_b<7, USE_MATCH, 3>(c, a, pass, shift, gtiles);
   else launch_pass_b<BITS, USE_MATCH, VF_SORT_MINBLOCKS>(c, a, pass, shift, gtiles);
