@@ -76,3 +76,19 @@ def test_package_does_not_import_oracle():
                 assert not bad.search(text), f"{f} uses the oracle"
     out = subprocess.run(["ldd", pkg.api.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_cpp_host_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """examples/pcop_host_demo.cpp (the C++ shim's shape): pcop.h is valid C++11 under -Wall -Wextra -pedantic -Werror,
+    the program links against libpcop.so, and on a box without a CUDA device it stops with the no-fallback error"""
+    import torch
+    exe = tmp_path / "demo"
+    pkg_dir = os.path.join(ROOT, "pointcloud_obstacle_processing_b200")
+    pkg.load_library()  # (builds libpcop.so if missing)
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "pcop_host_demo.cpp"), "-L", pkg_dir, "-lpcop", "-o", str(exe)])
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device path cannot be exercised")
+    env = dict(os.environ, LD_LIBRARY_PATH=pkg_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
