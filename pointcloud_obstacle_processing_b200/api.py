@@ -170,7 +170,14 @@ class ObstacleProcessor:
         self.params = params.copy()
 
     # ---- whole pipeline ------------------------------------------------------------
+    def _host_results_only(self):
+        """Frame.from_c copies out of HOST result pointers; with outputs | OUT_DEVICE they are device addresses."""
+        if self.params.outputs & abi.OUT_DEVICE:
+            raise ValueError("outputs | OUT_DEVICE leaves the result arrays on the GPU: call process_batch_raw() and "
+                             "read them with download() / copy_device()")
+
     def process(self, cloud) -> Frame:
+        self._host_results_only()
         cloud = _f32(cloud)
         r = FrameResult()
         self._check(self._lib.pcop_process(self._h, cloud.ctypes.data_as(C.c_void_p), cloud.shape[0], C.byref(r)))
@@ -186,6 +193,7 @@ class ObstacleProcessor:
 
     def process_batch(self, clouds, counts=None):
         """clouds: float32 [B, n, 4] (host).  Returns a list of Frame."""
+        self._host_results_only()
         clouds = np.ascontiguousarray(clouds, dtype=np.float32)
         assert clouds.ndim == 3 and clouds.shape[2] == 4
         if counts is None:
@@ -276,6 +284,7 @@ class ObstacleProcessor:
 
     def process_accumulated(self) -> Frame:
         """the pipeline on the accumulated cloud (od.cpp:699 ff); the accumulator is emptied (od.cpp:701)"""
+        self._host_results_only()
         r = FrameResult()
         self._check(self._lib.pcop_process_accumulated(self._h, C.byref(r)))
         return Frame.from_c(r)

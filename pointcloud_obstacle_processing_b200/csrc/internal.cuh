@@ -198,15 +198,21 @@ struct PlaneArgs {
   int* n_active;   // device counter (one int per pass slot, [64])
   int* h_n_active; // pinned host mirror
   const int* rng;  // [RNG_TABLE] rnd() values
+  int resident;    // take the frame-resident cluster kernel when the frames fit (0: host-looped kernels)
+  int large_tier;  // resident path: also launch the tier for frames above plane_small_tier_max() points
   PlaneConst pc;
   uint32_t* warnings;
   // outputs
-  int* n_out;  // [B] remaining count
+  float4* out;   // [B*cap] remaining cloud (planar_cloud_y, od.cpp:765)
+  int* out_src;  // [B*cap] index into `in` of each remaining point
+  int* n_out;    // [B] remaining count
 };
-// returns cudaSuccess or the first failing runtime error (synchronises once per pass)
+// The whole loop of od.cpp:376-399 for every frame of the wave.  Frames of up to 131072 points run in the
+// frame-resident cluster kernel (two launches, no host synchronisation); larger ones (or PCOP_PLANE_RESIDENT=0) in
+// the host-looped kernels, which synchronise once per pass.  Returns the first failing runtime error.
 cudaError_t run_plane(const Ctx& c, const PlaneArgs& a);
-// copies each frame's remaining cloud (planar_cloud_y) + source indices out of the ping-pong buffers
-void run_plane_finalize(const Ctx& c, const PlaneArgs& a, float4* out, int* out_src);
+// Largest plane-stage input the small tier of the resident path processes (see run_plane).
+int plane_small_tier_max();
 
 struct ClusterArgs {
   const float4* in;  // remaining cloud, frame f at in + f*in_stride
@@ -214,6 +220,7 @@ struct ClusterArgs {
   const int* n_in;
   float tol;
   int min_size, max_size;
+  int small_max;  // largest cloud the fused shared-memory kernel takes (0: generic path only)
   MinMax* minmax;
   EceFrame* ef;
   SortBufs sort;
@@ -236,11 +243,11 @@ struct ClusterArgs {
 // Largest cloud the fused shared-memory clustering kernel takes (stage_cluster_small.cu).
 constexpr int ECE_SMALL_MAX = 8960;
 // ECE_SMALL_MAX, or the value of the environment variable PCOP_ECE_SMALL_MAX clamped to [0, ECE_SMALL_MAX]
-// (0 forces every frame through the generic path; used by the tests to cover both paths)
+// (0 forces every frame through the generic path; used by the tests to cover both paths).  Read by pcop_create.
 int ece_small_limit();
-// returns true when the generic centroid/radius kernel still has to run (some frame may have taken the generic path)
-bool run_cluster(const Ctx& c, const ClusterArgs& a);
-void run_cluster_small(const Ctx& c, const ClusterArgs& a, int small_max);
+// returns true when the generic centroid/radius kernel still has to run (see stage_cluster.cu)
+bool run_cluster(const Ctx& c, const ClusterArgs& a, bool with_generic);
+void run_cluster_small(const Ctx& c, const ClusterArgs& a, int small_max, bool zero_skipped);
 void run_centroid_radius(const Ctx& c, const ClusterArgs& a);
 
 // ---- occupancy grid: shadow casting + obstacle marking (stage_occupancy.cu; od.cpp:466-672, 817-833) ----------

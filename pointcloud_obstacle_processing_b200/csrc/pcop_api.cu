@@ -1,18 +1,20 @@
 // C ABI of the library (include/pcop.h): handle, memory, wave scheduling, result packing.
 //
-// A call processes its frames in waves of up to max_batch frames.  Within a wave every stage
-// is one set of launches over all frames (blockIdx.y = frame); the only host synchronisations
-// are one per RANSAC pass (the loop count is data dependent, od.cpp:379) and two for the
-// result copy (sizes, then payload).  Requested outputs of all frames of a wave are packed on
-// the device into one contiguous buffer and come back in a single device->host copy.
+// A call processes its frames in waves.  Within a wave every stage is one set of launches over all
+// frames (blockIdx.y = frame) and nothing returns to the host between the input upload and the wave's
+// counts: the RANSAC loop of od.cpp:379 runs inside one cluster kernel per frame (stage_plane.cu).
+// Waves are dealt round-robin to the lanes (a lane = one stream + one set of wave buffers); ONE host
+// thread enqueues a wave on every lane, then waits for the oldest wave's counts (an event), enqueues
+// its payload copy with the exact size and refills the lane, so a wave's result copy and the host's
+// bookkeeping overlap the other lanes' kernels.  Requested outputs of all frames of a wave are packed
+// on the device into one contiguous buffer and come back in a single device->host copy.
+// Every buffer is allocated by pcop_create; the pinned result buffer only grows (a second call of the
+// same shape allocates nothing).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
-#include <atomic>
-#include <chrono>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "internal.cuh"
@@ -70,11 +72,11 @@ struct PackMeta {  // device -> host in one copy
   unsigned long long base[PK_N];  // byte offset of each array inside the pack buffer
   unsigned long long total_bytes;
   int total[PK_N];  // elements
+  int overflow;     // the wave's arrays do not fit the pack buffer (nothing was packed)
 };
 
 thread_local std::string g_global_error;
 
-constexpr int PCOP_INTERNAL_REDO_GENERIC = 1000;  // collect_wave -> process_waves, never returned to the caller
 constexpr int PCOP_MIN_LANE_WAVE = 8;  // a call is split over the lanes only when every lane gets at least this many frames
 
 }  // namespace
@@ -113,26 +115,14 @@ struct pcop_handle {
   int* d_rng = nullptr;
   int* d_pack_off = nullptr;  // [PK_N][maxB]
   PackMeta* d_meta = nullptr;
-  unsigned char* d_pack = nullptr;  // two halves of pack_cap bytes: wave k of a call packs into half k & 1
+  unsigned char* d_pack = nullptr;  // packed results of the wave in flight (PCOP_OUT_DEVICE: of all waves of the call)
+  unsigned long long* d_pack_cursor = nullptr;  // PCOP_OUT_DEVICE: bytes of d_pack used by the call so far
   cudaStream_t cstream = nullptr;   // result copies (device -> pinned host) run here, beside the next wave's kernels
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied = nullptr;  // the last payload copy out of d_pack
+  cudaEvent_t ev_meta = nullptr;    // the wave's counts / pack sizes are in pinned memory
   int wave_seq = 0;                 // waves of the running call seen by this lane
-  // early copy of the remaining cloud: it is final once the plane loop ends, so it travels to the host (strided 2-D
-  // copy, rows padded to the wave's largest remaining cloud) while the clustering kernels still run
-  struct PinnedChunk {
-    unsigned char* p;
-    size_t cap;
-  };
-  std::vector<PinnedChunk> rem_chunks;  // one per wave of the running call
-  cudaEvent_t ev_rem_ready = nullptr, ev_rem_copied = nullptr;
-  bool rem_copy_pending = false;
-  bool wave_rem_early = false;
-  int call_waves = 1;  // waves of the running call over all lanes
-  size_t wave_rem_total = 0;  // points of all remaining clouds of the wave
-  unsigned char* wave_rem_host = nullptr;
-  float4* d_rem_pack = nullptr;  // [maxB*cap] staging of the early copy (allocated on first use)
-  int* d_rem_pack_src = nullptr;
-  int* d_rem_off = nullptr;      // [maxB]
+  bool pending = false;             // a wave is enqueued and not yet collected
+  int pend_w0 = 0, pend_B = 0;
   double d2h_bytes = 0.0;
   float4* d_acc = nullptr;  // accumulated (world-frame) cloud, od.cpp:697
   unsigned char* d_occ = nullptr;  // occupancy grid scratch: int64 counts, int64 row averages, int8 cells
@@ -142,15 +132,6 @@ struct pcop_handle {
   unsigned char* d_raw = nullptr;  // staging for a raw PointCloud2 payload (grown on demand)
   size_t raw_cap = 0;
   int acc_count = 0;
-  // lane stagger (PCOP_STAGGER=1, experiment): the voxel stages of the lanes of one call run one after the other, so
-  // that a lane's latency-bound plane loop and clustering overlap the next lane's voxel stage
-  cudaEvent_t ev_vox_done = nullptr;
-  std::atomic<long long> vox_gen{0};  // call generation whose first voxel stage has been enqueued (event recorded)
-  pcop_handle* stagger_prev = nullptr;
-  long long call_gen = 0;
-  bool first_wave_of_call = false;
-  cudaEvent_t ev_block = nullptr;  // blocking-sync event for the host waits (nullptr: spin), see stream_wait
-  cudaEvent_t trace_origin = nullptr;  // PCOP_TRACE: start event of the running call (on lane 0's stream)
   size_t pack_cap = 0;
   uint32_t alloc_outputs = 0;
 
@@ -165,6 +146,7 @@ struct pcop_handle {
   unsigned long long sort_pass_keys = 0;
   unsigned char* h_pack = nullptr;
   size_t h_pack_cap = 0;
+  size_t h_pack_used = 0;  // of the running call
 
   // timing
   cudaEvent_t ev_call[2] = {nullptr, nullptr};
@@ -176,8 +158,20 @@ struct pcop_handle {
   double alg_bytes = 0.0;
   KernelTimers kt;
 
-  // lanes: the handle itself is lane 0; a batched call deals its waves round-robin to the lanes, one host thread
-  // and one stream per lane, so one lane's host synchronisations and result copies overlap the other lanes' kernels
+  // lanes: the handle itself is lane 0; a batched call deals its waves round-robin to the lanes (one stream and one
+  // set of wave buffers each), so one lane's result copy and the host's bookkeeping overlap the other lanes' kernels
+  int wave_frames = 0;             // frames per wave a batched call aims at (<= maxB; PCOP_WAVE_FRAMES at create)
+  bool trace = false;              // PCOP_TRACE at create
+  int ece_small_max = 0;           // ECE_SMALL_MAX or PCOP_ECE_SMALL_MAX (read at create)
+  int plane_resident = 1;          // 0: PCOP_PLANE_RESIDENT=0 at create (host-looped plane kernels)
+  bool expect_big_remaining = false;  // the last collected wave had a remaining cloud above ece_small_max
+  bool expect_large_plane = false;    // ... a plane-stage input above the small tier of the resident plane kernel
+  bool wave_plane_speculated = false; // the wave in flight ran the small tier only
+  const float4* plane_in = nullptr;   // plane-stage input of the wave in flight (for a repeat of the stage)
+  size_t plane_stride = 0;
+  const int* plane_n = nullptr;
+  bool wave_cluster_speculated = false;  // the wave in flight ran the fused clustering kernel only
+  int pend_max_n = 1;
   VoxFusedPlan vplan{};            // fused crop + voxel fast path (ok = 0: not applicable to these parameters)
   uint32_t* d_vf_flags = nullptr;  // [maxB]
   unsigned long long* d_vf_pair[2] = {nullptr, nullptr};
@@ -265,10 +259,11 @@ uint32_t effective_outputs(const pcop_params& p) {
 }
 
 size_t pack_capacity_bytes(uint32_t mask, int B, int cap) {
+  mask &= (uint32_t)PCOP_OUT_ALL;
   size_t bytes = 0;
   for (int k = 0; k < PK_N; ++k)
     if (mask & kPkMask[k]) bytes += ((size_t)B * (cap + 1)) * kPkElem[k] + 256;
-  return (bytes + 256 + 255) & ~(size_t)255;  // (the second half of the double buffer must stay 256-byte aligned)
+  return (bytes + 256 + 255) & ~(size_t)255;
 }
 
 template <class T>
@@ -302,7 +297,7 @@ int ensure_pack_capacity(pcop_handle* h, uint32_t mask) {
   if (h->d_pack) cudaFree(h->d_pack);  // not tracked in dev_allocs
   h->d_pack = nullptr;
   h->pack_cap = 0;
-  cudaError_t e = cudaMalloc((void**)&h->d_pack, 2 * need);
+  cudaError_t e = cudaMalloc((void**)&h->d_pack, need);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaMalloc(pack)", __FILE__, __LINE__);
   h->pack_cap = need;
   return PCOP_OK;
@@ -488,9 +483,11 @@ __global__ void k_plane_record(const PlaneFrame* __restrict__ pf, PlaneRecord* _
 
 // exclusive scans over the frames of every requested output's count row + array base offsets
 // (first the per-frame plane record + the derived count rows CNT_NINL / CNT_CLUS1, which the scans below read)
+// (PCOP_OUT_DEVICE: the arrays of all waves of a call stay in the pack buffer, so the wave's base is a device-side
+// cursor that this kernel advances; a wave that does not fit sets meta->overflow and is not packed)
 __global__ void k_pack_scan(int* __restrict__ counts, int maxB, int B, uint32_t mask, int* __restrict__ pack_off,
                             PackMeta* __restrict__ meta, const PlaneFrame* __restrict__ pf, PlaneRecord* __restrict__ rec,
-                            int plane_enabled) {
+                            int plane_enabled, unsigned long long* __restrict__ cursor, unsigned long long capacity) {
   __shared__ int total[PK_N];
   for (int f = threadIdx.x; f < B; f += blockDim.x)
     plane_record_one(pf, rec, counts + (size_t)CNT_NINL * maxB, counts + (size_t)CNT_CLUS * maxB,
@@ -523,51 +520,16 @@ __global__ void k_pack_scan(int* __restrict__ counts, int maxB, int B, uint32_t 
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long off = 0;
+    const unsigned long long start = cursor ? *cursor : 0ull;
+    unsigned long long off = start;
     for (int k = 0; k < PK_N; ++k) {
       meta->base[k] = off;
       meta->total[k] = total[k];
       off += ((unsigned long long)total[k] * kPkElemD[k] + 255ull) & ~255ull;
     }
-    meta->total_bytes = off;
-  }
-}
-
-// early result copy: exclusive prefix of the remaining-cloud sizes over the frames of the wave (one block), then the
-// clouds + source indices packed back to back
-__global__ void k_rem_offsets(const int* __restrict__ n_rem, int B, int* __restrict__ off) {
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < B; base += 1024) {
-    const int f = base + threadIdx.x;
-    const int v = (f < B) ? n_rem[f] : 0;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(FULL, incl, o);
-      if ((threadIdx.x & 31) >= o) incl += up;
-    }
-    __shared__ int wsum[32];
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    int wb = carry;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wb += wsum[w];
-    if (f < B) off[f] = wb + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = wb + incl;
-    __syncthreads();
-  }
-}
-__global__ void __launch_bounds__(256)
-    k_rem_pack(const float4* __restrict__ rem, const int* __restrict__ rem_src, const int* __restrict__ n_rem,
-               const int* __restrict__ off, int cap, float4* __restrict__ out_pts, int* __restrict__ out_src) {
-  const int f = blockIdx.y;
-  const int n = n_rem[f];
-  const size_t o = (size_t)off[f];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    out_pts[o + i] = rem[(size_t)f * cap + i];
-    out_src[o + i] = rem_src[(size_t)f * cap + i];
+    meta->total_bytes = off - start;
+    meta->overflow = (off > capacity) ? 1 : 0;
+    if (cursor && off <= capacity) *cursor = off;
   }
 }
 
@@ -585,7 +547,7 @@ __global__ void __launch_bounds__(256)
            const PackMeta* __restrict__ meta, unsigned char* __restrict__ pack) {
   const int which = blockIdx.z, f = blockIdx.y;
   const uint32_t* base = ps.src[which];
-  if (!base) return;
+  if (!base || meta->overflow) return;
   const int wpe = ps.words_per_elem[which];
   const int n = counts[(size_t)ps.count_row[which] * maxB + f];
   const uint32_t* s = base + (size_t)f * ps.frame_stride_words[which];
@@ -638,7 +600,7 @@ void resolve_kernel_timers(pcop_handle* h) {
 }
 
 Ctx make_ctx(pcop_handle* h, int B, int grid_cap = -1) {
-  return Ctx{h->stream, B, h->cap, &h->launches, &h->kt, (grid_cap > 0 && grid_cap < h->cap) ? grid_cap : h->cap, h->ev_block};
+  return Ctx{h->stream, B, h->cap, &h->launches, &h->kt, (grid_cap > 0 && grid_cap < h->cap) ? grid_cap : h->cap, nullptr};
 }
 
 PlaneConst make_plane_const(const pcop_params& p) {
@@ -672,8 +634,11 @@ PlaneArgs make_plane_args(pcop_handle* h, const float4* in, size_t stride, const
   a.n_active = h->d_n_active;
   a.h_n_active = h->h_n_active;
   a.rng = h->d_rng;
+  a.resident = h->plane_resident;
   a.pc = make_plane_const(h->params);
   a.warnings = h->d_warnings;
+  a.out = h->d_rem;
+  a.out_src = h->d_rem_src;
   a.n_out = h->cnt(CNT_REM);
   return a;
 }
@@ -686,6 +651,7 @@ ClusterArgs make_cluster_args(pcop_handle* h, const float4* in, size_t stride, c
   a.tol = h->params.euc_cluster_tolerance;
   a.min_size = h->params.euc_min_cluster_size;
   a.max_size = h->params.euc_max_cluster_size;
+  a.small_max = h->ece_small_max;
   a.minmax = h->d_minmax;
   a.ef = h->d_ef;
   a.sort = h->sort;
@@ -778,7 +744,30 @@ bool is_device_pointer(const void* p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-// All stages of one wave.  `in`/`stride` already on the device; counts row CNT_IN already set.
+// The plane loop of one wave on the stage input recorded in the handle.  large_tier: see run_plane.
+int run_wave_plane(pcop_handle* h, int B, int max_n, bool large_tier) {
+  const pcop_params& p = h->params;
+  Ctx c = make_ctx(h, B, max_n);  // (no frame holds more points than the largest input frame)
+  StageTimer t(h, PCOP_STAGE_PLANE);
+  h->wave_plane_speculated = false;
+  if (p.enable_plane) {
+    PlaneArgs a = make_plane_args(h, h->plane_in, h->plane_stride, h->plane_n);
+    a.n_in_copy = p.enable_sor ? nullptr : h->cnt(CNT_SOR);
+    a.large_tier = large_tier ? 1 : 0;
+    if (!(effective_outputs(p) & PCOP_OUT_PLANE)) a.inlier_idx = nullptr;  // the inlier list is only written on request
+    cudaError_t e = run_plane(c, a);
+    if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
+    h->wave_plane_speculated = h->plane_resident && !large_tier && max_n > plane_small_tier_max();
+  } else {
+    KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(h->plane_n, h->cnt(CNT_REM), B));
+    KL(c, "k_copy_cloud", k_copy_cloud<<<dim3(cdiv(c.grid_cap, CT_TILE), B), CT_THREADS, 0, h->stream>>>(
+                              h->plane_in, h->plane_stride, h->plane_n, h->d_rem, h->d_rem_src, h->cap));
+    count_launch(c, 2);
+  }
+  return PCOP_OK;
+}
+
+// All stages of one wave up to the plane loop.  `in`/`stride` already on the device; counts row CNT_IN already set.
 int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int max_n) {
   const pcop_params& p = h->params;
   Ctx c = make_ctx(h, B, max_n);  // no stage ever holds more points per frame than the largest input frame
@@ -796,7 +785,6 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
 
   const bool fused = h->vplan.ok && !h->force_generic;
   h->wave_used_fused = fused;
-  h->wave_rem_early = false;
   if (fused) {
     // crop + VoxelGrid in one pass over the input (stage_voxel_fused.cu); the cropped cloud itself is only
     // materialised when it is a requested output
@@ -856,11 +844,6 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
       }
     }
   }
-  if (h->first_wave_of_call) {  // (see stagger_prev)
-    cudaEventRecord(h->ev_vox_done, h->stream);
-    h->vox_gen.store(h->call_gen, std::memory_order_release);
-    h->first_wave_of_call = false;
-  }
   {
     StageTimer t(h, PCOP_STAGE_SOR);
     if (p.enable_sor) {
@@ -873,71 +856,27 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
       count_launch(c);
     }
   }
-  {
-    StageTimer t(h, PCOP_STAGE_PLANE);
-    if (p.enable_plane) {
-      PlaneArgs a = make_plane_args(h, cur, cur_stride, cur_n);
-      a.n_in_copy = p.enable_sor ? nullptr : h->cnt(CNT_SOR);
-      cudaError_t e = run_plane(c, a);
-      if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
-      c.grid_cap = std::max(1, std::min(c.grid_cap, h->h_n_active[1]));  // largest remaining cloud of the wave
-      if (h->rem_copy_pending) {  // the previous wave's early copy still reads d_rem
-        cudaStreamWaitEvent(h->stream, h->ev_rem_copied, 0);
-        h->rem_copy_pending = false;
-      }
-      run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
-      // Early result copy: the remaining cloud (80 % of the result bytes) is final now; the host knows its total size
-      // from the plane loop's last synchronisation, so it is packed and sent while the clustering kernels run.
-      const size_t total = (size_t)std::max(0, h->h_n_active[2]);
-      const size_t need = total * 20 + 256;
-      if ((effective_outputs(p) & PCOP_OUT_REMAINING) && !(effective_outputs(p) & PCOP_OUT_DEVICE) && B > 1 && total > 0 &&
-          !getenv("PCOP_NO_EARLY_COPY")) {
-        if (!h->d_rem_pack) {
-          const size_t BC = (size_t)h->maxB * h->cap;
-          if (cudaMalloc((void**)&h->d_rem_pack, BC * 16) != cudaSuccess || cudaMalloc((void**)&h->d_rem_pack_src, BC * 4) != cudaSuccess ||
-              cudaMalloc((void**)&h->d_rem_off, sizeof(int) * h->maxB) != cudaSuccess)
-            return fail_cuda(h, cudaGetLastError(), "cudaMalloc(early copy)", __FILE__, __LINE__);
-        }
-        if ((size_t)h->wave_seq >= h->rem_chunks.size()) h->rem_chunks.resize(h->wave_seq + 1, pcop_handle::PinnedChunk{nullptr, 0});
-        pcop_handle::PinnedChunk& ch = h->rem_chunks[h->wave_seq];
-        if (ch.cap < need) {
-          cudaStreamSynchronize(h->cstream);  // (an abandoned copy of a redone wave may still target the old chunk)
-          if (ch.p) cudaFreeHost(ch.p);
-          ch.p = nullptr;
-          ch.cap = 0;
-          const size_t ncap = need + need / 4 + 4096;
-          if (cudaHostAlloc((void**)&ch.p, ncap, cudaHostAllocDefault) != cudaSuccess)
-            return fail_cuda(h, cudaGetLastError(), "cudaHostAlloc(remaining)", __FILE__, __LINE__);
-          ch.cap = ncap;
-        }
-        KL(c, "k_rem_offsets", k_rem_offsets<<<1, 1024, 0, h->stream>>>(h->cnt(CNT_REM), B, h->d_rem_off));
-        KL(c, "k_rem_pack", k_rem_pack<<<dim3(std::max(1, std::min(cdiv(c.grid_cap, 256), 8)), B), 256, 0, h->stream>>>(
-            h->d_rem, h->d_rem_src, h->cnt(CNT_REM), h->d_rem_off, h->cap, h->d_rem_pack, h->d_rem_pack_src));
-        count_launch(c, 2);
-        cudaEventRecord(h->ev_rem_ready, h->stream);
-        cudaStreamWaitEvent(h->cstream, h->ev_rem_ready, 0);
-        const size_t src_off = (total * 16 + 255) & ~(size_t)255;
-        cudaMemcpyAsync(ch.p, h->d_rem_pack, total * 16, cudaMemcpyDeviceToHost, h->cstream);
-        cudaMemcpyAsync(ch.p + src_off, h->d_rem_pack_src, total * 4, cudaMemcpyDeviceToHost, h->cstream);
-        cudaEventRecord(h->ev_rem_copied, h->cstream);
-        h->rem_copy_pending = true;
-        h->wave_rem_early = true;
-        h->wave_rem_total = total;
-        h->wave_rem_host = ch.p;
-        h->d2h_bytes += (double)(total * 20);
-      }
-    } else {
-      KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(cur_n, h->cnt(CNT_REM), B));
-      KL(c, "k_copy_cloud", k_copy_cloud<<<dim3(cdiv(c.grid_cap, CT_TILE), B), CT_THREADS, 0, h->stream>>>(cur, cur_stride, cur_n, h->d_rem, h->d_rem_src, h->cap));
-      count_launch(c, 2);
-    }
-  }
+  h->plane_in = cur;
+  h->plane_stride = cur_stride;
+  h->plane_n = cur_n;
+  TRY(run_wave_plane(h, B, max_n, h->expect_large_plane));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(h, e, "stage launches", __FILE__, __LINE__);
+  return PCOP_OK;
+}
+
+// Clustering + centroid / radius of one wave.  The host does not know the remaining-cloud sizes yet; with_generic =
+// false launches only the fused small-cloud kernel (finish_wave repeats the stage with the generic kernels if a frame
+// turned out larger, see run_cluster).
+int run_wave_cluster(pcop_handle* h, int B, int max_n, bool with_generic) {
+  const pcop_params& p = h->params;
+  Ctx c = make_ctx(h, B, max_n);
   ClusterArgs ca = make_cluster_args(h, h->d_rem, h->cap, h->cnt(CNT_REM));
   bool generic_centroid = false;
   {
     StageTimer t(h, PCOP_STAGE_CLUSTER);
     if (p.enable_cluster) {
-      generic_centroid = run_cluster(c, ca);  // the fused small-cloud kernel writes the obstacles itself
+      generic_centroid = run_cluster(c, ca, with_generic);  // the fused small-cloud kernel writes the obstacles itself
     } else {
       cudaMemsetAsync(h->cnt(CNT_CLUS), 0, sizeof(int) * B, h->stream);
       cudaMemsetAsync(h->cnt(CNT_CLPTS), 0, sizeof(int) * B, h->stream);
@@ -947,24 +886,31 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
     StageTimer t(h, PCOP_STAGE_CENTROID);
     if (p.enable_cluster && generic_centroid) run_centroid_radius(c, ca);
   }
+  h->wave_cluster_speculated = p.enable_cluster && !generic_centroid && max_n > h->ece_small_max;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(h, e, "stage launches", __FILE__, __LINE__);
   return PCOP_OK;
 }
 
-// pack + copy back the requested outputs of a wave; fills out[0..B)
-int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop_frame_result* out_all, int w0,
-                 std::vector<size_t>* ptr_fixups) {
-  pcop_frame_result* out = out_all + w0;
-  Ctx c = make_ctx(h, B);
+struct WaveInput {
+  const float* xyzw;
+  size_t frame_stride_points;
+  const int32_t* n;
+  bool on_device;
+};
+
+// Second half of a wave: clustering, result packing, and the copy of the wave's counts / plane records / pack sizes
+// into pinned memory, followed by ev_meta.
+int enqueue_wave_back(pcop_handle* h, int B, int max_n, uint32_t mask, bool cluster_with_generic) {
+  TRY(run_wave_cluster(h, B, max_n, cluster_with_generic));
+  // pack the requested outputs of all frames of the wave
+  Ctx c = make_ctx(h, B, max_n);
   StageTimer t(h, PCOP_STAGE_D2H);
-  const int half = h->wave_seq & 1;
-  unsigned char* d_pack = h->d_pack + (size_t)half * h->pack_cap;
-  if (h->wave_seq >= 2) PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied[half], 0));  // half is free again
-  const uint32_t full_mask = mask;
-  if (h->wave_rem_early) mask &= ~(uint32_t)PCOP_OUT_REMAINING;  // already on its way (run_wave_stages)
+  const bool dev_results = (mask & PCOP_OUT_DEVICE) != 0;  // the arrays stay in d_pack (bump-allocated over the call)
+  if (!dev_results && h->wave_seq >= 1) PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));  // d_pack is free again
   KL(c, "k_pack_scan", k_pack_scan<<<1, 320, 0, h->stream>>>(h->d_counts, h->maxB, B, mask, h->d_pack_off, h->d_meta, h->d_pf, h->d_prec,
-                                             h->params.enable_plane ? 1 : 0));
+                                             h->params.enable_plane ? 1 : 0, dev_results ? h->d_pack_cursor : nullptr,
+                                             (unsigned long long)h->pack_cap));
   count_launch(c);
   const void* srcs[PK_N] = {h->d_crop_kept, h->d_vox_keys, h->d_vox,     h->d_sor_kept, h->d_inliers,
                             h->d_rem,       h->d_rem_src,  h->d_offsets, h->d_indices,  h->d_obst};
@@ -982,7 +928,7 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
     }
     if (any) {
       const int gx = std::max(1, std::min(cdiv(c.grid_cap, 256 * 4), 16));
-      KL(c, "k_pack", k_pack<<<dim3(gx, B, PK_N), 256, 0, h->stream>>>(ps, h->d_counts, h->maxB, h->d_pack_off, h->d_meta, d_pack));
+      KL(c, "k_pack", k_pack<<<dim3(gx, B, PK_N), 256, 0, h->stream>>>(ps, h->d_counts, h->maxB, h->d_pack_off, h->d_meta, h->d_pack));
       count_launch(c);
     }
   }
@@ -993,27 +939,110 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_meta, h->d_meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, h->stream));
   if (h->wave_used_fused)
     PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_vf_flags, h->d_vf_flags, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, h->stream));
-  PCOP_CUDA_TRY(stream_wait(h->stream, h->ev_block));
-  if (h->wave_used_fused)
-    for (int f = 0; f < B; ++f)
-      if (h->h_vf_flags[f]) return PCOP_INTERNAL_REDO_GENERIC;  // the fast voxel path declined a frame of this wave
+  PCOP_CUDA_TRY(cudaEventRecord(h->ev_meta, h->stream));
+  return PCOP_OK;
+}
+
+// Enqueues one wave on lane h: input upload, all stages and enqueue_wave_back.  Returns without waiting for any of it.
+int enqueue_wave(pcop_handle* h, const WaveInput& wi, int w0, int B, uint32_t mask) {
+  for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_used[s] = false;
+  const float4* in;
+  size_t stride;
+  const int32_t* n = wi.n;
+  {
+    StageTimer t(h, PCOP_STAGE_H2D);
+    memcpy(h->h_n_in, n + w0, sizeof(int) * B);  // (the lane's previous wave has been collected: the staging is free)
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->cnt(CNT_IN), h->h_n_in, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
+    if (wi.on_device) {
+      in = reinterpret_cast<const float4*>(wi.xyzw) + (size_t)w0 * wi.frame_stride_points;
+      stride = wi.frame_stride_points;
+    } else {
+      const float* src = wi.xyzw + (size_t)w0 * wi.frame_stride_points * 4;
+      bool uniform = true;
+      for (int f = 1; f < B; ++f) uniform = uniform && (n[w0 + f] == n[w0]);
+      if (B > 0 && uniform && n[w0] > 0) {
+        PCOP_CUDA_TRY(cudaMemcpy2DAsync(h->d_in, (size_t)h->cap * 16, src, wi.frame_stride_points * 16, (size_t)n[w0] * 16,
+                                        B, cudaMemcpyHostToDevice, h->stream));
+      } else {
+        for (int f = 0; f < B; ++f)
+          if (n[w0 + f] > 0)
+            PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_in + (size_t)f * h->cap, src + (size_t)f * wi.frame_stride_points * 4,
+                                          (size_t)n[w0 + f] * 16, cudaMemcpyHostToDevice, h->stream));
+      }
+      in = h->d_in;
+      stride = h->cap;
+    }
+  }
+  int max_n = 1;
+  for (int f = 0; f < B; ++f) max_n = std::max(max_n, (int)n[w0 + f]);
+  TRY(run_wave_stages(h, B, in, stride, max_n));
+  h->pending = true;
+  h->pend_w0 = w0;
+  h->pend_B = B;
+  h->pend_max_n = max_n;
+  return enqueue_wave_back(h, B, max_n, mask, h->expect_big_remaining);
+}
+
+
+// Waits for the lane's wave in flight, starts its payload copy and fills out[w0 .. w0 + B).  (Result pointers into
+// the pinned buffer are stored as offsets and fixed up when the call ends: the buffer may still grow.)
+int finish_wave(pcop_handle* h, const WaveInput& wi, uint32_t mask, pcop_frame_result* out_all) {
+  if (!h->pending) return PCOP_OK;
+  const int w0 = h->pend_w0, B = h->pend_B;
+  PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_meta));
+  if (h->wave_used_fused) {
+    bool redo = false;
+    for (int f = 0; f < B; ++f) redo = redo || h->h_vf_flags[f] != 0u;
+    if (redo) {  // the fast voxel path declined a frame of this wave (a survivor with a NaN y or z): generic path
+      h->force_generic = true;
+      const int st = enqueue_wave(h, wi, w0, B, mask);
+      h->force_generic = false;
+      TRY(st);
+      PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_meta));
+    }
+  }
+  bool plane_redone = false;
+  if (h->params.enable_plane && h->plane_resident) {
+    bool large = false;  // (CNT_SOR = the plane stage's input size)
+    for (int f = 0; f < B; ++f) large = large || h->h_counts[(size_t)CNT_SOR * h->maxB + f] > plane_small_tier_max();
+    if (large && h->wave_plane_speculated) {  // a frame too large for the small tier of the plane kernel: repeat from there
+      TRY(run_wave_plane(h, B, h->pend_max_n, true));
+      TRY(enqueue_wave_back(h, B, h->pend_max_n, mask, h->expect_big_remaining));
+      PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_meta));
+      plane_redone = true;
+    }
+    h->expect_large_plane = large;
+  }
+  (void)plane_redone;
+  if (h->params.enable_cluster) {
+    bool big = false;
+    for (int f = 0; f < B; ++f) big = big || h->h_counts[(size_t)CNT_REM * h->maxB + f] > h->ece_small_max;
+    if (big && h->wave_cluster_speculated) {  // a remaining cloud too large for the fused kernel: generic clustering
+      TRY(enqueue_wave_back(h, B, h->pend_max_n, mask, true));
+      PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_meta));
+    }
+    h->expect_big_remaining = big;
+  }
+  h->pending = false;
+  pcop_frame_result* out = out_all + w0;
   const PackMeta meta = *h->h_meta;
-  const bool dev_results = (full_mask & PCOP_OUT_DEVICE) != 0;  // the arrays stay in this wave's half of d_pack
-  if (dev_results && h->wave_seq >= 2) return fail(h, PCOP_ERR_CAPACITY, "PCOP_OUT_DEVICE: more than 2 waves per lane in one call");
-  const size_t base_off = (*h_pack_used + 255) & ~(size_t)255;
-  if (!dev_results) TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
-  // payload copy on the copy stream (the pack kernels have finished: the stream was just synchronised); the lane's
-  // next wave starts right away and only waits for this copy before it packs into the same half again
-  if (meta.total_bytes && !dev_results)
-    PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->cstream));
+  const bool dev_results = (mask & PCOP_OUT_DEVICE) != 0;
+  if (meta.overflow)
+    return fail(h, PCOP_ERR_CAPACITY, "PCOP_OUT_DEVICE: the result arrays of this call do not fit the device pack buffer");
+  const size_t base_off = (h->h_pack_used + 255) & ~(size_t)255;
+  if (!dev_results) {
+    TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
+    // payload copy on the copy stream (the pack kernels have finished: ev_meta follows them)
+    if (meta.total_bytes)
+      PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, h->d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->cstream));
+    PCOP_CUDA_TRY(cudaEventRecord(h->ev_copied, h->cstream));
+    h->h_pack_used = base_off + meta.total_bytes;
+  }
   h->d2h_bytes += (dev_results ? 0.0 : (double)meta.total_bytes) +
                   (double)(sizeof(int) * CNT_ROWS * h->maxB + sizeof(uint32_t) * B + sizeof(PlaneRecord) * B + sizeof(PackMeta));
-  PCOP_CUDA_TRY(cudaEventRecord(h->ev_copied[half], h->cstream));
   ++h->wave_seq;
-  *h_pack_used = base_off + meta.total_bytes;
 
   size_t run[PK_N] = {0};
-  size_t rem_run = 0;  // points of the early-copied remaining clouds before frame f
   auto H = [&](int row, int f) { return h->h_counts[(size_t)row * h->maxB + f]; };
   for (int f = 0; f < B; ++f) {
     pcop_frame_result& r = out[f];
@@ -1039,21 +1068,15 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
                                 (const void**)&r.plane_inlier_idx, (const void**)&r.remaining_cloud,
                                 (const void**)&r.remaining_src_idx, (const void**)&r.cluster_offsets,
                                 (const void**)&r.cluster_indices,  (const void**)&r.obstacles};
-    if (h->wave_rem_early && (full_mask & PCOP_OUT_REMAINING)) {
-      const size_t src_off = (h->wave_rem_total * 16 + 255) & ~(size_t)255;
-      r.remaining_cloud = reinterpret_cast<const float*>(h->wave_rem_host + rem_run * 16);
-      r.remaining_src_idx = reinterpret_cast<const int32_t*>(h->wave_rem_host + src_off + rem_run * 4);
-      rem_run += (size_t)r.n_remaining;
-    }
     for (int k = 0; k < PK_N; ++k) {
       if (!(mask & kPkMask[k])) continue;
-      if (dev_results) {  // device pointer into this wave's half of the pack buffer (it does not move)
-        *slots[k] = d_pack + (size_t)meta.base[k] + run[k] * kPkElem[k];
+      if (dev_results) {  // device pointer into the pack buffer (it does not move)
+        *slots[k] = h->d_pack + (size_t)meta.base[k] + run[k] * kPkElem[k];
       } else {
         // store the byte offset now; turned into a pointer once the host buffer can no longer move
         const size_t off = base_off + (size_t)meta.base[k] + run[k] * kPkElem[k];
         *slots[k] = (const void*)(uintptr_t)(off + 1);  // +1 so that offset 0 is distinguishable from NULL
-        ptr_fixups->push_back((size_t)((const unsigned char*)slots[k] - (const unsigned char*)out_all));
+        h->fixups.push_back((size_t)((const unsigned char*)slots[k] - (const unsigned char*)out_all));
       }
       run[k] += (size_t)H(kPkCount[k], f);
     }
@@ -1078,125 +1101,14 @@ int collect_wave(pcop_handle* h, int B, uint32_t mask, size_t* h_pack_used, pcop
     }
     h->alg_bytes += b;
   }
-  return PCOP_OK;
-}
-
-// Runs the given waves of a call on lane h, in order.
-// Blocks until the lane's results are in its pinned host buffer; fills out[] (pointers fixed up at the end).
-typedef std::vector<std::pair<int, int>> WaveList;  // (first frame, frames)
-
-int process_waves(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n,
-                  pcop_frame_result* out, const WaveList& waves, bool on_device, uint32_t mask) {
-  PCOP_CUDA_TRY(cudaSetDevice(h->device));
-  h->launches = 0;
-  h->alg_bytes = 0.0;
-  h->d2h_bytes = 0.0;
-  h->rem_copy_pending = false;
-  h->kt.used = 0;
-  h->sort_pass_keys = 0;
-  PCOP_CUDA_TRY(cudaMemsetAsync(h->sort.stats, 0, sizeof(unsigned long long), h->stream));
-  for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] = 0.f;
-  size_t h_pack_used = 0;
-  h->fixups.clear();
-  h->wave_seq = 0;
-  h->first_wave_of_call = true;
-  struct PublishGen {  // never leave the next lane waiting, whatever path this lane exits by
-    pcop_handle* h;
-    ~PublishGen() {
-      if (h->vox_gen.load(std::memory_order_acquire) < h->call_gen) {
-        cudaEventRecord(h->ev_vox_done, h->stream);
-        h->vox_gen.store(h->call_gen, std::memory_order_release);
-      }
-    }
-  } publish_gen{h};
-  for (const std::pair<int, int>& wv : waves) {
-    const int w0 = wv.first, B = wv.second;
-    for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_used[s] = false;
-    const float4* in;
-    size_t stride;
-    {
-      StageTimer t(h, PCOP_STAGE_H2D);
-      memcpy(h->h_n_in, n + w0, sizeof(int) * B);
-      PCOP_CUDA_TRY(cudaMemcpyAsync(h->cnt(CNT_IN), h->h_n_in, sizeof(int) * B, cudaMemcpyHostToDevice, h->stream));
-      if (on_device) {
-        in = reinterpret_cast<const float4*>(xyzw) + (size_t)w0 * frame_stride_points;
-        stride = frame_stride_points;
-      } else {
-        const float* src = xyzw + (size_t)w0 * frame_stride_points * 4;
-        bool uniform = true;
-        for (int f = 1; f < B; ++f) uniform = uniform && (n[w0 + f] == n[w0]);
-        if (B > 0 && uniform && n[w0] > 0) {
-          PCOP_CUDA_TRY(cudaMemcpy2DAsync(h->d_in, (size_t)h->cap * 16, src, frame_stride_points * 16, (size_t)n[w0] * 16,
-                                          B, cudaMemcpyHostToDevice, h->stream));
-        } else {
-          for (int f = 0; f < B; ++f)
-            if (n[w0 + f] > 0)
-              PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_in + (size_t)f * h->cap, src + (size_t)f * frame_stride_points * 4,
-                                            (size_t)n[w0 + f] * 16, cudaMemcpyHostToDevice, h->stream));
-        }
-        in = h->d_in;
-        stride = h->cap;
-      }
-    }
-    int max_n = 1;
-    for (int f = 0; f < B; ++f) max_n = std::max(max_n, (int)n[w0 + f]);
-    const bool trace = getenv("PCOP_TRACE") != nullptr;
-    const auto tt0 = std::chrono::steady_clock::now();
-    if (h->first_wave_of_call && h->stagger_prev) {
-      pcop_handle* pv = h->stagger_prev;
-      while (pv->vox_gen.load(std::memory_order_acquire) < h->call_gen) std::this_thread::yield();
-      PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, pv->ev_vox_done, 0));
-    }
-    TRY(run_wave_stages(h, B, in, stride, max_n));
-    const auto tt1 = std::chrono::steady_clock::now();
-    int cst = collect_wave(h, B, mask, &h_pack_used, out, w0, &h->fixups);
-    if (cst == PCOP_INTERNAL_REDO_GENERIC) {
-      h->force_generic = true;
-      cst = run_wave_stages(h, B, in, stride, max_n);
-      h->force_generic = false;
-      if (cst == PCOP_OK) cst = collect_wave(h, B, mask, &h_pack_used, out, w0, &h->fixups);
-    }
-    TRY(cst);
-    PCOP_CUDA_TRY(stream_wait(h->stream, h->ev_block));
-    if (trace) {
-      const auto tt2 = std::chrono::steady_clock::now();
-      cudaStreamSynchronize(h->cstream);
-      const auto tt3 = std::chrono::steady_clock::now();
-      auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-        return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
-      };
-      fprintf(stderr, "[pcop trace] lane %p wave %d+%d: stages(host, incl. plane syncs) %ld us, collect %ld us, copy tail %ld us\n",
-              (void*)h, w0, B, us(tt0, tt1), us(tt1, tt2), us(tt2, tt3));
-    }
-    for (int s = 0; s < PCOP_N_STAGES; ++s) {
-      if (!h->stage_used[s]) continue;
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, h->ev_stage[s][0], h->ev_stage[s][1]) == cudaSuccess) h->stage_us[s] += ms * 1000.f;
-    }
-    resolve_kernel_timers(h);
-    if (getenv("PCOP_TRACE")) {
-      fprintf(stderr, "[pcop trace]   lane %p device timeline, us since call start [begin-end]:", (void*)h);
-      for (int s = 0; s < PCOP_N_STAGES; ++s) {
-        float a = 0.f, b = 0.f;
-        if (h->stage_used[s] && h->trace_origin && cudaEventElapsedTime(&a, h->trace_origin, h->ev_stage[s][0]) == cudaSuccess &&
-            cudaEventElapsedTime(&b, h->trace_origin, h->ev_stage[s][1]) == cudaSuccess)
-          fprintf(stderr, " s%d[%.0f-%.0f]", s, a * 1000.f, b * 1000.f);
-      }
-      fprintf(stderr, "\n");
-    }
+  for (int s = 0; s < PCOP_N_STAGES; ++s) {
+    if (!h->stage_used[s]) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_stage[s][0], h->ev_stage[s][1]) == cudaSuccess) h->stage_us[s] += ms * 1000.f;
+    else cudaGetLastError();
   }
-  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_stats, h->sort.stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-  PCOP_CUDA_TRY(cudaEventRecord(h->ev_lane_done, h->cstream));
-  PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_lane_done, 0));  // the lane is done when its last result copy is
-  PCOP_CUDA_TRY(cudaEventRecord(h->ev_lane_done, h->stream));
-  PCOP_CUDA_TRY(stream_wait(h->stream, h->ev_block));
-  h->sort_pass_keys = *h->h_stats;
-  // the host pack buffer is final now: turn the stored offsets into pointers
-  for (size_t fx : h->fixups) {
-    const void** slot = (const void**)((unsigned char*)out + fx);
-    const size_t off = (size_t)(uintptr_t)(*slot) - 1;
-    *slot = h->h_pack + off;
-  }
+  resolve_kernel_timers(h);
+  if (h->trace) fprintf(stderr, "[pcop trace] lane %p wave %d+%d collected, %zu result bytes\n", (void*)h, w0, B, (size_t)meta.total_bytes);
   return PCOP_OK;
 }
 
@@ -1236,100 +1148,90 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     if ((size_t)n[f] > frame_stride_points && batch > 1) return fail(h, PCOP_ERR_BAD_PARAM, "frame_stride_points < n");
   }
   const uint32_t mask = effective_outputs(h->params);
-  const bool on_device = is_device_pointer(xyzw);
+  const WaveInput wi{xyzw, frame_stride_points, n, is_device_pointer(xyzw)};
   // lanes used by this call: per-kernel timing needs each kernel alone on the GPU, so it serialises the lanes
-  int n_lanes = 1 + (int)h->extra_lanes.size();
-  if (h->kt.enabled) n_lanes = 1;
-  n_lanes = std::max(1, std::min(n_lanes, batch / PCOP_MIN_LANE_WAVE));
-  // waves per lane (PCOP_WAVES_PER_LANE): larger waves run the kernels more efficiently, more waves overlap a
-  // wave's result copy with the lane's next wave
-  int wpl = 1;
-  if (const char* sv = getenv("PCOP_WAVES_PER_LANE")) wpl = (int)std::min<long>(std::max<long>(strtol(sv, nullptr, 10), 1), 16);
-  std::vector<WaveList> plan(n_lanes);
-  if (n_lanes > 1 && wpl == 1 && batch <= (h->maxB * n_lanes * 4) / 5) {
-    // one wave per lane, of growing size (weights 1 .. 1.5): the lanes share the GPU, finish one after the other,
-    // and every result copy but the last overlaps the kernels of the lanes still running.  (Measured on B200, 256
-    // frames, 2 lanes: 2.58 ms per call; even split 2.67 ms; an extra small tail wave 3.0 ms.)
-    static const double skew = [] {
-      const char* sv = getenv("PCOP_WAVE_SKEW");
-      return sv ? std::min(1.0, std::max(-0.9, atof(sv))) : 0.5;
-    }();
-    double wsum = 0.0;
-    for (int l = 0; l < n_lanes; ++l) wsum += 1.0 + skew * l / (n_lanes - 1);
-    int w0 = 0;
-    std::vector<int> forced;  // PCOP_WAVE_SIZES=a,b,c,...: explicit wave sizes (experiments)
-    if (const char* sv = getenv("PCOP_WAVE_SIZES"))
-      for (const char* q = sv; *q;) {
-        forced.push_back((int)strtol(q, const_cast<char**>(&q), 10));
-        if (*q == ',') ++q;
-      }
-    for (int l = 0; l < n_lanes; ++l) {
-      int B = (l + 1 == n_lanes) ? batch - w0 : (int)((1.0 + skew * l / (n_lanes - 1)) / wsum * batch);
-      if ((int)forced.size() == n_lanes && l + 1 < n_lanes) B = std::min(std::max(forced[l], 1), batch - w0);
-      B = std::min(B, h->maxB);
-      if (B > 0) plan[l].push_back({w0, B});
-      w0 += B;
-    }
-    for (int l = 0; w0 < batch; l = (l + 1) % n_lanes) {  // leftovers (capacity clamps)
-      const int B = std::min(h->maxB, batch - w0);
-      plan[l].push_back({w0, B});
-      w0 += B;
-    }
-  } else {
-    const int wave = std::min(h->maxB, std::max(PCOP_MIN_LANE_WAVE, (batch + n_lanes * wpl - 1) / (n_lanes * wpl)));
-    int l = 0;
-    for (int w0 = 0; w0 < batch; w0 += wave, l = (l + 1) % n_lanes) plan[l].push_back({w0, std::min(wave, batch - w0)});
-  }
   std::vector<pcop_handle*> lanes(1, h);
-  for (int l = 1; l < n_lanes; ++l) lanes.push_back(h->extra_lanes[l - 1]);
-  int call_waves = 0;
-  for (const WaveList& wl : plan) call_waves += (int)wl.size();
-  // off by default: measured on B200 (1024 frames, 4 lanes) the staggered schedule takes 7.2 ms per call against
-  // 6.3 ms for lanes that run the same stage at the same time (the voxel kernels do not saturate the GPU alone)
-  static const bool stagger = [] {
-    const char* sv = getenv("PCOP_STAGGER");
-    return sv && sv[0] == '1';
-  }();
-  const long long gen = ++h->call_gen;
-  for (int l = 0; l < n_lanes; ++l) {
-    lanes[l]->call_gen = gen;
-    lanes[l]->stagger_prev = (stagger && l > 0) ? lanes[l - 1] : nullptr;
+  if (!h->kt.enabled)
+    for (pcop_handle* l : h->extra_lanes) lanes.push_back(l);
+  // waves: about wave_frames frames each (never more than a lane holds), at least one per lane when the call is large
+  // enough, the last one half as large as the others (its result copy is the only one nothing overlaps)
+  std::vector<std::pair<int, int>> waves;  // (first frame, frames)
+  {
+    const int L = (int)lanes.size();
+    int nw = std::max(1, cdiv(batch, std::max(1, std::min(h->wave_frames, h->maxB))));
+    if (nw < L) nw = std::max(1, std::min(L, batch / PCOP_MIN_LANE_WAVE));
+    const int full = (nw > 1) ? std::min(h->maxB, cdiv(2 * batch, 2 * nw - 1)) : std::min(h->maxB, batch);
+    for (int w0 = 0; w0 < batch;) {
+      const int B = std::min(full, batch - w0);
+      waves.push_back({w0, B});
+      w0 += B;
+    }
   }
   for (pcop_handle* l : lanes) {
-    l->call_waves = call_waves;
     l->params = h->params;
     l->vplan = h->vplan;
-    l->trace_origin = h->ev_call[0];
+    l->launches = 0;
+    l->alg_bytes = 0.0;
+    l->d2h_bytes = 0.0;
+    l->kt.used = 0;
+    l->sort_pass_keys = 0;
+    l->h_pack_used = 0;
+    l->fixups.clear();
+    l->wave_seq = 0;
+    l->pending = false;
+    for (int s = 0; s < PCOP_N_STAGES; ++s) l->stage_us[s] = 0.f;
     TRY(ensure_pack_capacity(l, mask));
   }
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[0], h->stream));
-  for (int l = 1; l < n_lanes; ++l) PCOP_CUDA_TRY(cudaStreamWaitEvent(lanes[l]->stream, h->ev_call[0], 0));
-  std::vector<int> status(n_lanes, PCOP_OK);
-  std::vector<std::thread> workers;
-  for (int l = 1; l < n_lanes; ++l)
-    workers.emplace_back([&, l]() {
-      status[l] = process_waves(lanes[l], xyzw, frame_stride_points, n, out, plan[l], on_device, mask);
-    });
-  status[0] = process_waves(h, xyzw, frame_stride_points, n, out, plan[0], on_device, mask);
-  for (std::thread& t : workers) t.join();
-  for (int l = 0; l < n_lanes; ++l)
-    if (status[l] != PCOP_OK) {
-      if (l > 0) h->err = lanes[l]->err;
-      return status[l];
+  for (size_t l = 0; l < lanes.size(); ++l) {
+    if (l > 0) PCOP_CUDA_TRY(cudaStreamWaitEvent(lanes[l]->stream, h->ev_call[0], 0));
+    PCOP_CUDA_TRY(cudaMemsetAsync(lanes[l]->sort.stats, 0, sizeof(unsigned long long), lanes[l]->stream));
+    if (mask & PCOP_OUT_DEVICE) PCOP_CUDA_TRY(cudaMemsetAsync(lanes[l]->d_pack_cursor, 0, sizeof(unsigned long long), lanes[l]->stream));
+  }
+  int status = PCOP_OK;
+  for (size_t w = 0; w < waves.size() && status == PCOP_OK; ++w) {
+    pcop_handle* l = lanes[w % lanes.size()];
+    status = finish_wave(l, wi, mask, out);  // (the lane's previous wave, if any)
+    if (status == PCOP_OK) status = enqueue_wave(l, wi, waves[w].first, waves[w].second, mask);
+    if (status != PCOP_OK && l != h) h->err = l->err;
+  }
+  // collect what is still in flight, oldest first
+  for (size_t k = 0; k < lanes.size(); ++k) {
+    pcop_handle* l = lanes[(waves.size() + k) % lanes.size()];
+    const int st = finish_wave(l, wi, mask, out);
+    if (st != PCOP_OK && status == PCOP_OK) {
+      status = st;
+      if (l != h) h->err = l->err;
     }
-  for (int l = 1; l < n_lanes; ++l) PCOP_CUDA_TRY(cudaStreamWaitEvent(h->stream, lanes[l]->ev_lane_done, 0));
+  }
+  for (pcop_handle* l : lanes) {  // the call is done when every lane's last result copy has landed
+    cudaMemcpyAsync(l->h_stats, l->sort.stats, sizeof(unsigned long long), cudaMemcpyDeviceToHost, l->stream);
+    cudaEventRecord(l->ev_lane_done, l->cstream);
+    cudaStreamWaitEvent(l->stream, l->ev_lane_done, 0);
+    cudaEventRecord(l->ev_lane_done, l->stream);
+    if (l != h) cudaStreamWaitEvent(h->stream, l->ev_lane_done, 0);
+  }
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[1], h->stream));
   PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_call[1]));
+  if (status != PCOP_OK) return status;
   float ms = 0.f;
   PCOP_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]));
   h->last_elapsed_us = ms * 1000.f;
-  for (int l = 1; l < n_lanes; ++l) {  // per-call accounting is reported on the handle (sums over the lanes)
-    h->launches += lanes[l]->launches;
-    h->alg_bytes += lanes[l]->alg_bytes;
-    h->d2h_bytes += lanes[l]->d2h_bytes;
-    h->sort_pass_keys += lanes[l]->sort_pass_keys;
-    for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] += lanes[l]->stage_us[s];
-    merge_kernel_timers(h, lanes[l]);
+  for (pcop_handle* l : lanes) {
+    l->sort_pass_keys = *l->h_stats;
+    // the host pack buffers are final now: turn the stored offsets into pointers
+    for (size_t fx : l->fixups) {
+      const void** slot = (const void**)((unsigned char*)out + fx);
+      const size_t off = (size_t)(uintptr_t)(*slot) - 1;
+      *slot = l->h_pack + off;
+    }
+    if (l == h) continue;  // per-call accounting is reported on the handle (sums over the lanes)
+    h->launches += l->launches;
+    h->alg_bytes += l->alg_bytes;
+    h->d2h_bytes += l->d2h_bytes;
+    h->sort_pass_keys += l->sort_pass_keys;
+    for (int s = 0; s < PCOP_N_STAGES; ++s) h->stage_us[s] += l->stage_us[s];
+    merge_kernel_timers(h, l);
   }
   return PCOP_OK;
 }
@@ -1472,8 +1374,10 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
   A(dalloc(h, &h->d_crop, BC));
   A(dalloc(h, &h->d_vox, BC));
   A(dalloc(h, &h->d_sor, BC));
-  A(dalloc(h, &h->d_pbuf[0], BC));
-  A(dalloc(h, &h->d_pbuf[1], BC));
+  // plane ping-pong clouds (only frames that need a second pass touch them): the cropped cloud and the input staging
+  // are dead by then (the fused voxel path gathers from the caller's / staged input before the plane stage starts)
+  h->d_pbuf[0] = h->d_crop;
+  h->d_pbuf[1] = h->d_in;
   A(dalloc(h, &h->d_rem, BC));
   A(dalloc(h, &h->d_sorted, BC));
   A(dalloc(h, &h->d_obst, BC));
@@ -1505,8 +1409,9 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
     h->sort.desc = (uint32_t*)d;
   }
   A(dalloc(h, &h->d_vf_flags, B));
-  A(dalloc(h, &h->d_vf_pair[0], BC));
-  A(dalloc(h, &h->d_vf_pair[1], BC));
+  // (key, index) pairs of the fused voxel path: they overlay the search-grid point list of SOR / clustering
+  h->d_vf_pair[0] = reinterpret_cast<unsigned long long*>(h->d_sorted);
+  h->d_vf_pair[1] = reinterpret_cast<unsigned long long*>(h->d_sorted) + BC;
   A(halloc(h, &h->h_vf_flags, B));
   A(dalloc(h, &h->sort.maxkey, B));
   A(dalloc(h, &h->sort.npass, B));
@@ -1526,6 +1431,7 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
   A(dalloc(h, &h->d_rng, RNG_TABLE));
   A(dalloc(h, &h->d_pack_off, (size_t)PK_N * B));
   A(dalloc(h, &h->d_meta, 1));
+  A(dalloc(h, &h->d_pack_cursor, 1));
   A(halloc(h, &h->h_n_active, 16));
   A(halloc(h, &h->h_counts, (size_t)CNT_ROWS * B));
   A(halloc(h, &h->h_warnings, B));
@@ -1551,24 +1457,10 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
         return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
   if ((e = cudaEventCreateWithFlags(&h->ev_lane_done, cudaEventDisableTiming)) != cudaSuccess)
     return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
-  {
-    // host waits spin (cudaStreamSynchronize).  PCOP_SYNC=block makes them sleep on a blocking-sync event instead;
-    // measured on B200 boxes it only ever lost: -5 % with one process on 24 cores, 4x slower with 8 processes on 32
-    // cores (58.5 -> 13.6 G points/s), so it stays an opt-in for hosts that cannot spare the cores.
-    bool block = false;
-    if (const char* sv = getenv("PCOP_SYNC")) block = (sv[0] == 'b' || sv[0] == 'B');
-    if (block && (e = cudaEventCreateWithFlags(&h->ev_block, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess)
-      return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
-  }
   if ((e = cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail(fail_cuda(h, e, "cudaStreamCreate", __FILE__, __LINE__));
-  for (int i = 0; i < 2; ++i)
-    if ((e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess)
-      return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
-  if ((e = cudaEventCreateWithFlags(&h->ev_vox_done, cudaEventDisableTiming)) != cudaSuccess)
-    return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
-  if ((e = cudaEventCreateWithFlags(&h->ev_rem_ready, cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&h->ev_rem_copied, cudaEventDisableTiming)) != cudaSuccess)
+  if ((e = cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_meta, cudaEventDisableTiming)) != cudaSuccess)
     return bail(fail_cuda(h, e, "event", __FILE__, __LINE__));
   st = ensure_pack_capacity(h, effective_outputs(h->params));
   if (st != PCOP_OK) return bail(st);
@@ -1577,21 +1469,20 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
 }
 
 int pcop_create(const pcop_params* params, int device, size_t max_points, int max_batch, pcop_handle** out) {
-  if (!params || !out || max_points == 0 || max_points > (size_t)(1u << 30) || max_batch < 1)
-    return fail(nullptr, PCOP_ERR_BAD_PARAM, "pcop_create: bad argument");
+  // (frame-major launches put the tile index in gridDim.y, and look-back descriptors carry 30-bit prefixes)
+  if (!params || !out || max_points == 0 || max_points > (size_t)65535 * BT_TILE || max_batch < 1)
+    return fail(nullptr, PCOP_ERR_BAD_PARAM, "pcop_create: bad argument (max_points must be in [1, 268431360])");
   *out = nullptr;
-  // lanes: max_batch frames are in flight at once, split over the lanes (PCOP_LANES overrides the default: 2 lanes,
-  // one more per 256 frames of max_batch beyond 512, at most 4)
-  int n_lanes = std::min(4, std::max(2, max_batch / 256));
-  {  // every lane is a spinning host thread: two lanes when the box has fewer than 8 hardware threads per GPU
-    int ndev_all = 1;
-    if (cudaGetDeviceCount(&ndev_all) != cudaSuccess || ndev_all < 1) ndev_all = 1;
-    if (std::thread::hardware_concurrency() < 8u * (unsigned)ndev_all) n_lanes = 2;
-  }
+  // Lanes (PCOP_LANES, default 3 once max_batch allows waves of 64 frames): every lane owns the buffers of one wave;
+  // a batched call keeps one wave in flight per lane.  Wave size (PCOP_WAVE_FRAMES, default max_batch / 4, at least
+  // 64): large enough to fill the GPU, small enough that the last wave's result copy -- the only one nothing
+  // overlaps -- is short.  Both knobs are read here, once; nothing on the frame path looks at the environment.
+  int wave_frames = std::min(max_batch, std::max(64, max_batch / 4));
+  if (const char* s = getenv("PCOP_WAVE_FRAMES")) wave_frames = (int)std::min<long>(std::max<long>(strtol(s, nullptr, 10), 1), max_batch);
+  int n_lanes = std::max(1, std::min(3, max_batch / wave_frames));
   if (const char* s = getenv("PCOP_LANES")) n_lanes = (int)std::min<long>(std::max<long>(strtol(s, nullptr, 10), 1), 8);
   n_lanes = std::max(1, std::min(n_lanes, max_batch / PCOP_MIN_LANE_WAVE));
-  // capacity of a lane: 5/4 of an even share, so that one call of max_batch frames can be dealt in uneven waves
-  const int lane_batch = n_lanes == 1 ? max_batch : std::min(max_batch, ((max_batch + n_lanes - 1) / n_lanes * 5 + 3) / 4);
+  const int lane_batch = n_lanes == 1 ? max_batch : std::min(max_batch, wave_frames + wave_frames / 4);
   pcop_handle* h = nullptr;
   int st = create_lane(params, device, max_points, lane_batch, &h);
   if (st != PCOP_OK) return st;
@@ -1603,6 +1494,14 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
       return st;
     }
     h->extra_lanes.push_back(x);
+  }
+  h->wave_frames = std::min(wave_frames, lane_batch);
+  h->trace = getenv("PCOP_TRACE") != nullptr;
+  h->ece_small_max = ece_small_limit();
+  if (const char* s = getenv("PCOP_PLANE_RESIDENT")) h->plane_resident = (s[0] == '0') ? 0 : 1;  // (the tests cover both paths)
+  for (pcop_handle* l : h->extra_lanes) {
+    l->ece_small_max = h->ece_small_max;
+    l->plane_resident = h->plane_resident;
   }
   *out = h;
   return PCOP_OK;
@@ -1619,9 +1518,6 @@ void pcop_destroy(pcop_handle* h) {
   for (void* p : h->host_allocs) cudaFreeHost(p);
   if (h->d_pack) cudaFree(h->d_pack);
   if (h->d_raw) cudaFree(h->d_raw);
-  if (h->d_rem_pack) cudaFree(h->d_rem_pack);
-  if (h->d_rem_pack_src) cudaFree(h->d_rem_pack_src);
-  if (h->d_rem_off) cudaFree(h->d_rem_off);
   if (h->d_occ) cudaFree(h->d_occ);
   if (h->d_shadow) cudaFree(h->d_shadow);
   if (h->h_pack) cudaFreeHost(h->h_pack);
@@ -1632,14 +1528,8 @@ void pcop_destroy(pcop_handle* h) {
   for (int i = 0; i < 2; ++i)
     if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
   if (h->ev_lane_done) cudaEventDestroy(h->ev_lane_done);
-  if (h->ev_block) cudaEventDestroy(h->ev_block);
-  if (h->ev_vox_done) cudaEventDestroy(h->ev_vox_done);
-  for (int i = 0; i < 2; ++i)
-    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
-  if (h->ev_rem_ready) cudaEventDestroy(h->ev_rem_ready);
-  if (h->ev_rem_copied) cudaEventDestroy(h->ev_rem_copied);
-  for (pcop_handle::PinnedChunk& ch : h->rem_chunks)
-    if (ch.p) cudaFreeHost(ch.p);
+  if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+  if (h->ev_meta) cudaEventDestroy(h->ev_meta);
   if (h->cstream) cudaStreamDestroy(h->cstream);
   for (int s = 0; s < PCOP_N_STAGES; ++s)
     for (int i = 0; i < 2; ++i)
@@ -1789,11 +1679,6 @@ static int pc2_ingest(pcop_handle* h, const unsigned char* data, int32_t n, int3
     if (bytes > h->raw_cap) {
       PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
       if (h->d_raw) cudaFree(h->d_raw);
-  if (h->d_rem_pack) cudaFree(h->d_rem_pack);
-  if (h->d_rem_pack_src) cudaFree(h->d_rem_pack_src);
-  if (h->d_rem_off) cudaFree(h->d_rem_off);
-  if (h->d_occ) cudaFree(h->d_occ);
-  if (h->d_shadow) cudaFree(h->d_shadow);
       h->d_raw = nullptr;
       h->raw_cap = 0;
       PCOP_CUDA_TRY(cudaMalloc((void**)&h->d_raw, bytes + bytes / 4 + 256));
@@ -2036,9 +1921,9 @@ int pcop_plane(pcop_handle* h, const float* xyzw, int32_t s, float* remaining_xy
   TRY(upload_single(h, xyzw, s, CNT_SOR));
   Ctx c = make_ctx(h, 1, s);
   PlaneArgs a = make_plane_args(h, h->d_in, h->cap, h->cnt(CNT_SOR));
+  a.large_tier = 1;
   cudaError_t e = run_plane(c, a);
   if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
-  run_plane_finalize(c, a, h->d_rem, h->d_rem_src);
   KL(c, "k_plane_record", k_plane_record<<<1, 32, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS), h->cnt(CNT_CLUS1), 1, 1));
   TRY(fetch_count(h, CNT_REM, p));
   TRY(fetch_warnings(h, warnings));
@@ -2064,7 +1949,7 @@ int pcop_cluster(pcop_handle* h, const float* xyzw, int32_t p, int32_t* cluster_
   if (!(h->params.euc_cluster_tolerance > 0.0f)) return fail(h, PCOP_ERR_BAD_PARAM, "euc_cluster_tolerance must be > 0");
   TRY(upload_single(h, xyzw, p, CNT_REM));
   Ctx c = make_ctx(h, 1, p);
-  run_cluster(c, make_cluster_args(h, h->d_in, h->cap, h->cnt(CNT_REM)));
+  run_cluster(c, make_cluster_args(h, h->d_in, h->cap, h->cnt(CNT_REM)), /*with_generic=*/true);
   TRY(fetch_count(h, CNT_CLUS, c_out));
   TRY(fetch_count(h, CNT_CLPTS, l_out));
   TRY(download(h, cluster_offsets, h->d_offsets, (size_t)(*c_out + 1) * 4));

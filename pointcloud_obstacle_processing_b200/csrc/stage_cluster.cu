@@ -563,13 +563,18 @@ int ece_small_limit() {
   return (int)std::min<long>(std::max<long>(v, 0), ECE_SMALL_MAX);
 }
 
-// Frames with at most `small_max` points are clustered by the fused shared-memory kernel (which also writes
-// their obstacles); the others by the generic path.  Returns true when some frame may have taken the generic
-// path, i.e. the generic centroid/radius kernel still has to run.
-bool run_cluster(const Ctx& c, const ClusterArgs& a) {
-  const int small_max = ece_small_limit();
+// Frames with at most a.small_max points are clustered by the fused shared-memory kernel (which also writes
+// their obstacles); the others by the generic path.  The host does not know the remaining-cloud sizes when it
+// enqueues the stage (nothing synchronises between the input upload and the wave's counts), so:
+//   with_generic = false  only the fused kernel is launched; frames above small_max get empty results and the caller
+//                         repeats the stage with with_generic = true once it has seen the counts (pcop_api.cu);
+//   with_generic = true   the generic kernels run as well, on the frames above small_max only.
+// Returns true when the generic centroid/radius kernel still has to run.
+bool run_cluster(const Ctx& c, const ClusterArgs& a, bool with_generic) {
+  const int small_max = a.small_max;
   const bool maybe_big = c.grid_cap > small_max;  // grid_cap bounds every frame's point count
-  if (maybe_big) {
+  const bool generic = maybe_big && (with_generic || small_max <= 0);
+  if (generic) {
     ClusterArgs g = a;
     if (small_max > 0) {
       KL(c, "k_ece_route", k_ece_route<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.n_in, a.n_route, small_max, c.B));
@@ -578,8 +583,8 @@ bool run_cluster(const Ctx& c, const ClusterArgs& a) {
     }
     run_cluster_generic(c, g);
   }
-  if (small_max > 0) run_cluster_small(c, a, small_max);
-  return maybe_big;
+  if (small_max > 0) run_cluster_small(c, a, small_max, /*zero_skipped=*/!generic);
+  return generic;
 }
 
 void run_centroid_radius(const Ctx& c, const ClusterArgs& a) {

@@ -264,11 +264,19 @@ __device__ const int ES_FWD_OFF[62] = {ES_FWD_LIST(ES_FWD_OFF_ENTRY)};  // packe
 
 __global__ void __launch_bounds__(ES_THREADS, 1)
     k_ece_small(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, float tol, float r2,
-                int min_size, int max_size, int small_max, int* __restrict__ offsets, int* __restrict__ indices,
-                int* __restrict__ n_clusters, int* __restrict__ n_cluster_pts, float4* __restrict__ obstacles, int cap) {
+                int min_size, int max_size, int small_max, int zero_skipped, int* __restrict__ offsets,
+                int* __restrict__ indices, int* __restrict__ n_clusters, int* __restrict__ n_cluster_pts,
+                float4* __restrict__ obstacles, int cap) {
   const int f = blockIdx.x;
   const int n = n_in[f];
-  if (n > small_max) return;  // this frame takes the generic path
+  if (n > small_max) {  // this frame takes the generic path (zero_skipped: it has not run yet -- empty result for now)
+    if (zero_skipped && threadIdx.x == 0) {
+      n_clusters[f] = 0;
+      n_cluster_pts[f] = 0;
+      offsets[(size_t)f * (cap + 1)] = 0;
+    }
+    return;
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* tk = reinterpret_cast<uint32_t*>(smem_raw + ES_A);
   float* px = reinterpret_cast<float*>(smem_raw + ES_A);
@@ -752,12 +760,12 @@ __global__ void __launch_bounds__(ES_THREADS, 1)
 
 }  // namespace
 
-void run_cluster_small(const Ctx& c, const ClusterArgs& a, int small_max) {
+void run_cluster_small(const Ctx& c, const ClusterArgs& a, int small_max, bool zero_skipped) {
   cudaFuncSetAttribute(k_ece_small, cudaFuncAttributeMaxDynamicSharedMemorySize, ES_SMEM_BYTES);  // per device, idempotent
   const float r2 = (float)((double)a.tol * (double)a.tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
   KL(c, "k_ece_small", k_ece_small<<<c.B, ES_THREADS, ES_SMEM_BYTES, c.stream>>>(
-      a.in, a.in_stride, a.n_in, a.tol, r2, a.min_size, a.max_size, small_max, a.offsets, a.indices, a.n_clusters,
-      a.n_cluster_pts, a.obstacles, c.cap));
+      a.in, a.in_stride, a.n_in, a.tol, r2, a.min_size, a.max_size, small_max, zero_skipped ? 1 : 0, a.offsets, a.indices,
+      a.n_clusters, a.n_cluster_pts, a.obstacles, c.cap));
   count_launch(c);
 }
 

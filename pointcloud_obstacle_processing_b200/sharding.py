@@ -44,6 +44,9 @@ def gather_results(frames, total_frames: int, device: Optional[torch.device] = N
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     device = device or torch.device("cpu")
     nloc = len(frames)
+    for f in frames:
+        if f.cluster_offsets is None or f.cluster_indices is None or f.obstacles is None:
+            raise ValueError("gather_results needs frames processed with outputs | OUT_CLUSTERS | OUT_OBSTACLES")
     c = np.array([f.n_clusters for f in frames], np.int64)
     l = np.array([f.n_cluster_points for f in frames], np.int64)
     offs = _pad_cat([f.cluster_offsets for f in frames], np.int32)

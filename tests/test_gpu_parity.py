@@ -32,6 +32,18 @@ def vox_path(request, monkeypatch):
     return request.param
 
 
+@pytest.fixture(params=["resident", "hostloop"])
+def plane_path(request, monkeypatch):
+    """The plane loop has two device paths: the frame-resident cluster kernel (one launch runs every pass) and the
+    host-looped kernels (the fallback for frames above 131072 points); PCOP_PLANE_RESIDENT=0 (read when the handle is
+    created) forces the latter."""
+    if request.param == "hostloop":
+        monkeypatch.setenv("PCOP_PLANE_RESIDENT", "0")
+    else:
+        monkeypatch.delenv("PCOP_PLANE_RESIDENT", raising=False)
+    return request.param
+
+
 def all_outputs(p):
     p = p.copy()
     p.outputs = abi.OUT_ALL
@@ -80,7 +92,7 @@ def test_stage_sor(frames):
 
 
 @pytest.mark.parametrize("config", [1, 2, 3])
-def test_stage_plane(config, frames):
+def test_stage_plane(config, frames, plane_path):
     p = synth.params(config)
     cloud, _ = O.crop(p, frames[config])
     cloud, _, _ = O.voxel(p, cloud)
@@ -328,8 +340,73 @@ def _compare_plane(p, cloud):
     return o
 
 
+def _planes_cloud(rng, n, fracs, noise=0.01):
+    """planes of decreasing size (fractions of n) plus uniform clutter: the loop of od.cpp:379 needs one pass per plane
+    until at most 30 % of the cloud is left"""
+    parts = []
+    for k, fr in enumerate(fracs):
+        m = int(n * fr)
+        uv = rng.uniform(-20, 20, size=(m, 2))
+        nrm = rng.normal(size=3)
+        nrm /= np.linalg.norm(nrm)
+        e1 = np.cross(nrm, [1.0, 0.3, 0.2])
+        e1 /= np.linalg.norm(e1)
+        e2 = np.cross(nrm, e1)
+        parts.append(uv[:, :1] * e1 + uv[:, 1:] * e2 + nrm * (3.0 * k) + rng.normal(size=(m, 1)) * noise * nrm)
+    rest = n - sum(len(q) for q in parts)
+    parts.append(rng.uniform(-25, 25, size=(rest, 3)))
+    pts = np.concatenate(parts).astype(np.float32)
+    return pts[rng.permutation(len(pts))]
+
+
+@pytest.mark.parametrize("n,fracs", [(30000, (0.35, 0.25, 0.15, 0.1)), (9000, (0.3, 0.2, 0.12, 0.1, 0.08)),
+                                     (100000, (0.4, 0.2, 0.15))])
+def test_plane_multi_pass(n, fracs, plane_path):
+    """several passes inside one launch: the second and later passes generate their hypotheses in the kernel and
+    reload the cloud that the previous pass wrote"""
+    p = synth.params(2)
+    rng = np.random.default_rng(77 + n)
+    o = _compare_plane(p, _cloud(_planes_cloud(rng, n, fracs)))
+    assert o["n_passes"] >= 3, o["n_passes"]
+
+
+def test_plane_frame_above_resident_capacity_takes_host_loop():
+    """more than 131072 points do not fit the cluster's shared memory: same result from the host-looped kernels"""
+    p = synth.params(2)
+    rng = np.random.default_rng(5)
+    o = _compare_plane(p, _cloud(_planes_cloud(rng, 150000, (0.45, 0.3))))
+    assert o["n_passes"] >= 2
+
+
+def test_plane_batch_frames_with_different_pass_counts():
+    """frames of one wave leave the loop after different numbers of passes (each cluster runs its own loop); also
+    empty and tiny frames, and a frame whose RANSAC finds no plane"""
+    p = all_outputs(synth.params(2))
+    p.enable_crop = 0
+    p.enable_voxel = 0
+    rng = np.random.default_rng(11)
+    clouds = [_planes_cloud(rng, 20000, (0.8,)), _planes_cloud(rng, 20000, (0.35, 0.3, 0.2)),
+              _planes_cloud(rng, 15000, (0.3, 0.2, 0.15, 0.1)), np.zeros((0, 3), np.float32),
+              rng.uniform(-5, 5, size=(2, 3)).astype(np.float32), _planes_cloud(rng, 20000, (0.5, 0.25)),
+              np.repeat(rng.uniform(-5, 5, size=(1, 3)), 50, axis=0).astype(np.float32)]
+    cap = max(len(c) for c in clouds)
+    batch = np.zeros((len(clouds), cap, 4), np.float32)
+    counts = np.array([len(c) for c in clouds], np.int32)
+    for f, c in enumerate(clouds):
+        batch[f, :len(c), :3] = c
+        batch[f, :len(c), 3] = 1.0
+    with ObstacleProcessor(p, cap, max_batch=len(clouds)) as op:
+        res = op.process_batch(batch, counts)
+    passes = []
+    for f in range(len(clouds)):
+        o = O.process(p, batch[f, :counts[f]])
+        compare_frames(res[f], o, p, f"frame{f}: ")
+        passes.append(o.n_plane_passes)
+    assert len(set(passes)) >= 3, passes
+
+
 @pytest.mark.parametrize("frac_line", [0.5, 0.9, 1.0])
-def test_plane_collinear_samples_redrawn(frac_line):
+def test_plane_collinear_samples_redrawn(frac_line, plane_path):
     """samples that fail isSampleGood are redrawn (consuming random numbers): the hypothesis generator's parallel
     fast path must hand such frames to the sequential replay; an all-collinear cloud exhausts the 1000 redraws"""
     p = synth.params(2)
@@ -638,3 +715,41 @@ def test_bench_size_batch_is_position_independent():
             got = [digest(fr) for fr in res]
             bad = [f for f in range(B) if got[f] != want[order[f]]]
             assert not bad, f"call {rep}: {len(bad)} of {B} frames differ from their source frame, first {bad[:5]}"
+
+
+def test_pointcloud2_staging_growth_keeps_the_other_buffers(frames):
+    """a PointCloud2 message larger than the raw staging buffer makes the library grow that buffer; the occupancy,
+    shadow and result buffers of the same handle must survive it (round-1 finding: they were freed with it)"""
+    from shadow_util import rigid
+    p = all_outputs(synth.params(2))
+    p.grid_opacity = 40
+    p.block_size = 0.25
+    n = synth.points_per_frame(2)
+    clouds = synth.frames(2, 300, 4)
+    sw, ws = rigid(0.1, 0.45, 0.0, [p.x_max + 0.8, 0.5 * (p.y_min + p.y_max), 1.2])
+    with ObstacleProcessor(p, n, max_batch=4) as op:
+        for rnd, npts in enumerate((4000, 30000, 90000)):  # each message more than 1.25x the previous one
+            grid, counts, row_avg = op.occupancy_grid(clouds[0])
+            og, oc, oa = O.occupancy_grid(p, clouds[0])
+            assert_bits_equal(grid, og, "grid")
+            res = op.process_batch(clouds)
+            r0 = res[0]
+            sg, rec, w = op.handle_shadow_casting(grid, r0.remaining_cloud, r0.cluster_offsets, r0.cluster_indices, ws, sw)
+            osg, orec, ow = O.occupancy_shadows(p, og, r0.remaining_cloud, r0.cluster_offsets, r0.cluster_indices, ws, sw)
+            assert_bits_equal(sg, osg, f"shadow grid, round {rnd}")
+            data = _make_pointcloud2(clouds[1][:npts, :3], 32, (0, 4, 8), seed=rnd)
+            op.accumulate_reset()
+            assert op.accumulate_pointcloud2(data, npts, 32, 0, 4, 8) == npts
+            g = op.process_accumulated()
+            o = O.process(p, clouds[1][:npts])
+            compare_frames(g, o, p, f"accumulated, round {rnd}: ")
+            for f in range(4):
+                compare_frames(res[f], O.process(p, clouds[f]), p, f"round {rnd} frame {f}: ")
+
+
+def test_python_wrappers_reject_device_results():
+    p = synth.params(2)
+    p.outputs = abi.OUT_DEFAULT | abi.OUT_DEVICE
+    with ObstacleProcessor(p, 1000) as op:
+        with pytest.raises(ValueError):
+            op.process(np.zeros((10, 4), np.float32))
