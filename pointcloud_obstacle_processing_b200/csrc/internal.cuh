@@ -136,8 +136,11 @@ struct VoxFusedPlan {
   int b0[3];       // floor(lo_a * inv)
   uint32_t nx, ny, nz;  // cells of the crop box per axis
   int bits, npass, digit_bits;
+  // partition variant (stage_voxel_part.cu): bucket = key >> part_shift, nb buckets per frame
+  int part_ok, part_shift, nb, nb_pad;
 };
 VoxFusedPlan make_vox_fused_plan(const pcop_params& p);
+void vox_part_plan(VoxFusedPlan& pl, size_t max_points);  // fills the partition fields of a plan
 size_t vox_fused_hist_elems(int B);
 size_t vox_fused_desc_bytes(int B, int cap);
 struct VoxelFusedArgs {
@@ -160,6 +163,40 @@ struct VoxelFusedArgs {
   int want_keys;     // PCL's voxel keys are an output (PCOP_OUT_VOXEL); otherwise they are not computed
 };
 void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a);
+
+// ---- fused crop + VoxelGrid, partition variant (stage_voxel_part.cu) ----------------------------------------------
+int vox_part_chunks(int max_n);
+int vox_part_group_bound(const VoxFusedPlan& pl, int max_n);  // worst-case groups of a frame of max_n points
+size_t vox_part_hist_elems(int B);
+size_t vox_part_start_elems(int B);
+size_t vox_part_bucket_elems(int B);
+struct VoxelPartArgs {
+  const float4* in;  // wave input (uncropped), frame-strided
+  size_t in_stride;
+  const int* n_in;
+  VoxFusedPlan plan;
+  float leaf;
+  MinMax* minmax;            // [B] min/max of the crop survivors
+  VoxelFrame* vf;            // [B]
+  uint32_t* ghist;           // [B][chunks][nb_pad] per-chunk bucket counts -> offsets inside the bucket
+  uint32_t* bucket_start;    // [B][16385]
+  unsigned short* ne_bucket; // [B][16384] non-empty buckets in key order
+  uint32_t* ne_start;        // [B][16385] their element starts (then M)
+  unsigned short* gfirst;    // [B][group_stride] first non-empty ordinal of every group (+ end marker)
+  int* n_groups;             // [B]
+  float4* part;              // [B*cap] {x, y, z, original index} partitioned by bucket
+  unsigned* desc;            // [B][group_stride] look-back descriptors
+  int group_stride;
+  int group_launch;          // groups per frame the reduce grid covers (a frame with more raises flag bit 2)
+  uint32_t* flags;           // [B] bit 0: NaN y/z survivor (generic path), bit 1: bucket too large (LSD path), bit 2: see above
+  uint32_t* warnings;        // [B] zeroed by the stage's init kernel when non-null
+  int* n_crop;               // [B] out: M
+  float4* out;               // [B*cap] voxel centroids
+  uint32_t* out_keys;
+  int* n_out;                // [B] V
+  int want_keys;
+};
+void run_voxel_part(const Ctx& c, const VoxelPartArgs& a);
 
 struct SorArgs {
   const float4* in;

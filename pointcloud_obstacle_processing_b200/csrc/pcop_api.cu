@@ -37,6 +37,7 @@ enum {  // rows of the per-frame count table (device: d_counts[row*maxB + f])
   CNT_CLUS1,  // C + 1 (CSR offsets length)
   CNT_CELLS,  // occupied clique cells (ECE scratch)
   CNT_ROUTE,  // point count as seen by the generic clustering path (ECE scratch)
+  CNT_GROUPS, // groups of the partition voxel path (scratch; the host sizes the next wave's reduce grid by it)
   CNT_ROWS
 };
 
@@ -176,8 +177,18 @@ struct pcop_handle {
   uint32_t* d_vf_flags = nullptr;  // [maxB]
   unsigned long long* d_vf_pair[2] = {nullptr, nullptr};
   uint32_t* h_vf_flags = nullptr;
-  bool force_generic = false;      // set while a wave is redone by the generic path
+  int vox_mode = 0;                // 0 generic crop + voxel kernels, 1 fused LSD path, 2 fused partition path (at create)
+  int vox_redo = -1;               // >= 0 while a wave is repeated: the mode to take instead of vox_mode
+  bool vox_full_groups = false;    // ... with the worst-case reduce grid of the partition path
   bool wave_used_fused = false;
+  uint32_t* d_vp_hist = nullptr;
+  uint32_t* d_vp_bstart = nullptr;
+  uint32_t* d_vp_nstart = nullptr;
+  unsigned short* d_vp_ne = nullptr;
+  unsigned short* d_vp_gfirst = nullptr;
+  unsigned* d_vp_desc = nullptr;
+  int vp_gstride = 0;              // worst-case groups per frame + 1
+  int vp_group_hint = 0;           // groups per frame the next wave's reduce grid covers (adapts to the frames seen)
   std::vector<pcop_handle*> extra_lanes;
   std::vector<size_t> fixups;  // result-pointer slots of the running call (byte offsets into the caller's array)
   cudaEvent_t ev_lane_done = nullptr;
@@ -226,11 +237,16 @@ void fill_rng_table(uint32_t seed, int* out, int count) {
   }
 }
 
-// fused crop + voxel fast path unless PCOP_VOXEL_FUSED=0 (the tests cover both paths)
-VoxFusedPlan make_plan(const pcop_params& p) {
+// crop + VoxelGrid paths: the fused partition path when the plan allows it, else the fused LSD path, else the generic
+// kernels.  PCOP_VOXEL_FUSED=0 forces the generic kernels, =lsd the LSD path (the tests cover all three).
+VoxFusedPlan make_plan(const pcop_params& p, size_t max_points, int* mode) {
   VoxFusedPlan pl = make_vox_fused_plan(p);
+  vox_part_plan(pl, max_points);
   const char* s = getenv("PCOP_VOXEL_FUSED");
   if (s && s[0] == '0') pl.ok = 0;
+  if (s && (s[0] == 'l' || s[0] == 'L')) pl.part_ok = 0;
+  if (!pl.ok) pl.part_ok = 0;
+  *mode = pl.part_ok ? 2 : (pl.ok ? 1 : 0);
   return pl;
 }
 
@@ -772,7 +788,8 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
   const pcop_params& p = h->params;
   Ctx c = make_ctx(h, B, max_n);  // no stage ever holds more points per frame than the largest input frame
   const int tiles = cdiv(h->cap, CT_TILE);
-  const bool fused_path = h->vplan.ok && !h->force_generic;
+  const int vmode = (h->vox_redo >= 0) ? h->vox_redo : h->vox_mode;
+  const bool fused_path = vmode != 0;
   if (!fused_path || (effective_outputs(p) & PCOP_OUT_CROP)) {  // (the fused voxel path zeroes the warnings itself)
     KL(c, "k_zero_u32", k_zero_u32<<<cdiv(B, 256), 256, 0, h->stream>>>(h->d_warnings, B));
     count_launch(c);
@@ -783,9 +800,44 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
   const int* cur_n = h->cnt(CNT_IN);
   bool have_minmax = false;
 
-  const bool fused = h->vplan.ok && !h->force_generic;
+  const bool fused = fused_path;
   h->wave_used_fused = fused;
-  if (fused) {
+  if (fused && vmode == 2) {
+    {
+      StageTimer t(h, PCOP_STAGE_CROP);
+      if (effective_outputs(p) & PCOP_OUT_CROP) run_crop(c, make_crop_args(h, cur, cur_stride, cur_n));
+    }
+    StageTimer t(h, PCOP_STAGE_VOXEL);
+    VoxelPartArgs a{};
+    a.in = cur;
+    a.in_stride = cur_stride;
+    a.n_in = cur_n;
+    a.plan = h->vplan;
+    a.leaf = p.downsample_size;
+    a.minmax = h->d_minmax;
+    a.vf = h->d_vf;
+    a.ghist = h->d_vp_hist;
+    a.bucket_start = h->d_vp_bstart;
+    a.ne_bucket = h->d_vp_ne;
+    a.ne_start = h->d_vp_nstart;
+    a.gfirst = h->d_vp_gfirst;
+    a.n_groups = h->cnt(CNT_GROUPS);
+    a.part = h->d_sorted;  // (the search-grid point list of SOR / clustering is not live yet)
+    a.desc = h->d_vp_desc;
+    a.group_stride = h->vp_gstride;
+    a.group_launch = h->vox_full_groups ? h->vp_gstride - 1 : std::min(h->vp_group_hint, vox_part_group_bound(h->vplan, max_n));
+    a.flags = h->d_vf_flags;
+    a.warnings = (effective_outputs(p) & PCOP_OUT_CROP) ? nullptr : h->d_warnings;  // zeroed by k_vp_init
+    a.n_crop = h->cnt(CNT_CROP);
+    a.out = h->d_vox;
+    a.out_keys = h->d_vox_keys;
+    a.n_out = h->cnt(CNT_VOX);
+    a.want_keys = (effective_outputs(p) & PCOP_OUT_VOXEL) ? 1 : 0;
+    run_voxel_part(c, a);
+    cur = h->d_vox;
+    cur_stride = h->cap;
+    cur_n = h->cnt(CNT_VOX);
+  } else if (fused) {
     // crop + VoxelGrid in one pass over the input (stage_voxel_fused.cu); the cropped cloud itself is only
     // materialised when it is a requested output
     {
@@ -991,12 +1043,21 @@ int finish_wave(pcop_handle* h, const WaveInput& wi, uint32_t mask, pcop_frame_r
   const int w0 = h->pend_w0, B = h->pend_B;
   PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_meta));
   if (h->wave_used_fused) {
-    bool redo = false;
-    for (int f = 0; f < B; ++f) redo = redo || h->h_vf_flags[f] != 0u;
-    if (redo) {  // the fast voxel path declined a frame of this wave (a survivor with a NaN y or z): generic path
-      h->force_generic = true;
+    uint32_t fl = 0u;
+    for (int f = 0; f < B; ++f) fl |= h->h_vf_flags[f];
+    if (h->vox_mode == 2 && h->vox_redo < 0) {  // size the next wave's reduce grid: 1.25 x the largest frame seen, >= 64
+      int mg = 0;
+      for (int f = 0; f < B; ++f) mg = std::max(mg, h->h_counts[(size_t)CNT_GROUPS * h->maxB + f]);
+      h->vp_group_hint = std::min(h->vp_gstride - 1, std::max(64, mg + mg / 4 + 8));
+    }
+    if (fl) {
+      // the fused voxel path declined a frame of this wave: a survivor with a NaN y or z (generic kernels), a bucket
+      // above the partition path's limit (LSD path), or more groups than the reduce grid covered (worst-case grid)
+      h->vox_redo = (fl & 1u) ? 0 : ((fl & 2u) ? 1 : 2);
+      h->vox_full_groups = true;
       const int st = enqueue_wave(h, wi, w0, B, mask);
-      h->force_generic = false;
+      h->vox_redo = -1;
+      h->vox_full_groups = false;
       TRY(st);
       PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_meta));
     }
@@ -1170,6 +1231,7 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   for (pcop_handle* l : lanes) {
     l->params = h->params;
     l->vplan = h->vplan;
+    l->vox_mode = h->vox_mode;
     l->launches = 0;
     l->alg_bytes = 0.0;
     l->d2h_bytes = 0.0;
@@ -1342,7 +1404,7 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
     return fail(nullptr, PCOP_ERR_CUDA, "pcop_create: device is not sm_100-class (kernels are built for sm_100a only)");
   pcop_handle* h = new pcop_handle();
   h->params = *params;
-  h->vplan = make_plan(*params);
+  h->vplan = make_plan(*params, max_points, &h->vox_mode);
   h->device = device;
   h->cap = (int)max_points;
   h->maxB = max_batch;
@@ -1409,6 +1471,16 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
     h->sort.desc = (uint32_t*)d;
   }
   A(dalloc(h, &h->d_vf_flags, B));
+  if (h->vplan.part_ok) {
+    h->vp_gstride = vox_part_group_bound(h->vplan, h->cap) + 1;
+    h->vp_group_hint = h->vp_gstride - 1;
+    A(dalloc(h, &h->d_vp_hist, vox_part_hist_elems(B)));
+    A(dalloc(h, &h->d_vp_bstart, vox_part_start_elems(B)));
+    A(dalloc(h, &h->d_vp_nstart, vox_part_start_elems(B)));
+    A(dalloc(h, &h->d_vp_ne, vox_part_bucket_elems(B)));
+    A(dalloc(h, &h->d_vp_gfirst, (size_t)B * h->vp_gstride));
+    A(dalloc(h, &h->d_vp_desc, (size_t)B * h->vp_gstride));
+  }
   // (key, index) pairs of the fused voxel path: they overlay the search-grid point list of SOR / clustering
   h->d_vf_pair[0] = reinterpret_cast<unsigned long long*>(h->d_sorted);
   h->d_vf_pair[1] = reinterpret_cast<unsigned long long*>(h->d_sorted) + BC;
@@ -1549,7 +1621,7 @@ int pcop_set_params(pcop_handle* h, const pcop_params* params) {
     PCOP_CUDA_TRY(cudaMemcpy(h->d_rng, tbl.data(), sizeof(int) * RNG_TABLE, cudaMemcpyHostToDevice));
   }
   h->params = *params;
-  h->vplan = make_plan(*params);
+  h->vplan = make_plan(*params, (size_t)h->cap, &h->vox_mode);
   for (pcop_handle* l : h->extra_lanes) {
     const int ls = pcop_set_params(l, params);
     if (ls != PCOP_OK) {

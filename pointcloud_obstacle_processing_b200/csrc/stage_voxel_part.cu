@@ -1,0 +1,657 @@
+// Fused crop + VoxelGrid, partition variant (reference: the crop of od.cpp:195-215 followed by downsample_cloud
+// od.cpp:271-296 -> pcl::VoxelGrid::applyFilter).  Same composite key as stage_voxel_fused.cu
+// ((F_z - B_z) * ny * nx + (F_y - B_y) * nx + (F_x - B_x), the lexicographic order PCL's own keys have), but the
+// global four-pass LSD sort of (key, index) pairs is replaced by ONE partition pass on the key's top bits and a
+// block-local direct-address step on the low bits:
+//
+//   k_vp_hist      crop predicate + key of every point; per-(chunk, bucket) counts (bucket = key >> S, <= 16384 buckets
+//                  per frame, 16-bit shared-memory counters), min/max of the survivors, the NaN-y/z flag;
+//   k_vp_scan      per frame: bucket starts (exclusive scan), per-chunk offsets inside each bucket, M, and the work
+//                  list of the reduce kernel: consecutive non-empty buckets are grouped greedily up to 2048 elements
+//                  or the bitmap's range (65536 keys);
+//   k_vp_scatter   second read of the input: every survivor goes to a slot of its (chunk, bucket) range -- slot taken
+//                  with a shared-memory atomic -- as {x, y, z, original index};
+//   k_vp_reduce    one block per group (<= 2048 elements), everything in shared memory: a bitmap over the group's key
+//                  range gives every voxel its rank (popcount prefix) -- i.e. its sorted position, without sorting; a
+//                  counting pass groups the elements by voxel; every element finds its place inside its voxel's run by
+//                  counting the smaller original indices (runs are ~2 points); one thread per voxel then sums its run
+//                  sequentially (PCL's order: ORACLE CHOICE "ascending original index"), divides by the float count and
+//                  writes the centroid at (voxels of earlier groups: decoupled look-back) + rank.
+//
+// Per survivor the kernels issue ~150 instructions where the LSD path issues ~560, and the survivors make one round
+// trip through HBM instead of four.  The order inside a bucket range depends on the atomics, but nothing observable
+// does: every voxel's points are put in ascending original index before they are summed.
+//
+// Declined frames (internal flags, the host repeats the wave): a survivor with a NaN y or z (bit 0: generic path, as
+// in stage_voxel_fused.cu), a bucket above 2048 points (bit 1: LSD path), more groups than the launch covered (bit 2:
+// this path again with the worst-case grid).
+#include <cmath>
+#include <cstdlib>
+
+#include "internal.cuh"
+#include "primitives.cuh"
+
+namespace pcop {
+#ifdef PCOP_VP_DEBUG_CLK
+__device__ long long g_vp_reduce_clk[16];  // phase timestamps of one block (tools/vp_phases.py)
+#define VP_CLK(k)                                                                          \
+  do {                                                                                     \
+    if (blockIdx.x == 5 && blockIdx.y == 20 && threadIdx.x == 0) g_vp_reduce_clk[k] = clock64(); \
+  } while (0)
+#else
+#define VP_CLK(k) \
+  do {            \
+  } while (0)
+#endif
+
+namespace {
+
+constexpr int VP_THREADS = 256;
+constexpr int VP_WARPS = VP_THREADS / 32;
+constexpr int VP_NB_MAX = 16384;        // buckets per frame
+constexpr int VP_MAX_CHUNKS = 8;        // histogram / scatter blocks per frame
+constexpr int VP_EMAX = 2048;           // elements per group (and per bucket)
+constexpr int VPR_THREADS = 512;        // reduce kernel: 16 warps per group, 4 elements per thread, all kept in registers
+constexpr int VPR_WARPS = VPR_THREADS / 32;
+constexpr int VP_EPT = VP_EMAX / VPR_THREADS;
+constexpr int VP_BITMAP_WORDS = 2048;   // 65536 keys per group
+constexpr int VP_KMAX = 256;            // buckets per group (<= VP_BITMAP_WORDS * 32 >> S)
+constexpr int VP_SCAN_THREADS = 512;
+constexpr int VP_SCAN_WARPS = VP_SCAN_THREADS / 32;
+constexpr int VP_MAX_ROUNDS = VP_NB_MAX / 32;
+
+__device__ __forceinline__ bool vp_keep(const float4 p, const VoxFusedPlan& pl) {
+  // od.cpp:197-199, literal: drop iff isnan(x) || x<x_min || x>x_max || z<z_min || z>z_max || y<y_min || y>y_max
+  return !((p.x != p.x) || p.x < pl.lim[0] || p.x > pl.lim[1] || p.z < pl.lim[4] || p.z > pl.lim[5] || p.y < pl.lim[2] ||
+           p.y > pl.lim[3]);
+}
+__device__ __forceinline__ uint32_t vp_key(float x, float y, float z, const VoxFusedPlan& pl) {
+  const int cx = __float2int_rz(floorf(fmul(x, pl.inv))) - pl.b0[0];
+  const int cy = __float2int_rz(floorf(fmul(y, pl.inv))) - pl.b0[1];
+  const int cz = __float2int_rz(floorf(fmul(z, pl.inv))) - pl.b0[2];
+  return (uint32_t)cx + pl.nx * ((uint32_t)cy + pl.ny * (uint32_t)cz);
+}
+// chunk c of a frame of n points: [i0, i1), multiples of 4 * VP_THREADS so that the unrolled loops stay aligned
+// (a chunk holds fewer than 65536 points: the per-chunk counters are 16 bits wide, see vox_part_plan)
+__device__ __forceinline__ void vp_chunk(int n, int chunks, int c, int& i0, int& i1) {
+  const int cs = cdiv(cdiv(n, chunks), 4 * VP_THREADS) * (4 * VP_THREADS);
+  i0 = min(c * cs, n);
+  i1 = min(i0 + cs, n);
+}
+
+__global__ void k_vp_init(MinMax* mm, uint32_t* __restrict__ flags, uint32_t* __restrict__ warnings, int B) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < B) {
+    if (warnings) warnings[f] = 0u;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mm[f].mn[a] = ORD_POS_FLT_MAX;
+      mm[f].mx[a] = ORD_NEG_FLT_MAX;
+    }
+    flags[f] = 0u;
+  }
+}
+
+template <bool NEED_MINMAX>
+__global__ void __launch_bounds__(VP_THREADS)
+    k_vp_hist(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
+              uint32_t* __restrict__ ghist, MinMax* __restrict__ minmax, uint32_t* __restrict__ flags, int chunks) {
+  const int c = blockIdx.x, f = blockIdx.y;
+  extern __shared__ uint32_t vp_sh[];  // [nb_pad / 2]: two 16-bit counters per word
+  __shared__ float shmm[VP_WARPS][6];
+  const int nwords = pl.nb_pad >> 1;
+  for (int w = threadIdx.x; w < nwords; w += VP_THREADS) vp_sh[w] = 0u;
+  __syncthreads();
+  const int n = n_in[f];
+  int i0, i1;
+  vp_chunk(n, chunks, c, i0, i1);
+  const float4* src = in + (size_t)f * in_stride;
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+  float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  bool odd = false;  // a survivor whose y or z is not finite
+  for (int b0 = i0 + threadIdx.x; b0 < i1; b0 += 4 * VP_THREADS) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = b0 + u * VP_THREADS;
+      const float qnan = __uint_as_float(0x7fc00000u);
+      p[u] = (i < i1) ? __ldg(src + i) : make_float4(qnan, 0.f, 0.f, 0.f);  // (a NaN x is dropped by the predicate)
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (vp_keep(p[u], pl)) {
+        odd = odd || !(fabsf(p[u].y) <= 3.0e38f) || !(fabsf(p[u].z) <= 3.0e38f);
+        if (NEED_MINMAX) {
+          const float v[3] = {p[u].x, p[u].y, p[u].z};
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {  // compare-based: NaN never updates (oracle voxel_setup)
+            if (v[a] < mn[a]) mn[a] = v[a];
+            if (v[a] > mx[a]) mx[a] = v[a];
+          }
+        }
+        // (the clamp only matters for NaN y / z survivors, whose frame is declined anyway)
+        const uint32_t bucket = min(vp_key(p[u].x, p[u].y, p[u].z, pl) >> pl.part_shift, (uint32_t)pl.nb - 1u);
+        atomicAdd(&vp_sh[bucket >> 1], 1u << ((bucket & 1u) * 16u));
+      }
+    }
+  }
+  if (__any_sync(FULL, odd) && lane_id() == 0) atomicOr(&flags[f], 1u);
+  if (NEED_MINMAX) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+        mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+      }
+    }
+    if (lane_id() == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        shmm[warp_id()][a] = mn[a];
+        shmm[warp_id()][3 + a] = mx[a];
+      }
+    }
+  }
+  __syncthreads();
+  if (NEED_MINMAX && threadIdx.x < 6) {
+    const int a = threadIdx.x;
+    float v = shmm[0][a];
+    for (int w = 1; w < VP_WARPS; ++w) v = (a < 3) ? fminf(v, shmm[w][a]) : fmaxf(v, shmm[w][a]);
+    if (a < 3) atomicMin(&minmax[f].mn[a], f2ord(v));
+    else atomicMax(&minmax[f].mx[a - 3], f2ord(v));
+  }
+  uint32_t* gh = ghist + ((size_t)f * chunks + c) * nwords;
+  for (int w = threadIdx.x; w < nwords; w += VP_THREADS) gh[w] = vp_sh[w];
+}
+
+// PCL's voxel frame from the min/max of the survivors (same arithmetic as stage_voxel.cu's k_voxel_setup; the host
+// has proven that the overflow guard cannot fire)
+__device__ void vp_setup_one(const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf, int f) {
+  VoxelFrame v;
+  v.inv = fdiv(1.0f, leaf);
+  unsigned div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float mn = ord2f(minmax[f].mn[a]), mx = ord2f(minmax[f].mx[a]);
+    v.min_b[a] = cvt_f2i(floorf(fmul(mn, v.inv)));
+    const int max_b = cvt_f2i(floorf(fmul(mx, v.inv)));
+    div_b[a] = (unsigned)max_b - (unsigned)v.min_b[a] + 1u;
+  }
+  v.overflow = 0;
+  v.mul1 = div_b[0];
+  v.mul2 = div_b[0] * div_b[1];
+  vf[f] = v;
+}
+
+__device__ __forceinline__ unsigned warp_incl_scan(unsigned v) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned up = __shfl_up_sync(FULL, v, o);
+    if (lane >= o) v += up;
+  }
+  return v;
+}
+
+// warp 0: exclusive scan, in place, of the n <= 32 * PER entries of `a` (shared memory); returns the total in every lane
+template <int PER>
+__device__ __forceinline__ unsigned warp0_excl_scan(uint32_t* a, int n) {
+  const int lane = lane_id();
+  unsigned v[PER];
+  unsigned sum = 0u;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lane * PER + j;
+    v[j] = (i < n) ? a[i] : 0u;
+    sum += v[j];
+  }
+  const unsigned incl = warp_incl_scan(sum);
+  unsigned run = incl - sum;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int i = lane * PER + j;
+    if (i < n) a[i] = run;
+    run += v[j];
+  }
+  return __shfl_sync(FULL, incl, 31);
+}
+
+// per-(chunk, bucket) 16-bit counts of bucket b; in-place conversion to exclusive offsets inside the bucket when WRITE
+template <bool WRITE>
+__device__ __forceinline__ unsigned vp_bucket_total(unsigned short* gh16, int nb_pad, int chunks, int b) {
+  unsigned v[VP_MAX_CHUNKS];
+#pragma unroll
+  for (int c = 0; c < VP_MAX_CHUNKS; ++c) v[c] = (c < chunks) ? (unsigned)gh16[(size_t)c * nb_pad + b] : 0u;
+  unsigned t = 0u;
+#pragma unroll
+  for (int c = 0; c < VP_MAX_CHUNKS; ++c) {
+    if (WRITE && c < chunks) gh16[(size_t)c * nb_pad + b] = (unsigned short)min(t, 65535u);
+    t += v[c];
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(VP_SCAN_THREADS)
+    k_vp_scan(uint32_t* __restrict__ ghist, uint32_t* __restrict__ bucket_start, unsigned short* __restrict__ ne_bucket,
+              uint32_t* __restrict__ ne_start,
+              unsigned short* __restrict__ gfirst, int* __restrict__ n_groups, int* __restrict__ n_crop,
+              uint32_t* __restrict__ flags, const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf,
+              VoxFusedPlan pl, int chunks, int want_keys, int gmax, int gstride) {
+  const int f = blockIdx.x, tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  __shared__ uint32_t s_rt[VP_MAX_ROUNDS + 1];  // elements before each round of 32 buckets
+  __shared__ uint32_t s_rn[VP_MAX_ROUNDS + 1];  // non-empty buckets before each round
+  __shared__ unsigned s_total[2];
+  if (want_keys && tid == 0) vp_setup_one(minmax, leaf, vf, f);
+  unsigned short* gh16 = reinterpret_cast<unsigned short*>(ghist + (size_t)f * chunks * (pl.nb_pad >> 1));
+  uint32_t* bs = bucket_start + (size_t)f * (VP_NB_MAX + 1);
+  unsigned short* ne_out = ne_bucket + (size_t)f * VP_NB_MAX;
+  uint32_t* ns_out = ne_start + (size_t)f * (VP_NB_MAX + 1);  // element start of every non-empty bucket, then M
+  const int nrounds = pl.nb_pad >> 5;
+  // ---- pass 1: per round of 32 buckets, elements and non-empty buckets ------------------------------------------------
+  bool too_big = false;
+  for (int r = warp; r < nrounds; r += VP_SCAN_WARPS) {
+    const int b = 32 * r + lane;
+    const unsigned t = (b < pl.nb) ? vp_bucket_total<false>(gh16, pl.nb_pad, chunks, b) : 0u;
+    too_big = too_big || t > (unsigned)VP_EMAX;
+    const unsigned sum = __reduce_add_sync(FULL, t);
+    const unsigned ne = (unsigned)__popc(__ballot_sync(FULL, t != 0u));
+    if (lane == 0) {
+      s_rt[r] = sum;
+      s_rn[r] = ne;
+    }
+  }
+  if (too_big) atomicOr(&flags[f], 2u);
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned m = warp0_excl_scan<VP_MAX_ROUNDS / 32>(s_rt, nrounds);
+    const unsigned ne = warp0_excl_scan<VP_MAX_ROUNDS / 32>(s_rn, nrounds);
+    if (lane == 0) {
+      s_total[0] = m;
+      s_total[1] = ne;
+      n_crop[f] = (int)m;
+    }
+  }
+  __syncthreads();
+  const unsigned M = s_total[0];
+  const int NE = (int)s_total[1];
+  // ---- pass 2: bucket starts, per-chunk offsets inside each bucket, the list of non-empty buckets -----------------------
+  for (int r = warp; r < nrounds; r += VP_SCAN_WARPS) {
+    const int b = 32 * r + lane;
+    const unsigned t = (b < pl.nb) ? vp_bucket_total<true>(gh16, pl.nb_pad, chunks, b) : 0u;
+    const unsigned incl = warp_incl_scan(t);
+    bs[b] = s_rt[r] + incl - t;  // (buckets past nb are empty: start = M)
+    const unsigned nz = __ballot_sync(FULL, t != 0u);
+    if (t != 0u) {
+      const unsigned o = s_rn[r] + __popc(nz & lanemask_lt());
+      ne_out[o] = (unsigned short)b;
+      ns_out[o] = s_rt[r] + incl - t;
+    }
+  }
+  if (tid == 0) {
+    bs[pl.nb_pad] = M;
+    ns_out[NE] = M;
+  }
+  __syncthreads();  // (the block's global writes are visible to the block)
+  // ---- groups (warp 0): greedy -- a group takes consecutive non-empty buckets while it stays within VP_EMAX elements and
+  // K buckets (the bitmap's key range), so most groups are nearly full.  32 ordinals per step: the lanes hold the END
+  // positions of ordinals o .. o + 31; the group that starts at position gs / ordinal go closes in front of the first of
+  // them that would break a limit (the scan's global writes above are visible: __syncthreads). ---------------------------------------------------------------------------------------
+  if (warp != 0) return;
+  const int K = min(VP_KMAX, (VP_BITMAP_WORDS * 32) >> pl.part_shift);
+  unsigned short* gf = gfirst + (size_t)f * gstride;
+  int ng = 0;
+  if (NE > 0) {
+    unsigned gs = 0u;  // element start of the open group
+    int go = 0;        // its first ordinal
+    if (lane == 0) gf[0] = 0;
+    ng = 1;
+    for (int base = 0; base < NE; base += 32) {
+      const int o = base + lane;
+      const unsigned st = (o < NE) ? ns_out[o] : 0u, en = (o < NE) ? ns_out[o + 1] : 0u;
+      while (true) {
+        // (o > go: the bucket that opens a group always fits -- a larger one has already declined the frame)
+        const bool breaks = (o < NE) && (o > go) && (en - gs > (unsigned)VP_EMAX || o - go >= K);
+        const unsigned m = __ballot_sync(FULL, breaks);
+        if (!m) break;
+        const int l = __ffs(m) - 1;  // ordinal base + l opens the next group
+        go = base + l;
+        gs = __shfl_sync(FULL, st, l);
+        if (lane == 0 && ng < gmax) gf[ng] = (unsigned short)go;
+        ++ng;
+      }
+    }
+  }
+  if (lane == 0) {
+    n_groups[f] = ng;
+    if (ng <= gmax) gf[ng] = (unsigned short)NE;
+    else atomicOr(&flags[f], 4u);
+  }
+}
+
+__global__ void __launch_bounds__(VP_THREADS)
+    k_vp_scatter(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
+                 const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ bucket_start,
+                 const uint32_t* __restrict__ flags, float4* __restrict__ part, int cap, int chunks) {
+  const int c = blockIdx.x, f = blockIdx.y;
+  if (flags[f]) return;  // a declined frame: the wave is repeated by another path
+  extern __shared__ uint32_t vp_sh[];  // [nb_pad / 2] next free slot (relative to the bucket's start) of this chunk's ranges
+  const int nwords = pl.nb_pad >> 1;
+  const uint32_t* gh = ghist + ((size_t)f * chunks + c) * nwords;
+  const uint32_t* bs = bucket_start + (size_t)f * (VP_NB_MAX + 1);
+  for (int w = threadIdx.x; w < nwords; w += VP_THREADS) vp_sh[w] = gh[w];
+  __syncthreads();
+  const int n = n_in[f];
+  int i0, i1;
+  vp_chunk(n, chunks, c, i0, i1);
+  const float4* src = in + (size_t)f * in_stride;
+  float4* dst = part + (size_t)f * cap;
+  for (int b0 = i0 + threadIdx.x; b0 < i1; b0 += 4 * VP_THREADS) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = b0 + u * VP_THREADS;
+      const float qnan = __uint_as_float(0x7fc00000u);
+      p[u] = (i < i1) ? __ldg(src + i) : make_float4(qnan, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (vp_keep(p[u], pl)) {
+        const uint32_t bucket = vp_key(p[u].x, p[u].y, p[u].z, pl) >> pl.part_shift;
+        const uint32_t sh = (bucket & 1u) * 16u;
+        const uint32_t old = atomicAdd(&vp_sh[bucket >> 1], 1u << sh);  // (no carry: a bucket holds at most 2048 points)
+        const uint32_t pos = __ldg(bs + bucket) + ((old >> sh) & 0xffffu);
+        dst[pos] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(b0 + u * VP_THREADS));
+      }
+    }
+  }
+}
+
+struct VpReduceSmem {
+  uint32_t bitmap[VP_BITMAP_WORDS];         // one bit per key of the group's range
+  unsigned short wprefix[VP_BITMAP_WORDS];  // voxels before each bitmap word, inside its round of 32 words
+  uint32_t rbase[VP_BITMAP_WORDS / 32 + 1]; // voxels before each round of 32 bitmap words
+  uint32_t start[VP_EMAX + 1];              // per voxel: point count, then first position of its run
+  uint32_t srt[VP_EMAX / 32 + 1];           // scratch of the run-length scan
+  int sidx[VP_EMAX];                        // original indices, grouped by voxel (any order inside a run)
+  float sx[VP_EMAX], sy[VP_EMAX], sz[VP_EMAX];  // coordinates, grouped by voxel, ascending original index inside a run
+  uint32_t bkt_start[VP_KMAX + 1];          // element start of the group's buckets
+  unsigned vbase, nvox;
+};
+
+template <bool WITH_KEYS>
+__global__ void __launch_bounds__(VPR_THREADS, 3)
+    k_vp_reduce(const float4* __restrict__ part,
+                const uint32_t* __restrict__ ne_start, const unsigned short* __restrict__ gfirst,
+                const int* __restrict__ n_groups, const uint32_t* __restrict__ flags, VoxFusedPlan pl,
+                const VoxelFrame* __restrict__ vf, float4* __restrict__ out, uint32_t* __restrict__ out_keys,
+                int* __restrict__ n_out, unsigned* __restrict__ desc, int cap, int gstride) {
+  const int f = blockIdx.x, g = blockIdx.y;  // frame-major dispatch (shallow look-back, see stage_voxel_fused.cu)
+  const int ng = n_groups[f];
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  if (flags[f] || g >= ng) {  // a declined frame, or no such group (ng == 0: no survivors)
+    if (g == 0 && tid == 0) n_out[f] = 0;
+    return;
+  }
+  VP_CLK(0);
+  extern __shared__ __align__(16) unsigned char vp_raw[];
+  VpReduceSmem& sm = *reinterpret_cast<VpReduceSmem*>(vp_raw);
+  const unsigned short* gf = gfirst + (size_t)f * gstride;
+  const int o0 = gf[g], o1 = gf[g + 1], KB = o1 - o0;
+  const int S = pl.part_shift;
+  const int wpb = (1 << S) >> 5;  // bitmap words per bucket (S >= 5)
+  if (tid <= KB) sm.bkt_start[tid] = ne_start[(size_t)f * (VP_NB_MAX + 1) + o0 + tid];  // (entry NE holds M)
+  const int nwords = KB * wpb;  // <= VP_BITMAP_WORDS
+  for (int w = tid; w < nwords; w += VPR_THREADS) sm.bitmap[w] = 0u;
+  __syncthreads();
+  const uint32_t e0 = sm.bkt_start[0];
+  const int E = (int)(sm.bkt_start[KB] - e0);  // <= VP_EMAX
+  const float4* src = part + (size_t)f * cap + e0;
+  VP_CLK(1);
+
+  // ---- pass 1: every element sets the bit of its key (loads four at a time) ---------------------------------------------
+  uint32_t slot[VP_EPT];  // position of the element's key in the bitmap; later (voxel rank << 16) | place inside its run
+  float4 p[VP_EPT];       // the thread's elements ({x, y, z, original index}) stay in registers until they are staged
+#pragma unroll
+  for (int k = 0; k < VP_EPT; ++k) {
+    const int e = tid + k * VPR_THREADS;
+    p[k] = (e < E) ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < VP_EPT; ++k) {
+    const int e = tid + k * VPR_THREADS;
+    slot[k] = 0u;
+    if (e < E) {
+      const uint32_t key = vp_key(p[k].x, p[k].y, p[k].z, pl);
+      // the element's bucket inside the group: the last one that starts at or before its position
+      int lo = 0, hi = KB - 1;
+      const uint32_t pos = e0 + (uint32_t)e;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sm.bkt_start[mid] <= pos) lo = mid;
+        else hi = mid - 1;
+      }
+      const uint32_t s = ((uint32_t)lo << S) | (key & ((1u << S) - 1u));
+      slot[k] = s;
+      atomicOr(&sm.bitmap[s >> 5], 1u << (s & 31u));
+    }
+  }
+  __syncthreads();
+  VP_CLK(2);
+  // ---- voxel ranks: exclusive popcount prefix over the bitmap words, rounds of 32 words dealt to the warps -----------------
+  const int nr = cdiv(nwords, 32);
+  for (int r = warp; r < nr; r += VPR_WARPS) {
+    const int w = 32 * r + lane;
+    const unsigned c = (w < nwords) ? (unsigned)__popc(sm.bitmap[w]) : 0u;
+    const unsigned incl = warp_incl_scan(c);
+    sm.wprefix[w] = (unsigned short)(incl - c);
+    if (lane == 31) sm.rbase[r] = incl;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned v = warp0_excl_scan<VP_BITMAP_WORDS / 32 / 32>(sm.rbase, nr);
+    if (lane == 0) sm.nvox = v;
+  }
+  __syncthreads();
+  const int V = (int)sm.nvox;
+  unsigned* dd = desc + (size_t)f * gstride;
+  if (tid == 0) st_volatile_u32(dd + g, ((g == 0) ? LB_PREFIX : LB_AGG) | (unsigned)V);  // early publish
+  for (int v = tid; v <= V; v += VPR_THREADS) sm.start[v] = 0u;
+  __syncthreads();
+  VP_CLK(3);
+  // ---- pass 2: a place for every element inside its voxel's run (any order), run lengths -------------------------------
+#pragma unroll
+  for (int k = 0; k < VP_EPT; ++k) {
+    const int e = tid + k * VPR_THREADS;
+    if (e < E) {
+      const uint32_t s = slot[k];
+      const uint32_t r = sm.rbase[s >> 10] + (uint32_t)sm.wprefix[s >> 5] +
+                         (uint32_t)__popc(sm.bitmap[s >> 5] & ((1u << (s & 31u)) - 1u));
+      const uint32_t j = atomicAdd(&sm.start[r], 1u);
+      slot[k] = (r << 16) | j;
+    }
+  }
+  __syncthreads();
+  VP_CLK(4);
+  {  // exclusive scan of the run lengths, in place, rounds of 32 voxels dealt to the warps
+    const int vr = cdiv(V, 32);
+    for (int r = warp; r < vr; r += VPR_WARPS) {
+      const int v = 32 * r + lane;
+      const unsigned c = (v < V) ? sm.start[v] : 0u;
+      const unsigned incl = warp_incl_scan(c);
+      if (v < V) sm.start[v] = incl - c;
+      if (lane == 31) sm.srt[r] = incl;
+    }
+    __syncthreads();
+    if (warp == 0) warp0_excl_scan<VP_EMAX / 32 / 32>(sm.srt, vr);
+    __syncthreads();
+    for (int r = warp; r < vr; r += VPR_WARPS) {
+      const int v = 32 * r + lane;
+      if (v < V) sm.start[v] += sm.srt[r];
+    }
+    if (tid == 0) sm.start[V] = (unsigned)E;
+  }
+  __syncthreads();
+  VP_CLK(5);
+  // ---- pass 3: original indices grouped by voxel; then every element counts the smaller indices of its run and puts its
+  // coordinates at that place (runs are ~2 points; a dense blob costs its run length per element) -----------------------
+#pragma unroll
+  for (int k = 0; k < VP_EPT; ++k) {
+    const int e = tid + k * VPR_THREADS;
+    if (e < E) sm.sidx[sm.start[slot[k] >> 16] + (slot[k] & 0xffffu)] = __float_as_int(p[k].w);
+  }
+  __syncthreads();
+  VP_CLK(6);
+#pragma unroll
+  for (int k = 0; k < VP_EPT; ++k) {
+    const int e = tid + k * VPR_THREADS;
+    if (e < E) {
+      const uint32_t r = slot[k] >> 16;
+      const int s0 = (int)sm.start[r], cnt = (int)sm.start[r + 1] - s0;
+      int rank = 0;
+      if (cnt > 1) {
+        const int mine = __float_as_int(p[k].w);
+        for (int t = 0; t < cnt; ++t) rank += (sm.sidx[s0 + t] < mine) ? 1 : 0;
+      }
+      sm.sx[s0 + rank] = p[k].x;
+      sm.sy[s0 + rank] = p[k].y;
+      sm.sz[s0 + rank] = p[k].z;
+    }
+  }
+  VP_CLK(7);
+  // voxels of the earlier groups of this frame (decoupled look-back; the aggregate was published above)
+  if (warp == 0 && g > 0) {
+    unsigned excl = 0u;
+    int look = g - 1;
+    while (true) {
+      const int idx = look - lane;
+      unsigned d = LB_PREFIX;  // lanes past the first group read as "prefix 0"
+      if (idx >= 0) {
+        d = ld_volatile_u32(dd + idx);
+        while ((d >> 30) == 0u) d = ld_volatile_u32(dd + idx);
+      }
+      const unsigned is_prefix = __ballot_sync(FULL, (d >> 30) == 2u);
+      const int first = is_prefix ? (__ffs(is_prefix) - 1) : 31;
+      unsigned v = (lane <= first) ? (d & LB_VALUE) : 0u;
+      v = __reduce_add_sync(FULL, v);
+      excl += v;
+      if (is_prefix) break;
+      look -= 32;
+    }
+    if (lane == 0) {
+      st_volatile_u32(dd + g, LB_PREFIX | (excl + (unsigned)V));
+      sm.vbase = excl;
+    }
+  } else if (tid == 0 && g == 0) {
+    sm.vbase = 0u;
+  }
+  __syncthreads();
+  VP_CLK(8);
+  const unsigned vbase = sm.vbase;
+  if (g == ng - 1 && tid == 0) n_out[f] = (int)(vbase + (unsigned)V);
+  // ---- one thread per voxel: sequential sum of its run, centroid ----------------------------------------------------------
+  VoxelFrame vfr;
+  float fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;
+  if (WITH_KEYS) {
+    vfr = vf[f];
+    fb0 = (float)vfr.min_b[0];
+    fb1 = (float)vfr.min_b[1];
+    fb2 = (float)vfr.min_b[2];
+  }
+  for (int v = tid; v < V; v += VPR_THREADS) {
+    const int s0 = (int)sm.start[v], s1 = (int)sm.start[v + 1];
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    for (int t = s0; t < s1; ++t) {
+      ax = fadd(ax, sm.sx[t]);
+      ay = fadd(ay, sm.sy[t]);
+      az = fadd(az, sm.sz[t]);
+    }
+    const float c = (float)(s1 - s0);
+    const size_t o = (size_t)f * cap + vbase + (unsigned)v;
+    out[o] = make_float4(fdiv(ax, c), fdiv(ay, c), fdiv(az, c), 1.0f);
+    if (WITH_KEYS) {  // PCL's key of this voxel, from one of its points (voxel_grid.hpp: ijk = floor(p*inv) - min_b)
+      const int i0 = cvt_f2i(fsub(floorf(fmul(sm.sx[s0], vfr.inv)), fb0));
+      const int i1 = cvt_f2i(fsub(floorf(fmul(sm.sy[s0], vfr.inv)), fb1));
+      const int i2 = cvt_f2i(fsub(floorf(fmul(sm.sz[s0], vfr.inv)), fb2));
+      out_keys[o] = (uint32_t)i0 + (uint32_t)i1 * vfr.mul1 + (uint32_t)i2 * vfr.mul2;
+    }
+  }
+  VP_CLK(9);
+}
+
+}  // namespace
+
+// Buckets of the partition path for a plan made by make_vox_fused_plan: S low key bits per bucket so that a frame has
+// at most 2^nbits buckets, nbits = clamp(log2(max_points) - 3, 8, 14) (about 8 points per bucket on average when the
+// survivors fill the box evenly; real frames are far from even, which is what the 2048-point bucket limit is for).
+void vox_part_plan(VoxFusedPlan& pl, size_t max_points) {
+  pl.part_ok = 0;
+  if (!pl.ok) return;
+  if (max_points > (size_t)VP_MAX_CHUNKS * 61440) return;  // a chunk's 16-bit counters: the LSD path takes larger frames
+  int lg = 0;
+  while (((size_t)1 << lg) < max_points) ++lg;
+  const int nbits = std::min(14, std::max(8, lg - 3));
+  const int shift = std::max(5, pl.bits - nbits);
+  if (pl.bits - shift > 14 || shift > 16) return;  // too many buckets / a bucket wider than the bitmap: the LSD path
+  const unsigned long long total = (unsigned long long)pl.nx * pl.ny * pl.nz;
+  pl.part_shift = shift;
+  pl.nb = (int)((total + (1ull << shift) - 1) >> shift);
+  if (pl.nb < 1) pl.nb = 1;
+  if (pl.nb > VP_NB_MAX) return;
+  pl.nb_pad = (pl.nb + 31) & ~31;
+  pl.part_ok = 1;
+}
+
+int vox_part_chunks(int max_n) { return std::max(1, std::min(VP_MAX_CHUNKS, max_n / 12288)); }
+// worst-case number of groups of a frame of max_n points
+int vox_part_group_bound(const VoxFusedPlan& pl, int max_n) {
+  const int K = std::min(VP_KMAX, (VP_BITMAP_WORDS * 32) >> pl.part_shift);
+  const int ne = std::min(pl.nb, max_n);
+  const long long b = 2ll * max_n / VP_EMAX + ne / K + 3;  // (two consecutive groups hold more than VP_EMAX elements or K buckets)
+  return (int)std::min<long long>(b, 65535);
+}
+size_t vox_part_hist_elems(int B) { return (size_t)B * VP_MAX_CHUNKS * (VP_NB_MAX / 2); }
+size_t vox_part_start_elems(int B) { return (size_t)B * (VP_NB_MAX + 1); }
+size_t vox_part_bucket_elems(int B) { return (size_t)B * VP_NB_MAX; }
+
+void run_voxel_part(const Ctx& c, const VoxelPartArgs& a) {
+  const VoxFusedPlan& pl = a.plan;
+  const int chunks = vox_part_chunks(c.grid_cap);
+  const int gmax = std::max(1, std::min(a.group_launch, a.group_stride - 1));
+  cudaMemsetAsync(a.desc, 0, (size_t)c.B * a.group_stride * sizeof(unsigned), c.stream);
+  KL(c, "k_vp_init", k_vp_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, a.warnings, c.B));
+  const size_t hsm = (size_t)(pl.nb_pad / 2) * sizeof(uint32_t);
+  if (a.want_keys)
+    KL(c, "k_vp_hist", k_vp_hist<true><<<dim3(chunks, c.B), VP_THREADS, hsm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.ghist,
+                                                                                        a.minmax, a.flags, chunks));
+  else
+    KL(c, "k_vp_hist", k_vp_hist<false><<<dim3(chunks, c.B), VP_THREADS, hsm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.ghist,
+                                                                                         a.minmax, a.flags, chunks));
+  KL(c, "k_vp_scan", k_vp_scan<<<c.B, VP_SCAN_THREADS, 0, c.stream>>>(a.ghist, a.bucket_start, a.ne_bucket, a.ne_start, a.gfirst, a.n_groups,
+                                                                      a.n_crop, a.flags, a.minmax, a.leaf, a.vf, pl, chunks,
+                                                                      a.want_keys, gmax, a.group_stride));
+  KL(c, "k_vp_scatter", k_vp_scatter<<<dim3(chunks, c.B), VP_THREADS, hsm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.ghist,
+                                                                                       a.bucket_start, a.flags, a.part, c.cap,
+                                                                                       chunks));
+  const size_t rsm = sizeof(VpReduceSmem);
+  if (a.want_keys) {
+    cudaFuncSetAttribute(k_vp_reduce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+    KL(c, "k_vp_reduce", k_vp_reduce<true><<<dim3(c.B, gmax), VPR_THREADS, rsm, c.stream>>>(
+                             a.part, a.ne_start, a.gfirst, a.n_groups, a.flags, pl, a.vf, a.out, a.out_keys,
+                             a.n_out, a.desc, c.cap, a.group_stride));
+  } else {
+    cudaFuncSetAttribute(k_vp_reduce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+    KL(c, "k_vp_reduce", k_vp_reduce<false><<<dim3(c.B, gmax), VPR_THREADS, rsm, c.stream>>>(
+                             a.part, a.ne_start, a.gfirst, a.n_groups, a.flags, pl, a.vf, a.out, a.out_keys,
+                             a.n_out, a.desc, c.cap, a.group_stride));
+  }
+  count_launch(c, 5);
+}
+
+}  // namespace pcop
+
+#ifdef PCOP_VP_DEBUG_CLK
+extern "C" int pcop_debug_vp_reduce_cycles(long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, pcop::g_vp_reduce_clk, sizeof(long long) * 16);
+}
+#endif

@@ -21,12 +21,15 @@ def ece_path(request, monkeypatch):
     return request.param
 
 
-@pytest.fixture(params=["voxfused", "voxgeneric"])
+@pytest.fixture(params=["voxpart", "voxlsd", "voxgeneric"])
 def vox_path(request, monkeypatch):
-    """crop + VoxelGrid has a fused fast path (one pass over the input, keys relative to the crop box) and the generic
-    two-stage path; PCOP_VOXEL_FUSED=0 (read when the handle is created) forces the generic one."""
+    """crop + VoxelGrid has two fused fast paths (keys relative to the crop box: the partition path and the LSD-sort
+    path it falls back to) and the generic two-stage path; PCOP_VOXEL_FUSED=lsd / =0 (read when the handle is created)
+    force the second / third."""
     if request.param == "voxgeneric":
         monkeypatch.setenv("PCOP_VOXEL_FUSED", "0")
+    elif request.param == "voxlsd":
+        monkeypatch.setenv("PCOP_VOXEL_FUSED", "lsd")
     else:
         monkeypatch.delenv("PCOP_VOXEL_FUSED", raising=False)
     return request.param
@@ -135,6 +138,68 @@ def test_pipeline_voxel_paths(config, frames, vox_path):
             g = op.process(cloud)
         o = O.process(p, cloud)
         compare_frames(g, o, p, f"config{config}/{vox_path}: ")
+
+
+def _voxel_only(p):
+    p = p.copy()
+    p.enable_sor = p.enable_plane = p.enable_cluster = 0
+    p.outputs = abi.OUT_CROP | abi.OUT_VOXEL
+    return p
+
+
+def _check_voxel(p, clouds, counts=None, max_batch=None):
+    clouds = np.ascontiguousarray(clouds, np.float32)
+    B = clouds.shape[0]
+    counts = np.full(B, clouds.shape[1], np.int32) if counts is None else counts
+    with ObstacleProcessor(p, clouds.shape[1], max_batch=max_batch or B) as op:
+        res = op.process_batch(clouds, counts)
+    for f in range(B):
+        o = O.process(p, clouds[f, :counts[f]])
+        assert res[f].n_crop == o.n_crop and res[f].n_voxel == o.n_voxel, (f, res[f].n_crop, o.n_crop, res[f].n_voxel, o.n_voxel)
+        assert_bits_equal(res[f].voxel_keys, o.voxel_keys, f"frame {f} voxel keys")
+        assert_bits_equal(res[f].voxel_centroids, o.voxel_centroids, f"frame {f} voxel centroids")
+    return res
+
+
+def test_voxel_partition_path_long_runs_and_big_buckets(vox_path):
+    """voxels with far more than 8 points (ordered by the whole block), more than 64 of them in one group (the list
+    overflows), and a bucket above 4096 points (the frame goes to the LSD path); centroids must stay bit-exact because
+    every voxel is summed in ascending original index"""
+    p = _voxel_only(synth.params(2))
+    rng = np.random.default_rng(123)
+    n = 40000
+    frames_ = []
+    # frame 0: 27 voxels x ~110 points inside a 0.3 m cube + background
+    a = np.concatenate([rng.uniform(0.0, 0.3, size=(3000, 3)) + [5.0, 5.0, 0.0], rng.uniform(-30, 30, size=(n - 3000, 3)) * [1, 1, 0.03]])
+    # frame 1: 125 voxels x 240 points: long runs everywhere, bucket far above 4096 points
+    b = np.concatenate([rng.uniform(0.0, 0.5, size=(30000, 3)) + [-3.0, 2.0, -1.0], rng.uniform(-30, 30, size=(n - 30000, 3)) * [1, 1, 0.03]])
+    # frame 2: all points in ONE voxel
+    c = rng.uniform(0.01, 0.09, size=(n, 3)) + [1.0, 1.0, 0.0]
+    # frame 3: ~700 voxels x 12 points in a thin slab (more than 64 long runs per group)
+    d = np.concatenate([rng.uniform(0.0, 1.0, size=(9000, 3)) * [2.6, 2.6, 0.1] + [10.0, -8.0, 0.2], rng.uniform(-30, 30, size=(n - 9000, 3)) * [1, 1, 0.03]])
+    for q in (a, b, c, d):
+        q = q.astype(np.float32)
+        frames_.append(_cloud(q[rng.permutation(n)]))
+    _check_voxel(p, np.stack(frames_))
+
+
+def test_voxel_partition_path_more_groups_than_the_grid_covers():
+    """the reduce grid is sized from the frames seen so far; a later wave with many more groups is detected on the
+    device and repeated with the worst-case grid"""
+    p = _voxel_only(synth.params(2))
+    rng = np.random.default_rng(124)
+    n = 120000
+    dense = (rng.uniform(-2, 2, size=(n, 3)) * [1, 1, 0.2]).astype(np.float32)     # few buckets, few groups
+    spread = (rng.uniform(-39.9, 39.9, size=(n, 3)) * [1, 1, 0.05]).astype(np.float32)
+    spread[:, 2] = rng.uniform(-2.4, 1.4, size=n)                                    # every bucket occupied
+    with ObstacleProcessor(p, n, max_batch=2) as op:
+        for cloud in (dense, dense, spread, spread, dense):
+            c4 = _cloud(cloud)
+            g = op.process(c4)
+            o = O.process(p, c4)
+            assert g.n_voxel == o.n_voxel
+            assert_bits_equal(g.voxel_keys, o.voxel_keys, "voxel keys")
+            assert_bits_equal(g.voxel_centroids, o.voxel_centroids, "voxel centroids")
 
 
 def test_pipeline_survivor_with_nan_yz_redone_by_generic_path(frames):
