@@ -169,6 +169,7 @@ int vox_part_chunks(int max_n);
 int vox_part_group_bound(const VoxFusedPlan& pl, int max_n);  // worst-case groups of a frame of max_n points
 size_t vox_part_hist_elems(int B);
 size_t vox_part_start_elems(int B);
+size_t vox_part_chunk_start_elems(int B);
 size_t vox_part_bucket_elems(int B);
 struct VoxelPartArgs {
   const float4* in;  // wave input (uncropped), frame-strided
@@ -179,10 +180,10 @@ struct VoxelPartArgs {
   MinMax* minmax;            // [B] min/max of the crop survivors
   VoxelFrame* vf;            // [B]
   uint32_t* ghist;           // [B][chunks][nb_pad] per-chunk bucket counts -> offsets inside the bucket
-  uint32_t* bucket_start;    // [B][16385]
+  uint32_t* chunk_start;     // [B][chunks][nb_pad] first slot of every (chunk, bucket) range
   unsigned short* ne_bucket; // [B][16384] non-empty buckets in key order
   uint32_t* ne_start;        // [B][16385] their element starts (then M)
-  unsigned short* gfirst;    // [B][group_stride] first non-empty ordinal of every group (+ end marker)
+  uint2* grec;               // [B][group_stride] {element start, first non-empty ordinal} of every group (+ end marker)
   int* n_groups;             // [B]
   float4* part;              // [B*cap] {x, y, z, original index} partitioned by bucket
   unsigned* desc;            // [B][group_stride] look-back descriptors

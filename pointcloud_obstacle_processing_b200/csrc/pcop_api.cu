@@ -185,7 +185,7 @@ struct pcop_handle {
   uint32_t* d_vp_bstart = nullptr;
   uint32_t* d_vp_nstart = nullptr;
   unsigned short* d_vp_ne = nullptr;
-  unsigned short* d_vp_gfirst = nullptr;
+  uint2* d_vp_grec = nullptr;
   unsigned* d_vp_desc = nullptr;
   int vp_gstride = 0;              // worst-case groups per frame + 1
   int vp_group_hint = 0;           // groups per frame the next wave's reduce grid covers (adapts to the frames seen)
@@ -817,10 +817,10 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
     a.minmax = h->d_minmax;
     a.vf = h->d_vf;
     a.ghist = h->d_vp_hist;
-    a.bucket_start = h->d_vp_bstart;
+    a.chunk_start = h->d_vp_bstart;
     a.ne_bucket = h->d_vp_ne;
     a.ne_start = h->d_vp_nstart;
-    a.gfirst = h->d_vp_gfirst;
+    a.grec = h->d_vp_grec;
     a.n_groups = h->cnt(CNT_GROUPS);
     a.part = h->d_sorted;  // (the search-grid point list of SOR / clustering is not live yet)
     a.desc = h->d_vp_desc;
@@ -1475,10 +1475,10 @@ static int create_lane(const pcop_params* params, int device, size_t max_points,
     h->vp_gstride = vox_part_group_bound(h->vplan, h->cap) + 1;
     h->vp_group_hint = h->vp_gstride - 1;
     A(dalloc(h, &h->d_vp_hist, vox_part_hist_elems(B)));
-    A(dalloc(h, &h->d_vp_bstart, vox_part_start_elems(B)));
+    A(dalloc(h, &h->d_vp_bstart, vox_part_chunk_start_elems(B)));
     A(dalloc(h, &h->d_vp_nstart, vox_part_start_elems(B)));
     A(dalloc(h, &h->d_vp_ne, vox_part_bucket_elems(B)));
-    A(dalloc(h, &h->d_vp_gfirst, (size_t)B * h->vp_gstride));
+    A(dalloc(h, &h->d_vp_grec, (size_t)B * h->vp_gstride));
     A(dalloc(h, &h->d_vp_desc, (size_t)B * h->vp_gstride));
   }
   // (key, index) pairs of the fused voxel path: they overlay the search-grid point list of SOR / clustering

@@ -8,7 +8,7 @@
 //                  per frame, 16-bit shared-memory counters), min/max of the survivors, the NaN-y/z flag;
 //   k_vp_scan      per frame: bucket starts (exclusive scan), per-chunk offsets inside each bucket, M, and the work
 //                  list of the reduce kernel: consecutive non-empty buckets are grouped greedily up to 2048 elements
-//                  or the bitmap's range (65536 keys);
+//                  or the bitmap's range (131072 keys);
 //   k_vp_scatter   second read of the input: every survivor goes to a slot of its (chunk, bucket) range -- slot taken
 //                  with a shared-memory atomic -- as {x, y, z, original index};
 //   k_vp_reduce    one block per group (<= 2048 elements), everything in shared memory: a bitmap over the group's key
@@ -26,6 +26,7 @@
 // in stage_voxel_fused.cu), a bucket above 2048 points (bit 1: LSD path), more groups than the launch covered (bit 2:
 // this path again with the worst-case grid).
 #include <cmath>
+#include <cstddef>
 #include <cstdlib>
 
 #include "internal.cuh"
@@ -54,7 +55,7 @@ constexpr int VP_EMAX = 2048;           // elements per group (and per bucket)
 constexpr int VPR_THREADS = 512;        // reduce kernel: 16 warps per group, 4 elements per thread, all kept in registers
 constexpr int VPR_WARPS = VPR_THREADS / 32;
 constexpr int VP_EPT = VP_EMAX / VPR_THREADS;
-constexpr int VP_BITMAP_WORDS = 2048;   // 65536 keys per group
+constexpr int VP_BITMAP_WORDS = 4096;   // 131072 keys per group
 constexpr int VP_KMAX = 256;            // buckets per group (<= VP_BITMAP_WORDS * 32 >> S)
 constexpr int VP_SCAN_THREADS = 512;
 constexpr int VP_SCAN_WARPS = VP_SCAN_THREADS / 32;
@@ -217,25 +218,20 @@ __device__ __forceinline__ unsigned warp0_excl_scan(uint32_t* a, int n) {
   return __shfl_sync(FULL, incl, 31);
 }
 
-// per-(chunk, bucket) 16-bit counts of bucket b; in-place conversion to exclusive offsets inside the bucket when WRITE
-template <bool WRITE>
-__device__ __forceinline__ unsigned vp_bucket_total(unsigned short* gh16, int nb_pad, int chunks, int b) {
-  unsigned v[VP_MAX_CHUNKS];
+// per-(chunk, bucket) 16-bit counts of bucket b -> v[], returns their sum
+__device__ __forceinline__ unsigned vp_bucket_total(const unsigned short* gh16, int nb_pad, int chunks, int b, unsigned (&v)[VP_MAX_CHUNKS]) {
 #pragma unroll
   for (int c = 0; c < VP_MAX_CHUNKS; ++c) v[c] = (c < chunks) ? (unsigned)gh16[(size_t)c * nb_pad + b] : 0u;
   unsigned t = 0u;
 #pragma unroll
-  for (int c = 0; c < VP_MAX_CHUNKS; ++c) {
-    if (WRITE && c < chunks) gh16[(size_t)c * nb_pad + b] = (unsigned short)min(t, 65535u);
-    t += v[c];
-  }
+  for (int c = 0; c < VP_MAX_CHUNKS; ++c) t += v[c];
   return t;
 }
 
 __global__ void __launch_bounds__(VP_SCAN_THREADS)
-    k_vp_scan(uint32_t* __restrict__ ghist, uint32_t* __restrict__ bucket_start, unsigned short* __restrict__ ne_bucket,
+    k_vp_scan(const uint32_t* __restrict__ ghist, uint32_t* __restrict__ chunk_start, unsigned short* __restrict__ ne_bucket,
               uint32_t* __restrict__ ne_start,
-              unsigned short* __restrict__ gfirst, int* __restrict__ n_groups, int* __restrict__ n_crop,
+              uint2* __restrict__ grec, int* __restrict__ n_groups, int* __restrict__ n_crop,
               uint32_t* __restrict__ flags, const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf,
               VoxFusedPlan pl, int chunks, int want_keys, int gmax, int gstride) {
   const int f = blockIdx.x, tid = threadIdx.x, lane = lane_id(), warp = warp_id();
@@ -243,8 +239,8 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   __shared__ uint32_t s_rn[VP_MAX_ROUNDS + 1];  // non-empty buckets before each round
   __shared__ unsigned s_total[2];
   if (want_keys && tid == 0) vp_setup_one(minmax, leaf, vf, f);
-  unsigned short* gh16 = reinterpret_cast<unsigned short*>(ghist + (size_t)f * chunks * (pl.nb_pad >> 1));
-  uint32_t* bs = bucket_start + (size_t)f * (VP_NB_MAX + 1);
+  const unsigned short* gh16 = reinterpret_cast<const unsigned short*>(ghist + (size_t)f * chunks * (pl.nb_pad >> 1));
+  uint32_t* cs_out = chunk_start + (size_t)f * chunks * pl.nb_pad;
   unsigned short* ne_out = ne_bucket + (size_t)f * VP_NB_MAX;
   uint32_t* ns_out = ne_start + (size_t)f * (VP_NB_MAX + 1);  // element start of every non-empty bucket, then M
   const int nrounds = pl.nb_pad >> 5;
@@ -252,7 +248,8 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   bool too_big = false;
   for (int r = warp; r < nrounds; r += VP_SCAN_WARPS) {
     const int b = 32 * r + lane;
-    const unsigned t = (b < pl.nb) ? vp_bucket_total<false>(gh16, pl.nb_pad, chunks, b) : 0u;
+    unsigned v[VP_MAX_CHUNKS];
+    const unsigned t = (b < pl.nb) ? vp_bucket_total(gh16, pl.nb_pad, chunks, b, v) : 0u;
     too_big = too_big || t > (unsigned)VP_EMAX;
     const unsigned sum = __reduce_add_sync(FULL, t);
     const unsigned ne = (unsigned)__popc(__ballot_sync(FULL, t != 0u));
@@ -278,9 +275,15 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   // ---- pass 2: bucket starts, per-chunk offsets inside each bucket, the list of non-empty buckets -----------------------
   for (int r = warp; r < nrounds; r += VP_SCAN_WARPS) {
     const int b = 32 * r + lane;
-    const unsigned t = (b < pl.nb) ? vp_bucket_total<true>(gh16, pl.nb_pad, chunks, b) : 0u;
+    unsigned v[VP_MAX_CHUNKS];
+    const unsigned t = (b < pl.nb) ? vp_bucket_total(gh16, pl.nb_pad, chunks, b, v) : 0u;
     const unsigned incl = warp_incl_scan(t);
-    bs[b] = s_rt[r] + incl - t;  // (buckets past nb are empty: start = M)
+    unsigned run = s_rt[r] + incl - t;  // the bucket's start (buckets past nb are empty: start = M)
+#pragma unroll
+    for (int c = 0; c < VP_MAX_CHUNKS; ++c) {  // absolute first slot of every (chunk, bucket) range, for the scatter kernel
+      if (c < chunks) cs_out[(size_t)c * pl.nb_pad + b] = run;
+      run += v[c];
+    }
     const unsigned nz = __ballot_sync(FULL, t != 0u);
     if (t != 0u) {
       const unsigned o = s_rn[r] + __popc(nz & lanemask_lt());
@@ -288,10 +291,7 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
       ns_out[o] = s_rt[r] + incl - t;
     }
   }
-  if (tid == 0) {
-    bs[pl.nb_pad] = M;
-    ns_out[NE] = M;
-  }
+  if (tid == 0) ns_out[NE] = M;
   __syncthreads();  // (the block's global writes are visible to the block)
   // ---- groups (warp 0): greedy -- a group takes consecutive non-empty buckets while it stays within VP_EMAX elements and
   // K buckets (the bitmap's key range), so most groups are nearly full.  32 ordinals per step: the lanes hold the END
@@ -299,12 +299,12 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   // them that would break a limit (the scan's global writes above are visible: __syncthreads). ---------------------------------------------------------------------------------------
   if (warp != 0) return;
   const int K = min(VP_KMAX, (VP_BITMAP_WORDS * 32) >> pl.part_shift);
-  unsigned short* gf = gfirst + (size_t)f * gstride;
+  uint2* gf = grec + (size_t)f * gstride;  // {element start, first non-empty ordinal} of every group, then {M, NE}
   int ng = 0;
   if (NE > 0) {
     unsigned gs = 0u;  // element start of the open group
     int go = 0;        // its first ordinal
-    if (lane == 0) gf[0] = 0;
+    if (lane == 0) gf[0] = make_uint2(0u, 0u);
     ng = 1;
     for (int base = 0; base < NE; base += 32) {
       const int o = base + lane;
@@ -317,147 +317,187 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
         const int l = __ffs(m) - 1;  // ordinal base + l opens the next group
         go = base + l;
         gs = __shfl_sync(FULL, st, l);
-        if (lane == 0 && ng < gmax) gf[ng] = (unsigned short)go;
+        if (lane == 0 && ng < gmax) gf[ng] = make_uint2(gs, (unsigned)go);
         ++ng;
       }
     }
   }
   if (lane == 0) {
     n_groups[f] = ng;
-    if (ng <= gmax) gf[ng] = (unsigned short)NE;
+    if (ng <= gmax) gf[ng] = make_uint2(M, (unsigned)NE);
     else atomicOr(&flags[f], 4u);
   }
 }
 
 __global__ void __launch_bounds__(VP_THREADS)
     k_vp_scatter(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
-                 const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ bucket_start,
-                 const uint32_t* __restrict__ flags, float4* __restrict__ part, int cap, int chunks) {
+                 const uint32_t* __restrict__ chunk_start, const uint32_t* __restrict__ flags, float4* __restrict__ part,
+                 int cap, int chunks) {
   const int c = blockIdx.x, f = blockIdx.y;
   if (flags[f]) return;  // a declined frame: the wave is repeated by another path
-  extern __shared__ uint32_t vp_sh[];  // [nb_pad / 2] next free slot (relative to the bucket's start) of this chunk's ranges
-  const int nwords = pl.nb_pad >> 1;
-  const uint32_t* gh = ghist + ((size_t)f * chunks + c) * nwords;
-  const uint32_t* bs = bucket_start + (size_t)f * (VP_NB_MAX + 1);
-  for (int w = threadIdx.x; w < nwords; w += VP_THREADS) vp_sh[w] = gh[w];
+  extern __shared__ uint32_t vp_sh[];  // [nb_pad] next free slot of every (this chunk, bucket) range
+  const uint32_t* cs = chunk_start + ((size_t)f * chunks + c) * pl.nb_pad;
+  for (int b = threadIdx.x; b < pl.nb_pad; b += VP_THREADS) vp_sh[b] = cs[b];
   __syncthreads();
   const int n = n_in[f];
   int i0, i1;
   vp_chunk(n, chunks, c, i0, i1);
   const float4* src = in + (size_t)f * in_stride;
   float4* dst = part + (size_t)f * cap;
+  // software-pipelined: the next four loads are in flight while the current four points are placed
+  const float qnan = __uint_as_float(0x7fc00000u);
+  float4 nxt[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + threadIdx.x + u * VP_THREADS;
+    nxt[u] = (i < i1) ? __ldg(src + i) : make_float4(qnan, 0.f, 0.f, 0.f);
+  }
   for (int b0 = i0 + threadIdx.x; b0 < i1; b0 += 4 * VP_THREADS) {
     float4 p[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = b0 + u * VP_THREADS;
-      const float qnan = __uint_as_float(0x7fc00000u);
-      p[u] = (i < i1) ? __ldg(src + i) : make_float4(qnan, 0.f, 0.f, 0.f);
+      p[u] = nxt[u];
+      const int i = b0 + (4 + u) * VP_THREADS;
+      nxt[u] = (i < i1) ? __ldg(src + i) : make_float4(qnan, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (vp_keep(p[u], pl)) {
         const uint32_t bucket = vp_key(p[u].x, p[u].y, p[u].z, pl) >> pl.part_shift;
-        const uint32_t sh = (bucket & 1u) * 16u;
-        const uint32_t old = atomicAdd(&vp_sh[bucket >> 1], 1u << sh);  // (no carry: a bucket holds at most 2048 points)
-        const uint32_t pos = __ldg(bs + bucket) + ((old >> sh) & 0xffffu);
+        const uint32_t pos = atomicAdd(&vp_sh[bucket], 1u);
         dst[pos] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(b0 + u * VP_THREADS));
       }
     }
   }
 }
 
-struct VpReduceSmem {
+struct alignas(16) VpReduceSmem {
   uint32_t bitmap[VP_BITMAP_WORDS];         // one bit per key of the group's range
-  unsigned short wprefix[VP_BITMAP_WORDS];  // voxels before each bitmap word, inside its round of 32 words
-  uint32_t rbase[VP_BITMAP_WORDS / 32 + 1]; // voxels before each round of 32 bitmap words
-  uint32_t start[VP_EMAX + 1];              // per voxel: point count, then first position of its run
-  uint32_t srt[VP_EMAX / 32 + 1];           // scratch of the run-length scan
+  unsigned short wprefix[VP_BITMAP_WORDS];  // voxels before each bitmap word, inside its round of 128 words
+  uint32_t rbase[VP_BITMAP_WORDS / 128 + 4];  // voxels before each round of 128 bitmap words (sized to keep `start` 16-byte aligned)
+  uint32_t start[VP_EMAX + 4];              // per voxel: point count, then first position of its run
+  uint32_t srt[VP_EMAX / 128 + 1];          // scratch of the run-length scan
   int sidx[VP_EMAX];                        // original indices, grouped by voxel (any order inside a run)
   float sx[VP_EMAX], sy[VP_EMAX], sz[VP_EMAX];  // coordinates, grouped by voxel, ascending original index inside a run
   uint32_t bkt_start[VP_KMAX + 1];          // element start of the group's buckets
+  unsigned short bkt_id[VP_KMAX];
+  unsigned char ord_tab[VP_ORD_TAB];        // bucket id - first bucket id -> ordinal inside the group
   unsigned vbase, nvox;
 };
 
+static_assert(offsetof(VpReduceSmem, start) % 16 == 0 && offsetof(VpReduceSmem, wprefix) % 8 == 0, "vector accesses");
+
+// exclusive scan of four consecutive values per lane over a round of 128 values: returns the lane's exclusive prefix
+// inside the round (of its first value) and the round's total (all lanes)
+__device__ __forceinline__ unsigned vp_round_scan(const unsigned (&c)[4], unsigned& total) {
+  const unsigned mine = c[0] + c[1] + c[2] + c[3];
+  const unsigned incl = warp_incl_scan(mine);
+  total = __shfl_sync(FULL, incl, 31);
+  return incl - mine;
+}
+
 template <bool WITH_KEYS>
 __global__ void __launch_bounds__(VPR_THREADS, 3)
-    k_vp_reduce(const float4* __restrict__ part,
-                const uint32_t* __restrict__ ne_start, const unsigned short* __restrict__ gfirst,
+    k_vp_reduce(const float4* __restrict__ part, const uint32_t* __restrict__ ne_start,
+                const unsigned short* __restrict__ ne_bucket, const uint2* __restrict__ grec,
                 const int* __restrict__ n_groups, const uint32_t* __restrict__ flags, VoxFusedPlan pl,
                 const VoxelFrame* __restrict__ vf, float4* __restrict__ out, uint32_t* __restrict__ out_keys,
                 int* __restrict__ n_out, unsigned* __restrict__ desc, int cap, int gstride) {
   const int f = blockIdx.x, g = blockIdx.y;  // frame-major dispatch (shallow look-back, see stage_voxel_fused.cu)
-  const int ng = n_groups[f];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-  if (flags[f] || g >= ng) {  // a declined frame, or no such group (ng == 0: no survivors)
+  // (four independent loads; the records of a frame that has fewer groups are stale but harmless)
+  const int ng = n_groups[f];
+  const uint32_t declined = flags[f];
+  const uint2 r0 = grec[(size_t)f * gstride + g], r1 = grec[(size_t)f * gstride + g + 1];
+  if (declined || g >= ng) {  // a declined frame, or no such group (ng == 0: no survivors)
     if (g == 0 && tid == 0) n_out[f] = 0;
     return;
   }
   VP_CLK(0);
   extern __shared__ __align__(16) unsigned char vp_raw[];
   VpReduceSmem& sm = *reinterpret_cast<VpReduceSmem*>(vp_raw);
-  const unsigned short* gf = gfirst + (size_t)f * gstride;
-  const int o0 = gf[g], o1 = gf[g + 1], KB = o1 - o0;
-  const int S = pl.part_shift;
-  const int wpb = (1 << S) >> 5;  // bitmap words per bucket (S >= 5)
-  if (tid <= KB) sm.bkt_start[tid] = ne_start[(size_t)f * (VP_NB_MAX + 1) + o0 + tid];  // (entry NE holds M)
-  const int nwords = KB * wpb;  // <= VP_BITMAP_WORDS
-  for (int w = tid; w < nwords; w += VPR_THREADS) sm.bitmap[w] = 0u;
-  __syncthreads();
-  const uint32_t e0 = sm.bkt_start[0];
-  const int E = (int)(sm.bkt_start[KB] - e0);  // <= VP_EMAX
+  const uint32_t e0 = r0.x;
+  const int E = (int)(r1.x - r0.x);  // <= VP_EMAX
+  const int o0 = (int)r0.y, KB = (int)(r1.y - r0.y);
   const float4* src = part + (size_t)f * cap + e0;
-  VP_CLK(1);
-
-  // ---- pass 1: every element sets the bit of its key (loads four at a time) ---------------------------------------------
-  uint32_t slot[VP_EPT];  // position of the element's key in the bitmap; later (voxel rank << 16) | place inside its run
-  float4 p[VP_EPT];       // the thread's elements ({x, y, z, original index}) stay in registers until they are staged
+  // the thread's elements ({x, y, z, original index}) stay in registers until they are staged in sorted order
+  float4 p[VP_EPT];
 #pragma unroll
   for (int k = 0; k < VP_EPT; ++k) {
     const int e = tid + k * VPR_THREADS;
     p[k] = (e < E) ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  const int S = pl.part_shift;
+  const int wpb = (1 << S) >> 5;  // bitmap words per bucket (S >= 5)
+  const int nwords = KB * wpb;    // <= VP_BITMAP_WORDS
+  int my_bucket = 0;
+  if (tid < KB) {
+    my_bucket = ne_bucket[(size_t)f * VP_NB_MAX + o0 + tid];
+    sm.bkt_id[tid] = (unsigned short)my_bucket;
+  }
+  if (tid <= KB) sm.bkt_start[tid] = ne_start[(size_t)f * (VP_NB_MAX + 1) + o0 + tid];  // (entry NE holds M)
+  for (int w = 4 * tid; w < nwords; w += 4 * VPR_THREADS)  // (whole uint4s: the scans read them as such)
+    *reinterpret_cast<uint4*>(&sm.bitmap[w]) = make_uint4(0u, 0u, 0u, 0u);
+  for (int v = 4 * tid; v < E + 4; v += 4 * VPR_THREADS) *reinterpret_cast<uint4*>(&sm.start[v]) = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const int b_first = sm.bkt_id[0];
+  const bool direct = (int)sm.bkt_id[KB - 1] - b_first < VP_ORD_TAB;  // (else: binary search on the bucket starts)
+  if (direct && tid < KB) sm.ord_tab[my_bucket - b_first] = (unsigned char)tid;
+  __syncthreads();
+  VP_CLK(1);
+
+  // ---- pass 1: every element sets the bit of its key ---------------------------------------------------------------------
+  uint32_t slot[VP_EPT];  // position of the element's key in the bitmap; later (voxel rank << 16) | place inside its run
 #pragma unroll
   for (int k = 0; k < VP_EPT; ++k) {
     const int e = tid + k * VPR_THREADS;
     slot[k] = 0u;
     if (e < E) {
       const uint32_t key = vp_key(p[k].x, p[k].y, p[k].z, pl);
-      // the element's bucket inside the group: the last one that starts at or before its position
-      int lo = 0, hi = KB - 1;
-      const uint32_t pos = e0 + (uint32_t)e;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (sm.bkt_start[mid] <= pos) lo = mid;
-        else hi = mid - 1;
+      int ord;
+      if (direct) {
+        ord = sm.ord_tab[(int)(key >> S) - b_first];
+      } else {  // the last bucket that starts at or before the element's position
+        int lo = 0, hi = KB - 1;
+        const uint32_t pos = e0 + (uint32_t)e;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (sm.bkt_start[mid] <= pos) lo = mid;
+          else hi = mid - 1;
+        }
+        ord = lo;
       }
-      const uint32_t s = ((uint32_t)lo << S) | (key & ((1u << S) - 1u));
+      const uint32_t s = ((uint32_t)ord << S) | (key & ((1u << S) - 1u));
       slot[k] = s;
       atomicOr(&sm.bitmap[s >> 5], 1u << (s & 31u));
     }
   }
   __syncthreads();
   VP_CLK(2);
-  // ---- voxel ranks: exclusive popcount prefix over the bitmap words, rounds of 32 words dealt to the warps -----------------
-  const int nr = cdiv(nwords, 32);
+  // ---- voxel ranks: exclusive popcount prefix over the bitmap words; a warp takes a round of 128 words, four consecutive
+  // words per lane (one 16-byte load) ----------------------------------------------------------------------------------------
+  const int nr = cdiv(nwords, 128);
   for (int r = warp; r < nr; r += VPR_WARPS) {
-    const int w = 32 * r + lane;
-    const unsigned c = (w < nwords) ? (unsigned)__popc(sm.bitmap[w]) : 0u;
-    const unsigned incl = warp_incl_scan(c);
-    sm.wprefix[w] = (unsigned short)(incl - c);
-    if (lane == 31) sm.rbase[r] = incl;
+    const int w = 128 * r + 4 * lane;
+    const uint4 bw = (w < nwords) ? *reinterpret_cast<const uint4*>(&sm.bitmap[w]) : make_uint4(0u, 0u, 0u, 0u);  // (nwords % 4 == 0)
+    const unsigned c[4] = {(unsigned)__popc(bw.x), (unsigned)__popc(bw.y), (unsigned)__popc(bw.z), (unsigned)__popc(bw.w)};
+    unsigned total;
+    const unsigned ex = vp_round_scan(c, total);
+    if (w < nwords) {
+      const unsigned a0 = ex, a1 = a0 + c[0], a2 = a1 + c[1], a3 = a2 + c[2];
+      *reinterpret_cast<uint2*>(&sm.wprefix[w]) = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
+    }
+    if (lane == 0) sm.rbase[r] = total;
   }
   __syncthreads();
   if (warp == 0) {
-    const unsigned v = warp0_excl_scan<VP_BITMAP_WORDS / 32 / 32>(sm.rbase, nr);
+    const unsigned v = warp0_excl_scan<1>(sm.rbase, nr);  // (<= 32 rounds)
     if (lane == 0) sm.nvox = v;
   }
   __syncthreads();
   const int V = (int)sm.nvox;
   unsigned* dd = desc + (size_t)f * gstride;
   if (tid == 0) st_volatile_u32(dd + g, ((g == 0) ? LB_PREFIX : LB_AGG) | (unsigned)V);  // early publish
-  for (int v = tid; v <= V; v += VPR_THREADS) sm.start[v] = 0u;
-  __syncthreads();
   VP_CLK(3);
   // ---- pass 2: a place for every element inside its voxel's run (any order), run lengths -------------------------------
 #pragma unroll
@@ -465,7 +505,7 @@ __global__ void __launch_bounds__(VPR_THREADS, 3)
     const int e = tid + k * VPR_THREADS;
     if (e < E) {
       const uint32_t s = slot[k];
-      const uint32_t r = sm.rbase[s >> 10] + (uint32_t)sm.wprefix[s >> 5] +
+      const uint32_t r = sm.rbase[s >> 12] + (uint32_t)sm.wprefix[s >> 5] +
                          (uint32_t)__popc(sm.bitmap[s >> 5] & ((1u << (s & 31u)) - 1u));
       const uint32_t j = atomicAdd(&sm.start[r], 1u);
       slot[k] = (r << 16) | j;
@@ -473,23 +513,33 @@ __global__ void __launch_bounds__(VPR_THREADS, 3)
   }
   __syncthreads();
   VP_CLK(4);
-  {  // exclusive scan of the run lengths, in place, rounds of 32 voxels dealt to the warps
-    const int vr = cdiv(V, 32);
-    for (int r = warp; r < vr; r += VPR_WARPS) {
-      const int v = 32 * r + lane;
-      const unsigned c = (v < V) ? sm.start[v] : 0u;
-      const unsigned incl = warp_incl_scan(c);
-      if (v < V) sm.start[v] = incl - c;
-      if (lane == 31) sm.srt[r] = incl;
+  {  // exclusive scan of the run lengths, in place: rounds of 128 voxels, four consecutive voxels per lane
+    const int vr = cdiv(V, 128);
+    unsigned keep[4] = {0u, 0u, 0u, 0u};
+    int my_r = -1;
+    for (int r = warp; r < vr; r += VPR_WARPS) {  // (at most one round per warp: V <= 2048 = 16 rounds)
+      const int v = 128 * r + 4 * lane;
+      const uint4 cw = *reinterpret_cast<const uint4*>(&sm.start[v]);  // (entries past V are zero)
+      const unsigned c[4] = {cw.x, cw.y, cw.z, cw.w};
+      unsigned total;
+      const unsigned ex = vp_round_scan(c, total);
+      keep[0] = ex;
+      keep[1] = ex + c[0];
+      keep[2] = keep[1] + c[1];
+      keep[3] = keep[2] + c[2];
+      my_r = r;
+      if (lane == 0) sm.srt[r] = total;
     }
     __syncthreads();
-    if (warp == 0) warp0_excl_scan<VP_EMAX / 32 / 32>(sm.srt, vr);
+    if (warp == 0) warp0_excl_scan<1>(sm.srt, vr);
     __syncthreads();
-    for (int r = warp; r < vr; r += VPR_WARPS) {
-      const int v = 32 * r + lane;
-      if (v < V) sm.start[v] += sm.srt[r];
+    if (my_r >= 0) {
+      const unsigned base = sm.srt[my_r];
+      const int v = 128 * my_r + 4 * lane;
+      *reinterpret_cast<uint4*>(&sm.start[v]) = make_uint4(base + keep[0], base + keep[1], base + keep[2], base + keep[3]);
     }
-    if (tid == 0) sm.start[V] = (unsigned)E;
+    __syncthreads();
+    if (tid == 0) sm.start[V] = (unsigned)E;  // (V may be the first entry of a round that no warp took)
   }
   __syncthreads();
   VP_CLK(5);
@@ -518,7 +568,43 @@ __global__ void __launch_bounds__(VPR_THREADS, 3)
       sm.sz[s0 + rank] = p[k].z;
     }
   }
+  __syncthreads();
   VP_CLK(7);
+  // ---- one thread per voxel: sequential sum of its run, centroid (kept in registers while warp 0 resolves the look-back) --
+  VoxelFrame vfr;
+  float fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;
+  if (WITH_KEYS) {
+    vfr = vf[f];
+    fb0 = (float)vfr.min_b[0];
+    fb1 = (float)vfr.min_b[1];
+    fb2 = (float)vfr.min_b[2];
+  }
+  constexpr int VPT = VP_EMAX / VPR_THREADS;  // voxels per thread
+  float4 cen[VPT];
+  uint32_t vkey[VPT];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int v = tid + k * VPR_THREADS;
+    cen[k] = make_float4(0.f, 0.f, 0.f, 1.0f);
+    vkey[k] = 0u;
+    if (v < V) {
+      const int s0 = (int)sm.start[v], s1 = (int)sm.start[v + 1];
+      float ax = 0.0f, ay = 0.0f, az = 0.0f;
+      for (int t = s0; t < s1; ++t) {
+        ax = fadd(ax, sm.sx[t]);
+        ay = fadd(ay, sm.sy[t]);
+        az = fadd(az, sm.sz[t]);
+      }
+      const float c = (float)(s1 - s0);
+      cen[k] = make_float4(fdiv(ax, c), fdiv(ay, c), fdiv(az, c), 1.0f);
+      if (WITH_KEYS) {  // PCL's key of this voxel, from one of its points (voxel_grid.hpp: ijk = floor(p*inv) - min_b)
+        const int i0 = cvt_f2i(fsub(floorf(fmul(sm.sx[s0], vfr.inv)), fb0));
+        const int i1 = cvt_f2i(fsub(floorf(fmul(sm.sy[s0], vfr.inv)), fb1));
+        const int i2 = cvt_f2i(fsub(floorf(fmul(sm.sz[s0], vfr.inv)), fb2));
+        vkey[k] = (uint32_t)i0 + (uint32_t)i1 * vfr.mul1 + (uint32_t)i2 * vfr.mul2;
+      }
+    }
+  }
   // voxels of the earlier groups of this frame (decoupled look-back; the aggregate was published above)
   if (warp == 0 && g > 0) {
     unsigned excl = 0u;
@@ -549,31 +635,13 @@ __global__ void __launch_bounds__(VPR_THREADS, 3)
   VP_CLK(8);
   const unsigned vbase = sm.vbase;
   if (g == ng - 1 && tid == 0) n_out[f] = (int)(vbase + (unsigned)V);
-  // ---- one thread per voxel: sequential sum of its run, centroid ----------------------------------------------------------
-  VoxelFrame vfr;
-  float fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;
-  if (WITH_KEYS) {
-    vfr = vf[f];
-    fb0 = (float)vfr.min_b[0];
-    fb1 = (float)vfr.min_b[1];
-    fb2 = (float)vfr.min_b[2];
-  }
-  for (int v = tid; v < V; v += VPR_THREADS) {
-    const int s0 = (int)sm.start[v], s1 = (int)sm.start[v + 1];
-    float ax = 0.0f, ay = 0.0f, az = 0.0f;
-    for (int t = s0; t < s1; ++t) {
-      ax = fadd(ax, sm.sx[t]);
-      ay = fadd(ay, sm.sy[t]);
-      az = fadd(az, sm.sz[t]);
-    }
-    const float c = (float)(s1 - s0);
-    const size_t o = (size_t)f * cap + vbase + (unsigned)v;
-    out[o] = make_float4(fdiv(ax, c), fdiv(ay, c), fdiv(az, c), 1.0f);
-    if (WITH_KEYS) {  // PCL's key of this voxel, from one of its points (voxel_grid.hpp: ijk = floor(p*inv) - min_b)
-      const int i0 = cvt_f2i(fsub(floorf(fmul(sm.sx[s0], vfr.inv)), fb0));
-      const int i1 = cvt_f2i(fsub(floorf(fmul(sm.sy[s0], vfr.inv)), fb1));
-      const int i2 = cvt_f2i(fsub(floorf(fmul(sm.sz[s0], vfr.inv)), fb2));
-      out_keys[o] = (uint32_t)i0 + (uint32_t)i1 * vfr.mul1 + (uint32_t)i2 * vfr.mul2;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int v = tid + k * VPR_THREADS;
+    if (v < V) {
+      const size_t o = (size_t)f * cap + vbase + (unsigned)v;
+      out[o] = cen[k];
+      if (WITH_KEYS) out_keys[o] = vkey[k];
     }
   }
   VP_CLK(9);
@@ -602,7 +670,13 @@ void vox_part_plan(VoxFusedPlan& pl, size_t max_points) {
   pl.part_ok = 1;
 }
 
-int vox_part_chunks(int max_n) { return std::max(1, std::min(VP_MAX_CHUNKS, max_n / 12288)); }
+int vox_part_chunks(int max_n) {
+  static const int per_chunk = [] {
+    const char* s = getenv("PCOP_VP_CHUNK_POINTS");  // (tuning knob, read once per process)
+    return s ? std::max(4096, atoi(s)) : 24576;
+  }();
+  return std::max(1, std::min(VP_MAX_CHUNKS, max_n / per_chunk));
+}
 // worst-case number of groups of a frame of max_n points
 int vox_part_group_bound(const VoxFusedPlan& pl, int max_n) {
   const int K = std::min(VP_KMAX, (VP_BITMAP_WORDS * 32) >> pl.part_shift);
@@ -612,6 +686,7 @@ int vox_part_group_bound(const VoxFusedPlan& pl, int max_n) {
 }
 size_t vox_part_hist_elems(int B) { return (size_t)B * VP_MAX_CHUNKS * (VP_NB_MAX / 2); }
 size_t vox_part_start_elems(int B) { return (size_t)B * (VP_NB_MAX + 1); }
+size_t vox_part_chunk_start_elems(int B) { return (size_t)B * VP_MAX_CHUNKS * VP_NB_MAX; }
 size_t vox_part_bucket_elems(int B) { return (size_t)B * VP_NB_MAX; }
 
 void run_voxel_part(const Ctx& c, const VoxelPartArgs& a) {
@@ -627,22 +702,23 @@ void run_voxel_part(const Ctx& c, const VoxelPartArgs& a) {
   else
     KL(c, "k_vp_hist", k_vp_hist<false><<<dim3(chunks, c.B), VP_THREADS, hsm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.ghist,
                                                                                          a.minmax, a.flags, chunks));
-  KL(c, "k_vp_scan", k_vp_scan<<<c.B, VP_SCAN_THREADS, 0, c.stream>>>(a.ghist, a.bucket_start, a.ne_bucket, a.ne_start, a.gfirst, a.n_groups,
+  KL(c, "k_vp_scan", k_vp_scan<<<c.B, VP_SCAN_THREADS, 0, c.stream>>>(a.ghist, a.chunk_start, a.ne_bucket, a.ne_start, a.grec, a.n_groups,
                                                                       a.n_crop, a.flags, a.minmax, a.leaf, a.vf, pl, chunks,
                                                                       a.want_keys, gmax, a.group_stride));
-  KL(c, "k_vp_scatter", k_vp_scatter<<<dim3(chunks, c.B), VP_THREADS, hsm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.ghist,
-                                                                                       a.bucket_start, a.flags, a.part, c.cap,
-                                                                                       chunks));
+  const size_t ssm = (size_t)pl.nb_pad * sizeof(uint32_t);  // (<= 64 KB)
+  cudaFuncSetAttribute(k_vp_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
+  KL(c, "k_vp_scatter", k_vp_scatter<<<dim3(chunks, c.B), VP_THREADS, ssm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.chunk_start,
+                                                                                       a.flags, a.part, c.cap, chunks));
   const size_t rsm = sizeof(VpReduceSmem);
   if (a.want_keys) {
     cudaFuncSetAttribute(k_vp_reduce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
     KL(c, "k_vp_reduce", k_vp_reduce<true><<<dim3(c.B, gmax), VPR_THREADS, rsm, c.stream>>>(
-                             a.part, a.ne_start, a.gfirst, a.n_groups, a.flags, pl, a.vf, a.out, a.out_keys,
+                             a.part, a.ne_start, a.ne_bucket, a.grec, a.n_groups, a.flags, pl, a.vf, a.out, a.out_keys,
                              a.n_out, a.desc, c.cap, a.group_stride));
   } else {
     cudaFuncSetAttribute(k_vp_reduce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
     KL(c, "k_vp_reduce", k_vp_reduce<false><<<dim3(c.B, gmax), VPR_THREADS, rsm, c.stream>>>(
-                             a.part, a.ne_start, a.gfirst, a.n_groups, a.flags, pl, a.vf, a.out, a.out_keys,
+                             a.part, a.ne_start, a.ne_bucket, a.grec, a.n_groups, a.flags, pl, a.vf, a.out, a.out_keys,
                              a.n_out, a.desc, c.cap, a.group_stride));
   }
   count_launch(c, 5);
