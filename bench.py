@@ -3,17 +3,22 @@
 
 A "step" = one pass of the whole hot path (crop -> VoxelGrid -> RANSAC plane loop -> Euclidean clustering ->
 centroid/radius) over one batch of synthetic HDL-64-style 120 000-point frames (BASELINE.json configs[1],
-parameters of SURVEY.md 8d config 2), `--batch` frames per GPU per step.
+parameters of SURVEY.md 8d config 2), `--batch` frames per GPU per step, through the C ABI (one pcop_process_batch
+call per step).
 
-  value     points/s, whole job, frames already resident in HBM (the batch, 1.97 GB at 1024 frames, is larger
-            than the 126 MB L2, so every step re-reads its input from HBM; no explicit L2 flush)
-  e2e       the same through the C ABI with HOST (pinned) frames: H2D of the frames and D2H of the results
-            inside the timed region
-  roofline  the dominant kernel, timed live with CUDA-event pairs on the library's stream during the timed steps
+  value     points/s, whole job: frames already resident in HBM (the batch, 1.97 GB at 1024 frames, is larger than
+            the 126 MB L2, so every step re-reads its input from HBM; no explicit L2 flush), EVERY requested result
+            array delivered to pinned host memory inside the step (the boundary's semantics)
+  e2e       the same with HOST (pinned) frames: H2D of the frames and D2H of the results inside the timed region
+  roofline  SURVEY 8(d) figure of the dominant STAGE: algorithmic bytes of the stage / its device time, measured live
+            with CUDA events on the library's stream (a second pass of the same K steps); `pipeline_roofline` is the
+            whole pipeline, `stages` every stage, `kernels` every kernel (scratch-inclusive traffic efficiency)
+  configs   BASELINE.json configs[0], [2], [3] (single-frame latency + a small batch) and configs[4] (4096 frames
+            per GPU per step in one call)
   cpu_baseline  the CPU oracle (PCL-semantics restatement, oracle/) on a bounded sample of the same frames
 
-`--impl reference` times that CPU restatement with all host threads (the reference itself needs ROS + PCL and
-cannot be built in this image).
+`--impl reference` times that CPU restatement with all host threads on the same config (the reference itself needs
+ROS + PCL and cannot be built in this image).
 """
 import argparse
 import ctypes as C
@@ -33,6 +38,14 @@ sys.path.insert(0, ROOT)
 
 CONFIG = 2  # BASELINE.json configs[1]: HDL-64-style 120k-point frame
 METRIC = "points/sec per B200 job (HDL-64 120k-point frames: crop + 0.1 m voxel + RANSAC ground removal + Euclidean clustering + centroid/radius)"
+
+
+def workload_config(n, batch, world):
+    """`config` of the JSON line; identical for both arms (--impl ours / reference)."""
+    return {"workload": "BASELINE configs[1]: HDL-64-style 120k-point frame, crop + 0.1 m voxel + ground-plane RANSAC + "
+                        "Euclidean clustering + centroid/radius (SURVEY 8d config 2 parameters)",
+            "points_per_frame": n, "frames_per_gpu_per_step": batch,
+            "parallelism": f"frames sharded over {world} GPU(s), no intra-frame collective"}
 
 
 def measured_peak_gbs():
@@ -109,38 +122,98 @@ def oracle_frames_per_sec(params, frames, threads):
 
 
 def run_reference(args, rank, world, emit):
-    """--impl reference: the CPU restatement (oracle port) with all host threads, same metric/config."""
+    """--impl reference: the CPU restatement (oracle port) with all host threads; same metric, config and frames per
+    step as the other arm (1024 frames take about a second per step on 16 threads)."""
     if rank != 0:
         return
     from pointcloud_obstacle_processing_b200 import synth
     n = synth.points_per_frame(CONFIG)
     threads = os.cpu_count() or 1
-    sample = max(threads, min(args.batch, 8 * threads))
-    frames = synth.frames(CONFIG, 0, sample)
+    frames = synth.frames(CONFIG, 0, args.batch)
     params = synth.params(CONFIG)
-    for _ in range(args.warmup):
-        oracle_frames_per_sec(params, frames[:threads], threads)
+    for _ in range(min(args.warmup, 1)):
+        oracle_frames_per_sec(params, frames[:2 * threads], threads)
     times = []
     for _ in range(args.steps):
         _, dt = oracle_frames_per_sec(params, frames, threads)
         times.append(dt)
     total = sum(times)
-    fps = args.steps * sample / total
+    fps = args.steps * args.batch / total
     pps = fps * n
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": "points/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: HDL-64-style 120k-point frame, crop + 0.1 m voxel + ground-plane "
-                               "RANSAC + Euclidean clustering", "points_per_frame": n, "frames_per_step": sample},
+        "config": workload_config(n, args.batch, world),
         "frames_per_sec": fps,
         "cpu_baseline": {"value": pps, "unit": "points/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} synthetic config-2 frames per step, frame-parallel over {threads} host "
-                                   f"threads; PCL-semantics CPU restatement (oracle/), not PCL itself"},
+                         "sample": f"{args.batch} synthetic config-2 frames per step (the other arm's batch), "
+                                   f"frame-parallel over {threads} host threads; PCL-semantics CPU restatement "
+                                   f"(oracle/), not PCL itself; one warm-up pass over {2 * threads} frames"},
         "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def frame_alg_bytes(p, r):
+    """SURVEY 8(d) algorithmic bytes of one frame result, per stage group."""
+    b = {"crop+voxel": 0.0, "sor": 0.0, "plane": 0.0, "cluster+centroid": 0.0}
+    if p.enable_crop:
+        b["crop+voxel"] += 16.0 * r.n_input + 20.0 * r.n_crop
+    if p.enable_voxel:
+        b["crop+voxel"] += 16.0 * r.n_crop + 20.0 * r.n_voxel
+    if p.enable_sor:
+        b["sor"] += 16.0 * r.n_voxel + 20.0 * r.n_sor
+    if p.enable_plane:
+        pk = r.n_sor
+        for k in range(min(r.n_plane_passes, len(r.plane_pass_inliers))):
+            ik = r.plane_pass_inliers[k]
+            b["plane"] += 16.0 * pk + 16.0 * (pk - ik) + 4.0 * ik + 16.0
+            pk -= ik
+    if p.enable_cluster:
+        b["cluster+centroid"] += 32.0 * r.n_remaining + 8.0 * r.n_cluster_points + 4.0 * (r.n_clusters + 1) + 16.0 * r.n_clusters
+    return b
+
+
+def small_config(cfg, batch, reps, local_rank, peak, torch):
+    """BASELINE configs[0] / [2] / [3]: single-frame latency (host in -> results on host) and a small device-resident
+    batch, with its SURVEY 8(d) fraction."""
+    from pointcloud_obstacle_processing_b200 import ObstacleProcessor, synth
+    n = synth.points_per_frame(cfg)
+    p = synth.params(cfg)
+    host = torch.empty((batch, n, 4), dtype=torch.float32).pin_memory()
+    synth.frames(cfg, 0, batch, out=host.numpy())
+    dev = host.to(f"cuda:{local_rank}")
+    counts = np.full(batch, n, np.int32)
+    out = {"points_per_frame": n, "batch": batch}
+    with ObstacleProcessor(p, n, max_batch=1, device=local_rank) as op1:
+        for _ in range(5):
+            op1.process_batch_raw(host.data_ptr(), n, counts[:1])
+        ts = []
+        for i in range(reps):
+            a = time.perf_counter()
+            op1.process_batch_raw(host.data_ptr() + (i % batch) * n * 16, n, counts[:1])
+            ts.append((time.perf_counter() - a) * 1e3)
+        ts.sort()
+        out["p50_ms"] = ts[len(ts) // 2]
+        out["launches_per_frame"] = int(op1.last_launch_count)
+    with ObstacleProcessor(p, n, max_batch=batch, device=local_rank) as op:
+        for _ in range(3):
+            res = op.process_batch_raw(dev.data_ptr(), n, counts)
+        torch.cuda.synchronize()
+        steps = 5
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = op.process_batch_raw(dev.data_ptr(), n, counts)
+        dt = (time.perf_counter() - t0) / steps
+        alg = op.last_algorithmic_bytes
+        out.update({"points_per_sec": batch * n / dt, "frames_per_sec": batch / dt, "ms_per_step": dt * 1e3,
+                    "roofline_frac": alg / dt / 1e9 / peak,
+                    "counts_frame0": {k: int(getattr(res[0], k)) for k in ("n_crop", "n_voxel", "n_remaining", "n_clusters")}})
+    del dev, host
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -161,6 +234,7 @@ def main():
     ap.add_argument("--latency-reps", type=int, default=200)
     ap.add_argument("--cpu-sample", type=int, default=128, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[0], [2], [3], [4] section")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -173,12 +247,18 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pointcloud_obstacle_processing_b200 import ObstacleProcessor, synth
+    from pointcloud_obstacle_processing_b200 import ObstacleProcessor, synth, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        try:  # one rank per GPU; the box's hardware threads are shared out so that the ranks' host threads do not migrate
+            ncpu = os.cpu_count() or 1
+            per = max(1, ncpu // world)
+            os.sched_setaffinity(0, set(range(local_rank * per, min(ncpu, (local_rank + 1) * per))))
+        except Exception:
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -196,13 +276,7 @@ def main():
     dev = host.to(f"cuda:{local_rank}", non_blocking=False)
     counts = np.full(B, n, np.int32)
     from pointcloud_obstacle_processing_b200 import _ctypes_abi as abi
-    # `value`: frames resident in HBM and results LEFT in HBM (outputs | OUT_DEVICE: the result pointers are device
-    # pointers for a GPU-side consumer -- here the NCCL result gather reads them in place); counts, warnings and the
-    # plane record still come back to the host every step.  `value_results_to_host` and `e2e` copy every result
-    # array to pinned host memory.
-    params_dev = params.copy()
-    params_dev.outputs = abi.OUT_DEFAULT | abi.OUT_DEVICE
-    op = ObstacleProcessor(params_dev, n, max_batch=B, device=local_rank)
+    op = ObstacleProcessor(params, n, max_batch=B, device=local_rank)
 
     def step_device():
         return op.process_batch_raw(dev.data_ptr(), n, counts)
@@ -210,74 +284,25 @@ def main():
     def step_host():
         return op.process_batch_raw(host.data_ptr(), n, counts)
 
-    # ---- final result gather, once per step: per-frame obstacle counts (all-gather), then the obstacle
-    # records padded to the largest rank total (gather to rank 0), over NCCL.  The per-frame fields are read as numpy
-    # views over the ctypes result array; the records of consecutive frames of a wave are adjacent in the library's
-    # pinned result buffer, so they are staged run by run (a handful of memmoves per step).
-    # The exchange is asynchronous and double-buffered: the collectives of step k run on NCCL's stream while step k+1
-    # computes; gather_flush() waits for the outstanding ones before a timed region ends.
-    from pointcloud_obstacle_processing_b200._ctypes_abi import FrameResult
-    PADCAP = B * 128  # obstacle records per rank and step (fixed: no size negotiation, no host synchronisation)
-    slots = []
-    if world > 1:
-        for _ in range(2):
-            slots.append({
-                "obs_stage": torch.empty((PADCAP, 4), dtype=torch.float32).pin_memory(),
-                "cnt_stage": torch.empty(B + 1, dtype=torch.int32).pin_memory(),
-                "dev_cnt": torch.empty(B + 1, dtype=torch.int32, device=dev.device),
-                "all_cnt": torch.empty((world, B + 1), dtype=torch.int32, device=dev.device),
-                "pad": torch.zeros((PADCAP, 4), dtype=torch.float32, device=dev.device),
-                "out": torch.empty((world, PADCAP, 4), dtype=torch.float32, device=dev.device) if rank == 0 else None,
-                "work": []})
-    gather_step = [0]
-    results_on_device = [True]
-    off_c, off_p, rec = FrameResult.n_clusters.offset, FrameResult.obstacles.offset, C.sizeof(FrameResult)
-
-    def gather_flush():
-        for sl in slots:
-            for w in sl["work"]:
-                w.wait()
-            sl["work"] = []
+    # ---- final result gather, once per step: cluster_offsets, cluster_indices and obstacles of every frame
+    # to rank 0 over NCCL (sizes first, then the three arrays padded to a fixed per-rank capacity).  Asynchronous and
+    # double-buffered: the collectives of step k run on NCCL's stream while step k+1 computes; flush() waits for the
+    # outstanding ones before a timed region ends.
+    gather = sharding.ResultGather(B, torch.device("cuda", local_rank)) if world > 1 else None
 
     def gather_results(res):
-        if world == 1 or os.environ.get("PCOP_BENCH_NO_GATHER"):
-            return
-        sl = slots[gather_step[0] & 1]
-        gather_step[0] += 1
-        for w in sl["work"]:  # the slot's buffers are free again once its previous exchange has completed
-            w.wait()
-        raw = np.frombuffer(res, dtype=np.uint8).reshape(len(res), rec)
-        ns = raw[:, off_c:off_c + 4].copy().view(np.int32).ravel()
-        ptrs = raw[:, off_p:off_p + 8].copy().view(np.uint64).ravel()
-        tot = int(ns.sum())
-        assert tot <= PADCAP, "more obstacle records than the exchange buffer holds"
-        sl["cnt_stage"][:B].copy_(torch.from_numpy(ns))
-        sl["cnt_stage"][B] = tot
-        sl["dev_cnt"].copy_(sl["cnt_stage"], non_blocking=True)
-        w1 = dist.all_gather_into_tensor(sl["all_cnt"].view(-1), sl["dev_cnt"], async_op=True)
-        if tot:
-            live = np.flatnonzero(ns > 0)
-            ends = ptrs[live] + 16 * ns[live].astype(np.uint64)
-            brk = np.flatnonzero(ptrs[live][1:] != ends[:-1]) + 1  # a new run starts where the records are not adjacent
-            starts = np.concatenate([[0], brk])
-            stops = np.concatenate([brk, [len(live)]])
-            o = 0
-            for a, b_ in zip(starts, stops):
-                nrec = int(ns[live[a:b_]].sum())
-                if results_on_device[0]:  # device -> device, straight out of the library's result buffer
-                    op.copy_device(sl["pad"].data_ptr() + 16 * o, int(ptrs[live[a]]), 16 * nrec)
-                else:
-                    C.memmove(sl["obs_stage"].data_ptr() + 16 * o, int(ptrs[live[a]]), 16 * nrec)
-                o += nrec
-            if not results_on_device[0]:
-                sl["pad"][:tot].copy_(sl["obs_stage"][:tot], non_blocking=True)
-        w2 = dist.gather(sl["pad"], list(sl["out"].unbind(0)) if rank == 0 else None, dst=0, async_op=True)
-        sl["work"] = [w1, w2]
+        if gather is not None and not os.environ.get("PCOP_BENCH_NO_GATHER"):
+            gather.submit(res)
 
-    # ---- device-resident run ---------------------------------------------------------------------
+    def gather_flush():
+        if gather is not None:
+            gather.flush()
+
+    peak, peak_kind = measured_peak_gbs()
+    # ---- headline: frames resident in HBM, every result array delivered to pinned host memory ------------------------
     for _ in range(max(args.warmup, 3)):
         gather_results(step_device())
-    stage_acc = {}
+    gather_flush()
     launches = 0
     alg_bytes = 0.0
     dev_us = 0.0
@@ -293,24 +318,34 @@ def main():
         gather_flush()
         barrier()
         wall = time.perf_counter() - t0
-    # ---- the same K steps with every result array copied to pinned host memory -----------------------------
-    op.set_params(params)
-    results_on_device[0] = False
+    stage_alg = {}
+    for r in res:
+        for k, v in frame_alg_bytes(params, r).items():
+            stage_alg[k] = stage_alg.get(k, 0.0) + v
+    counts_sum = {k: sum(getattr(r, k) for r in res) for k in
+                  ("n_input", "n_crop", "n_voxel", "n_remaining", "n_clusters", "n_cluster_points")}
+    plane_passes = sum(r.n_plane_passes for r in res)
+
+    # ---- extra: the same K steps with the result arrays LEFT in HBM (outputs | OUT_DEVICE: device pointers for a
+    # GPU-side consumer; counts, warnings and plane records still reach the host) -------------------------------------
+    params_dev = params.copy()
+    params_dev.outputs = abi.OUT_DEFAULT | abi.OUT_DEVICE
+    op.set_params(params_dev)
     for _ in range(2):
-        gather_results(step_device())
+        step_device()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        gather_results(step_device())
-    gather_flush()
+        step_device()
     barrier()
-    wall_host_results = time.perf_counter() - t0
-    # (the passes below keep the host-result mode: the single lane of the instrumented pass runs four waves)
-    # ---- instrumented pass: the same K steps with a CUDA-event pair around every launch on the library's streams.
-    # Per-kernel timing needs each kernel alone on the GPU, so the library serialises its lanes here; this pass
-    # feeds `roofline`, `kernels` and `stage_ms_per_step` only, never `value`.
+    wall_dev_results = time.perf_counter() - t0
+    op.set_params(params)
+
+    # ---- instrumented pass: the same K steps with a CUDA-event pair around every launch and every stage on the
+    # library's stream.  Per-kernel timing needs each kernel alone on the GPU, so the library serialises its lanes
+    # here; this pass feeds `roofline`, `stages`, `kernels` only, never `value`.
     kernel_times = {}
-    sort_keys = 0
+    stage_acc = {}
     wall_instr = None
     if not args.no_kernel_timing:
         op.enable_kernel_timing(True)
@@ -320,21 +355,14 @@ def main():
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step_device()
-            sort_keys += op.last_sort_pass_keys
             for k, v in op.stage_times_us().items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
         barrier()
         wall_instr = time.perf_counter() - t0
         kernel_times = op.kernel_times()
         op.enable_kernel_timing(False)
-    counts_sum = {k: sum(getattr(r, k) for r in res) for k in
-                  ("n_input", "n_crop", "n_voxel", "n_remaining", "n_clusters", "n_cluster_points")}
-    d2h_bytes = sum(r.n_remaining * 20 + (r.n_clusters + 1) * 4 + r.n_cluster_points * 4 + r.n_clusters * 16
-                    for r in res) + B * 600
 
     # ---- end-to-end run (host frames in, results out) ------------------------------------------------
-    op.set_params(params)
-    results_on_device[0] = False
     for _ in range(2):
         step_host()
     barrier()
@@ -349,16 +377,46 @@ def main():
     d2h_bytes = d2h_exact / args.steps  # counted by the library from the copies it issued
 
     # ---- max over ranks -----------------------------------------------------------------------------
-    t = torch.tensor([wall, wall_e2e, dev_us * 1e-6, wall_host_results], dtype=torch.float64, device=dev.device)
+    t = torch.tensor([wall, wall_e2e, dev_us * 1e-6, wall_dev_results], dtype=torch.float64, device=dev.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall, wall_e2e, dev_s, wall_host_results = [float(x) for x in t.tolist()]
+    wall, wall_e2e, dev_s, wall_dev_results = [float(x) for x in t.tolist()]
+
+    # ---- BASELINE configs[4]: 4096 frames per GPU per step, ONE pcop_process_batch call per step (the handle keeps
+    # max_batch = B frames of wave buffers; the call runs 4096 / wave frames waves).  The 4096 frames are the step's B
+    # distinct frames repeated (7.86 GB resident in HBM).
+    cfg5 = None
+    if not args.no_configs:
+        reps5 = max(1, 4096 // B)
+        big = dev.repeat(reps5, 1, 1) if reps5 > 1 else dev
+        nb = big.shape[0]
+        counts5 = np.full(nb, n, np.int32)
+        for _ in range(1):
+            op.process_batch_raw(big.data_ptr(), n, counts5)
+        barrier()
+        t0 = time.perf_counter()
+        steps5 = 2
+        for _ in range(steps5):
+            gather_results(op.process_batch_raw(big.data_ptr(), n, counts5)[:B])
+        gather_flush()
+        barrier()
+        w5 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev.device)
+        if world > 1:
+            dist.all_reduce(w5, op=dist.ReduceOp.MAX)
+        w5 = float(w5.item())
+        cfg5 = {"frames_per_gpu_per_step": nb, "calls_per_step": 1, "steps": steps5,
+                "points_per_sec": world * steps5 * nb * n / w5, "frames_per_sec": world * steps5 * nb / w5,
+                "ms_per_step": 1000.0 * w5 / steps5,
+                "roofline_frac": (alg_bytes / (args.steps * B)) * (world * steps5 * nb) / w5 / 1e9 / (peak * world),
+                "what": f"{nb} frames ({B} distinct frames x {reps5}) resident in HBM, results to pinned host memory, "
+                        f"whole job over {world} GPU(s)"}
+        del big
+        torch.cuda.empty_cache()
 
     # ---- single-frame latency (rank 0) -----------------------------------------------------------------
     lat = None
     if rank == 0 and args.latency_reps > 0:
         op1 = ObstacleProcessor(params, n, max_batch=1, device=local_rank)
-        one = host[0].numpy()
         for _ in range(10):
             op1.process_batch_raw(host.data_ptr(), n, counts[:1])
         ts = []
@@ -368,8 +426,28 @@ def main():
             ts.append((time.perf_counter() - a) * 1e3)
         ts.sort()
         lat = {"p50_ms": ts[len(ts) // 2], "p90_ms": ts[int(len(ts) * 0.9)], "min_ms": ts[0], "reps": len(ts),
+               "launches_per_frame": int(op1.last_launch_count),
                "what": "one 120k-point frame, host pinned in -> results on host, wall clock"}
         op1.close()
+    op.close()
+    del dev
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs (rank 0, N = 1 only) -------------------------------------------------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = {}
+        for key, cfg, batch in (("1", 1, 64), ("3", 3, 16), ("4", 4, 8)):
+            try:
+                configs[key] = small_config(cfg, batch, 50, local_rank, peak, torch)
+            except Exception as e:  # (a config must not take the headline down with it)
+                configs[key] = {"error": repr(e)}
+        configs["1"]["what"] = "BASELINE configs[0]: VLP-16-style 30k-point frame, params.yaml verbatim (incl. SOR)"
+        configs["3"]["what"] = "BASELINE configs[2]: 640x480 organized depth cloud, 0.02 m voxel, tolerance 0.05"
+        configs["4"]["what"] = "BASELINE configs[3]: adversarial 1M-point frame, a few very large clusters"
+    if cfg5 is not None:
+        configs = configs or {}
+        configs["5"] = cfg5
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
     cpu = None
@@ -387,99 +465,105 @@ def main():
     if rank == 0:
         total_frames = world * args.steps * B
         total_points = total_frames * n
-        peak, peak_kind = measured_peak_gbs()
         value = total_points / wall
-        # dominant kernel, timed live
-        roof = None
+        # ---- stages and kernels, timed live -----------------------------------------------------------------
+        stage_us = {"crop+voxel": stage_acc.get("crop", 0.0) + stage_acc.get("voxel", 0.0), "sor": stage_acc.get("sor", 0.0),
+                    "plane": stage_acc.get("plane", 0.0),
+                    "cluster+centroid": stage_acc.get("cluster", 0.0) + stage_acc.get("centroid", 0.0)}
+        stages = {}
+        for k, us in stage_us.items():
+            if us <= 0.0 or stage_alg.get(k, 0.0) <= 0.0:
+                continue
+            byt = stage_alg[k] * args.steps  # (the last step's frames; every step processes the same frames)
+            gbs = byt / (us * 1e-6) / 1e9
+            stages[k] = {"algorithmic_bytes_per_frame": stage_alg[k] / B, "us_per_frame": us / (args.steps * B),
+                         "achieved_GBps": gbs, "frac": gbs / peak}
         ktable = {}
+        stage_of = {"k_vp_": "crop+voxel", "k_vf_": "crop+voxel", "k_crop": "crop+voxel", "k_voxel": "crop+voxel", "k_sort": "crop+voxel",
+                    "k_plane": "plane", "k_ece": "cluster+centroid", "k_centroid": "cluster+centroid", "k_sor": "sor"}
         if kernel_times:
             tot_us = sum(v[0] for v in kernel_times.values())
-            for k, (us, cnt) in sorted(kernel_times.items(), key=lambda kv: -kv[1][0]):
-                ktable[k] = {"total_us": round(us, 1), "launches": cnt, "share": round(us / tot_us, 4)}
-            top = max(kernel_times.items(), key=lambda kv: kv[1][0])
-            name, (us, cnt) = top
-            per_frame = {k: v / B for k, v in counts_sum.items()}
             N_, M_, V_, P_ = (counts_sum[k] * args.steps for k in ("n_input", "n_crop", "n_voxel", "n_remaining"))
             L_, C_ = (counts_sum[k] * args.steps for k in ("n_cluster_points", "n_clusters"))
-            alg_all = {  # algorithmic bytes of ALL launches of a kernel over the instrumented steps (DESIGN.md "kernels")
-                "k_vf_sort_pass": 16.0 * sort_keys,              # 8-byte (key, index) element read + written once per pass
-                "k_vf_crop_key": 16.0 * N_ + 8.0 * M_,           # input read once, (key, index) of the survivors written
-                "k_vf_reduce": 8.0 * M_ + 16.0 * M_ + 20.0 * V_,  # sorted pairs + point gather in, voxels + keys out
-                "k_sort_pass": 16.0 * sort_keys,
-                "k_crop": 16.0 * N_ + 20.0 * M_,                 # SURVEY 8d crop row
-                "k_voxel_keys": 16.0 * M_ + 4.0 * M_,
-                "k_voxel_centroid": 16.0 * M_ + 8.0 * M_ + 20.0 * V_,
-                "k_plane_score": 16.0 * V_,
-                "k_plane_moments": 16.0 * V_,
-                "k_plane_extract": 16.0 * V_ + 20.0 * P_,
-                "k_ece_small": 32.0 * P_ + 8.0 * L_ + 20.0 * C_,  # SURVEY 8d ECE + centroid/radius rows (fused kernel)
+            # bytes each kernel moves by design (its own reads + writes INCLUDING scratch such as the partitioned
+            # elements; not the SURVEY 8d figure, which is per stage): a traffic-efficiency measure per kernel
+            moved = {
+                "k_vp_hist": 16.0 * N_,
+                "k_vp_scatter": 16.0 * N_ + 16.0 * M_,
+                "k_vp_reduce": 16.0 * M_ + 16.0 * V_,
+                "k_plane_loop": 16.0 * V_ + 20.0 * P_,
+                "k_ece_small": 32.0 * P_ + 8.0 * L_ + 20.0 * C_,
                 "k_pack": 2.0 * (20.0 * P_ + 4.0 * L_ + 20.0 * C_),
             }
-            for k in ktable:
-                if k in alg_all and kernel_times[k][0] > 0:
-                    ktable[k]["achieved_GBps"] = round(alg_all[k] / (kernel_times[k][0] * 1e-6) / 1e9, 1)
-                    ktable[k]["frac_of_hbm_peak"] = round(ktable[k]["achieved_GBps"] / peak, 4)
-            alg = alg_all.get(name)
-            # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/ncu_full_r01f_summary.csv:
-            # dram__bytes_read.sum + dram__bytes_write.sum at 256 frames per launch), scaled by the units per launch
-            ncu_dram_bytes_per_unit = {
-                "k_vf_sort_pass": ((0.2129e9 + 182.2e6) / 26.35e6, sort_keys),  # per key moved (mean of the 4 passes)
-                "k_vf_reduce": ((1.0779e9 + 207.2e6) / 26.35e6, M_),            # per sorted pair
-                "k_vf_crop_key": ((0.4921e9 + 177.0e6) / 30.72e6, N_),          # per input point
-            }
-            if alg is not None and us > 0:
-                ach = alg / (us * 1e-6) / 1e9
-                tr = ncu_dram_bytes_per_unit.get(name)
-                roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": (tr[0] * tr[1] / cnt) if tr else None,
-                        "traffic_source": "profiles/ncu_full_r01f_summary.csv (ncu --set full, 256 frames per launch), "
-                                          "scaled to this run's units per launch" if tr else None,
-                        "peak_source": peak_kind,
-                        "launches": cnt, "avg_launch_us": us / cnt,
-                        "timed": "second pass of the same K steps with a CUDA-event pair around every launch on the "
-                                 "library's stream (lanes serialised so that each kernel runs alone)",
-                        "algorithmic_bytes_per_launch": alg / cnt,
-                        "share_of_kernel_time": us / tot_us}
-            else:
-                roof = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                        "traffic": None, "peak_source": peak_kind}
+            for k, (us, cnt) in sorted(kernel_times.items(), key=lambda kv: -kv[1][0]):
+                e = {"total_us": round(us, 1), "launches": cnt, "avg_launch_us": round(us / max(cnt, 1), 2),
+                     "share": round(us / tot_us, 4),
+                     "stage": next((s for pre, s in stage_of.items() if k.startswith(pre)), "pack/other")}
+                if k in moved and us > 0:
+                    e["moved_GBps_scratch_inclusive"] = round(moved[k] / (us * 1e-6) / 1e9, 1)
+                    e["moved_frac_of_hbm_peak"] = round(e["moved_GBps_scratch_inclusive"] / peak, 4)
+                ktable[k] = e
+        roof = None
+        if stages:
+            dom = max(stages.items(), key=lambda kv: kv[1]["us_per_frame"])
+            name, st = dom
+            dom_kernel = max(((k, v) for k, v in ktable.items() if v["stage"] == name), key=lambda kv: kv[1]["total_us"],
+                             default=(None, None))[0]
+            # DRAM bytes of the stage's kernels from the committed `ncu --set full` capture (profiles/, 256 frames per
+            # launch: dram__bytes_read.sum + dram__bytes_write.sum), per frame
+            ncu_dram_per_frame = {"crop+voxel": (527.8e6 + 133.0e6 + 1020.9e6 + 620.0e6) / 256.0,
+                                  "plane": 249.5e6 / 256.0, "cluster+centroid": 20.9e6 / 256.0}
+            roof = {"bound": "hbm", "stage": name, "kernel": dom_kernel, "achieved": st["achieved_GBps"], "peak": peak,
+                    "unit": "GB/s", "frac": st["frac"],
+                    "traffic": ncu_dram_per_frame.get(name, 0.0) * B if name in ncu_dram_per_frame else None,
+                    "traffic_source": "profiles/ncu_full_r02a_summary.csv (ncu --set full, 256 frames per launch), scaled "
+                                      "to this step's frames; per step like `algorithmic_bytes_per_step`",
+                    "algorithmic_bytes_per_step": st["algorithmic_bytes_per_frame"] * B,
+                    "us_per_step": st["us_per_frame"] * B, "peak_source": peak_kind,
+                    "what": "SURVEY 8(d): the stage's distinct inputs read once + distinct outputs written once (sort / "
+                            "partition scratch not counted) / the stage's device time; dominant stage of the step",
+                    "timed": "second pass of the same K steps with CUDA-event pairs around every stage and launch on the "
+                             "library's stream (lanes serialised so that each kernel runs alone)"}
         pipe_gbs = world * alg_bytes / wall / 1e9 if wall > 0 else None
+        h2d = B * n * 16 + B * 4
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: HDL-64-style 120k-point frame, crop + 0.1 m voxel + ground-plane "
-                                   "RANSAC + Euclidean clustering + centroid/radius (SURVEY 8d config 2 parameters)",
-                       "points_per_frame": n, "frames_per_gpu_per_step": B,
-                       "results": "left in HBM (PCOP_OUT_DEVICE; counts and plane records on the host); "
-                                  "value_results_to_host and e2e copy them to pinned host memory",
-                       "l2": "no flush: the per-step input batch (%.0f MB) exceeds the 126 MB L2" % (B * n * 16 / 1e6),
-                       "parallelism": f"frames sharded over {world} GPU(s), no intra-frame collective"},
+            "config": workload_config(n, B, world),
+            "results": "every requested result array (remaining cloud + source indices, cluster CSR, obstacle records) "
+                       "delivered to pinned host memory inside the step" +
+                       ("; cluster_offsets / cluster_indices / obstacles of all ranks gathered to rank 0 over NCCL" if world > 1 else ""),
+            "l2": "no flush: the per-step input batch (%.0f MB) exceeds the 126 MB L2" % (B * n * 16 / 1e6),
             "frames_per_sec": total_frames / wall,
-            "value_results_to_host": {"value": total_points / wall_host_results, "unit": "points/s",
-                                      "ms_per_step": 1000.0 * wall_host_results / args.steps,
-                                      "what": "same K steps, frames resident in HBM, every result array copied to pinned "
-                                              "host memory inside the step"},
+            "value_results_left_in_hbm": {"value": total_points / wall_dev_results, "unit": "points/s",
+                                          "ms_per_step": 1000.0 * wall_dev_results / args.steps,
+                                          "what": "same K steps with outputs | PCOP_OUT_DEVICE: result arrays stay in HBM for "
+                                                  "a GPU-side consumer, only counts and plane records reach the host"},
             "device_ms_per_step": 1000.0 * dev_s / args.steps,
             "instrumented_ms_per_step": 1000.0 * wall_instr / args.steps if wall_instr else None,
-            "lanes": int(os.environ.get("PCOP_LANES", str(2 if (os.cpu_count() or 1) < 8 * torch.cuda.device_count() else min(4, max(2, B // 256))))),
-            "e2e": {"value": total_points / wall_e2e, "unit": "points/s", "h2d_bytes_per_step": B * n * 16 + B * 4,
+            "e2e": {"value": total_points / wall_e2e, "unit": "points/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(d2h_bytes), "frames_per_sec": total_frames / wall_e2e,
-                    "ms_per_step": 1000.0 * wall_e2e / args.steps},
+                    "ms_per_step": 1000.0 * wall_e2e / args.steps,
+                    "h2d_GBps_aggregate": world * h2d / (wall_e2e / args.steps) / 1e9,
+                    "bound": "host-to-device copy of the frames (16 B per point over PCIe / the host memory path, shared "
+                             "by the GPUs of the box)"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roof,
             "pipeline_roofline": {"algorithmic_bytes_per_frame": alg_bytes / (args.steps * B),
                                   "achieved_GBps": pipe_gbs, "peak": peak * world, "frac": pipe_gbs / (peak * world) if pipe_gbs else None,
-                                  "what": "sum of SURVEY 8d stage bytes over all frames of all GPUs / elapsed (whole pipeline); peak = measured HBM peak x GPUs"},
+                                  "what": "sum of SURVEY 8d stage bytes over all frames of all GPUs / elapsed of the timed region "
+                                          "(whole pipeline incl. result delivery); peak = measured HBM peak x GPUs"},
+            "stages": stages,
             "stage_ms_per_step": {k: round(v / args.steps / 1000.0, 3) for k, v in stage_acc.items()},
             "kernels": ktable,
-            "counts_per_frame": {k: v / B for k, v in counts_sum.items()},
+            "counts_per_frame": dict({k: v / B for k, v in counts_sum.items()}, plane_passes=plane_passes / B),
             "latency": lat,
+            "configs": configs,
             "cpu_baseline": cpu,
         }
         emit(line)
-    op.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -162,7 +162,14 @@ struct pcop_handle {
   // lanes: the handle itself is lane 0; a batched call deals its waves round-robin to the lanes (one stream and one
   // set of wave buffers each), so one lane's result copy and the host's bookkeeping overlap the other lanes' kernels
   int wave_frames = 0;             // frames per wave a batched call aims at (<= maxB; PCOP_WAVE_FRAMES at create)
-  bool trace = false;              // PCOP_TRACE at create
+  bool trace = false;              // PCOP_TRACE at create: per-wave device timeline of every call on stderr
+  struct TraceRec {
+    int w0, B;
+    size_t bytes;
+    cudaEvent_t meta, c0, c1;  // counts on the host / payload copy start / end
+  };
+  std::vector<TraceRec> trace_recs;
+  size_t trace_used = 0;
   int ece_small_max = 0;           // ECE_SMALL_MAX or PCOP_ECE_SMALL_MAX (read at create)
   int plane_resident = 1;          // 0: PCOP_PLANE_RESIDENT=0 at create (host-looped plane kernels)
   bool expect_big_remaining = false;  // the last collected wave had a remaining cloud above ece_small_max
@@ -991,6 +998,16 @@ int enqueue_wave_back(pcop_handle* h, int B, int max_n, uint32_t mask, bool clus
   PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_meta, h->d_meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, h->stream));
   if (h->wave_used_fused)
     PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_vf_flags, h->d_vf_flags, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+  if (h->trace) {
+    if (h->trace_used == h->trace_recs.size()) {
+      pcop_handle::TraceRec r{};
+      cudaEventCreate(&r.meta);
+      cudaEventCreate(&r.c0);
+      cudaEventCreate(&r.c1);
+      h->trace_recs.push_back(r);
+    }
+    cudaEventRecord(h->trace_recs[h->trace_used].meta, h->stream);
+  }
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_meta, h->stream));
   return PCOP_OK;
 }
@@ -1094,8 +1111,16 @@ int finish_wave(pcop_handle* h, const WaveInput& wi, uint32_t mask, pcop_frame_r
   if (!dev_results) {
     TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
     // payload copy on the copy stream (the pack kernels have finished: ev_meta follows them)
+    if (h->trace) cudaEventRecord(h->trace_recs[h->trace_used].c0, h->cstream);
     if (meta.total_bytes)
       PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, h->d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->cstream));
+    if (h->trace) {
+      pcop_handle::TraceRec& tr = h->trace_recs[h->trace_used++];
+      cudaEventRecord(tr.c1, h->cstream);
+      tr.w0 = w0;
+      tr.B = B;
+      tr.bytes = (size_t)meta.total_bytes;
+    }
     PCOP_CUDA_TRY(cudaEventRecord(h->ev_copied, h->cstream));
     h->h_pack_used = base_off + meta.total_bytes;
   }
@@ -1169,7 +1194,6 @@ int finish_wave(pcop_handle* h, const WaveInput& wi, uint32_t mask, pcop_frame_r
     else cudaGetLastError();
   }
   resolve_kernel_timers(h);
-  if (h->trace) fprintf(stderr, "[pcop trace] lane %p wave %d+%d collected, %zu result bytes\n", (void*)h, w0, B, (size_t)meta.total_bytes);
   return PCOP_OK;
 }
 
@@ -1215,7 +1239,10 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   if (!h->kt.enabled)
     for (pcop_handle* l : h->extra_lanes) lanes.push_back(l);
   // waves: about wave_frames frames each (never more than a lane holds), at least one per lane when the call is large
-  // enough, the last one half as large as the others (its result copy is the only one nothing overlaps)
+  // enough, the last one half as large as the others (its result copy is the only one nothing overlaps).  Measured on
+  // B200 (1024 HDL-64 frames, 3 lanes, results to the host): waves of 256 / 192 / 128 / 96 frames 6.73 / 6.88 / 6.25 /
+  // 6.36 ms per call; a tail of one quarter-size wave per lane 6.39 ms (a wave has a latency floor of ~0.7 ms
+  // whatever its size, so small tail waves cost more than their copies save).
   std::vector<std::pair<int, int>> waves;  // (first frame, frames)
   {
     const int L = (int)lanes.size();
@@ -1240,6 +1267,7 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     l->h_pack_used = 0;
     l->fixups.clear();
     l->wave_seq = 0;
+    l->trace_used = 0;
     l->pending = false;
     for (int s = 0; s < PCOP_N_STAGES; ++s) l->stage_us[s] = 0.f;
     TRY(ensure_pack_capacity(l, mask));
@@ -1279,6 +1307,22 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
   float ms = 0.f;
   PCOP_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]));
   h->last_elapsed_us = ms * 1000.f;
+  if (h->trace) {
+    fprintf(stderr, "[pcop trace] call of %d frames: %.0f us on the device\n", batch, ms * 1000.f);
+    for (size_t li = 0; li < lanes.size(); ++li) {
+      for (size_t k = 0; k < lanes[li]->trace_used; ++k) {
+        const pcop_handle::TraceRec& tr = lanes[li]->trace_recs[k];
+        float a = 0.f, b = 0.f, c = 0.f;
+        cudaEventElapsedTime(&a, h->ev_call[0], tr.meta);
+        cudaEventElapsedTime(&b, h->ev_call[0], tr.c0);
+        cudaEventElapsedTime(&c, h->ev_call[0], tr.c1);
+        fprintf(stderr, "[pcop trace]   lane %zu wave %4d+%-4d counts at %7.0f us, payload copy %7.0f .. %7.0f us (%.1f MB, %.1f GB/s)\n", li,
+                tr.w0, tr.B, a * 1000.f, b * 1000.f, c * 1000.f, tr.bytes / 1e6, tr.bytes / 1e3 / std::max(1e-3f, (c - b) * 1000.f));
+      }
+      lanes[li]->trace_used = 0;
+    }
+    cudaGetLastError();
+  }
   for (pcop_handle* l : lanes) {
     l->sort_pass_keys = *l->h_stats;
     // the host pack buffers are final now: turn the stored offsets into pointers
@@ -1546,10 +1590,10 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
     return fail(nullptr, PCOP_ERR_BAD_PARAM, "pcop_create: bad argument (max_points must be in [1, 268431360])");
   *out = nullptr;
   // Lanes (PCOP_LANES, default 3 once max_batch allows waves of 64 frames): every lane owns the buffers of one wave;
-  // a batched call keeps one wave in flight per lane.  Wave size (PCOP_WAVE_FRAMES, default max_batch / 4, at least
+  // a batched call keeps one wave in flight per lane.  Wave size (PCOP_WAVE_FRAMES, default max_batch / 8, at least
   // 64): large enough to fill the GPU, small enough that the last wave's result copy -- the only one nothing
   // overlaps -- is short.  Both knobs are read here, once; nothing on the frame path looks at the environment.
-  int wave_frames = std::min(max_batch, std::max(64, max_batch / 4));
+  int wave_frames = std::min(max_batch, std::max(64, max_batch / 8));
   if (const char* s = getenv("PCOP_WAVE_FRAMES")) wave_frames = (int)std::min<long>(std::max<long>(strtol(s, nullptr, 10), 1), max_batch);
   int n_lanes = std::max(1, std::min(3, max_batch / wave_frames));
   if (const char* s = getenv("PCOP_LANES")) n_lanes = (int)std::min<long>(std::max<long>(strtol(s, nullptr, 10), 1), 8);
@@ -1569,6 +1613,7 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   }
   h->wave_frames = std::min(wave_frames, lane_batch);
   h->trace = getenv("PCOP_TRACE") != nullptr;
+  for (pcop_handle* l : h->extra_lanes) l->trace = h->trace;
   h->ece_small_max = ece_small_limit();
   if (const char* s = getenv("PCOP_PLANE_RESIDENT")) h->plane_resident = (s[0] == '0') ? 0 : 1;  // (the tests cover both paths)
   for (pcop_handle* l : h->extra_lanes) {

@@ -371,6 +371,8 @@ __global__ void __launch_bounds__(VP_THREADS)
   }
 }
 
+constexpr int VP_ORD_TAB = 1024;  // span of bucket ids a group may cover for the direct bucket -> ordinal table
+
 struct alignas(16) VpReduceSmem {
   uint32_t bitmap[VP_BITMAP_WORDS];         // one bit per key of the group's range
   unsigned short wprefix[VP_BITMAP_WORDS];  // voxels before each bitmap word, inside its round of 128 words

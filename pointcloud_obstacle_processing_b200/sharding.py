@@ -105,3 +105,126 @@ def _unpack(c, l, offs, idx, obs):
         ob.append(obs[pb:pb + 4 * c[k]].reshape(-1, 4).copy())
         pb += 4 * c[k]
     return GatheredResults(np.asarray(c), np.asarray(l), co, ci, ob)
+
+
+class ResultGather:
+    """Per-step result gather for batched runs, straight from the library's result arrays.
+
+    Every step each rank hands in its ctypes result array (`process_batch_raw`); the per-frame `cluster_offsets`,
+    `cluster_indices` and `obstacles` arrays -- adjacent in the library's pinned result buffer wave by wave, so they are
+    staged run by run with a handful of memmoves -- go to `dst` in two collectives: an all-gather of the per-frame
+    (C, L) counts and a gather of one int32 payload per rank ([offsets | indices | obstacle records], padded to a fixed
+    capacity so that no rank has to wait for another's sizes).  Asynchronous and double-buffered: the collectives of
+    step k run on the backend's stream while step k + 1 computes; `flush()` waits for the outstanding ones,
+    `last()` unpacks the most recent completed exchange on `dst` (GatheredResults, frames in rank-major order).
+    """
+
+    def __init__(self, frames_per_rank: int, device: torch.device, group=None, dst: int = 0,
+                 ints_per_frame: int = 10240):
+        import ctypes as C
+        from ._ctypes_abi import FrameResult
+        self._C = C
+        self.B = frames_per_rank
+        self.device = device
+        self.group = group
+        self.dst = dst
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.cap = frames_per_rank * ints_per_frame  # int32 elements per rank and step
+        self.rec = C.sizeof(FrameResult)
+        self.off = {k: getattr(FrameResult, k).offset for k in
+                    ("n_clusters", "n_cluster_points", "cluster_offsets", "cluster_indices", "obstacles")}
+        pin = device.type == "cuda"
+        self.slots = []
+        for _ in range(2):
+            stage = torch.empty(self.cap, dtype=torch.int32)
+            head = torch.empty(2 * frames_per_rank + 4, dtype=torch.int32)
+            self.slots.append({
+                "stage": stage.pin_memory() if pin else stage, "head": head.pin_memory() if pin else head,
+                "dev_head": torch.empty_like(head, device=device), "all_head": torch.empty((self.world, head.numel()), dtype=torch.int32, device=device),
+                "pad": torch.zeros(self.cap, dtype=torch.int32, device=device),
+                "out": torch.empty((self.world, self.cap), dtype=torch.int32, device=device) if self.rank == dst else None,
+                "work": [], "used": False})
+        self.step = 0
+        self.bytes_per_step = 0
+
+    def _runs(self, ptrs, sizes):
+        """(first frame index, bytes) of every maximal run of frames whose arrays are adjacent in memory"""
+        live = np.flatnonzero(sizes > 0)
+        if len(live) == 0:
+            return []
+        p, s = ptrs[live], sizes[live].astype(np.uint64)
+        brk = np.flatnonzero(p[1:] != p[:-1] + s[:-1]) + 1
+        starts = np.concatenate([[0], brk])
+        stops = np.concatenate([brk, [len(live)]])
+        return [(int(p[a]), int(s[a:b].sum())) for a, b in zip(starts, stops)]
+
+    def submit(self, res):
+        C = self._C
+        sl = self.slots[self.step & 1]
+        self.step += 1
+        for w in sl["work"]:  # the slot's buffers are free again once its previous exchange has completed
+            w.wait()
+        nf = len(res)
+        assert nf <= self.B
+        raw = np.frombuffer(res, dtype=np.uint8).reshape(nf, self.rec)
+        col32 = lambda k: raw[:, self.off[k]:self.off[k] + 4].copy().view(np.int32).ravel()
+        col64 = lambda k: raw[:, self.off[k]:self.off[k] + 8].copy().view(np.uint64).ravel()
+        c, l = col32("n_clusters"), col32("n_cluster_points")
+        parts = (("cluster_offsets", (c.astype(np.int64) + 1) * 4), ("cluster_indices", l.astype(np.int64) * 4),
+                 ("obstacles", c.astype(np.int64) * 16))
+        totals = [int(sz.sum()) // 4 for _, sz in parts]
+        if sum(totals) > self.cap:
+            raise ValueError(f"ResultGather: {sum(totals)} int32 per step exceed the exchange capacity {self.cap} "
+                             f"(raise ints_per_frame)")
+        base = sl["stage"].data_ptr()
+        o = 0
+        for key, sz in parts:
+            if (col64(key)[sz > 0] == 0).any():
+                raise ValueError("ResultGather needs frames processed with outputs | OUT_CLUSTERS | OUT_OBSTACLES (host results)")
+            for ptr, nbytes in self._runs(col64(key), sz):
+                C.memmove(base + o, ptr, nbytes)
+                o += nbytes
+        used = o // 4
+        h = sl["head"]
+        h[0], h[1], h[2], h[3] = nf, totals[0], totals[1], totals[2]
+        h[4:4 + nf] = torch.from_numpy(c)
+        h[4 + self.B:4 + self.B + nf] = torch.from_numpy(l)
+        sl["dev_head"].copy_(h, non_blocking=True)
+        sl["pad"][:used].copy_(sl["stage"][:used], non_blocking=True)
+        self.bytes_per_step = 4 * (used + h.numel())
+        if self.world == 1:
+            sl["all_head"][0].copy_(sl["dev_head"])
+            sl["out"][0].copy_(sl["pad"])
+            sl["work"] = []
+        else:
+            w1 = dist.all_gather_into_tensor(sl["all_head"].view(-1), sl["dev_head"], group=self.group, async_op=True)
+            w2 = dist.gather(sl["pad"], list(sl["out"].unbind(0)) if self.rank == self.dst else None, dst=self.dst,
+                             group=self.group, async_op=True)
+            sl["work"] = [w1, w2]
+        sl["used"] = True
+
+    def flush(self):
+        for sl in self.slots:
+            for w in sl["work"]:
+                w.wait()
+            sl["work"] = []
+
+    def last(self):
+        """GatheredResults of the most recent exchange (on `dst`; None elsewhere)"""
+        self.flush()
+        if self.rank != self.dst or self.step == 0:
+            return None
+        sl = self.slots[(self.step - 1) & 1]
+        heads = sl["all_head"].cpu().numpy()
+        outs = sl["out"].cpu().numpy()
+        cs, ls, os_, is_, bs = [], [], [], [], []
+        for r in range(self.world):
+            h = heads[r]
+            nf, to, ti, tb = int(h[0]), int(h[1]), int(h[2]), int(h[3])
+            cs.append(h[4:4 + nf].astype(np.int64))
+            ls.append(h[4 + self.B:4 + self.B + nf].astype(np.int64))
+            os_.append(outs[r][:to])
+            is_.append(outs[r][to:to + ti])
+            bs.append(outs[r][to + ti:to + ti + tb].view(np.float32))
+        return _unpack(np.concatenate(cs), np.concatenate(ls), np.concatenate(os_), np.concatenate(is_), np.concatenate(bs))

@@ -92,3 +92,53 @@ def test_cpp_host_compiles_links_and_fails_loudly_without_gpu(tmp_path):
     env = dict(os.environ, LD_LIBRARY_PATH=pkg_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([str(exe)], capture_output=True, text=True, env=env)
     assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+def _build_cpp(tmp_path, name):
+    exe = tmp_path / name
+    pkg_dir = os.path.join(ROOT, "pointcloud_obstacle_processing_b200")
+    pkg.load_library()  # (builds libpcop.so if missing)
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", name + ".cpp"), "-L", pkg_dir, "-lpcop", "-o", str(exe)])
+    env = dict(os.environ, LD_LIBRARY_PATH=pkg_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    return exe, env
+
+
+def test_cpp_digest_host_compiles(tmp_path):
+    _build_cpp(tmp_path, "pcop_host_digest")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config,frames", [(1, (0, 7)), (2, (0, 5))])
+def test_cpp_host_on_the_gpu_matches_the_golden_fixtures(tmp_path, config, frames):
+    """the node's host side is C++: a pure C++ caller of the C ABI (examples/pcop_host_digest.cpp, no Python between it and
+    libpcop.so) processes recorded frames on the GPU -- frame by frame and as one batch -- and the digests of every result
+    array must equal the oracle's golden fixtures: counts and CRC-32 of every index array and of the float arrays' bits"""
+    import json
+    import numpy as np
+    from pointcloud_obstacle_processing_b200 import synth
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "pipeline_golden.json")))["cases"]
+    exe, env = _build_cpp(tmp_path, "pcop_host_digest")
+    n = synth.points_per_frame(config)
+    clouds = np.stack([synth.frame(config, f) for f in frames])
+    path = tmp_path / "frames.bin"
+    clouds.astype(np.float32).tofile(path)
+    r = subprocess.run([str(exe), str(path), str(n), str(len(frames)), str(config)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    lines = [l.split() for l in r.stdout.splitlines() if l.startswith("frame ")]
+    assert len(lines) == 2 * len(frames)
+    crc_keys = ("crop_kept_idx", "voxel_keys", "voxel_centroids_bits", "sor_kept_idx", "plane_inlier_idx", "remaining_src_idx",
+                "remaining_cloud_bits", "cluster_offsets", "cluster_indices")
+    cnt_keys = ("n_input", "n_crop", "n_voxel", "n_sor", "n_remaining", "n_clusters", "n_cluster_points", "n_plane_passes",
+                "n_plane_inliers", "warnings")
+    for l in lines:
+        g = gold[f"config{config}_frame{frames[int(l[1])]}"]
+        counts = [int(x) for x in l[4:14]]
+        assert counts == [g["counts"][k] for k in cnt_keys], (l[:3], counts)
+        crcs = [int(x) for x in l[16:25]]
+        want = [g["crc"][k] for k in crc_keys]
+        if config == 2:  # SOR disabled: the library returns no array, the oracle reports the identity
+            crcs[3] = want[3]
+        assert crcs == want, (l[:3], crcs, want)
+        obs = np.array([float(x) for x in l[27:]], np.float64).reshape(-1, 4)
+        np.testing.assert_allclose(obs, np.array(g["obstacles"]).reshape(-1, 4), rtol=1e-5, atol=1e-5)

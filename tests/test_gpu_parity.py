@@ -818,3 +818,36 @@ def test_python_wrappers_reject_device_results():
     with ObstacleProcessor(p, 1000) as op:
         with pytest.raises(ValueError):
             op.process(np.zeros((10, 4), np.float32))
+
+
+def test_no_device_allocation_after_the_first_call():
+    """every buffer is allocated by pcop_create (the pinned result buffer grows once): repeated calls of the same shape
+    must not change the free device memory (cudaMemGetInfo)"""
+    import torch
+    p = synth.params(2)
+    n = synth.points_per_frame(2)
+    clouds = synth.frames(2, 500, 24)
+    counts = np.full(24, n, np.int32)
+    with ObstacleProcessor(p, n, max_batch=24) as op:
+        op.process_batch_raw(clouds.ctypes.data, n, counts)
+        torch.cuda.synchronize()
+        free0, _ = torch.cuda.mem_get_info()
+        for _ in range(3):
+            op.process_batch_raw(clouds.ctypes.data, n, counts)
+            op.process_batch_raw(clouds.ctypes.data, n, counts[:1])
+        torch.cuda.synchronize()
+        free1, _ = torch.cuda.mem_get_info()
+    assert free1 == free0, (free0, free1)
+
+
+def test_batch_larger_than_max_batch_runs_in_waves():
+    """a call may hold more frames than max_batch (the handle's wave buffers): it is processed in as many waves as it
+    takes; results of all frames stay valid until the next call"""
+    p = synth.params(2)
+    n = synth.points_per_frame(2)
+    B = 40
+    clouds = synth.frames(2, 600, B)
+    with ObstacleProcessor(p, n, max_batch=16) as op:
+        res = op.process_batch(clouds)
+    for f in (0, 7, 16, 23, 39):
+        compare_frames(res[f], O.process(p, clouds[f]), p, f"frame{f}: ")

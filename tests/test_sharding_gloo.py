@@ -4,6 +4,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -80,3 +81,126 @@ def test_gather_single_process():
     g = sharding.gather_results(ref, 2)
     assert g.n_clusters.tolist() == [f.n_clusters for f in ref]
     assert all(np.array_equal(a, f.cluster_indices) for a, f in zip(g.cluster_indices, ref))
+
+
+def _raw_results(frames):
+    """a ctypes pcop_frame_result array over oracle results (host pointers, as process_batch_raw returns them)"""
+    import ctypes as C
+    from pointcloud_obstacle_processing_b200._ctypes_abi import FrameResult
+    res = (FrameResult * len(frames))()
+    keep = []
+    # arrays of consecutive frames adjacent in memory (as in the library's pinned result buffer) for the first two
+    # frames, separate allocations for the others: the gather must stage both layouts
+    for k, f in enumerate(frames):
+        res[k].n_clusters = f.n_clusters
+        res[k].n_cluster_points = f.n_cluster_points
+    def place(field, arrays, ctype):
+        joint = np.concatenate([np.ascontiguousarray(a).reshape(-1) for a in arrays[:2]]) if len(arrays) >= 2 else None
+        o = 0
+        for k, a in enumerate(arrays):
+            a = np.ascontiguousarray(a).reshape(-1)
+            if k < 2 and joint is not None:
+                view = joint[o:o + a.size]
+                o += a.size
+                keep.append(joint)
+            else:
+                view = a.copy()
+                keep.append(view)
+            setattr(res[k], field, C.cast(view.ctypes.data, C.POINTER(ctype)) if view.size else C.cast(keep[0].ctypes.data, C.POINTER(ctype)))
+    place("cluster_offsets", [f.cluster_offsets for f in frames], C.c_int32)
+    place("cluster_indices", [f.cluster_indices for f in frames], C.c_int32)
+    place("obstacles", [f.obstacles for f in frames], C.c_float)
+    return res, keep
+
+
+def _worker_rg(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    per = 3
+    mine = _frames_for(rank * per, rank * per + per)
+    rg = sharding.ResultGather(per, torch.device("cpu"), ints_per_frame=40000)
+    for _ in range(3):  # several steps: the two exchange slots are reused
+        res, keep = _raw_results(mine)
+        rg.submit(res)
+    g = rg.last()
+    if rank == 0:
+        q.put((g.n_clusters.tolist(), [o.tolist() for o in g.cluster_offsets],
+               [i.tolist() for i in g.cluster_indices], [b.tolist() for b in g.obstacles]))
+    else:
+        assert g is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_result_gather_world2_gloo():
+    """the per-step gather bench.py runs over NCCL (cluster_offsets, cluster_indices, obstacles of every frame to rank 0),
+    here over gloo from raw ctypes result arrays"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_rg, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _frames_for(0, 6)
+    assert got[0] == [f.n_clusters for f in ref]
+    for k, f in enumerate(ref):
+        assert got[1][k] == f.cluster_offsets.tolist()
+        assert got[2][k] == f.cluster_indices.tolist()
+        assert np.array_equal(np.array(got[3][k], np.float32).reshape(-1, 4), f.obstacles)
+
+
+def _worker_nccl(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from pointcloud_obstacle_processing_b200 import ObstacleProcessor
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    per = 6
+    p = synth.params(2)
+    clouds = synth.frames(2, 40 + rank * per, per)
+    rg = sharding.ResultGather(per, torch.device("cuda", rank))
+    with ObstacleProcessor(p, clouds.shape[1], max_batch=per, device=rank) as op:
+        for _ in range(3):
+            res = op.process_batch_raw(clouds.ctypes.data, clouds.shape[1], np.full(per, clouds.shape[1], np.int32))
+            rg.submit(res)
+        g = rg.last()
+    if rank == 0:
+        q.put((g.n_clusters.tolist(), [o.tolist() for o in g.cluster_offsets],
+               [i.tolist() for i in g.cluster_indices], [b.tolist() for b in g.obstacles]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_result_gather_world2_nccl_matches_single_process_results():
+    """two ranks, one GPU each: every rank runs its frame shard through the CUDA library, rank 0 receives the CSR
+    clusters and obstacle records of all frames over NCCL; must equal the oracle on the concatenated frames"""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import oracle_lib as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_nccl, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    prm = synth.params(2)
+    ref = [O.process(prm, synth.frame(2, 40 + k)) for k in range(12)]
+    assert got[0] == [f.n_clusters for f in ref]
+    for k, f in enumerate(ref):
+        assert got[1][k] == f.cluster_offsets.tolist()
+        assert got[2][k] == f.cluster_indices.tolist()
+        np.testing.assert_allclose(np.array(got[3][k], np.float32).reshape(-1, 4), f.obstacles, rtol=1e-5, atol=1e-5)
