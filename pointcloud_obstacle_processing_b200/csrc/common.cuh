@@ -110,6 +110,7 @@ struct PlaneFrame {  // state of the plane loop of one frame
   int model_ok;      // selected + valid
   int need_more;     // the adaptive-k replay ran past the hypotheses scored so far
   int n_inliers_last;
+  double log_prob;   // det_log(1 - probability) (frame-resident path: evaluated once per frame)
   float4 coeff_sel;  // RANSAC winner
   float4 coeff_ref;  // after refinement
   float4 hyp[MAX_HYP];

@@ -251,6 +251,8 @@ struct PlaneArgs {
 cudaError_t run_plane(const Ctx& c, const PlaneArgs& a);
 // Largest plane-stage input the small tier of the resident path processes (see run_plane).
 int plane_small_tier_max();
+// Largest plane-stage input the resident path processes at all.
+int plane_resident_max();
 
 struct ClusterArgs {
   const float4* in;  // remaining cloud, frame f at in + f*in_stride
@@ -277,6 +279,8 @@ struct ClusterArgs {
   int* n_clusters;
   int* n_cluster_pts;
   float4* obstacles;  // [B*cap]
+  double* partial;    // [B][partial_stride] scratch of the centroid pass (sums of the pieces of large clusters)
+  int partial_stride;
 };
 // Largest cloud the fused shared-memory clustering kernel takes (stage_cluster_small.cu).
 constexpr int ECE_SMALL_MAX = 8960;

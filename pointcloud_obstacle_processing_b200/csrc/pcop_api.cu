@@ -174,6 +174,9 @@ struct pcop_handle {
   int plane_resident = 1;          // 0: PCOP_PLANE_RESIDENT=0 at create (host-looped plane kernels)
   bool expect_big_remaining = false;  // the last collected wave had a remaining cloud above ece_small_max
   bool expect_large_plane = false;    // ... a plane-stage input above the small tier of the resident plane kernel
+  int plane_hostloop_waves = 0;       // waves left that take the host-looped plane kernels (a frame was above the resident limit)
+  int vox_lsd_waves = 0;              // waves left that take the LSD voxel path (the partition path declined a bucket)
+  bool wave_plane_resident = false;   // the wave in flight ran the resident plane path
   bool wave_plane_speculated = false; // the wave in flight ran the small tier only
   const float4* plane_in = nullptr;   // plane-stage input of the wave in flight (for a repeat of the stage)
   size_t plane_stride = 0;
@@ -693,6 +696,8 @@ ClusterArgs make_cluster_args(pcop_handle* h, const float4* in, size_t stride, c
   a.n_clusters = h->cnt(CNT_CLUS);
   a.n_cluster_pts = h->cnt(CNT_CLPTS);
   a.obstacles = h->d_obst;
+  a.partial = h->d_partial;
+  a.partial_stride = cdiv(h->cap, TS_CHUNK) * 10;
   return a;
 }
 
@@ -777,10 +782,12 @@ int run_wave_plane(pcop_handle* h, int B, int max_n, bool large_tier) {
     PlaneArgs a = make_plane_args(h, h->plane_in, h->plane_stride, h->plane_n);
     a.n_in_copy = p.enable_sor ? nullptr : h->cnt(CNT_SOR);
     a.large_tier = large_tier ? 1 : 0;
+    if (h->plane_hostloop_waves > 0) a.resident = 0;
+    h->wave_plane_resident = a.resident != 0;
     if (!(effective_outputs(p) & PCOP_OUT_PLANE)) a.inlier_idx = nullptr;  // the inlier list is only written on request
     cudaError_t e = run_plane(c, a);
     if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
-    h->wave_plane_speculated = h->plane_resident && !large_tier && max_n > plane_small_tier_max();
+    h->wave_plane_speculated = a.resident && !large_tier && max_n > plane_small_tier_max();
   } else {
     KL(c, "k_copy_counts", k_copy_counts<<<cdiv(B, 256), 256, 0, h->stream>>>(h->plane_n, h->cnt(CNT_REM), B));
     KL(c, "k_copy_cloud", k_copy_cloud<<<dim3(cdiv(c.grid_cap, CT_TILE), B), CT_THREADS, 0, h->stream>>>(
@@ -795,7 +802,7 @@ int run_wave_stages(pcop_handle* h, int B, const float4* in, size_t stride, int 
   const pcop_params& p = h->params;
   Ctx c = make_ctx(h, B, max_n);  // no stage ever holds more points per frame than the largest input frame
   const int tiles = cdiv(h->cap, CT_TILE);
-  const int vmode = (h->vox_redo >= 0) ? h->vox_redo : h->vox_mode;
+  const int vmode = (h->vox_redo >= 0) ? h->vox_redo : ((h->vox_mode == 2 && h->vox_lsd_waves > 0) ? 1 : h->vox_mode);
   const bool fused_path = vmode != 0;
   if (!fused_path || (effective_outputs(p) & PCOP_OUT_CROP)) {  // (the fused voxel path zeroes the warnings itself)
     KL(c, "k_zero_u32", k_zero_u32<<<cdiv(B, 256), 256, 0, h->stream>>>(h->d_warnings, B));
@@ -1067,6 +1074,8 @@ int finish_wave(pcop_handle* h, const WaveInput& wi, uint32_t mask, pcop_frame_r
       for (int f = 0; f < B; ++f) mg = std::max(mg, h->h_counts[(size_t)CNT_GROUPS * h->maxB + f]);
       h->vp_group_hint = std::min(h->vp_gstride - 1, std::max(64, mg + mg / 4 + 8));
     }
+    if (h->vox_lsd_waves > 0) --h->vox_lsd_waves;
+    if (fl & 2u) h->vox_lsd_waves = 64;  // dense buckets tend to come back: the next waves go straight to the LSD path
     if (fl) {
       // the fused voxel path declined a frame of this wave: a survivor with a NaN y or z (generic kernels), a bucket
       // above the partition path's limit (LSD path), or more groups than the reduce grid covered (worst-case grid)
@@ -1079,19 +1088,23 @@ int finish_wave(pcop_handle* h, const WaveInput& wi, uint32_t mask, pcop_frame_r
       PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_meta));
     }
   }
-  bool plane_redone = false;
   if (h->params.enable_plane && h->plane_resident) {
-    bool large = false;  // (CNT_SOR = the plane stage's input size)
-    for (int f = 0; f < B; ++f) large = large || h->h_counts[(size_t)CNT_SOR * h->maxB + f] > plane_small_tier_max();
-    if (large && h->wave_plane_speculated) {  // a frame too large for the small tier of the plane kernel: repeat from there
+    bool large = false, huge = false;  // (CNT_SOR = the plane stage's input size)
+    for (int f = 0; f < B; ++f) {
+      const int s = h->h_counts[(size_t)CNT_SOR * h->maxB + f];
+      large = large || s > plane_small_tier_max();
+      huge = huge || s > plane_resident_max();
+    }
+    if (h->plane_hostloop_waves > 0) --h->plane_hostloop_waves;
+    if (huge) h->plane_hostloop_waves = 64;  // such frames tend to come back: host-looped kernels for the next waves
+    if (h->wave_plane_resident && (huge || (large && h->wave_plane_speculated))) {
+      // a frame too large for the tiers that ran: repeat the wave from the plane stage on
       TRY(run_wave_plane(h, B, h->pend_max_n, true));
       TRY(enqueue_wave_back(h, B, h->pend_max_n, mask, h->expect_big_remaining));
       PCOP_CUDA_TRY(cudaEventSynchronize(h->ev_meta));
-      plane_redone = true;
     }
     h->expect_large_plane = large;
   }
-  (void)plane_redone;
   if (h->params.enable_cluster) {
     bool big = false;
     for (int f = 0; f < B; ++f) big = big || h->h_counts[(size_t)CNT_REM * h->maxB + f] > h->ece_small_max;
@@ -1667,6 +1680,8 @@ int pcop_set_params(pcop_handle* h, const pcop_params* params) {
   }
   h->params = *params;
   h->vplan = make_plan(*params, (size_t)h->cap, &h->vox_mode);
+  h->vox_lsd_waves = 0;
+  h->plane_hostloop_waves = 0;
   for (pcop_handle* l : h->extra_lanes) {
     const int ls = pcop_set_params(l, params);
     if (ls != PCOP_OK) {
@@ -2039,6 +2054,7 @@ int pcop_plane(pcop_handle* h, const float* xyzw, int32_t s, float* remaining_xy
   Ctx c = make_ctx(h, 1, s);
   PlaneArgs a = make_plane_args(h, h->d_in, h->cap, h->cnt(CNT_SOR));
   a.large_tier = 1;
+  if (s > plane_resident_max()) a.resident = 0;  // (the host knows the size here)
   cudaError_t e = run_plane(c, a);
   if (e != cudaSuccess) return fail_cuda(h, e, "run_plane", __FILE__, __LINE__);
   KL(c, "k_plane_record", k_plane_record<<<1, 32, 0, h->stream>>>(h->d_pf, h->d_prec, h->cnt(CNT_NINL), h->cnt(CNT_CLUS), h->cnt(CNT_CLUS1), 1, 1));

@@ -432,11 +432,61 @@ __global__ void __launch_bounds__(256)
   indices[(size_t)f * cap + j] = (int)vs[j];
 }
 
-// one block per cluster (grid-stride over the frame's clusters): centroid in double, then radius
+// Centroid + bounding radius of every kept cluster (msg/PointWithRad.msg; distance arithmetic of od.cpp:457-464).
+// Work items: a cluster of up to CR_CHUNK members is one item (one block sums it, takes the mean and the radius); a
+// larger cluster is cut into CR_CHUNK-member pieces whose partial sums are combined in piece order by a second kernel
+// (deterministic, whatever the block scheduling), and a third pass takes the radius (a maximum: order-free).  Every
+// block enumerates the items by walking the cluster offsets (the host does not know the cluster sizes).
+constexpr int CR_CHUNK = 8192;
+constexpr int CR_GRID = 128;
+
+struct CrItem {
+  int c, piece, pieces, pslot;  // cluster, piece of it, number of pieces, first partial slot of the cluster
+};
+// item `want` of the frame (items in cluster order, pieces in order), or c = -1 past the end
+__device__ __forceinline__ CrItem cr_find_item(const int* __restrict__ offs, int C, int want, bool big_only) {
+  int item = 0, pslot = 0;
+  for (int c = 0; c < C; ++c) {
+    const int pieces = max(1, cdiv(offs[c + 1] - offs[c], CR_CHUNK));
+    const int cnt = (big_only && pieces == 1) ? 0 : pieces;
+    if (want < item + cnt) return CrItem{c, want - item, pieces, pslot};
+    item += cnt;
+    if (pieces > 1) pslot += pieces;
+  }
+  return CrItem{-1, 0, 0, 0};
+}
+
+__device__ __forceinline__ void cr_block_sum3(double& sx, double& sy, double& sz, double (*sh)[3]) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    sx += __shfl_xor_sync(FULL, sx, o);
+    sy += __shfl_xor_sync(FULL, sy, o);
+    sz += __shfl_xor_sync(FULL, sz, o);
+  }
+  __syncthreads();  // (sh may still be read from the previous item)
+  if (lane_id() == 0) {
+    sh[warp_id()][0] = sx;
+    sh[warp_id()][1] = sy;
+    sh[warp_id()][2] = sz;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float cr_block_max(float r, float* shr) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, o));
+  __syncthreads();
+  if (lane_id() == 0) shr[warp_id()] = r;
+  __syncthreads();
+  float rr = shr[0];
+  for (int w = 1; w < 8; ++w) rr = fmaxf(rr, shr[w]);
+  return rr;
+}
+
+// pass 1: every item's sum; single-piece clusters are finished here
 __global__ void __launch_bounds__(256)
     k_centroid_radius(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ offsets,
                       const int* __restrict__ indices, const int* __restrict__ n_clusters, float4* __restrict__ obstacles,
-                      int cap) {
+                      double* __restrict__ partial, int partial_stride, int cap) {
   const int f = blockIdx.y;
   const int C = n_clusters[f];
   const float4* src = in + (size_t)f * in_stride;
@@ -445,8 +495,10 @@ __global__ void __launch_bounds__(256)
   __shared__ double sh[8][3];
   __shared__ float shc[3];
   __shared__ float shr[8];
-  for (int c = blockIdx.x; c < C; c += gridDim.x) {
-    const int b = offs[c], e = offs[c + 1];
+  for (int item = blockIdx.x;; item += gridDim.x) {
+    const CrItem it = cr_find_item(offs, C, item, false);
+    if (it.c < 0) break;
+    const int b = offs[it.c] + it.piece * CR_CHUNK, e = min(offs[it.c + 1], b + CR_CHUNK);
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int j = b + threadIdx.x; j < e; j += blockDim.x) {
       const float4 p = __ldg(src + idx[j]);
@@ -454,18 +506,15 @@ __global__ void __launch_bounds__(256)
       sy += (double)p.y;
       sz += (double)p.z;
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      sx += __shfl_xor_sync(FULL, sx, o);
-      sy += __shfl_xor_sync(FULL, sy, o);
-      sz += __shfl_xor_sync(FULL, sz, o);
+    cr_block_sum3(sx, sy, sz, sh);
+    if (it.pieces > 1) {  // a piece of a large cluster: partial sum for k_centroid_combine
+      if (threadIdx.x < 3) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+        if (it.pslot + it.piece < partial_stride / 3) partial[(size_t)f * partial_stride + (size_t)(it.pslot + it.piece) * 3 + threadIdx.x] = s;
+      }
+      continue;
     }
-    if (lane_id() == 0) {
-      sh[warp_id()][0] = sx;
-      sh[warp_id()][1] = sy;
-      sh[warp_id()][2] = sz;
-    }
-    __syncthreads();
     if (threadIdx.x < 3) {
       double s = 0.0;
       for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
@@ -476,19 +525,58 @@ __global__ void __launch_bounds__(256)
     float r = 0.0f;
     for (int j = b + threadIdx.x; j < e; j += blockDim.x) {
       const float4 p = __ldg(src + idx[j]);
-      const float d = sqrtf(dist2(p.x, p.y, p.z, cx, cy, cz));  // od.cpp:457-464 arithmetic
-      r = fmaxf(r, d);
+      r = fmaxf(r, sqrtf(dist2(p.x, p.y, p.z, cx, cy, cz)));  // od.cpp:457-464 arithmetic
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) r = fmaxf(r, __shfl_xor_sync(FULL, r, o));
-    if (lane_id() == 0) shr[warp_id()] = r;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float rr = shr[0];
-      for (int w = 1; w < 8; ++w) rr = fmaxf(rr, shr[w]);
-      obstacles[(size_t)f * cap + c] = make_float4(cx, cy, cz, rr);
+    const float rr = cr_block_max(r, shr);
+    if (threadIdx.x == 0) obstacles[(size_t)f * cap + it.c] = make_float4(cx, cy, cz, rr);
+  }
+}
+
+// pass 2 (one warp per frame): centroids of the large clusters from their pieces' sums, in piece order; radius 0 for now
+__global__ void __launch_bounds__(32)
+    k_centroid_combine(const int* __restrict__ offsets, const int* __restrict__ n_clusters, float4* __restrict__ obstacles,
+                       const double* __restrict__ partial, int partial_stride, int cap) {
+  const int f = blockIdx.x;
+  const int C = n_clusters[f];
+  const int* offs = offsets + (size_t)f * (cap + 1);
+  int pslot = 0;
+  for (int c = 0; c < C; ++c) {
+    const int n = offs[c + 1] - offs[c];
+    const int pieces = max(1, cdiv(n, CR_CHUNK));
+    if (pieces == 1) continue;
+    if (threadIdx.x < 3) {
+      double s = 0.0;
+      for (int k = 0; k < pieces; ++k)
+        if (pslot + k < partial_stride / 3) s += partial[(size_t)f * partial_stride + (size_t)(pslot + k) * 3 + threadIdx.x];
+      (&obstacles[(size_t)f * cap + c].x)[threadIdx.x] = (float)(s / (double)n);
     }
-    __syncthreads();
+    if (threadIdx.x == 3) obstacles[(size_t)f * cap + c].w = 0.0f;
+    pslot += pieces;
+  }
+}
+
+// pass 3: radius of the large clusters, piece by piece (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256)
+    k_radius_big(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ offsets,
+                 const int* __restrict__ indices, const int* __restrict__ n_clusters, float4* __restrict__ obstacles, int cap) {
+  const int f = blockIdx.y;
+  const int C = n_clusters[f];
+  const float4* src = in + (size_t)f * in_stride;
+  const int* offs = offsets + (size_t)f * (cap + 1);
+  const int* idx = indices + (size_t)f * cap;
+  __shared__ float shr[8];
+  for (int item = blockIdx.x;; item += gridDim.x) {
+    const CrItem it = cr_find_item(offs, C, item, true);
+    if (it.c < 0) break;
+    const int b = offs[it.c] + it.piece * CR_CHUNK, e = min(offs[it.c + 1], b + CR_CHUNK);
+    const float4 cen = obstacles[(size_t)f * cap + it.c];
+    float r = 0.0f;
+    for (int j = b + threadIdx.x; j < e; j += blockDim.x) {
+      const float4 p = __ldg(src + idx[j]);
+      r = fmaxf(r, sqrtf(dist2(p.x, p.y, p.z, cen.x, cen.y, cen.z)));
+    }
+    const float rr = cr_block_max(r, shr);
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned*>(&obstacles[(size_t)f * cap + it.c].w), __float_as_uint(rr));
   }
 }
 
@@ -588,9 +676,15 @@ bool run_cluster(const Ctx& c, const ClusterArgs& a, bool with_generic) {
 }
 
 void run_centroid_radius(const Ctx& c, const ClusterArgs& a) {
-  KL(c, "k_centroid_radius", k_centroid_radius<<<dim3(64, c.B), 256, 0, c.stream>>>(a.in, a.in_stride, a.offsets, a.indices, a.n_clusters,
-                                                         a.obstacles, c.cap));
+  KL(c, "k_centroid_radius", k_centroid_radius<<<dim3(CR_GRID, c.B), 256, 0, c.stream>>>(a.in, a.in_stride, a.offsets, a.indices, a.n_clusters,
+                                                                                       a.obstacles, a.partial, a.partial_stride, c.cap));
   count_launch(c);
+  if (c.grid_cap > CR_CHUNK) {  // some cluster may be larger than one piece
+    KL(c, "k_centroid_combine", k_centroid_combine<<<c.B, 32, 0, c.stream>>>(a.offsets, a.n_clusters, a.obstacles, a.partial, a.partial_stride, c.cap));
+    KL(c, "k_radius_big", k_radius_big<<<dim3(CR_GRID, c.B), 256, 0, c.stream>>>(a.in, a.in_stride, a.offsets, a.indices, a.n_clusters,
+                                                                               a.obstacles, c.cap));
+    count_launch(c, 2);
+  }
 }
 
 }  // namespace pcop

@@ -395,9 +395,8 @@ __global__ void __launch_bounds__(CT_THREADS)
 // `navail` hypotheses have been scored so far: if the loop asks for a later one it returns true ("need more") and
 // decides nothing (the remaining hypotheses are scored, then this runs again).  count(h) = inliers of hypothesis h.
 template <class CountFn>
-__device__ __forceinline__ bool plane_select_replay(const PlaneConst& pc, int n, int nh, int navail, const int* hyp_valid,
-                                                    CountFn count, int& sel_out) {
-  const double log_probability = det_log(dsub(1.0, pc.probability));
+__device__ __forceinline__ bool plane_select_replay(const PlaneConst& pc, double log_probability, int n, int nh, int navail,
+                                                    const int* hyp_valid, CountFn count, int& sel_out) {
   const double one_over_indices = ddiv(1.0, (double)n);
   const double eps = 2.220446049250313e-16;
   int best = -2147483647;
@@ -431,7 +430,8 @@ __global__ void k_plane_select(PlaneFrame* __restrict__ pf, PlaneConst pc, int B
   P.need_more = 0;
   int sel = -1;
   const int* counts = P.counts;
-  if (plane_select_replay(pc, P.n, P.n_hyp, navail, P.hyp_valid, [counts](int h) { return counts[h]; }, sel)) {
+  if (plane_select_replay(pc, det_log(dsub(1.0, pc.probability)), P.n, P.n_hyp, navail, P.hyp_valid,
+                          [counts](int h) { return counts[h]; }, sel)) {
     P.need_more = 1;
     return;
   }
@@ -804,6 +804,7 @@ struct PlShared {
   int warp_excl[PL_MAX_WARPS];
   double msh[PL_MAX_GROUPS][8][9];   // per-warp moment sums of the chunk in flight
   int mcnt[PL_MAX_GROUPS][8];
+  double log_prob;  // det_log(1 - probability), from k_plane_gen0
   float4 coeff_sel, coeff_ref;
   int model_ok, need_more, nh, gen_end;
 };
@@ -817,6 +818,11 @@ __device__ __forceinline__ void group_bar_sync(int g) {
   else if (GROUPS > 2 && g == 2) asm volatile("bar.sync 3, 256;" ::: "memory");
   else if (GROUPS > 2) asm volatile("bar.sync 4, 256;" ::: "memory");
 }
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ unsigned cluster_ctarank() {
   unsigned r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -855,6 +861,7 @@ __global__ void __launch_bounds__(32)
     P.coeff_ref = make_float4(0.f, 0.f, 0.f, 0.f);
     P.active = active;
   }
+  if (lane == 1) P.log_prob = det_log(dsub(1.0, pc.probability));  // (constant of the adaptive-k rule, once per frame)
   for (int k = lane; k < PCOP_MAX_PLANE_PASSES_RECORDED; k += 32) {
     P.pass_points[k] = 0;
     P.pass_inliers[k] = 0;
@@ -914,7 +921,7 @@ __device__ __forceinline__ void pl_push_counts(PlShared& S, unsigned rank, int h
 __device__ __forceinline__ void pl_select(PlShared& S, const PlaneConst& pc, int n, int navail) {
   int sel = -1;
   const PlShared* Sp = &S;
-  const bool more = plane_select_replay(pc, n, S.nh, navail, S.hyp_valid,
+  const bool more = plane_select_replay(pc, S.log_prob, n, S.nh, navail, S.hyp_valid,
                                         [Sp](int h) {
                                           int c = 0;
 #pragma unroll
@@ -976,21 +983,34 @@ __global__ void __cluster_dims__(PL_CL, 1, 1) __launch_bounds__(THREADS, THREADS
     // slices: whole CT2048 chunks, so that a chunk never spans two CTAs
     const int SL = min(slice_cap, cdiv(cdiv(n, PL_CL), TS_CHUNK) * TS_CHUNK);
     const int lo = min((int)rank * SL, n), hi = min(lo + SL, n), sn = hi - lo;
-    // (ld.global.cg: an earlier pass of this launch may have left stale L1 lines; four loads in flight per thread)
-    for (int i0 = tid; i0 < sn; i0 += 4 * PL_THREADS) {
-      float4 p[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * PL_THREADS;
-        p[u] = (i < sn) ? __ldcg(pts + lo + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (first) {
+      // pass 0: the input was written by an earlier kernel, so the asynchronous copy path (cp.async, 4 bytes per
+      // coordinate straight into the x / y / z planes, no registers, everything in flight at once) is safe
+      for (int i = tid; i < sn; i += PL_THREADS) {
+        const float* g = reinterpret_cast<const float*>(pts + lo + i);
+        cp_async_f32(&sx[i], g);
+        cp_async_f32(&sy[i], g + 1);
+        cp_async_f32(&sz[i], g + 2);
       }
+      cp_async_wait_all();
+    } else {
+      // later passes read a cloud that other CTAs of the cluster wrote during this launch: ld.global.cg (an earlier
+      // pass may have left stale L1 lines), four loads in flight per thread
+      for (int i0 = tid; i0 < sn; i0 += 4 * PL_THREADS) {
+        float4 p[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * PL_THREADS;
-        if (i < sn) {
-          sx[i] = p[u].x;
-          sy[i] = p[u].y;
-          sz[i] = p[u].z;
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * PL_THREADS;
+          p[u] = (i < sn) ? __ldcg(pts + lo + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * PL_THREADS;
+          if (i < sn) {
+            sx[i] = p[u].x;
+            sy[i] = p[u].y;
+            sz[i] = p[u].z;
+          }
         }
       }
     }
@@ -998,6 +1018,7 @@ __global__ void __cluster_dims__(PL_CL, 1, 1) __launch_bounds__(THREADS, THREADS
       if (tid == 0) {
         S.nh = P.n_hyp;
         S.gen_end = P.gen_end;
+        S.log_prob = P.log_prob;
       }
       if (tid < MAX_HYP) {
         S.hyp[tid] = P.hyp[tid];
@@ -1240,9 +1261,10 @@ static cudaError_t run_plane_hostloop(const Ctx& c, const PlaneArgs& a);
 static void run_plane_finalize(const Ctx& c, const PlaneArgs& a, float4* out, int* out_src);
 
 int plane_small_tier_max() { return PL_CL * PL_SLICE_SMALL; }
+int plane_resident_max() { return PL_RESIDENT_MAX; }
 
 cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
-  if (!a.resident || c.grid_cap > PL_RESIDENT_MAX) {
+  if (!a.resident) {
     const cudaError_t e = run_plane_hostloop(c, a);
     if (e != cudaSuccess) return e;
     run_plane_finalize(c, a, a.out, a.out_src);
@@ -1259,7 +1281,8 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
   static_assert(sizeof(PlShared) % 16 == 0, "alignment of the regions behind PlShared");
   auto smem_bytes = [](int slice_cap) { return sizeof(PlShared) + (size_t)(PL_CL * slice_cap / TS_CHUNK) * 80 + (size_t)slice_cap * 12; };
   // small tier: slices of at most 8192 points (two CTAs per SM)
-  const int small_slice = std::min(PL_SLICE_SMALL, std::max(4096, cdiv(cdiv(c.grid_cap, PL_CL), TS_CHUNK) * TS_CHUNK));
+  const int bound = std::min(c.grid_cap, PL_RESIDENT_MAX);  // (frames above PL_RESIDENT_MAX points: see below)
+  const int small_slice = std::min(PL_SLICE_SMALL, std::max(4096, cdiv(cdiv(bound, PL_CL), TS_CHUNK) * TS_CHUNK));
   const int small_max = PL_CL * small_slice;
   {
     const size_t smem = smem_bytes(small_slice);
@@ -1272,9 +1295,10 @@ cudaError_t run_plane(const Ctx& c, const PlaneArgs& a) {
   // Larger frames (up to 131072 points) take the one-CTA-per-SM tier.  The host does not know the sizes of the clouds that
   // reach the plane stage, so the tier is launched only when the caller expects such frames (a.large_tier: a frame of an
   // earlier wave was that large, or the stage is being repeated because one of this wave turned out to be); frames it
-  // would have taken are left untouched by the small tier and reported through plane_small_tier_max().
+  // would have taken are left untouched by the small tier and reported through plane_small_tier_max().  Frames above
+  // plane_resident_max() points fit neither tier: the caller repeats the stage with a.resident = 0 (host-looped kernels).
   if (c.grid_cap > small_max && a.large_tier) {
-    const int slice_cap = cdiv(cdiv(c.grid_cap, PL_CL), TS_CHUNK) * TS_CHUNK;
+    const int slice_cap = cdiv(cdiv(bound, PL_CL), TS_CHUNK) * TS_CHUNK;
     const size_t smem = smem_bytes(slice_cap);
     cudaFuncSetAttribute(k_plane_loop<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     KL(c, "k_plane_loop_large", k_plane_loop<1024><<<dim3(PL_CL, c.B), 1024, smem, c.stream>>>(
