@@ -80,7 +80,7 @@ int main() {
                 r.cluster_offsets[c + 1] - r.cluster_offsets[c], r.obstacles[4 * c], r.obstacles[4 * c + 1],
                 r.obstacles[4 * c + 2], r.obstacles[4 * c + 3]);
 
-  // sensor 1.2 m above the far end of the arena, looking along -x (what the two TF lookups of od.cpp:580 / 562 return)
+  // sensor 1.2 m above the far end of the arena, looking along -x (what the two TF lookups of od.cpp:592 / 570 return)
   const float to_world[16] = {-1, 0, 0, 5.3f, 0, -1, 0, 1.89f, 0, 0, 1, 1.2f, 0, 0, 0, 1};
   const float to_sensor[16] = {-1, 0, 0, 5.3f, 0, -1, 0, 1.89f, 0, 0, 1, -1.2f, 0, 0, 0, 1};  // its inverse
   uint32_t warn = 0;

@@ -13,8 +13,9 @@
  *                                                                                 -> pcop_centroid_radius
  *   the whole stage sequence of cloud_cb (od.cpp:699-927)                         -> pcop_process / pcop_process_batch
  *   od.cpp:688-698  PointCloud2 decode + world transform + accumulate             -> pcop_accumulate_pointcloud2 / pcop_accumulate
+ *   od.cpp:290-294  toROSMsg of the intermediate clouds (debug publishers)           -> pcop_cloud_to_pointcloud2
  *   od.cpp:727  build_initial_occupancy_grid_dataset  (grid part od.cpp:134-157, 184-269) -> pcop_occupancy_grid
- *   od.cpp:817-833  handle_shadow_casting per cluster (od.cpp:466-672) + obstacle marks   -> pcop_occupancy_shadows
+ *   od.cpp:817-833  handle_shadow_casting per cluster (od.cpp:467-672) + obstacle marks   -> pcop_occupancy_shadows
  *
  * Plain C: POD structs, raw pointers and sizes, integer status codes.  No C++
  * exceptions, PCL, ROS or torch types cross this boundary.
@@ -75,8 +76,9 @@ enum {
   PCOP_OUT_ALL = 127,
   /* Modifier: leave the requested arrays in device memory.  The pcop_frame_result pointers are then DEVICE pointers
    * (valid until the next pcop_process* call on the handle; counts, warnings and the plane record are still host
-   * values) for a consumer that lives on the GPU: the next GPU stage, a peer-to-peer / NCCL transfer, or
-   * pcop_download.  A call may then hold at most 2 waves per lane (batch <= 2 * max_batch), else PCOP_ERR_CAPACITY. */
+   * values) for a consumer that lives on the GPU: the next GPU stage, a peer-to-peer / NCCL transfer,
+   * pcop_cloud_to_pointcloud2 or pcop_download.  The arrays of all waves of a call stay in the handle's pack buffers
+   * (sized by pcop_create for the worst case of one wave); a call whose results do not fit returns PCOP_ERR_CAPACITY. */
   PCOP_OUT_DEVICE = 256
 };
 
@@ -243,23 +245,35 @@ int pcop_accumulate_pointcloud2(pcop_handle* h, const unsigned char* data, int32
 int pcop_pointcloud2_to_xyz(pcop_handle* h, const unsigned char* data, int32_t n_points, int32_t point_step, int32_t off_x,
                             int32_t off_y, int32_t off_z, float* out_xyzw);
 
+/* ---- PointCloud2 wire egress (replaces the pcl::toROSMsg calls of the debug publishers, od.cpp:290-294, 332-339,
+ * 401-426) -------------------------------------------------------------------------------------------------
+ * pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZ>) copies the PointXYZ records verbatim into sensor_msgs/PointCloud2.data:
+ * point_step 16, fields x / y / z FLOAT32 (datatype 7, count 1) at offsets 0 / 4 / 8, the padding float travels along;
+ * width = n, height = 1, row_step = 16 n, is_bigendian = false.  pcop_cloud_to_pointcloud2 writes that payload for
+ * (point_step, offsets) = (16, 0, 4, 8); for any other layout it writes the three FLOAT32 fields of every record and
+ * zeroes the other bytes.
+ *   xyzw      the cloud (host or device pointer, e.g. a result array of a PCOP_OUT_DEVICE call), n records
+ *   out_data  n * point_step bytes (host or device pointer) */
+int pcop_cloud_to_pointcloud2(pcop_handle* h, const float* xyzw, int32_t n, int32_t point_step, int32_t off_x, int32_t off_y,
+                              int32_t off_z, unsigned char* out_data);
+
 /* ---- occupancy grid, initial data set (replaces od.cpp:134-157 + 175-269) ---------------------------------
  * The node's published product starts as a count of the crop survivors per block_size x block_size cell (rows along
  * -x from x_max, columns along +y from y_min), a per-row integer average and the threshold
  *   cell = (count < row_average * (1 - dev_percent)) ? 100 : 0        (float compare, od.cpp:258).
  * pcop_occupancy_dims: width/height as od.cpp:958-959.  pcop_occupancy_grid: xyzw = NULL takes the accumulated cloud
  * (pcop_accumulate*); grid_data[width*height] int8; counts[width*height] / row_avg[height] int64 are optional.
- * Shadow casting and the obstacle marks (od.cpp:466-672, 817-833): pcop_occupancy_shadows below. */
+ * Shadow casting and the obstacle marks (od.cpp:467-672, 817-833): pcop_occupancy_shadows below. */
 int pcop_occupancy_dims(const pcop_handle* h, int32_t* width, int32_t* height);
 int pcop_occupancy_grid(pcop_handle* h, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts, int64_t* row_avg);
 
-/* ---- occupancy grid, shadow casting + obstacle marks (replaces od.cpp:466-672 and the loops of od.cpp:817-833) ----
- * For every cluster of >= 2 points (handle_shadow_casting, od.cpp:572-662): the members go into the sensor frame
- * (world_to_sensor16 = the "kinect2_link" <- "world" TF lookup of od.cpp:580, row-major 4x4 float, applied with
+/* ---- occupancy grid, shadow casting + obstacle marks (replaces od.cpp:467-672 and the loops of od.cpp:817-833) ----
+ * For every cluster of >= 2 points (handle_shadow_casting, od.cpp:584-672): the members go into the sensor frame
+ * (world_to_sensor16 = the "kinect2_link" <- "world" TF lookup of od.cpp:592, row-major 4x4 float, applied with
  * pcl::transformPointCloud's coefficient formula); the first member with the smallest sensor x starts the shadow, the
- * largest x and the y range give its height and width; calculate_shadow_cast (od.cpp:539-570) gives the end point,
- * which goes back to the world frame through sensor_to_world16 (od.cpp:562, 626); a fan of ceil(width / block_size) + 3
- * lines (traceShadow, od.cpp:466-537) is drawn with cells set to grid_opacity.  Afterwards every remaining point with
+ * largest x and the y range give its height and width; calculate_shadow_cast (od.cpp:540-582) gives the end point,
+ * which goes back to the world frame through sensor_to_world16 (od.cpp:570, 634); a fan of ceil(width / block_size) + 3
+ * lines (traceShadow, od.cpp:467-538) is drawn with cells set to grid_opacity.  Afterwards every remaining point with
  * a non-NaN x marks its cell 100 (od.cpp:823-833).
  *   remaining_xyzw / cluster_offsets / cluster_indices   the arrays of a pcop_frame_result (host or device pointers)
  *   grid_data [height*width]   in/out (host or device pointer): the grid pcop_occupancy_grid produced

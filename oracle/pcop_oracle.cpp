@@ -985,6 +985,30 @@ int pcop_oracle_pointcloud2_to_xyz(const unsigned char* data, int32_t n_points, 
   return PCOP_OK;
 }
 
+// pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZ>) -> pcl::toPCLPointCloud2 (od.cpp:290-294 and the other debug
+// publishers): msg.data is a memcpy of the PointXYZ array, point_step = sizeof(PointXYZ) = 16, fields x, y, z FLOAT32 at
+// offsets 0, 4, 8.  Other layouts (not produced by the reference; offered for consumers with their own record format):
+// the three fields at their offsets, the rest of the record zero.
+int pcop_oracle_xyz_to_pointcloud2(const float* xyzw, int32_t n_points, int32_t point_step, int32_t off_x, int32_t off_y,
+                                   int32_t off_z, unsigned char* out_data) {
+  if ((n_points > 0 && (!xyzw || !out_data)) || n_points < 0 || point_step < 12 || off_x < 0 || off_y < 0 || off_z < 0 ||
+      off_x + 4 > point_step || off_y + 4 > point_step || off_z + 4 > point_step)
+    return PCOP_ERR_BAD_PARAM;
+  const bool verbatim = point_step == 16 && off_x == 0 && off_y == 4 && off_z == 8;
+  for (int32_t i = 0; i < n_points; ++i) {
+    unsigned char* rec = out_data + (size_t)i * (size_t)point_step;
+    if (verbatim) {
+      std::memcpy(rec, xyzw + 4 * (size_t)i, 16);
+      continue;
+    }
+    std::memset(rec, 0, (size_t)point_step);
+    std::memcpy(rec + off_x, xyzw + 4 * (size_t)i + 0, 4);
+    std::memcpy(rec + off_y, xyzw + 4 * (size_t)i + 1, 4);
+    std::memcpy(rec + off_z, xyzw + 4 * (size_t)i + 2, 4);
+  }
+  return PCOP_OK;
+}
+
 // od.cpp:958-960: (int)ceil((fabs(lo) + fabs(hi)) / block_size).  ORACLE CHOICE: the unqualified fabs binds to
 // ::fabs(double), so the sum and the division are evaluated in double.
 int pcop_oracle_occupancy_dims(const pcop_params* pr, int32_t* width, int32_t* height) {
@@ -1046,12 +1070,12 @@ int pcop_oracle_occupancy_grid(const pcop_params* pr, const float* xyzw, int32_t
 }
 
 // ---------------------------------------------------------------------------
-// Shadow casting + obstacle marking on the occupancy grid (od.cpp:466-672, 817-833).
+// Shadow casting + obstacle marking on the occupancy grid (od.cpp:467-672, 817-833).
 //
 // ORACLE CHOICES (the reference leaves these to the platform or runs into undefined behaviour):
 //  * unqualified fabs / sqrt / asin / tan / ceil bind to the double overloads of <math.h>; asin and tan are the
 //    deterministic det_asin / det_tan (det_math.hpp, < 1e-15 from libm away from |D| = pi/2);
-//  * the TF lookups (od.cpp:562, 580, 626) are explicit row-major 4x4 float matrices, applied with
+//  * the TF lookups (od.cpp:570, 580, 626) are explicit row-major 4x4 float matrices, applied with
 //    pcl::transformPointCloud's coefficient formula (pcop_oracle_transform, dense cloud);
 //  * get_occupancy_grid_x_y's while-loops stop at PCOP_OCC_COUNT_CAP = 2^20 steps (the reference would run on, and
 //    overflow its int counter, for a point that far outside the arena);
@@ -1105,7 +1129,7 @@ static P4 transform_one(const float* m, const P4& p) {
   return o;
 }
 
-// traceShadow (od.cpp:466-537), literal; returns false when the line is too long to draw
+// traceShadow (od.cpp:467-538), literal; returns false when the line is too long to draw
 static bool trace_shadow(float v1x, float v1y, float v2x, float v2y, int8_t* grid, int W, long long size, int8_t opacity) {
   int x0 = cvt_f2i(v1x), x1 = cvt_f2i(v2x), y0 = cvt_f2i(v1y), y1 = cvt_f2i(v2y);
   // abs() of the int differences; evaluated in 64 bits (no overflow)
@@ -1153,7 +1177,7 @@ int pcop_oracle_occupancy_shadows(const pcop_params* pr, const float* remaining_
   const float bs = pr->block_size;
   const int8_t opacity = (int8_t)pr->grid_opacity;  // int stored into a char cell (od.cpp:508)
   uint32_t warn = 0;
-  for (int32_t c = 0; c < n_clusters; ++c) {  // handle_shadow_casting (od.cpp:572-662), one call per cluster (od.cpp:817-821)
+  for (int32_t c = 0; c < n_clusters; ++c) {  // handle_shadow_casting (od.cpp:584-672), one call per cluster (od.cpp:817-821)
     int32_t* rec = shadow_records ? shadow_records + 6 * (size_t)c : nullptr;
     if (rec) std::fill(rec, rec + 6, 0);
     const int32_t o0 = cluster_offsets[c], o1 = cluster_offsets[c + 1];
@@ -1170,7 +1194,7 @@ int pcop_oracle_occupancy_shadows(const pcop_params* pr, const float* remaining_
     }
     volatile float hdiff = hmax - hmin;
     const float width = std::fabs(hdiff);  // od.cpp:616
-    // calculate_shadow_cast (od.cpp:539-570)
+    // calculate_shadow_cast (od.cpp:540-582)
     const float a = vmin_pt.z;
     const float b = std::fabs(vmin_pt.x);
     volatile float aa = a * a, bb = b * b;
@@ -1198,7 +1222,7 @@ int pcop_oracle_occupancy_shadows(const pcop_params* pr, const float* remaining_
     const P4 world_end = transform_one(sensor_to_world16, end);
     int end_x, end_y, start_x, start_y;
     occupancy_xy_capped(world_end.y, world_end.x, pr->y_min, pr->x_max, bs, &end_x, &end_y);  // od.cpp:569
-    const P4 world_start = transform_one(sensor_to_world16, vmin_pt);                        // od.cpp:626-634
+    const P4 world_start = transform_one(sensor_to_world16, vmin_pt);                        // od.cpp:634-634
     occupancy_xy_capped(world_start.y, world_start.x, pr->y_min, pr->x_max, bs, &start_x, &start_y);
     // od.cpp:642-643: first += ceil((width / block_size) / 2)   (int += double)
     volatile float wb = width / bs;

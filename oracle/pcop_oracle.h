@@ -50,6 +50,10 @@ int pcop_oracle_transform(const float* xyzw, int32_t n, const float* m16, int32_
  * padding float is 1.0f (default-constructed point, the field copy does not touch it). */
 int pcop_oracle_pointcloud2_to_xyz(const unsigned char* data, int32_t n_points, int32_t point_step, int32_t off_x,
                                    int32_t off_y, int32_t off_z, float* out_xyzw);
+/* Wire egress (od.cpp:290-294): pcl::toROSMsg of a PointXYZ cloud -- the records verbatim for the (16, 0, 4, 8) layout;
+ * for any other layout the three FLOAT32 fields at their offsets, other bytes zero. */
+int pcop_oracle_xyz_to_pointcloud2(const float* xyzw, int32_t n_points, int32_t point_step, int32_t off_x, int32_t off_y,
+                                   int32_t off_z, unsigned char* out_data);
 
 /* Initial occupancy-grid data set (od.cpp:134-157, 175-269, sizes od.cpp:958-960), literal: per crop survivor the cell
  * found by the two while-loops (float arithmetic), int64 counts, per-row integer average, cell = 100 when
@@ -59,8 +63,8 @@ int pcop_oracle_occupancy_dims(const pcop_params* pr, int32_t* width, int32_t* h
 int pcop_oracle_occupancy_grid(const pcop_params* pr, const float* xyzw, int32_t n, int8_t* grid_data, int64_t* counts,
                                int64_t* row_avg);
 
-/* Shadow casting + obstacle marking on the grid (od.cpp:466-672, 817-833): per cluster of >= 2 points the members go
- * into the sensor frame (world_to_sensor16 = the "kinect2_link" <- "world" lookup of od.cpp:580), the point with the
+/* Shadow casting + obstacle marking on the grid (od.cpp:467-672, 817-833): per cluster of >= 2 points the members go
+ * into the sensor frame (world_to_sensor16 = the "kinect2_link" <- "world" lookup of od.cpp:592), the point with the
  * smallest sensor x starts a fan of ceil(width / block_size) + 3 lines (traceShadow, cells set to grid_opacity) towards
  * the shadow end point (calculate_shadow_cast, back through sensor_to_world16); then every remaining point marks its
  * cell 100.  grid_data [height*width] is updated in place.  shadow_records (optional, [C][6]) = start_x, start_y,

@@ -39,6 +39,7 @@ EXPORTS = [
     "pcop_transform",
     "pcop_accumulate_pointcloud2",
     "pcop_pointcloud2_to_xyz",
+    "pcop_cloud_to_pointcloud2",
     "pcop_occupancy_dims",
     "pcop_occupancy_grid",
     "pcop_occupancy_shadows",
@@ -93,6 +94,7 @@ def load_library():
     L.pcop_transform.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.pcop_accumulate_pointcloud2.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp]
     L.pcop_pointcloud2_to_xyz.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.pcop_cloud_to_pointcloud2.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.pcop_download.argtypes = [vp, vp, vp, C.c_size_t]
     L.pcop_occupancy_dims.argtypes = [vp, vp, vp]
     L.pcop_occupancy_grid.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
@@ -232,6 +234,20 @@ class ObstacleProcessor:
                                                       off_y, off_z, out.ctypes.data_as(C.c_void_p)))
         return out[:n_points].copy()
 
+    def cloud_to_pointcloud2(self, cloud, point_step=16, off_x=0, off_y=4, off_z=8, device_ptr=None, n=None):
+        """pcl::toROSMsg of a PointXYZ cloud (od.cpp:290-294): the sensor_msgs/PointCloud2 payload as a uint8 array
+        [n * point_step].  `cloud` is a host array [n, 4], or pass device_ptr + n for a device-resident result array."""
+        if device_ptr is None:
+            cloud = _f32(cloud)
+            n = cloud.shape[0]
+            src = cloud.ctypes.data_as(C.c_void_p)
+        else:
+            src = C.c_void_p(int(device_ptr))
+        out = np.empty(max(n * point_step, 1), np.uint8)
+        self._check(self._lib.pcop_cloud_to_pointcloud2(self._h, src, n, point_step, off_x, off_y, off_z,
+                                                        out.ctypes.data_as(C.c_void_p)))
+        return out[:n * point_step]
+
     def occupancy_grid(self, cloud=None):
         """build_initial_occupancy_grid_dataset (od.cpp:175-269) without the crop output: returns (grid int8 [H, W],
         counts int64 [H, W], row_avg int64 [H]).  cloud=None: the accumulated cloud."""
@@ -251,9 +267,9 @@ class ObstacleProcessor:
 
     def handle_shadow_casting(self, grid, remaining_cloud, cluster_offsets, cluster_indices, world_to_sensor,
                               sensor_to_world):
-        """handle_shadow_casting for every cluster + the obstacle marks (od.cpp:572-662, 817-833) on `grid`
+        """handle_shadow_casting for every cluster + the obstacle marks (od.cpp:584-672, 817-833) on `grid`
         (int8 [H, W], e.g. from occupancy_grid()).  The two 4x4 matrices stand for the TF lookups
-        "kinect2_link" <- "world" (od.cpp:580) and "world" <- "kinect2_link" (od.cpp:562, 626).
+        "kinect2_link" <- "world" (od.cpp:592) and "world" <- "kinect2_link" (od.cpp:570, 634).
         Returns (grid int8 [H, W], shadow_records int32 [C, 6], warnings)."""
         w, h = C.c_int32(), C.c_int32()
         self._check(self._lib.pcop_occupancy_dims(self._h, C.byref(w), C.byref(h)))

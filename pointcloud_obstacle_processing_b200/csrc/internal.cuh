@@ -292,7 +292,7 @@ bool run_cluster(const Ctx& c, const ClusterArgs& a, bool with_generic);
 void run_cluster_small(const Ctx& c, const ClusterArgs& a, int small_max, bool zero_skipped);
 void run_centroid_radius(const Ctx& c, const ClusterArgs& a);
 
-// ---- occupancy grid: shadow casting + obstacle marking (stage_occupancy.cu; od.cpp:466-672, 817-833) ----------
+// ---- occupancy grid: shadow casting + obstacle marking (stage_occupancy.cu; od.cpp:467-672, 817-833) ----------
 struct Mat34 {
   float m[12];  // rows 0..2 of a row-major 4x4 (pcl::transformPointCloud's coefficient formula)
 };
@@ -302,7 +302,7 @@ struct OccShadowArgs {
   const int* offsets;   // [n_clusters + 1] CSR
   const int* indices;   // [L]
   int n_clusters;
-  Mat34 world_to_sensor, sensor_to_world;  // the two TF lookups of od.cpp:580 / 562, 626
+  Mat34 world_to_sensor, sensor_to_world;  // the two TF lookups of od.cpp:592 / 570, 634
   float y_min, x_max, block_size;
   int W;
   long long size;       // W * H

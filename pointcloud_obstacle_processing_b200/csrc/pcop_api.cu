@@ -398,6 +398,37 @@ __global__ void __launch_bounds__(256)
   out[i] = o;
 }
 
+// pcl::PointXYZ -> sensor_msgs/PointCloud2 payload (pcl::toROSMsg, od.cpp:290-294): the (16, 0, 4, 8) layout is the
+// record itself; any other layout gets the three FLOAT32 fields at their offsets (any alignment), other bytes zero
+__device__ __forceinline__ void pc2_store_f32(unsigned char* p, float v) {
+  const uint32_t b = __float_as_uint(v);
+  if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0u) {
+    *reinterpret_cast<uint32_t*>(p) = b;
+  } else {
+    p[0] = (unsigned char)b;
+    p[1] = (unsigned char)(b >> 8);
+    p[2] = (unsigned char)(b >> 16);
+    p[3] = (unsigned char)(b >> 24);
+  }
+}
+__global__ void __launch_bounds__(256)
+    k_pc2_egress(const float4* __restrict__ in, int n, int point_step, int off_x, int off_y, int off_z,
+                 unsigned char* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(in + i);
+  unsigned char* rec = out + (size_t)i * (size_t)point_step;
+  if (point_step == 16 && off_x == 0 && off_y == 4 && off_z == 8 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0u) {
+    *reinterpret_cast<float4*>(rec) = p;  // toROSMsg: the whole record, padding included
+    return;
+  }
+  for (int b = 0; b < point_step; ++b) rec[b] = 0;
+  pc2_store_f32(rec + off_x, p.x);
+  pc2_store_f32(rec + off_y, p.y);
+  pc2_store_f32(rec + off_z, p.z);
+  if (point_step == 16 && off_x == 0 && off_y == 4 && off_z == 8) pc2_store_f32(rec + 12, p.w);
+}
+
 // ---- occupancy grid, initial data set (od.cpp:134-157, 175-269) ---------------------------------------------------
 // get_occupancy_grid_x_y's while-loops in closed form: the smallest k >= 0 for which the loop condition fails.  The
 // edge value fl(a +- fl((k+1)*bs)) is monotone in k, so a floor estimate followed by a walk of a few steps lands on
@@ -1853,6 +1884,43 @@ int pcop_pointcloud2_to_xyz(pcop_handle* h, const unsigned char* data, int32_t n
   return PCOP_OK;
 }
 
+int pcop_cloud_to_pointcloud2(pcop_handle* h, const float* xyzw, int32_t n, int32_t point_step, int32_t off_x, int32_t off_y,
+                              int32_t off_z, unsigned char* out_data) {
+  if (!h || n < 0 || (n > 0 && (!xyzw || !out_data))) return fail(h, PCOP_ERR_BAD_PARAM, "null argument");
+  if (point_step < 12 || off_x < 0 || off_y < 0 || off_z < 0 || off_x + 4 > point_step || off_y + 4 > point_step ||
+      off_z + 4 > point_step)
+    return fail(h, PCOP_ERR_BAD_PARAM, "PointCloud2 field offsets do not fit point_step");
+  if (n > h->cap) return fail(h, PCOP_ERR_CAPACITY, "cloud has more points than max_points");
+  PCOP_CUDA_TRY(cudaSetDevice(h->device));
+  if (n == 0) return PCOP_OK;
+  const float4* src = reinterpret_cast<const float4*>(xyzw);
+  if (!is_device_pointer(xyzw)) {
+    PCOP_CUDA_TRY(cudaMemcpyAsync(h->d_in, xyzw, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+    src = h->d_in;
+  }
+  const size_t bytes = (size_t)n * (size_t)point_step;
+  unsigned char* dst = out_data;
+  const bool out_on_device = is_device_pointer(out_data);
+  if (!out_on_device) {  // staged through the raw-payload buffer of the ingest path
+    if (bytes > h->raw_cap) {
+      PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+      if (h->d_raw) cudaFree(h->d_raw);
+      h->d_raw = nullptr;
+      h->raw_cap = 0;
+      PCOP_CUDA_TRY(cudaMalloc((void**)&h->d_raw, bytes + bytes / 4 + 256));
+      h->raw_cap = bytes + bytes / 4 + 256;
+    }
+    dst = h->d_raw;
+  }
+  Ctx c = make_ctx(h, 1, n);
+  KL(c, "k_pc2_egress", k_pc2_egress<<<cdiv(n, 256), 256, 0, h->stream>>>(src, n, point_step, off_x, off_y, off_z, dst));
+  count_launch(c);
+  PCOP_CUDA_TRY(cudaGetLastError());
+  if (!out_on_device) TRY(download(h, out_data, dst, bytes));
+  PCOP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return PCOP_OK;
+}
+
 int pcop_occupancy_dims(const pcop_handle* h, int32_t* width, int32_t* height) {
   if (!h || !width || !height || !(h->params.block_size > 0.0f)) return PCOP_ERR_BAD_PARAM;
   const pcop_params& p = h->params;  // od.cpp:958-959 (double: the unqualified fabs is ::fabs(double))
@@ -1907,7 +1975,7 @@ int pcop_occupancy_grid(pcop_handle* h, const float* xyzw, int32_t n, int8_t* gr
   return PCOP_OK;
 }
 
-// Shadow casting + obstacle marking (od.cpp:466-672, 817-833) on a grid produced by pcop_occupancy_grid
+// Shadow casting + obstacle marking (od.cpp:467-672, 817-833) on a grid produced by pcop_occupancy_grid
 int pcop_occupancy_shadows(pcop_handle* h, const float* remaining_xyzw, int32_t n_remaining, const int32_t* cluster_offsets,
                            const int32_t* cluster_indices, int32_t n_clusters, const float* world_to_sensor16,
                            const float* sensor_to_world16, int8_t* grid_data, int32_t* shadow_records, uint32_t* warnings) {

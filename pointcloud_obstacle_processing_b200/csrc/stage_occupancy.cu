@@ -1,5 +1,5 @@
-// Shadow casting + obstacle marking on the occupancy grid (reference: traceShadow od.cpp:466-537,
-// calculate_shadow_cast od.cpp:539-570, handle_shadow_casting od.cpp:572-662, the per-cluster loop and the marking
+// Shadow casting + obstacle marking on the occupancy grid (reference: traceShadow od.cpp:467-538,
+// calculate_shadow_cast od.cpp:540-582, handle_shadow_casting od.cpp:584-672, the per-cluster loop and the marking
 // loop of cloud_cb od.cpp:817-833).
 //
 //   k_occ_shadow   one block per cluster: members into the sensor frame, the four extrema by a (value, position)
@@ -95,7 +95,7 @@ __device__ void ext_block_reduce(Ext& e, Ext* sh /* [SH_THREADS / 32] */) {
   for (int w = 1; w < SH_THREADS / 32; ++w) ext_merge<LESS>(e, sh[w].v, sh[w].pos);
 }
 
-// traceShadow (od.cpp:466-537); false: the line is too long to draw
+// traceShadow (od.cpp:467-538); false: the line is too long to draw
 __device__ bool trace_shadow(float v1x, float v1y, float v2x, float v2y, signed char* __restrict__ grid, int W, long long size,
                              signed char opacity) {
   int x0 = cvt_f2i(v1x), x1 = cvt_f2i(v2x), y0 = cvt_f2i(v1y), y1 = cvt_f2i(v2y);
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_occ_shadow(OccShadowArgs a) {
     const float vertical_max = x0nan ? q0.x : vmax.v;
     const float horizontal_min = y0nan ? q0.y : hmin.v, horizontal_max = y0nan ? q0.y : hmax.v;
     const float width = fabsf(fsub(horizontal_max, horizontal_min));  // od.cpp:616
-    // calculate_shadow_cast (od.cpp:539-570)
+    // calculate_shadow_cast (od.cpp:540-582)
     const float sa = vmin_pt.z;
     const float sb = fabsf(vmin_pt.x);
     const float sc = (float)__dsqrt_rn((double)fadd(fmul(sa, sa), fmul(sb, sb)));
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_occ_shadow(OccShadowArgs a) {
     const float4 world_end = xform(a.sensor_to_world, end);
     int end_x = occ_up_capped(a.y_min, a.block_size, world_end.y);     // od.cpp:569: (x, y) := (point.y, point.x)
     const int end_y = occ_down_capped(a.x_max, a.block_size, world_end.x);
-    const float4 world_start = xform(a.sensor_to_world, vmin_pt);      // od.cpp:626-637
+    const float4 world_start = xform(a.sensor_to_world, vmin_pt);      // od.cpp:634-637
     int start_x = occ_up_capped(a.y_min, a.block_size, world_start.y);
     const int start_y = occ_down_capped(a.x_max, a.block_size, world_start.x);
     // od.cpp:642-643: first += ceil((width / block_size) / 2)   (int += double)

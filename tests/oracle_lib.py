@@ -200,6 +200,16 @@ def transform(cloud, m, is_dense=False):
     return out
 
 
+def xyz_to_pointcloud2(cloud, point_step, off_x, off_y, off_z):
+    """pcl::toROSMsg restatement (od.cpp:290-294)"""
+    cloud, cp = _c(cloud, np.float32)
+    n = cloud.shape[0]
+    out = np.full(max(n * point_step, 1), 0xAB, np.uint8)
+    st = lib().pcop_oracle_xyz_to_pointcloud2(cp, n, point_step, off_x, off_y, off_z, out.ctypes.data_as(_fp))
+    assert st == 0, st
+    return out[:n * point_step]
+
+
 def pointcloud2_to_xyz(data, n_points, point_step, off_x, off_y, off_z):
     """pcl::fromPCLPointCloud2<PointXYZ> restatement (od.cpp:689)"""
     buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data, np.uint8)
@@ -225,7 +235,7 @@ def occupancy_grid(params, cloud):
 
 
 def occupancy_shadows(params, grid, remaining, offsets, indices, world_to_sensor, sensor_to_world):
-    """handle_shadow_casting per cluster + obstacle marks (od.cpp:572-662, 817-833): (grid, records [C, 6], warnings)"""
+    """handle_shadow_casting per cluster + obstacle marks (od.cpp:584-672, 817-833): (grid, records [C, 6], warnings)"""
     grid = np.array(grid, dtype=np.int8, order="C", copy=True)
     cloud = np.ascontiguousarray(remaining, np.float32).reshape(-1, 4)
     off = np.ascontiguousarray(offsets, np.int32)

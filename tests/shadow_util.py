@@ -1,4 +1,4 @@
-"""Synthetic scenes for the shadow-casting tests (od.cpp:466-672, 817-833): TEST INFRASTRUCTURE."""
+"""Synthetic scenes for the shadow-casting tests (od.cpp:467-672, 817-833): TEST INFRASTRUCTURE."""
 import numpy as np
 
 from pointcloud_obstacle_processing_b200 import synth

@@ -653,7 +653,7 @@ def test_batch_parity_on_64_frames():
 
 @pytest.mark.parametrize("seed,opacity", [(1, 0), (2, 50), (3, 77), (4, -5)])
 def test_occupancy_shadows_synthetic(seed, opacity):
-    """od.cpp:466-672, 817-833 on synthetic clusters and an arbitrary sensor pose: start / end cells, line counts and
+    """od.cpp:467-672, 817-833 on synthetic clusters and an arbitrary sensor pose: start / end cells, line counts and
     every grid cell bit-exact against the oracle"""
     from shadow_util import rigid, shadow_scene
     p = synth.params(1)
@@ -851,3 +851,37 @@ def test_batch_larger_than_max_batch_runs_in_waves():
         res = op.process_batch(clouds)
     for f in (0, 7, 16, 23, 39):
         compare_frames(res[f], O.process(p, clouds[f]), p, f"frame{f}: ")
+
+
+@pytest.mark.parametrize("point_step,offs", [(16, (0, 4, 8)), (32, (0, 4, 8)), (22, (1, 9, 14)), (12, (8, 0, 4))])
+def test_pointcloud2_egress(point_step, offs, frames):
+    """pcl::toROSMsg of the debug publishers (od.cpp:290-294): the PointCloud2 payload of a cloud, bit for bit; the
+    reference's own layout (16, 0, 4, 8) is the PointXYZ array itself, padding float included"""
+    p = all_outputs(synth.params(2))
+    cloud = frames[2]
+    with ObstacleProcessor(p, len(cloud)) as op:
+        fr = op.process(cloud)
+        for c in (fr.voxel_centroids, fr.remaining_cloud, cloud[:1], cloud[:0]):
+            g = op.cloud_to_pointcloud2(c, point_step, *offs)
+            o = O.xyz_to_pointcloud2(c, point_step, *offs)
+            assert_bits_equal(g, o, f"PointCloud2 payload ({len(c)} points)")
+        if point_step == 16:
+            assert g.tobytes() == np.ascontiguousarray(cloud[:0]).tobytes()
+            rt = op.pointcloud2_to_xyz(op.cloud_to_pointcloud2(fr.remaining_cloud), fr.n_remaining, 16, 0, 4, 8)
+            assert_bits_equal(rt, fr.remaining_cloud, "egress -> ingest round trip")
+
+
+def test_pointcloud2_egress_from_device_results():
+    """a result array left on the GPU (outputs | OUT_DEVICE) serialised without a detour through the host"""
+    p = synth.params(2)
+    cloud = synth.frame(2, 3)
+    with ObstacleProcessor(p, len(cloud)) as op:
+        host = op.process(cloud)
+    pd = p.copy()
+    pd.outputs = abi.OUT_DEFAULT | abi.OUT_DEVICE
+    with ObstacleProcessor(pd, len(cloud)) as op:
+        res = op.process_batch_raw(np.ascontiguousarray(cloud).ctypes.data, len(cloud), np.array([len(cloud)], np.int32))
+        import ctypes as C
+        ptr = C.cast(res[0].remaining_cloud, C.c_void_p).value
+        g = op.cloud_to_pointcloud2(None, device_ptr=ptr, n=res[0].n_remaining)
+    assert_bits_equal(g, O.xyz_to_pointcloud2(host.remaining_cloud, 16, 0, 4, 8), "payload of the device-resident remaining cloud")

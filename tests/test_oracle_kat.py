@@ -486,7 +486,7 @@ def test_occupancy_grid_against_literal_python_loops():
     assert counts.sum() > 1000
 
 
-# ---- occupancy grid: shadow casting + obstacle marks (od.cpp:466-672, 817-833) ------------------------------------
+# ---- occupancy grid: shadow casting + obstacle marks (od.cpp:467-672, 817-833) ------------------------------------
 from shadow_util import rigid as rigid_pair, shadow_scene  # noqa: E402
 
 
@@ -580,7 +580,7 @@ def literal_shadows(p, grid, cloud, offsets, indices, ws, sw):
 
 @pytest.mark.parametrize("seed,opacity", [(1, 0), (2, 50), (3, 77)])
 def test_occupancy_shadows_against_literal_python(seed, opacity):
-    """the oracle's shadow casting against an independent literal restatement of od.cpp:466-672, 817-833"""
+    """the oracle's shadow casting against an independent literal restatement of od.cpp:467-672, 817-833"""
     p = synth.params(1)
     p.grid_opacity = opacity
     cloud, offsets, indices = shadow_scene(seed)
@@ -607,7 +607,7 @@ def test_occupancy_shadows_degenerate_inputs():
     g_none, rec, warn = O.occupancy_shadows(p, grid0, cloud, np.zeros(1, np.int32), np.zeros(0, np.int32), ws, sw)
     assert rec.shape == (0, 6) and warn == 0 and (g_none == 100).sum() > 0 and (g_none == 33).sum() == 0
     bad = cloud.copy()
-    bad[indices[offsets[0]], 1] = np.nan  # first member of the largest cluster: its NaN y is never replaced (od.cpp:600-609)
+    bad[indices[offsets[0]], 1] = np.nan  # first member of the largest cluster: its NaN y is never replaced (od.cpp:608-620)
     g_nan, rec_nan, warn = O.occupancy_shadows(p, grid0, bad, offsets, indices, ws, sw)
     assert rec_nan[0, 4] == 0  # width = NaN -> the line-count comparison is false at once (od.cpp:645)
     far_sw, _ = rigid_pair(0.0, 0.0, 0.0, [-3.0e6, 3.0e6, 0.0])  # both cell searches run into the 2^20 step cap
@@ -635,3 +635,24 @@ def test_det_asin_tan_against_libm():
     assert math.isnan(L.pcop_oracle_det_asin(1.0000001)) and math.isnan(L.pcop_oracle_det_asin(float("nan")))
     for x in np.concatenate([rng.uniform(-1.5, 1.5, 2000), [0.0, 0.7, -1.2]]):
         assert abs(L.pcop_oracle_det_tan(x) - math.tan(x)) <= 1e-14 * max(1.0, abs(math.tan(x)))
+
+
+def test_pointcloud2_egress_layout_and_round_trip():
+    """pcl::toROSMsg of a PointXYZ cloud (od.cpp:290-294): the reference layout (16, 0, 4, 8) is the record array
+    itself (padding float included); other layouts carry the three fields and zeros, and the ingest restatement
+    (od.cpp:689) reads them back bit for bit"""
+    rng = np.random.default_rng(17)
+    cloud = rng.normal(size=(257, 4)).astype(np.float32)
+    cloud[3, 1] = np.nan
+    cloud[:, 3] = 1.0
+    assert O.xyz_to_pointcloud2(cloud, 16, 0, 4, 8).tobytes() == cloud.tobytes()
+    for step, offs in ((32, (0, 4, 8)), (22, (1, 9, 14)), (12, (8, 0, 4))):
+        data = O.xyz_to_pointcloud2(cloud, step, *offs)
+        assert data.shape == (257 * step,)
+        rec = data.reshape(257, step)
+        covered = np.zeros(step, bool)
+        for o in offs:
+            covered[o:o + 4] = True
+        assert not rec[:, ~covered].any()
+        back = O.pointcloud2_to_xyz(data, 257, step, *offs)
+        assert back.view(np.uint32).tolist() == cloud.view(np.uint32).tolist()
