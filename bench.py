@@ -348,19 +348,31 @@ def main():
     stage_acc = {}
     wall_instr = None
     if not args.no_kernel_timing:
-        op.enable_kernel_timing(True)
-        step_device()  # untimed: the single lane of this pass grows its pinned result buffer once
-        op.enable_kernel_timing(True)  # (re-enabling clears the accumulated totals)
+        # (its own handle: ONE lane with 256-frame waves -- the three lanes of the timed runs keep 3 x 128 frames in
+        # flight, a single lane of 128-frame waves would leave the latency-bound kernels a third of that)
+        saved = {k: os.environ.get(k) for k in ("PCOP_LANES", "PCOP_WAVE_FRAMES")}
+        os.environ["PCOP_LANES"] = "1"
+        os.environ["PCOP_WAVE_FRAMES"] = str(min(256, B))
+        op_i = ObstacleProcessor(params, n, max_batch=B, device=local_rank)
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        op_i.process_batch_raw(dev.data_ptr(), n, counts)  # untimed: grows the pinned result buffer, adapts the grids
+        op_i.enable_kernel_timing(True)
+        op_i.process_batch_raw(dev.data_ptr(), n, counts)
+        op_i.enable_kernel_timing(True)  # (re-enabling clears the accumulated totals)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            step_device()
-            for k, v in op.stage_times_us().items():
+            op_i.process_batch_raw(dev.data_ptr(), n, counts)
+            for k, v in op_i.stage_times_us().items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
         barrier()
         wall_instr = time.perf_counter() - t0
-        kernel_times = op.kernel_times()
-        op.enable_kernel_timing(False)
+        kernel_times = op_i.kernel_times()
+        op_i.close()
 
     # ---- end-to-end run (host frames in, results out) ------------------------------------------------
     for _ in range(2):
@@ -523,7 +535,7 @@ def main():
                     "what": "SURVEY 8(d): the stage's distinct inputs read once + distinct outputs written once (sort / "
                             "partition scratch not counted) / the stage's device time; dominant stage of the step",
                     "timed": "second pass of the same K steps with CUDA-event pairs around every stage and launch on the "
-                             "library's stream (lanes serialised so that each kernel runs alone)"}
+                             "library's stream: one lane, 256-frame waves, so that each kernel runs alone"}
         pipe_gbs = world * alg_bytes / wall / 1e9 if wall > 0 else None
         h2d = B * n * 16 + B * 4
         line = {
