@@ -289,13 +289,42 @@ def main():
     # double-buffered: the collectives of step k run on NCCL's stream while step k+1 computes; flush() waits for the
     # outstanding ones before a timed region ends.
     gather = sharding.ResultGather(B, torch.device("cuda", local_rank)) if world > 1 else None
+    # The staging of step k's arrays (a few dozen asynchronous copies out of the library's pinned result buffer) and the
+    # launch of its collectives run on a helper thread while the main thread is already inside the library call of step
+    # k + 1 (the library keeps a call's results valid while the next call runs, so at most one step may be pending).
+    import queue
+    gq = queue.Queue(maxsize=1)
+    gerr = []
+
+    def gather_worker():
+        torch.cuda.set_device(local_rank)
+        while True:
+            item = gq.get()
+            if item is None:
+                gq.task_done()
+                return
+            try:
+                gather.submit(item)
+            except Exception as e:  # surfaced by gather_flush()
+                gerr.append(e)
+            gq.task_done()
+
+    gthread = None
+    if gather is not None and not os.environ.get("PCOP_BENCH_NO_GATHER"):
+        gthread = threading.Thread(target=gather_worker, daemon=True)
+        gthread.start()
 
     def gather_results(res):
-        if gather is not None and not os.environ.get("PCOP_BENCH_NO_GATHER"):
-            gather.submit(res)
+        if gthread is not None:
+            gq.join()      # the previous step's staging has been enqueued ...
+            gather.wait_staged()  # ... and has run: its result buffer is free for the call after this one
+            gq.put(res)
 
     def gather_flush():
-        if gather is not None:
+        if gthread is not None:
+            gq.join()
+            if gerr:
+                raise gerr[0]
             gather.flush()
 
     peak, peak_kind = measured_peak_gbs()
@@ -409,8 +438,7 @@ def main():
         t0 = time.perf_counter()
         steps5 = 2
         for _ in range(steps5):
-            gather_results(op.process_batch_raw(big.data_ptr(), n, counts5)[:B])
-        gather_flush()
+            op.process_batch_raw(big.data_ptr(), n, counts5)
         barrier()
         w5 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev.device)
         if world > 1:
@@ -421,7 +449,7 @@ def main():
                 "ms_per_step": 1000.0 * w5 / steps5,
                 "roofline_frac": (alg_bytes / (args.steps * B)) * (world * steps5 * nb) / w5 / 1e9 / (peak * world),
                 "what": f"{nb} frames ({B} distinct frames x {reps5}) resident in HBM, results to pinned host memory, "
-                        f"whole job over {world} GPU(s)"}
+                        f"whole job over {world} GPU(s), no cross-rank gather"}
         del big
         torch.cuda.empty_cache()
 
@@ -576,6 +604,9 @@ def main():
             "cpu_baseline": cpu,
         }
         emit(line)
+    if gthread is not None:
+        gq.put(None)
+        gthread.join(timeout=10)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

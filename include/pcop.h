@@ -193,7 +193,10 @@ int pcop_abi_version(void);
 /* Replace parameters (no reallocation; capacity unchanged). */
 int pcop_set_params(pcop_handle* h, const pcop_params* params);
 
-/* One frame through every enabled stage (cloud_cb process branch, od.cpp:699-927). */
+/* One frame through every enabled stage (cloud_cb process branch, od.cpp:699-927).
+ * Host result arrays live in pinned buffers owned by the handle; the handle alternates between two of them, so the
+ * pointers a call returns stay valid until the call AFTER the next one on the same handle (a consumer -- the next
+ * pipeline stage, a multi-GPU gather -- may still read the results of call k while call k + 1 runs). */
 int pcop_process(pcop_handle* h, const float* xyzw, int32_t n, pcop_frame_result* out);
 
 /*

@@ -145,7 +145,12 @@ struct pcop_handle {
   int* h_n_in = nullptr;  // staging for the per-frame input sizes
   unsigned long long* h_stats = nullptr;
   unsigned long long sort_pass_keys = 0;
-  unsigned char* h_pack = nullptr;
+  // pinned result buffers: two per lane, used by alternate calls, so the pointers a call returns stay valid while the
+  // NEXT call runs (a consumer may still be reading them, e.g. the multi-GPU result gather)
+  unsigned char* h_pack_buf[2] = {nullptr, nullptr};
+  size_t h_pack_buf_cap[2] = {0, 0};
+  int h_pack_sel = 0;
+  unsigned char* h_pack = nullptr;  // = h_pack_buf[h_pack_sel]
   size_t h_pack_cap = 0;
   size_t h_pack_used = 0;  // of the running call
 
@@ -343,6 +348,8 @@ int ensure_host_pack(pcop_handle* h, size_t need) {
   }
   h->h_pack = q;
   h->h_pack_cap = ncap;
+  h->h_pack_buf[h->h_pack_sel] = q;
+  h->h_pack_buf_cap[h->h_pack_sel] = ncap;
   return PCOP_OK;
 }
 
@@ -1309,6 +1316,9 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     l->kt.used = 0;
     l->sort_pass_keys = 0;
     l->h_pack_used = 0;
+    l->h_pack_sel ^= 1;
+    l->h_pack = l->h_pack_buf[l->h_pack_sel];
+    l->h_pack_cap = l->h_pack_buf_cap[l->h_pack_sel];
     l->fixups.clear();
     l->wave_seq = 0;
     l->trace_used = 0;
@@ -1681,7 +1691,8 @@ void pcop_destroy(pcop_handle* h) {
   if (h->d_raw) cudaFree(h->d_raw);
   if (h->d_occ) cudaFree(h->d_occ);
   if (h->d_shadow) cudaFree(h->d_shadow);
-  if (h->h_pack) cudaFreeHost(h->h_pack);
+  for (int i = 0; i < 2; ++i)
+    if (h->h_pack_buf[i]) cudaFreeHost(h->h_pack_buf[i]);
   if (h->kt.ev) {
     for (int i = 0; i < 2 * KernelTimers::MAX_SLOTS; ++i) cudaEventDestroy(h->kt.ev[i]);
     delete[] h->kt.ev;

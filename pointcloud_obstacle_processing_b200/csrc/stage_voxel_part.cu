@@ -329,7 +329,10 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   }
 }
 
-__global__ void __launch_bounds__(VP_THREADS)
+// (512 threads: the kernel waits on its input loads -- 60 % of its stall samples -- and the 50 KB of cursors allow four
+// blocks per SM, so the wider block doubles the loads in flight)
+constexpr int VPS_THREADS = 512;
+__global__ void __launch_bounds__(VPS_THREADS)
     k_vp_scatter(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
                  const uint32_t* __restrict__ chunk_start, const uint32_t* __restrict__ flags, float4* __restrict__ part,
                  int cap, int chunks) {
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(VP_THREADS)
   if (flags[f]) return;  // a declined frame: the wave is repeated by another path
   extern __shared__ uint32_t vp_sh[];  // [nb_pad] next free slot of every (this chunk, bucket) range
   const uint32_t* cs = chunk_start + ((size_t)f * chunks + c) * pl.nb_pad;
-  for (int b = threadIdx.x; b < pl.nb_pad; b += VP_THREADS) vp_sh[b] = cs[b];
+  for (int b = threadIdx.x; b < pl.nb_pad; b += VPS_THREADS) vp_sh[b] = cs[b];
   __syncthreads();
   const int n = n_in[f];
   int i0, i1;
@@ -349,15 +352,15 @@ __global__ void __launch_bounds__(VP_THREADS)
   float4 nxt[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    const int i = i0 + threadIdx.x + u * VP_THREADS;
+    const int i = i0 + threadIdx.x + u * VPS_THREADS;
     nxt[u] = (i < i1) ? __ldg(src + i) : make_float4(qnan, 0.f, 0.f, 0.f);
   }
-  for (int b0 = i0 + threadIdx.x; b0 < i1; b0 += 4 * VP_THREADS) {
+  for (int b0 = i0 + threadIdx.x; b0 < i1; b0 += 4 * VPS_THREADS) {
     float4 p[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       p[u] = nxt[u];
-      const int i = b0 + (4 + u) * VP_THREADS;
+      const int i = b0 + (4 + u) * VPS_THREADS;
       nxt[u] = (i < i1) ? __ldg(src + i) : make_float4(qnan, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(VP_THREADS)
       if (vp_keep(p[u], pl)) {
         const uint32_t bucket = vp_key(p[u].x, p[u].y, p[u].z, pl) >> pl.part_shift;
         const uint32_t pos = atomicAdd(&vp_sh[bucket], 1u);
-        dst[pos] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(b0 + u * VP_THREADS));
+        dst[pos] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(b0 + u * VPS_THREADS));
       }
     }
   }
@@ -709,7 +712,7 @@ void run_voxel_part(const Ctx& c, const VoxelPartArgs& a) {
                                                                       a.want_keys, gmax, a.group_stride));
   const size_t ssm = (size_t)pl.nb_pad * sizeof(uint32_t);  // (<= 64 KB)
   cudaFuncSetAttribute(k_vp_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
-  KL(c, "k_vp_scatter", k_vp_scatter<<<dim3(chunks, c.B), VP_THREADS, ssm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.chunk_start,
+  KL(c, "k_vp_scatter", k_vp_scatter<<<dim3(chunks, c.B), VPS_THREADS, ssm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.chunk_start,
                                                                                        a.flags, a.part, c.cap, chunks));
   const size_t rsm = sizeof(VpReduceSmem);
   if (a.want_keys) {

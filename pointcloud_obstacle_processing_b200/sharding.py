@@ -107,6 +107,32 @@ def _unpack(c, l, offs, idx, obs):
     return GatheredResults(np.asarray(c), np.asarray(l), co, ci, ob)
 
 
+_cudart = None
+
+
+def _cuda_memcpy_h2d_async(dst_dev: int, src_host: int, nbytes: int, stream: int):
+    """cudaMemcpyAsync(host -> device) on raw addresses (the result arrays are library-owned pinned memory)"""
+    global _cudart
+    import ctypes as C
+    if _cudart is None:
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                _cudart = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _cudart is None:
+            import glob
+            import os
+            hits = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+            _cudart = C.CDLL(hits[0])
+        _cudart.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        _cudart.cudaMemcpyAsync.restype = C.c_int
+    st = _cudart.cudaMemcpyAsync(C.c_void_p(dst_dev), C.c_void_p(src_host), C.c_size_t(nbytes), 1, C.c_void_p(stream))
+    if st != 0:
+        raise RuntimeError(f"cudaMemcpyAsync failed with status {st}")
+
+
 class ResultGather:
     """Per-step result gather for batched runs, straight from the library's result arrays.
 
@@ -120,7 +146,7 @@ class ResultGather:
     """
 
     def __init__(self, frames_per_rank: int, device: torch.device, group=None, dst: int = 0,
-                 ints_per_frame: int = 10240):
+                 ints_per_frame: int = 8192):
         import ctypes as C
         from ._ctypes_abi import FrameResult
         self._C = C
@@ -177,21 +203,33 @@ class ResultGather:
         if sum(totals) > self.cap:
             raise ValueError(f"ResultGather: {sum(totals)} int32 per step exceed the exchange capacity {self.cap} "
                              f"(raise ints_per_frame)")
-        base = sl["stage"].data_ptr()
+        # CUDA: the arrays go straight from the library's pinned result buffer into the device exchange buffer
+        # (asynchronous copies on the current stream; the library keeps a call's results valid while the next call
+        # runs).  CPU (gloo tests): staged with memmove.
+        on_gpu = self.device.type == "cuda"
+        base = sl["pad"].data_ptr() if on_gpu else sl["stage"].data_ptr()
+        stream = torch.cuda.current_stream(self.device).cuda_stream if on_gpu else None
         o = 0
         for key, sz in parts:
             if (col64(key)[sz > 0] == 0).any():
                 raise ValueError("ResultGather needs frames processed with outputs | OUT_CLUSTERS | OUT_OBSTACLES (host results)")
             for ptr, nbytes in self._runs(col64(key), sz):
-                C.memmove(base + o, ptr, nbytes)
+                if on_gpu:
+                    _cuda_memcpy_h2d_async(base + o, ptr, nbytes, stream)
+                else:
+                    C.memmove(base + o, ptr, nbytes)
                 o += nbytes
         used = o // 4
+        if on_gpu:  # wait_staged(): the result arrays have been read
+            self._staged = torch.cuda.Event()
+            self._staged.record(torch.cuda.current_stream(self.device))
         h = sl["head"]
         h[0], h[1], h[2], h[3] = nf, totals[0], totals[1], totals[2]
         h[4:4 + nf] = torch.from_numpy(c)
         h[4 + self.B:4 + self.B + nf] = torch.from_numpy(l)
         sl["dev_head"].copy_(h, non_blocking=True)
-        sl["pad"][:used].copy_(sl["stage"][:used], non_blocking=True)
+        if not on_gpu:
+            sl["pad"][:used].copy_(sl["stage"][:used], non_blocking=True)
         self.bytes_per_step = 4 * (used + h.numel())
         if self.world == 1:
             sl["all_head"][0].copy_(sl["dev_head"])
@@ -203,6 +241,13 @@ class ResultGather:
                              group=self.group, async_op=True)
             sl["work"] = [w1, w2]
         sl["used"] = True
+
+    def wait_staged(self):
+        """blocks until the last submit()'s copies out of the library's result buffer have run (call it before the
+        call after next overwrites that buffer)"""
+        ev = getattr(self, "_staged", None)
+        if ev is not None:
+            ev.synchronize()
 
     def flush(self):
         for sl in self.slots:
