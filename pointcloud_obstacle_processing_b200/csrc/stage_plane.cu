@@ -818,11 +818,6 @@ __device__ __forceinline__ void group_bar_sync(int g) {
   else if (GROUPS > 2 && g == 2) asm volatile("bar.sync 3, 256;" ::: "memory");
   else if (GROUPS > 2) asm volatile("bar.sync 4, 256;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ unsigned cluster_ctarank() {
   unsigned r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -983,28 +978,21 @@ __global__ void __cluster_dims__(PL_CL, 1, 1) __launch_bounds__(THREADS, THREADS
     // slices: whole CT2048 chunks, so that a chunk never spans two CTAs
     const int SL = min(slice_cap, cdiv(cdiv(n, PL_CL), TS_CHUNK) * TS_CHUNK);
     const int lo = min((int)rank * SL, n), hi = min(lo + SL, n), sn = hi - lo;
-    if (first) {
-      // pass 0: the input was written by an earlier kernel, so the asynchronous copy path (cp.async, 4 bytes per
-      // coordinate straight into the x / y / z planes, no registers, everything in flight at once) is safe
-      for (int i = tid; i < sn; i += PL_THREADS) {
-        const float* g = reinterpret_cast<const float*>(pts + lo + i);
-        cp_async_f32(&sx[i], g);
-        cp_async_f32(&sy[i], g + 1);
-        cp_async_f32(&sz[i], g + 2);
-      }
-      cp_async_wait_all();
-    } else {
-      // later passes read a cloud that other CTAs of the cluster wrote during this launch: ld.global.cg (an earlier
-      // pass may have left stale L1 lines), four loads in flight per thread
-      for (int i0 = tid; i0 < sn; i0 += 4 * PL_THREADS) {
-        float4 p[4];
+    {
+      // slice load, eight 16-byte loads in flight per thread (the load is latency-bound: four in flight took 12 k cycles,
+      // and cp.async with 4-byte elements -- three per point straight into the planes -- is bound by the LDGSTS issue
+      // rate at 11.5 k).  Pass 0 reads the stage input (written by an earlier kernel); later passes read a cloud that
+      // other CTAs of the cluster wrote during this launch: ld.global.cg, an earlier pass may have left stale L1 lines.
+      const bool fresh = !first;
+      for (int i0 = tid; i0 < sn; i0 += 8 * PL_THREADS) {
+        float4 p[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * PL_THREADS;
-          p[u] = (i < sn) ? __ldcg(pts + lo + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          p[u] = (i < sn) ? (fresh ? __ldcg(pts + lo + i) : __ldg(pts + lo + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * PL_THREADS;
           if (i < sn) {
             sx[i] = p[u].x;
