@@ -563,9 +563,11 @@ __global__ void __launch_bounds__(VPR_THREADS, 3)
     if (e < E) {
       const uint32_t r = slot[k] >> 16;
       const int s0 = (int)sm.start[r], cnt = (int)sm.start[r + 1] - s0;
-      int rank = 0;
-      if (cnt > 1) {
+      // (a run of two needs no order: a + b == b + a; its elements keep the places they drew in pass 2)
+      int rank = (int)(slot[k] & 0xffffu);
+      if (cnt > 2) {
         const int mine = __float_as_int(p[k].w);
+        rank = 0;
         for (int t = 0; t < cnt; ++t) rank += (sm.sidx[s0 + t] < mine) ? 1 : 0;
       }
       sm.sx[s0 + rank] = p[k].x;
@@ -601,7 +603,8 @@ __global__ void __launch_bounds__(VPR_THREADS, 3)
         az = fadd(az, sm.sz[t]);
       }
       const float c = (float)(s1 - s0);
-      cen[k] = make_float4(fdiv(ax, c), fdiv(ay, c), fdiv(az, c), 1.0f);
+      // (x / 1.0f == x exactly: the single-point voxels, more than half of them, skip the three divisions)
+      cen[k] = (s1 - s0 == 1) ? make_float4(ax, ay, az, 1.0f) : make_float4(fdiv(ax, c), fdiv(ay, c), fdiv(az, c), 1.0f);
       if (WITH_KEYS) {  // PCL's key of this voxel, from one of its points (voxel_grid.hpp: ijk = floor(p*inv) - min_b)
         const int i0 = cvt_f2i(fsub(floorf(fmul(sm.sx[s0], vfr.inv)), fb0));
         const int i1 = cvt_f2i(fsub(floorf(fmul(sm.sy[s0], vfr.inv)), fb1));

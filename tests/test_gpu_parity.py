@@ -885,3 +885,20 @@ def test_pointcloud2_egress_from_device_results():
         ptr = C.cast(res[0].remaining_cloud, C.c_void_p).value
         g = op.cloud_to_pointcloud2(None, device_ptr=ptr, n=res[0].n_remaining)
     assert_bits_equal(g, O.xyz_to_pointcloud2(host.remaining_cloud, 16, 0, 4, 8), "payload of the device-resident remaining cloud")
+
+
+@pytest.mark.parametrize("config,batch,check", [(3, 6, (0, 3, 5)), (4, 3, (0, 2))])
+def test_batch_of_large_frames_through_the_generic_paths(config, batch, check):
+    """BASELINE configs[2] / [3] batched, as bench.py runs them: remaining clouds far above the fused clustering kernel's
+    8960 points (generic clustering after one speculative miss), dense voxel buckets (LSD voxel path after one declined
+    wave), a plane input above the resident kernel's small tier; two calls, so that the second one runs with the
+    handle's adapted choices"""
+    p = all_outputs(synth.params(config))
+    clouds = synth.frames(config, 20, batch)
+    with ObstacleProcessor(p, clouds.shape[1], max_batch=batch) as op:
+        first = op.process_batch(clouds)
+        res = op.process_batch(clouds)
+    for f in check:
+        o = O.process(p, clouds[f])
+        compare_frames(first[f], o, p, f"config {config} first call frame {f}: ")
+        compare_frames(res[f], o, p, f"config {config} second call frame {f}: ")
