@@ -214,10 +214,7 @@ struct VfPassSmem {
 #ifndef VF_SORT_MINBLOCKS
 #define VF_SORT_MINBLOCKS 4
 #endif
-// REREAD (experiment, off by default, not yet measured): rank on the key halves only and fetch the 8-byte elements
-// again (L1 / L2) when the tile is staged, as the big-tile compactions do with their payload: 16 registers instead of
-// 32 for the elements, no spills at 4 blocks per SM, 48 registers at 5.
-template <int BITS, bool USE_MATCH, int MINB = VF_SORT_MINBLOCKS, bool REREAD = false>
+template <int BITS, bool USE_MATCH, int MINB = VF_SORT_MINBLOCKS>
 __global__ void __launch_bounds__(RS_THREADS, MINB)
     k_vf_sort_pass(const unsigned long long* __restrict__ pair_in, unsigned long long* __restrict__ pair_out,
                    const int* __restrict__ count, const uint32_t* __restrict__ bin_base,
@@ -239,20 +236,15 @@ __global__ void __launch_bounds__(RS_THREADS, MINB)
 
   for (int i = threadIdx.x; i < (RS_THREADS / 32) * BINS; i += RS_THREADS) (&sm.warp_hist[0][0])[i] = 0u;
 
-  unsigned long long pr[REREAD ? 1 : VF_ITEMS];  // (key << 32) | index: one 8-byte load / store per element
-  uint32_t keyhalf[REREAD ? VF_ITEMS : 1];
+  unsigned long long pr[VF_ITEMS];  // (key << 32) | index: one 8-byte load / store per element
   unsigned short rank[VF_ITEMS];
   const int wbase_idx = tbase + warp * (32 * VF_ITEMS) + lane;
 #pragma unroll
   for (int k = 0; k < VF_ITEMS; ++k) {
     const int i = wbase_idx + k * 32;
-    if constexpr (REREAD) keyhalf[k] = (i < n) ? reinterpret_cast<const uint32_t*>(pin)[2 * (size_t)i + 1] : ~0u;
-    else pr[k] = (i < n) ? pin[i] : ~0ull;
+    pr[k] = (i < n) ? pin[i] : ~0ull;
   }
-  auto key_of = [&](int k) -> uint32_t {
-    if constexpr (REREAD) return keyhalf[k];
-    else return (uint32_t)(pr[k] >> 32);
-  };
+  auto key_of = [&](int k) -> uint32_t { return (uint32_t)(pr[k] >> 32); };
   __syncthreads();
   // rank keys inside the warp, row by row => stable.  All match masks first (independent, so their latencies
   // overlap), then one shared atomic per distinct digit of a row (issued by the lowest lane of the match group);
@@ -348,8 +340,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB)
     if (i < n) {
       const uint32_t d = (key_of(k) >> shift) & (BINS - 1);
       const uint32_t p = sm.tile_off[d] + sm.warp_hist[warp][d] + rank[k];
-      if constexpr (REREAD) sm.spair[p] = pin[i];
-      else sm.spair[p] = pr[k];
+      sm.spair[p] = pr[k];
     }
   }
   // decoupled look-back per digit over the earlier tiles of this frame
@@ -509,49 +500,28 @@ __global__ void __launch_bounds__(CT_THREADS)
   if (tbase + CT_TILE >= m && threadIdx.x == 0) n_out[f] = (int)incl_total;
 }
 
-template <int BITS, bool USE_MATCH, int MINB, bool REREAD = false>
+template <int BITS, bool USE_MATCH, int MINB>
 void launch_pass_b(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
-  cudaFuncSetAttribute(k_vf_sort_pass<BITS, USE_MATCH, MINB, REREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(k_vf_sort_pass<BITS, USE_MATCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(VfPassSmem<BITS>));
   const int src = pass & 1;
-  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS, USE_MATCH, MINB, REREAD><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
+  KL(c, "k_vf_sort_pass", k_vf_sort_pass<BITS, USE_MATCH, MINB><<<dim3(c.B, gtiles), RS_THREADS, sizeof(VfPassSmem<BITS>), c.stream>>>(
       a.pair[src], a.pair[src ^ 1], a.n_crop, a.sort.hist, a.sort.desc, pass, shift, c.cap, gtiles, a.sort.stats));
   count_launch(c);
 }
+// Blocks per SM the register allocation aims at: measured on B200 (5 x 1024 HDL-64 frames, all four passes): 3 blocks (80
+// registers) 10.42 ms, 4 blocks (64 registers, kept) 10.71 ms and the same step time, 5 blocks (48 registers + spills)
+// 12.09 ms, 6 blocks 13.14 ms.
 template <int BITS, bool USE_MATCH>
 void launch_pass_m(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
-  // blocks per SM the register allocation aims at (experiment knob).  Measured on B200 (5 x 1024 HDL-64 frames, all
-  // four passes): 3 blocks (80 registers) 10.42 ms, 4 blocks (64 registers, default) 10.71 ms and the same step time,
-  // 5 blocks (48 registers + spills) 12.09 ms, 6 blocks 13.14 ms
-  static const int minb = [] {
-    const char* s = getenv(USE_MATCH ? "PCOP_VF_SORT_MINB_MATCH" : "PCOP_VF_SORT_MINB_BALLOT");
-    return s ? atoi(s) : VF_SORT_MINBLOCKS;
-  }();
-  static const int reread = [] {
-    const char* s = getenv("PCOP_VF_SORT_REREAD");
-    return s ? atoi(s) : 0;
-  }();
-  if (BITS == 7 && reread && minb == 5) launch_pass_b<7, USE_MATCH, 5, true>(c, a, pass, shift, gtiles);
-  else if (BITS == 7 && reread && minb == 6) launch_pass_b<7, USE_MATCH, 6, true>(c, a, pass, shift, gtiles);
-  else if (BITS == 7 && reread) launch_pass_b<7, USE_MATCH, 4, true>(c, a, pass, shift, gtiles);
-  else if (BITS == 7 && minb == 5) launch_pass_b<7, USE_MATCH, 5>(c, a, pass, shift, gtiles);
-  else if (BITS == 7 && minb == 6) launch_pass_b<7, USE_MATCH, 6>(c, a, pass, shift, gtiles);
-  else if (BITS == 7 && minb == 3) launch_pass_b<7, USE_MATCH, 3>(c, a, pass, shift, gtiles);
-  else launch_pass_b<BITS, USE_MATCH, VF_SORT_MINBLOCKS>(c, a, pass, shift, gtiles);
+  launch_pass_b<BITS, USE_MATCH, VF_SORT_MINBLOCKS>(c, a, pass, shift, gtiles);
 }
 
-// match_mask bit p set: pass p ranks with MATCH.ANY (few distinct digits per warp), else with per-bit ballots
+// measured (B200, HDL-64 keys, 4 x 7 bits): MATCH.ANY on the two most significant digits (coarse y / z cells: few
+// distinct values per warp) and per-bit ballots on the others: 1.70 ms per 3 x 256 frames; all MATCH 1.94; all ballots 1.82
 template <int BITS>
 void launch_pass(const Ctx& c, const VoxelFusedArgs& a, int pass, int shift, int gtiles) {
-  static const int match_mask = [] {
-    const char* s = getenv("PCOP_VF_MATCH_MASK");
-    return s ? atoi(s) : -1;
-  }();
-  // measured (B200, HDL-64 keys, 4 x 7 bits): MATCH.ANY on the two most significant digits (coarse y / z cells: few
-  // distinct values per warp) and ballots on the others: 1.70 ms per 3 x 256 frames; all MATCH 1.94; all ballots 1.82
-  const bool top = (pass >= a.plan.npass - 2);
-  const bool use_match = (match_mask >= 0) ? ((match_mask >> pass) & 1) : top;
-  if (use_match) launch_pass_m<BITS, true>(c, a, pass, shift, gtiles);
+  if (pass >= a.plan.npass - 2) launch_pass_m<BITS, true>(c, a, pass, shift, gtiles);
   else launch_pass_m<BITS, false>(c, a, pass, shift, gtiles);
 }
 
@@ -587,8 +557,7 @@ VoxFusedPlan make_vox_fused_plan(const pcop_params& p) {
   pl.bits = bits;
   // measured on B200: four 7-bit passes over the 25-bit HDL-64 keys beat three 9-bit ones (a pass costs almost the
   // same for 128..512 bins per key, but the per-tile digit work doubles), so digits are capped at 8 bits by default
-  int max_digit = 8;
-  if (const char* s = getenv("PCOP_VF_BITS")) max_digit = std::min(VF_MAX_BITS, std::max(4, atoi(s)));  // tuning knob
+  const int max_digit = 8;
   pl.npass = (bits + max_digit - 1) / max_digit;
   if (pl.npass > VF_MAX_PASSES) return pl;
   pl.digit_bits = std::max(4, (bits + pl.npass - 1) / pl.npass);
@@ -619,17 +588,10 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   // registers, all 16 loads of a thread in flight) 4.58 ms, 5 blocks (46 registers) 3.97 ms, 6 blocks (32 registers)
   // 3.18 ms, 8 blocks 3.26 ms: the kernel is latency-bound (look-back wait, histogram flush), so resident warps beat
   // loads in flight per thread.
-  static const int crop_minb = [] {
-    const char* s = getenv("PCOP_VF_CROP_MINB");
-    return s ? atoi(s) : 6;
-  }();
 #define VF_CROP_LAUNCH(KEYS, MINB)                                                                              \
   KL(c, "k_vf_crop_key", k_vf_crop_key<KEYS, MINB><<<dim3(c.B, gbtiles), CT_THREADS, 0, c.stream>>>(            \
       a.in, a.in_stride, a.n_in, pl, a.pair[0], a.n_crop, a.minmax, a.sort.hist, a.flags, a.desc, c.cap, btiles))
   if (a.want_keys) VF_CROP_LAUNCH(true, 6);
-  else if (crop_minb == 4) VF_CROP_LAUNCH(false, 4);
-  else if (crop_minb == 5) VF_CROP_LAUNCH(false, 5);
-  else if (crop_minb == 8) VF_CROP_LAUNCH(false, 8);
   else VF_CROP_LAUNCH(false, 6);
 #undef VF_CROP_LAUNCH
   KL(c, "k_vf_scan", k_vf_scan<<<dim3(pl.npass, c.B), VF_MAX_BINS, 0, c.stream>>>(a.sort.hist, a.minmax, a.leaf, a.vf, a.want_keys));
@@ -648,14 +610,10 @@ void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a) {
   const int fin = pl.npass & 1;
   const int tiles = cdiv(c.cap, CT_TILE), gt = cdiv(c.grid_cap, CT_TILE);
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);
-  static const int contiguous = [] {
-    // measured (B200, 4 x 256 HDL-64 frames): dispatching a frame's tiles together (so that its input stays in L2
-    // for the gathers) is slower than frame-major dispatch, 1.56 vs 1.13 ms per step, even with the aggregates
-    // published before the gathers: the look-back chain inside a frame costs more than the second DRAM fetch of a
-    // sector.  Kept as an experiment knob.
-    const char* s = getenv("PCOP_VF_REDUCE_CONTIGUOUS");
-    return s ? atoi(s) : 0;
-  }();
+  // (dispatching a frame's tiles together, so that its input stays in L2 for the gathers, was slower than frame-major
+  // dispatch: 1.56 vs 1.13 ms per 4 x 256 frames -- the look-back chain inside a frame costs more than the second DRAM
+  // fetch of a sector)
+  const int contiguous = 0;
   const dim3 rgrid = contiguous ? dim3(gt, c.B) : dim3(c.B, gt);
   if (a.want_keys)
     KL(c, "k_vf_reduce", k_vf_reduce<true><<<rgrid, CT_THREADS, 0, c.stream>>>(
