@@ -12,6 +12,7 @@
 // same shape allocates nothing).
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -309,7 +310,7 @@ int dalloc(pcop_handle* h, T** p, size_t n) {
 template <class T>
 int halloc(pcop_handle* h, T** p, size_t n) {
   void* q = nullptr;
-  cudaError_t e = cudaHostAlloc(&q, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault);
+  cudaError_t e = cudaHostAlloc(&q, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocMapped);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc", __FILE__, __LINE__);
   h->host_allocs.push_back(q);
   *p = (T*)q;
@@ -339,7 +340,7 @@ int ensure_host_pack(pcop_handle* h, size_t need) {
   size_t ncap = std::max<size_t>(need, h->h_pack_cap * 2);
   ncap = std::max<size_t>(ncap, 1 << 20);
   unsigned char* q = nullptr;
-  cudaError_t e = cudaHostAlloc((void**)&q, ncap, cudaHostAllocDefault);
+  cudaError_t e = cudaHostAlloc((void**)&q, ncap, cudaHostAllocMapped);
   if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostAlloc(pack)", __FILE__, __LINE__);
   if (h->cstream) cudaStreamSynchronize(h->cstream);  // copies into the old buffer must have landed
   if (h->h_pack) {
@@ -623,6 +624,21 @@ __global__ void __launch_bounds__(256)
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = s[i];
   }
+}
+
+// The wave's counts, warnings, plane records, pack sizes and voxel-path flags go to the host as plain stores into
+// pinned (device-mapped) memory: as DMA copies they queue behind another lane's 17 MB payload copy on the same copy
+// engine (measured: 0.15-0.35 ms per wave, which also knocks the lanes out of step).
+struct MetaOut {
+  const uint32_t* src[5];
+  uint32_t* dst[5];
+  int words[5];
+};
+__global__ void __launch_bounds__(256) k_meta_out(MetaOut m) {
+  const int k = blockIdx.y;
+  const uint32_t* s = m.src[k];
+  uint32_t* d = m.dst[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.words[k]; i += gridDim.x * blockDim.x) d[i] = s[i];
 }
 
 struct StageTimer {
@@ -1005,8 +1021,7 @@ struct WaveInput {
 
 // Second half of a wave: clustering, result packing, and the copy of the wave's counts / plane records / pack sizes
 // into pinned memory, followed by ev_meta.
-int enqueue_wave_back(pcop_handle* h, int B, int max_n, uint32_t mask, bool cluster_with_generic) {
-  TRY(run_wave_cluster(h, B, max_n, cluster_with_generic));
+int enqueue_wave_pack(pcop_handle* h, int B, int max_n, uint32_t mask) {
   // pack the requested outputs of all frames of the wave
   Ctx c = make_ctx(h, B, max_n);
   StageTimer t(h, PCOP_STAGE_D2H);
@@ -1036,13 +1051,23 @@ int enqueue_wave_back(pcop_handle* h, int B, int max_n, uint32_t mask, bool clus
       count_launch(c);
     }
   }
-  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_counts, h->d_counts, sizeof(int) * CNT_ROWS * h->maxB, cudaMemcpyDeviceToHost,
-                                h->stream));
-  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_warnings, h->d_warnings, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, h->stream));
-  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_prec, h->d_prec, sizeof(PlaneRecord) * B, cudaMemcpyDeviceToHost, h->stream));
-  PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_meta, h->d_meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, h->stream));
-  if (h->wave_used_fused)
-    PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_vf_flags, h->d_vf_flags, sizeof(uint32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+  {
+    MetaOut m{};
+    int k = 0;
+    auto seg = [&](const void* src, void* dst, size_t bytes) {
+      m.src[k] = (const uint32_t*)src;
+      m.dst[k] = (uint32_t*)dst;
+      m.words[k] = (int)(bytes / 4);
+      ++k;
+    };
+    seg(h->d_counts, h->h_counts, sizeof(int) * CNT_ROWS * h->maxB);
+    seg(h->d_warnings, h->h_warnings, sizeof(uint32_t) * B);
+    seg(h->d_prec, h->h_prec, sizeof(PlaneRecord) * B);
+    seg(h->d_meta, h->h_meta, sizeof(PackMeta));
+    if (h->wave_used_fused) seg(h->d_vf_flags, h->h_vf_flags, sizeof(uint32_t) * B);
+    KL(c, "k_meta_out", k_meta_out<<<dim3(4, k), 256, 0, h->stream>>>(m));
+    count_launch(c);
+  }
   if (h->trace) {
     if (h->trace_used == h->trace_recs.size()) {
       pcop_handle::TraceRec r{};
@@ -1055,6 +1080,11 @@ int enqueue_wave_back(pcop_handle* h, int B, int max_n, uint32_t mask, bool clus
   }
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_meta, h->stream));
   return PCOP_OK;
+}
+
+int enqueue_wave_back(pcop_handle* h, int B, int max_n, uint32_t mask, bool cluster_with_generic) {
+  TRY(run_wave_cluster(h, B, max_n, cluster_with_generic));
+  return enqueue_wave_pack(h, B, max_n, mask);
 }
 
 // Enqueues one wave on lane h: input upload, all stages and enqueue_wave_back.  Returns without waiting for any of it.
@@ -1154,26 +1184,31 @@ int finish_wave(pcop_handle* h, const WaveInput& wi, uint32_t mask, pcop_frame_r
   }
   h->pending = false;
   pcop_frame_result* out = out_all + w0;
-  const PackMeta meta = *h->h_meta;
   const bool dev_results = (mask & PCOP_OUT_DEVICE) != 0;
+  const PackMeta meta = *h->h_meta;
   if (meta.overflow)
     return fail(h, PCOP_ERR_CAPACITY, "PCOP_OUT_DEVICE: the result arrays of this call do not fit the device pack buffer");
   const size_t base_off = (h->h_pack_used + 255) & ~(size_t)255;
+  if (h->trace) cudaEventRecord(h->trace_recs[h->trace_used].c0, h->cstream);
   if (!dev_results) {
     TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
-    // payload copy on the copy stream (the pack kernels have finished: ev_meta follows them)
-    if (h->trace) cudaEventRecord(h->trace_recs[h->trace_used].c0, h->cstream);
-    if (meta.total_bytes)
-      PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off, h->d_pack, meta.total_bytes, cudaMemcpyDeviceToHost, h->cstream));
-    if (h->trace) {
-      pcop_handle::TraceRec& tr = h->trace_recs[h->trace_used++];
-      cudaEventRecord(tr.c1, h->cstream);
-      tr.w0 = w0;
-      tr.B = B;
-      tr.bytes = (size_t)meta.total_bytes;
-    }
+    // payload copy on the copy stream (the pack kernels have finished: ev_meta follows them), in pieces: one large
+    // device-to-host copy holds up the kernels of the other lanes for as long as it runs (measured: 6.4 ms per
+    // 1024-frame call with one 17 MB copy per wave, 5.7 ms with 0.5-1 MB pieces, 5.9 / 6.2 ms with 2 / 4 MB pieces,
+    // 6.3 ms with 256 KB pieces -- the host thread becomes the limit -- and 5.3 ms with no copy at all)
+    const size_t piece = (size_t)1 << 20;
+    for (size_t o = 0; o < meta.total_bytes; o += piece)
+      PCOP_CUDA_TRY(cudaMemcpyAsync(h->h_pack + base_off + o, h->d_pack + o, std::min<size_t>(piece, meta.total_bytes - o),
+                                    cudaMemcpyDeviceToHost, h->cstream));
     PCOP_CUDA_TRY(cudaEventRecord(h->ev_copied, h->cstream));
     h->h_pack_used = base_off + meta.total_bytes;
+  }
+  if (h->trace) {
+    pcop_handle::TraceRec& tr = h->trace_recs[h->trace_used++];
+    cudaEventRecord(tr.c1, h->cstream);
+    tr.w0 = w0;
+    tr.B = B;
+    tr.bytes = dev_results ? 0 : (size_t)meta.total_bytes;
   }
   h->d2h_bytes += (dev_results ? 0.0 : (double)meta.total_bytes) +
                   (double)(sizeof(int) * CNT_ROWS * h->maxB + sizeof(uint32_t) * B + sizeof(PlaneRecord) * B + sizeof(PackMeta));
@@ -1273,6 +1308,11 @@ void merge_kernel_timers(pcop_handle* h, pcop_handle* l) {
   s.n_names = 0;
 }
 
+static std::chrono::steady_clock::time_point g_trace_t0;
+static double trace_host_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - g_trace_t0).count();
+}
+
 int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, const int32_t* n, int32_t batch,
                  pcop_frame_result* out) {
   if (!h) return fail(nullptr, PCOP_ERR_BAD_PARAM, "null handle");
@@ -1327,16 +1367,23 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     TRY(ensure_pack_capacity(l, mask));
   }
   PCOP_CUDA_TRY(cudaEventRecord(h->ev_call[0], h->stream));
+  if (h->trace) g_trace_t0 = std::chrono::steady_clock::now();
   for (size_t l = 0; l < lanes.size(); ++l) {
     if (l > 0) PCOP_CUDA_TRY(cudaStreamWaitEvent(lanes[l]->stream, h->ev_call[0], 0));
     PCOP_CUDA_TRY(cudaMemsetAsync(lanes[l]->sort.stats, 0, sizeof(unsigned long long), lanes[l]->stream));
-    if (mask & PCOP_OUT_DEVICE) PCOP_CUDA_TRY(cudaMemsetAsync(lanes[l]->d_pack_cursor, 0, sizeof(unsigned long long), lanes[l]->stream));
+    if (mask & PCOP_OUT_DEVICE)
+      PCOP_CUDA_TRY(cudaMemsetAsync(lanes[l]->d_pack_cursor, 0, sizeof(unsigned long long), lanes[l]->stream));
   }
   int status = PCOP_OK;
   for (size_t w = 0; w < waves.size() && status == PCOP_OK; ++w) {
     pcop_handle* l = lanes[w % lanes.size()];
+    const double th0 = h->trace ? trace_host_us() : 0.0;
     status = finish_wave(l, wi, mask, out);  // (the lane's previous wave, if any)
+    const double th1 = h->trace ? trace_host_us() : 0.0;
     if (status == PCOP_OK) status = enqueue_wave(l, wi, waves[w].first, waves[w].second, mask);
+    if (h->trace)
+      fprintf(stderr, "[pcop trace]   host: wave %4d+%-4d lane %zu: finish of the lane's previous wave %7.0f .. %7.0f us, enqueue .. %7.0f us\n",
+              waves[w].first, waves[w].second, w % lanes.size(), th0, th1, trace_host_us());
     if (status != PCOP_OK && l != h) h->err = l->err;
   }
   // collect what is still in flight, oldest first
@@ -1667,7 +1714,6 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   }
   h->wave_frames = std::min(wave_frames, lane_batch);
   h->trace = getenv("PCOP_TRACE") != nullptr;
-  for (pcop_handle* l : h->extra_lanes) l->trace = h->trace;
   h->ece_small_max = ece_small_limit();
   if (const char* s = getenv("PCOP_PLANE_RESIDENT")) h->plane_resident = (s[0] == '0') ? 0 : 1;  // (the tests cover both paths)
   for (pcop_handle* l : h->extra_lanes) {
