@@ -165,7 +165,7 @@ struct VoxelFusedArgs {
 void run_voxel_fused(const Ctx& c, const VoxelFusedArgs& a);
 
 // ---- fused crop + VoxelGrid, partition variant (stage_voxel_part.cu) ----------------------------------------------
-int vox_part_chunks(int max_n);
+int vox_part_chunks(int max_n, int B);
 int vox_part_group_bound(const VoxFusedPlan& pl, int max_n);  // worst-case groups of a frame of max_n points
 size_t vox_part_hist_elems(int B);
 size_t vox_part_start_elems(int B);

@@ -598,6 +598,29 @@ __global__ void k_pack_scan(int* __restrict__ counts, int maxB, int B, uint32_t 
   }
 }
 
+// The wave's counts, warnings, plane records, pack sizes and voxel-path flags go to the host as plain stores into
+// pinned (device-mapped) memory: as DMA copies they queue behind another lane's 17 MB payload copy on the same copy
+// engine (measured: 0.15-0.35 ms per wave, which also knocks the lanes out of step).
+struct MetaOut {
+  const uint32_t* src[5];
+  uint32_t* dst[5];
+  int words[5];
+  int frames;  // k_pack: the blocks of this many frames share the work (0: none)
+};
+__device__ __forceinline__ void meta_out_segment(const uint32_t* __restrict__ s, uint32_t* __restrict__ d, int words, int first,
+                                                 int stride) {
+  for (int i = first; i < words; i += stride) d[i] = s[i];
+}
+// (the segment index is compared against constants: indexing the parameter struct with a run-time value would make
+// every thread copy it to local memory first)
+__device__ __forceinline__ void meta_out(const MetaOut& m, int k, int first, int stride) {
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+    if (j == k && m.src[j]) meta_out_segment(m.src[j], m.dst[j], m.words[j], first, stride);
+}
+__global__ void __launch_bounds__(256) k_meta_out(MetaOut m) {
+  meta_out(m, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
 struct PackSrc {
   const uint32_t* src[PK_N];  // nullptr: not requested
   unsigned long long frame_stride_words[PK_N];
@@ -609,8 +632,10 @@ struct PackSrc {
 // everything is moved as 32-bit words (the 16-byte arrays as uint4)
 __global__ void __launch_bounds__(256)
     k_pack(PackSrc ps, const int* __restrict__ counts, int maxB, const int* __restrict__ pack_off,
-           const PackMeta* __restrict__ meta, unsigned char* __restrict__ pack) {
+           const PackMeta* __restrict__ meta, unsigned char* __restrict__ pack, MetaOut mo) {
   const int which = blockIdx.z, f = blockIdx.y;
+  if (f < mo.frames && which < 5)  // (metadata, see MetaOut: spread over the blocks of the first frames)
+    meta_out(mo, which, (f * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x, mo.frames * gridDim.x * blockDim.x);
   const uint32_t* base = ps.src[which];
   if (!base || meta->overflow) return;
   const int wpe = ps.words_per_elem[which];
@@ -624,21 +649,6 @@ __global__ void __launch_bounds__(256)
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = s[i];
   }
-}
-
-// The wave's counts, warnings, plane records, pack sizes and voxel-path flags go to the host as plain stores into
-// pinned (device-mapped) memory: as DMA copies they queue behind another lane's 17 MB payload copy on the same copy
-// engine (measured: 0.15-0.35 ms per wave, which also knocks the lanes out of step).
-struct MetaOut {
-  const uint32_t* src[5];
-  uint32_t* dst[5];
-  int words[5];
-};
-__global__ void __launch_bounds__(256) k_meta_out(MetaOut m) {
-  const int k = blockIdx.y;
-  const uint32_t* s = m.src[k];
-  uint32_t* d = m.dst[k];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.words[k]; i += gridDim.x * blockDim.x) d[i] = s[i];
 }
 
 struct StageTimer {
@@ -1045,28 +1055,29 @@ int enqueue_wave_pack(pcop_handle* h, int B, int max_n, uint32_t mask) {
       ps.words_per_elem[k] = kPkElem[k] / 4;
       any = any || ps.src[k];
     }
-    if (any) {
-      const int gx = std::max(1, std::min(cdiv(c.grid_cap, 256 * 4), 16));
-      KL(c, "k_pack", k_pack<<<dim3(gx, B, PK_N), 256, 0, h->stream>>>(ps, h->d_counts, h->maxB, h->d_pack_off, h->d_meta, h->d_pack));
-      count_launch(c);
-    }
-  }
-  {
     MetaOut m{};
-    int k = 0;
+    int nseg = 0;
     auto seg = [&](const void* src, void* dst, size_t bytes) {
-      m.src[k] = (const uint32_t*)src;
-      m.dst[k] = (uint32_t*)dst;
-      m.words[k] = (int)(bytes / 4);
-      ++k;
+      m.src[nseg] = (const uint32_t*)src;
+      m.dst[nseg] = (uint32_t*)dst;
+      m.words[nseg] = (int)(bytes / 4);
+      ++nseg;
     };
     seg(h->d_counts, h->h_counts, sizeof(int) * CNT_ROWS * h->maxB);
     seg(h->d_warnings, h->h_warnings, sizeof(uint32_t) * B);
     seg(h->d_prec, h->h_prec, sizeof(PlaneRecord) * B);
     seg(h->d_meta, h->h_meta, sizeof(PackMeta));
     if (h->wave_used_fused) seg(h->d_vf_flags, h->h_vf_flags, sizeof(uint32_t) * B);
-    KL(c, "k_meta_out", k_meta_out<<<dim3(4, k), 256, 0, h->stream>>>(m));
-    count_launch(c);
+    static_assert(PK_N >= 5, "one pack block per metadata segment");
+    if (any) {  // the (frame < 4, array k < 5) blocks of the pack kernel also carry metadata segment k out
+      const int gx = std::max(1, std::min(cdiv(c.grid_cap, 256 * 4), 16));
+      m.frames = std::min(B, 4);
+      KL(c, "k_pack", k_pack<<<dim3(gx, B, PK_N), 256, 0, h->stream>>>(ps, h->d_counts, h->maxB, h->d_pack_off, h->d_meta, h->d_pack, m));
+      count_launch(c);
+    } else {
+      KL(c, "k_meta_out", k_meta_out<<<dim3(4, nseg), 256, 0, h->stream>>>(m));
+      count_launch(c);
+    }
   }
   if (h->trace) {
     if (h->trace_used == h->trace_recs.size()) {

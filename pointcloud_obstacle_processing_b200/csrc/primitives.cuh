@@ -21,6 +21,23 @@ __device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Spin until a look-back descriptor is published (status bits non-zero).  Forward progress rests on the dispatch order
+// described below; a build with -DPCOP_LOOKBACK_SPIN_LIMIT=<n> turns a wait of more than n polls into a trap (a
+// sticky launch error the API reports) instead of a hang -- for runs under tools that serialise or reorder blocks.
+__device__ __forceinline__ unsigned lookback_wait(const unsigned* p) {
+  unsigned d = ld_volatile_u32(p);
+#ifdef PCOP_LOOKBACK_SPIN_LIMIT
+  unsigned long long polls = 0ull;
+#endif
+  while ((d >> 30) == 0u) {
+#ifdef PCOP_LOOKBACK_SPIN_LIMIT
+    if (++polls > (unsigned long long)(PCOP_LOOKBACK_SPIN_LIMIT)) __trap();
+#endif
+    d = ld_volatile_u32(p);
+  }
+  return d;
+}
+
 // ---- decoupled look-back ------------------------------------------------------
 // One 32-bit descriptor per tile: status in bits 31..30 (0 = not ready, 1 = tile aggregate,
 // 2 = inclusive prefix), value in bits 29..0.  Status and value travel in one word, so no
@@ -46,8 +63,7 @@ __device__ __forceinline__ unsigned lookback_warp(unsigned* desc_frame, int tile
     const int idx = look - lane;
     unsigned d = LB_PREFIX;  // lanes past the first tile read as "prefix 0"
     if (idx >= 0) {
-      d = ld_volatile_u32(desc_frame + idx);
-      while ((d >> 30) == 0u) d = ld_volatile_u32(desc_frame + idx);
+      d = lookback_wait(desc_frame + idx);
     }
     const unsigned is_prefix = __ballot_sync(FULL, (d >> 30) == 2u);
     const int first = is_prefix ? (__ffs(is_prefix) - 1) : 31;  // nearest tile that already knows its inclusive prefix

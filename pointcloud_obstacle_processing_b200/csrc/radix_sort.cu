@@ -189,8 +189,7 @@ __global__ void __launch_bounds__(RS_THREADS, 6)
     uint32_t excl = 0;
     if (tile > 0) {
       for (int t = tile - 1; t >= 0; --t) {
-        unsigned v = ld_volatile_u32(dd + (size_t)t * RS_BINS);
-        while ((v >> 30) == 0u) v = ld_volatile_u32(dd + (size_t)t * RS_BINS);
+        const unsigned v = lookback_wait(dd + (size_t)t * RS_BINS);
         excl += v & LB_VALUE;
         if ((v >> 30) == 2u) break;
       }

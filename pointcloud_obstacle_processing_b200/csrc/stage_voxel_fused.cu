@@ -352,8 +352,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB)
       if (tile > 0) {
         unsigned* dd = dd_frame + d;
         for (int t = tile - 1; t >= 0; --t) {
-          unsigned v = ld_volatile_u32(dd + (size_t)t * BINS);
-          while ((v >> 30) == 0u) v = ld_volatile_u32(dd + (size_t)t * BINS);
+          const unsigned v = lookback_wait(dd + (size_t)t * BINS);
           excl += v & LB_VALUE;
           if ((v >> 30) == 2u) break;
         }

@@ -621,8 +621,7 @@ __global__ void __launch_bounds__(VPR_THREADS, 3)
       const int idx = look - lane;
       unsigned d = LB_PREFIX;  // lanes past the first group read as "prefix 0"
       if (idx >= 0) {
-        d = ld_volatile_u32(dd + idx);
-        while ((d >> 30) == 0u) d = ld_volatile_u32(dd + idx);
+        d = lookback_wait(dd + idx);
       }
       const unsigned is_prefix = __ballot_sync(FULL, (d >> 30) == 2u);
       const int first = is_prefix ? (__ffs(is_prefix) - 1) : 31;
@@ -680,7 +679,12 @@ void vox_part_plan(VoxFusedPlan& pl, size_t max_points) {
 
 // histogram / scatter blocks per frame: chunks of ~24 576 points (measured: 8 / 4 / 3 chunks per 120 k-point frame 5.53 /
 // 5.46 / 5.40 ms per step; fewer chunks, less per-(chunk, bucket) traffic, but fewer blocks to fill the GPU with)
-int vox_part_chunks(int max_n) { return std::max(1, std::min(VP_MAX_CHUNKS, max_n / 24576)); }
+// A call of a few frames cannot fill the GPU with four blocks per frame: twice the chunks (half the points per block)
+// while the frames are fewer than 32 (single-frame latency: hist + scatter 54 -> 3x us).
+int vox_part_chunks(int max_n, int B) {
+  const int per = (B < 32) ? 12288 : 24576;
+  return std::max(1, std::min(VP_MAX_CHUNKS, max_n / per));
+}
 // worst-case number of groups of a frame of max_n points
 int vox_part_group_bound(const VoxFusedPlan& pl, int max_n) {
   const int K = std::min(VP_KMAX, (VP_BITMAP_WORDS * 32) >> pl.part_shift);
@@ -695,7 +699,7 @@ size_t vox_part_bucket_elems(int B) { return (size_t)B * VP_NB_MAX; }
 
 void run_voxel_part(const Ctx& c, const VoxelPartArgs& a) {
   const VoxFusedPlan& pl = a.plan;
-  const int chunks = vox_part_chunks(c.grid_cap);
+  const int chunks = vox_part_chunks(c.grid_cap, c.B);
   const int gmax = std::max(1, std::min(a.group_launch, a.group_stride - 1));
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * a.group_stride * sizeof(unsigned), c.stream);
   KL(c, "k_vp_init", k_vp_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, a.warnings, c.B));
