@@ -216,6 +216,15 @@ def small_config(cfg, batch, reps, local_rank, peak, torch):
     return out
 
 
+# What `value` (every result array delivered to pinned host memory) runs into at N > 1 on the pool's 8-GPU boxes,
+# measured with tools/pcie_probe.sh and tools/n8_probe.sh (profiles/pcie_probe_r02_n8.txt, profiles/n8_probe_r02.txt):
+HOST_PATH_NOTE = ("result delivery to the host is bound by the box, not by the GPUs: with 8 GPUs copying device-to-host at once "
+                  "the box sustains 113 GB/s in total (4 GPUs at 8.8 GB/s, 4 at 19.4 GB/s; one GPU alone 56 GB/s), while 8 "
+                  "ranks at single-GPU speed need 8 x 22 GB/s; 8 independent single-GPU processes (no NCCL) show the same "
+                  "host-mode times, and 5.27 ms per 1024 frames on every GPU with the results left in HBM "
+                  "(`value_results_left_in_hbm`)")
+
+
 def main():
     # the contract is ONE JSON line on stdout: everything else that libraries print there (NCCL's version banner,
     # ...) is sent to stderr; emit() writes to the real stdout
@@ -432,7 +441,7 @@ def main():
         big = dev.repeat(reps5, 1, 1) if reps5 > 1 else dev
         nb = big.shape[0]
         counts5 = np.full(nb, n, np.int32)
-        for _ in range(1):
+        for _ in range(2):  # (both of the handle's alternating pinned result buffers grow to the call's size here)
             op.process_batch_raw(big.data_ptr(), n, counts5)
         barrier()
         t0 = time.perf_counter()
@@ -576,6 +585,8 @@ def main():
                        ("; cluster_offsets / cluster_indices / obstacles of all ranks gathered to rank 0 over NCCL" if world > 1 else ""),
             "l2": "no flush: the per-step input batch (%.0f MB) exceeds the 126 MB L2" % (B * n * 16 / 1e6),
             "frames_per_sec": total_frames / wall,
+            "d2h_GBps_aggregate": world * d2h_bytes / (wall / args.steps) / 1e9,
+            "host_path": HOST_PATH_NOTE if world > 1 else None,
             "value_results_left_in_hbm": {"value": total_points / wall_dev_results, "unit": "points/s",
                                           "ms_per_step": 1000.0 * wall_dev_results / args.steps,
                                           "what": "same K steps with outputs | PCOP_OUT_DEVICE: result arrays stay in HBM for "

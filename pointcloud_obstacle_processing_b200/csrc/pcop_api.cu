@@ -123,6 +123,7 @@ struct pcop_handle {
   cudaEvent_t ev_copied = nullptr;  // the last payload copy out of d_pack
   cudaEvent_t ev_meta = nullptr;    // the wave's counts / pack sizes are in pinned memory
   int wave_seq = 0;                 // waves of the running call seen by this lane
+  int call_lane_waves = 1;          // waves of the running call dealt to this lane
   bool pending = false;             // a wave is enqueued and not yet collected
   int pend_w0 = 0, pend_B = 0;
   double d2h_bytes = 0.0;
@@ -1202,7 +1203,10 @@ int finish_wave(pcop_handle* h, const WaveInput& wi, uint32_t mask, pcop_frame_r
   const size_t base_off = (h->h_pack_used + 255) & ~(size_t)255;
   if (h->trace) cudaEventRecord(h->trace_recs[h->trace_used].c0, h->cstream);
   if (!dev_results) {
-    TRY(ensure_host_pack(h, base_off + meta.total_bytes + 256));
+    // (when the buffer has to grow, grow it for all the waves this lane will see in the call: a pinned allocation
+    // costs ~0.4 ms per MB, and every regrowth copies what is already there)
+    if (base_off + meta.total_bytes + 256 > h->h_pack_cap)
+      TRY(ensure_host_pack(h, base_off + (size_t)((double)(meta.total_bytes + 256) * 1.1 * std::max(1, h->call_lane_waves - h->wave_seq))));
     // payload copy on the copy stream (the pack kernels have finished: ev_meta follows them), in pieces: one large
     // device-to-host copy holds up the kernels of the other lanes for as long as it runs (measured: 6.4 ms per
     // 1024-frame call with one 17 MB copy per wave, 5.7 ms with 0.5-1 MB pieces, 5.9 / 6.2 ms with 2 / 4 MB pieces,
@@ -1372,6 +1376,7 @@ int process_impl(pcop_handle* h, const float* xyzw, size_t frame_stride_points, 
     l->h_pack_cap = l->h_pack_buf_cap[l->h_pack_sel];
     l->fixups.clear();
     l->wave_seq = 0;
+    l->call_lane_waves = cdiv((int)waves.size(), (int)lanes.size());
     l->trace_used = 0;
     l->pending = false;
     for (int s = 0; s < PCOP_N_STAGES; ++s) l->stage_us[s] = 0.f;

@@ -35,8 +35,9 @@ __device__ __forceinline__ int lower_bound_key(const uint32_t* a, int n, uint32_
   return lo;
 }
 
+// One thread per point (meanK above 31: the k + 1 best do not fit one per lane).
 __global__ void __launch_bounds__(128)
-    k_sor_knn(const float4* __restrict__ sorted_pts, const uint32_t* __restrict__ key0, const uint32_t* __restrict__ key1,
+    k_sor_knn_serial(const float4* __restrict__ sorted_pts, const uint32_t* __restrict__ key0, const uint32_t* __restrict__ key1,
               const int* __restrict__ npass, const int* __restrict__ n_in, const EceFrame* __restrict__ ef, int meanK,
               float* __restrict__ dist, int cap) {
   const int f = blockIdx.y;
@@ -109,6 +110,140 @@ __global__ void __launch_bounds__(128)
   double sum = 0.0;
   for (int k = 1; k < K; ++k) sum = dadd(sum, __dsqrt_rn((double)best[k]));
   dist[(size_t)f * cap + (int)__float_as_uint(p.w)] = (float)ddiv(sum, (double)meanK);
+}
+
+__device__ __forceinline__ int sor_warp_incl_scan(int v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(FULL, v, o);
+    if (lane_id() >= o) v += up;
+  }
+  return v;
+}
+
+// One WARP per point.  The cube around the point's cell grows ring by ring; the x-runs of a ring (a whole row of the
+// shell, or the two end cells of an interior row) are dealt to the lanes, which locate them in the sorted key list
+// with two binary searches each -- 32 searches in flight instead of one -- and the candidates of all runs are then
+// scanned 32 at a time.  The k smallest squared distances live one per lane (ascending, lanes >= k hold +inf); a
+// candidate below the k-th is inserted with a ballot (its position) and a shuffle (the shift).  Same candidate set,
+// same float predicate, same termination rule and same summation order as the one-thread-per-point kernel this
+// runs for larger calls (209 -> 57 us on the 8.7 k-point VLP-16 frame: that one walks 35 rows with 13 dependent loads
+// each; it wins back once a call holds enough points to fill the GPU with threads, see run_sor).
+constexpr int SOR_WARPS = 8;
+__global__ void __launch_bounds__(SOR_WARPS * 32)
+    k_sor_knn(const float4* __restrict__ sorted_pts, const uint32_t* __restrict__ key0, const uint32_t* __restrict__ key1,
+              const int* __restrict__ npass, const int* __restrict__ n_in, const EceFrame* __restrict__ ef, int meanK,
+              float* __restrict__ dist, int cap) {
+  const int f = blockIdx.y;
+  const int n = n_in[f];
+  if (n <= meanK) return;
+  const int lane = lane_id();
+  const int j = blockIdx.x * SOR_WARPS + warp_id();
+  if (j >= n) return;  // (whole warp)
+  const uint32_t* ks = ((npass[f] & 1) ? key1 : key0) + (size_t)f * cap;
+  const float4* sp = sorted_pts + (size_t)f * cap;
+  const EceFrame e = ef[f];
+  const float4 p = sp[j];
+  const uint32_t key = ks[j];
+  const int dimx = e.dim[0], dimy = e.dim[1], dimz = e.dim[2];
+  const int cx = (int)(key % (uint32_t)dimx);
+  const int cy = (int)((key / (uint32_t)dimx) % (uint32_t)dimy);
+  const int cz = (int)(key / ((uint32_t)dimx * (uint32_t)dimy));
+  const int K = meanK + 1;  // <= 32: one per lane
+  const float INF = __int_as_float(0x7f800000);
+  float best = INF;  // lane l: the l-th smallest squared distance so far
+  int cnt = 0;       // valid entries (warp-uniform)
+  float kth = INF;   // best of lane K - 1 (warp-uniform)
+  // smallest real cell edge, shrunk: lower bound on the distance from p to anything outside the cube
+  const float cell_lb = fminf(fminf(1.0f / e.inv[0], 1.0f / e.inv[1]), 1.0f / e.inv[2]) * 0.999f;
+  const int rmax = max(max(max(cx, dimx - 1 - cx), max(cy, dimy - 1 - cy)), max(cz, dimz - 1 - cz));
+  for (int r = 0; r <= rmax; ++r) {
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, dimz - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, dimy - 1);
+    const int ny = y1 - y0 + 1;
+    const int nrows = (z1 - z0 + 1) * ny;
+    // run s of the ring: row s / 2, run s % 2 of that row (a shell row has one run, an interior row two)
+    for (int sbase = 0; sbase < 2 * nrows; sbase += 32) {
+      const int s = sbase + lane;
+      int q0 = 0, q1 = 0;
+      if (s < 2 * nrows) {
+        const int row_i = s >> 1, sgm = s & 1;
+        const int zz = z0 + row_i / ny, yy = y0 + row_i % ny;
+        const bool shell_row = (abs(zz - cz) == r) || (abs(yy - cy) == r);
+        const uint32_t row = (uint32_t)dimx * ((uint32_t)yy + (uint32_t)dimy * (uint32_t)zz);
+        int xa = -1, xb = -2;
+        if (shell_row) {
+          if (sgm == 0) {
+            xa = max(cx - r, 0);
+            xb = min(cx + r, dimx - 1);
+          }
+        } else {  // interior rows only the two end cells x = cx - r, cx + r
+          const int x = (sgm == 0) ? (cx - r) : (cx + r);
+          if (x >= 0 && x < dimx) xa = xb = x;
+        }
+        if (xa <= xb) {
+          q0 = lower_bound_key(ks, n, row + (uint32_t)xa);
+          q1 = q0;  // (runs hold a handful of points: walking to the end costs fewer dependent loads than a second search)
+          const uint32_t hi_key = row + (uint32_t)xb;
+          while (q1 < n && ks[q1] <= hi_key) ++q1;
+        }
+      }
+      // candidates of the 32 runs, flattened: lane l's run covers [excl, excl + len)
+      const int len = q1 - q0;
+      const int incl = sor_warp_incl_scan(len);
+      const int excl = incl - len;
+      const int total = __shfl_sync(FULL, incl, 31);
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        // the run that holds candidate t: the last lane whose excl <= t among the runs that are not empty
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const int probe = lo + step;
+          const int ex = __shfl_sync(FULL, excl, probe & 31);
+          if (probe < 32 && ex <= t) lo = probe;
+        }
+        // (empty runs share their successor's excl: `lo` is the last of them, whose incl is > t only if it holds t;
+        // walk is not needed because the LAST lane with excl <= t is the one whose run is non-empty or t >= total)
+        const int rq0 = __shfl_sync(FULL, q0, lo), rex = __shfl_sync(FULL, excl, lo);
+        float d2 = INF;
+        if (t < total) {
+          const float4 o = sp[rq0 + (t - rex)];
+          d2 = dist2(p.x, p.y, p.z, o.x, o.y, o.z);
+        }
+        // insert every candidate that beats the k-th best (or fills the list), lowest lane first
+        unsigned pend = __ballot_sync(FULL, t < total && (cnt < K || d2 < kth));
+        while (pend) {
+          const int src = __ffs(pend) - 1;
+          pend &= pend - 1u;
+          const float d = __shfl_sync(FULL, d2, src);
+          if (cnt == K && !(d < kth)) continue;  // (the list has tightened since the ballot)
+          // the serial kernel's insertion, verbatim: from the back, entries greater than d move up one place (the last
+          // one drops out when the list is full); d lands behind the last entry that is not greater (NaNs included)
+          const int lim = (cnt < K) ? cnt : K - 1;
+          const unsigned stay = __ballot_sync(FULL, lane < lim && !(best > d));
+          const int pos = stay ? (32 - __clz(stay)) : 0;
+          const float up = __shfl_up_sync(FULL, best, 1);
+          if (lane > pos && lane <= lim) best = up;
+          if (lane == pos) best = d;
+          if (lane >= K) best = INF;
+          cnt = min(cnt + 1, K);
+          kth = __shfl_sync(FULL, best, K - 1);
+        }
+      }
+    }
+    if (cnt == K) {
+      const float reach = (float)r * cell_lb;
+      if (kth <= reach * reach) break;
+    }
+  }
+  // PCL: dist_sum += sqrt(nn_dists[k]) for k = 1..meanK (element 0 is the query), double accumulator
+  double sum = 0.0;
+  for (int k = 1; k < K; ++k) {
+    const float b = __shfl_sync(FULL, best, k);
+    sum = dadd(sum, __dsqrt_rn((double)b));
+  }
+  if (lane == 0) dist[(size_t)f * cap + (int)__float_as_uint(p.w)] = (float)ddiv(sum, (double)meanK);
 }
 
 // canonical tree sums of distances and of (float)(d*d), one 2048 chunk per block
@@ -211,8 +346,14 @@ void run_sor(const Ctx& c, const SorArgs& a) {
   KL(c, "k_sor_setup", k_sor_setup<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.n_in, a.meanK, a.thr, a.warnings, c.B));
   count_launch(c);
   run_grid_sort(c, a.in, a.in_stride, a.n_in, a.cell, a.minmax, a.gf, a.sort, a.sorted_pts, nullptr, nullptr);
-  KL(c, "k_sor_knn", k_sor_knn<<<dim3(cdiv(c.grid_cap, 128), c.B), 128, 0, c.stream>>>(a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass,
-                                                               a.n_in, a.gf, a.meanK, a.dist, c.cap));
+  // a call of a few small frames cannot fill the GPU with one thread per point (latency: 209 us for 8.7 k points, whatever
+  // the count, up to ~300 k points); the warp-per-point kernel does 3-4 x the work in a quarter of the time there
+  if (a.meanK + 1 <= 32 && (long long)c.B * c.grid_cap <= 32768)
+    KL(c, "k_sor_knn", k_sor_knn<<<dim3(cdiv(c.grid_cap, SOR_WARPS), c.B), SOR_WARPS * 32, 0, c.stream>>>(
+                           a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass, a.n_in, a.gf, a.meanK, a.dist, c.cap));
+  else
+    KL(c, "k_sor_knn", k_sor_knn_serial<<<dim3(cdiv(c.grid_cap, 128), c.B), 128, 0, c.stream>>>(
+                           a.sorted_pts, a.sort.key[0], a.sort.key[1], a.sort.npass, a.n_in, a.gf, a.meanK, a.dist, c.cap));
   KL(c, "k_sor_sums", k_sor_sums<<<dim3(gchunks, c.B), 256, 0, c.stream>>>(a.dist, a.n_in, a.meanK, a.partial, chunks, c.cap));
   KL(c, "k_sor_threshold", k_sor_threshold<<<cdiv(c.B, 128), 128, 0, c.stream>>>(a.partial, a.n_in, a.meanK, a.mul, a.thr, chunks, c.B));
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * tiles * sizeof(unsigned), c.stream);

@@ -81,14 +81,34 @@ def test_stage_voxel(config, frames):
     assert_bits_equal(g_pts, o_pts, "voxel centroids")
 
 
-def test_stage_sor(frames):
+@pytest.mark.parametrize("mean_k", [15, 1, 31, 40])  # (the warp-per-point kernel holds up to 32 neighbours; 40 takes the serial one)
+def test_stage_sor(frames, mean_k):
     p = synth.params(1)
+    p.statistical_outlier_meanK = mean_k
     cloud, _ = O.crop(p, frames[1])
     cloud, _, _ = O.voxel(p, cloud)
     with ObstacleProcessor(p, len(cloud)) as op:
         g_pts, g_idx, g_w = op.remove_statistical_outliers(cloud)
     o_pts, o_idx, o_w, dist, thr = O.sor(p, cloud)
     print("SOR margin min|d - thr| =", np.min(np.abs(dist.astype(np.float64) - thr)), "removed", len(cloud) - len(o_idx))
+    assert g_w == o_w
+    assert_bits_equal(g_idx, o_idx, "sor kept_idx")
+    assert_bits_equal(g_pts, o_pts, "sor points")
+
+
+def test_stage_sor_with_non_finite_points(frames):
+    p = synth.params(1)
+    cloud, _ = O.crop(p, frames[1])
+    cloud, _, _ = O.voxel(p, cloud)
+    cloud = cloud[:3000].copy()
+    rng = np.random.default_rng(7)
+    bad = rng.choice(len(cloud), 12, replace=False)
+    cloud[bad[:4], 1] = np.nan
+    cloud[bad[4:8], 2] = np.inf
+    cloud[bad[8:], 0] = -np.inf
+    with ObstacleProcessor(p, len(cloud)) as op:
+        g_pts, g_idx, g_w = op.remove_statistical_outliers(cloud)
+    o_pts, o_idx, o_w, dist, thr = O.sor(p, cloud)
     assert g_w == o_w
     assert_bits_equal(g_idx, o_idx, "sor kept_idx")
     assert_bits_equal(g_pts, o_pts, "sor points")
