@@ -1071,7 +1071,8 @@ int enqueue_wave_pack(pcop_handle* h, int B, int max_n, uint32_t mask) {
     if (h->wave_used_fused) seg(h->d_vf_flags, h->h_vf_flags, sizeof(uint32_t) * B);
     static_assert(PK_N >= 5, "one pack block per metadata segment");
     if (any) {  // the (frame < 4, array k < 5) blocks of the pack kernel also carry metadata segment k out
-      const int gx = std::max(1, std::min(cdiv(c.grid_cap, 256 * 4), 16));
+      // (parts per (frame, array): 16 for the batched waves; a call of a few large frames gets enough to fill the GPU)
+      const int gx = std::max(1, std::min(cdiv(c.grid_cap, 256 * 4), std::max(16, 592 / B)));
       m.frames = std::min(B, 4);
       KL(c, "k_pack", k_pack<<<dim3(gx, B, PK_N), 256, 0, h->stream>>>(ps, h->d_counts, h->maxB, h->d_pack_off, h->d_meta, h->d_pack, m));
       count_launch(c);

@@ -614,7 +614,10 @@ static void run_cluster_generic(const Ctx& c, const ClusterArgs& a) {
   KL(c, "k_ece_cell_heads", k_ece_cell_heads<<<dim3(gtiles, c.B), CT_THREADS, 0, c.stream>>>(
       a.sort.key[0], a.sort.key[1], a.sort.npass, a.n_in, a.ef, a.sorted_pts, a.cell_start, a.cell_key,
       /*cell_rep (scratch, reused for the root list afterwards)=*/a.roots, a.n_cells, a.desc, c.cap, tiles));
-  KL(c, "k_ece_cell_union", k_ece_cell_union<<<dim3(max(1, min(cdiv(c.grid_cap, 16), 512)), c.B), 256, 0, c.stream>>>(
+  // (a warp per cell, grid-stride: the kernel waits on its binary searches, so a call of one or two large frames gets
+  // enough blocks to fill every SM with eight of them)
+  const int union_blocks = max(1, min(cdiv(c.grid_cap, 16), max(512, 1184 / c.B)));
+  KL(c, "k_ece_cell_union", k_ece_cell_union<<<dim3(union_blocks, c.B), 256, 0, c.stream>>>(
       a.sorted_pts, a.cell_start, a.cell_key, a.roots, a.n_cells, a.n_in, a.ef, a.parent, r2, c.cap));
   count_launch(c, 2);
   // frames whose extent does not fit 1024 clique cells per axis: per-point neighbour scan
