@@ -80,23 +80,15 @@ __device__ __forceinline__ void vp_chunk(int n, int chunks, int c, int& i0, int&
   i1 = min(i0 + cs, n);
 }
 
-__global__ void k_vp_init(MinMax* mm, uint32_t* __restrict__ flags, uint32_t* __restrict__ warnings, int B) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f < B) {
-    if (warnings) warnings[f] = 0u;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      mm[f].mn[a] = ORD_POS_FLT_MAX;
-      mm[f].mx[a] = ORD_NEG_FLT_MAX;
-    }
-    flags[f] = 0u;
-  }
-}
+// Per (frame, chunk) the histogram kernel leaves a record of VP_CHUNK_TAIL words behind the chunk's counters: min / max
+// of its survivors (6 floats) and its NaN-y/z flag.  The scan kernel combines the chunks, so nothing has to be zeroed or
+// initialised before the histogram runs (round 2 first spent a launch per wave on that).
+constexpr int VP_CHUNK_TAIL = 8;
 
 template <bool NEED_MINMAX>
 __global__ void __launch_bounds__(VP_THREADS)
     k_vp_hist(const float4* __restrict__ in, size_t in_stride, const int* __restrict__ n_in, VoxFusedPlan pl,
-              uint32_t* __restrict__ ghist, MinMax* __restrict__ minmax, uint32_t* __restrict__ flags, int chunks) {
+              uint32_t* __restrict__ ghist, int chunks) {
   const int c = blockIdx.x, f = blockIdx.y;
   extern __shared__ uint32_t vp_sh[];  // [nb_pad / 2]: two 16-bit counters per word
   __shared__ float shmm[VP_WARPS][6];
@@ -136,7 +128,8 @@ __global__ void __launch_bounds__(VP_THREADS)
       }
     }
   }
-  if (__any_sync(FULL, odd) && lane_id() == 0) atomicOr(&flags[f], 1u);
+  const int any_odd = __syncthreads_or(odd ? 1 : 0);
+  uint32_t* gh = ghist + ((size_t)f * chunks + c) * (nwords + VP_CHUNK_TAIL);
   if (NEED_MINMAX) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -153,30 +146,28 @@ __global__ void __launch_bounds__(VP_THREADS)
         shmm[warp_id()][3 + a] = mx[a];
       }
     }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      const int a = threadIdx.x;
+      float v = shmm[0][a];
+      for (int w = 1; w < VP_WARPS; ++w) v = (a < 3) ? fminf(v, shmm[w][a]) : fmaxf(v, shmm[w][a]);
+      gh[nwords + a] = __float_as_uint(v);
+    }
   }
-  __syncthreads();
-  if (NEED_MINMAX && threadIdx.x < 6) {
-    const int a = threadIdx.x;
-    float v = shmm[0][a];
-    for (int w = 1; w < VP_WARPS; ++w) v = (a < 3) ? fminf(v, shmm[w][a]) : fmaxf(v, shmm[w][a]);
-    if (a < 3) atomicMin(&minmax[f].mn[a], f2ord(v));
-    else atomicMax(&minmax[f].mx[a - 3], f2ord(v));
-  }
-  uint32_t* gh = ghist + ((size_t)f * chunks + c) * nwords;
+  if (threadIdx.x == 6) gh[nwords + 6] = any_odd ? 1u : 0u;
   for (int w = threadIdx.x; w < nwords; w += VP_THREADS) gh[w] = vp_sh[w];
 }
 
 // PCL's voxel frame from the min/max of the survivors (same arithmetic as stage_voxel.cu's k_voxel_setup; the host
 // has proven that the overflow guard cannot fire)
-__device__ void vp_setup_one(const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf, int f) {
+__device__ void vp_setup_one(const float (&mnv)[3], const float (&mxv)[3], float leaf, VoxelFrame* __restrict__ vf, int f) {
   VoxelFrame v;
   v.inv = fdiv(1.0f, leaf);
   unsigned div_b[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float mn = ord2f(minmax[f].mn[a]), mx = ord2f(minmax[f].mx[a]);
-    v.min_b[a] = cvt_f2i(floorf(fmul(mn, v.inv)));
-    const int max_b = cvt_f2i(floorf(fmul(mx, v.inv)));
+    v.min_b[a] = cvt_f2i(floorf(fmul(mnv[a], v.inv)));
+    const int max_b = cvt_f2i(floorf(fmul(mxv[a], v.inv)));
     div_b[a] = (unsigned)max_b - (unsigned)v.min_b[a] + 1u;
   }
   v.overflow = 0;
@@ -218,41 +209,77 @@ __device__ __forceinline__ unsigned warp0_excl_scan(uint32_t* a, int n) {
   return __shfl_sync(FULL, incl, 31);
 }
 
-// per-(chunk, bucket) 16-bit counts of bucket b -> v[], returns their sum
-__device__ __forceinline__ unsigned vp_bucket_total(const unsigned short* gh16, int nb_pad, int chunks, int b, unsigned (&v)[VP_MAX_CHUNKS]) {
+// per-(chunk, bucket) 16-bit counts of the four buckets b0 .. b0 + 3 (b0 % 4 == 0: one 8-byte load per chunk) ->
+// v[chunk][k]; t[k] = the buckets' totals
+__device__ __forceinline__ void vp_bucket_totals4(const unsigned short* gh16, size_t chunk_stride16, int chunks, int b0,
+                                                  unsigned (&v)[VP_MAX_CHUNKS][4], unsigned (&t)[4]) {
 #pragma unroll
-  for (int c = 0; c < VP_MAX_CHUNKS; ++c) v[c] = (c < chunks) ? (unsigned)gh16[(size_t)c * nb_pad + b] : 0u;
-  unsigned t = 0u;
+  for (int k = 0; k < 4; ++k) t[k] = 0u;
 #pragma unroll
-  for (int c = 0; c < VP_MAX_CHUNKS; ++c) t += v[c];
-  return t;
+  for (int c = 0; c < VP_MAX_CHUNKS; ++c) {
+    uint2 w = make_uint2(0u, 0u);
+    if (c < chunks) w = *reinterpret_cast<const uint2*>(gh16 + (size_t)c * chunk_stride16 + b0);
+    v[c][0] = w.x & 0xffffu;
+    v[c][1] = w.x >> 16;
+    v[c][2] = w.y & 0xffffu;
+    v[c][3] = w.y >> 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] += v[c][k];
+  }
 }
 
 __global__ void __launch_bounds__(VP_SCAN_THREADS)
     k_vp_scan(const uint32_t* __restrict__ ghist, uint32_t* __restrict__ chunk_start, unsigned short* __restrict__ ne_bucket,
               uint32_t* __restrict__ ne_start,
               uint2* __restrict__ grec, int* __restrict__ n_groups, int* __restrict__ n_crop,
-              uint32_t* __restrict__ flags, const MinMax* __restrict__ minmax, float leaf, VoxelFrame* __restrict__ vf,
+              uint32_t* __restrict__ flags, uint32_t* __restrict__ warnings, float leaf, VoxelFrame* __restrict__ vf,
               VoxFusedPlan pl, int chunks, int want_keys, int gmax, int gstride) {
   const int f = blockIdx.x, tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-  __shared__ uint32_t s_rt[VP_MAX_ROUNDS + 1];  // elements before each round of 32 buckets
-  __shared__ uint32_t s_rn[VP_MAX_ROUNDS + 1];  // non-empty buckets before each round
+  __shared__ uint32_t s_rt[VP_MAX_ROUNDS / 4 + 1];  // elements before each round of 128 buckets
+  __shared__ uint32_t s_rn[VP_MAX_ROUNDS / 4 + 1];  // non-empty buckets before each round
   __shared__ unsigned s_total[2];
-  if (want_keys && tid == 0) vp_setup_one(minmax, leaf, vf, f);
-  const unsigned short* gh16 = reinterpret_cast<const unsigned short*>(ghist + (size_t)f * chunks * (pl.nb_pad >> 1));
+  const int nwords = pl.nb_pad >> 1;
+  const uint32_t* gh = ghist + (size_t)f * chunks * (nwords + VP_CHUNK_TAIL);
+  const size_t chunk_stride16 = 2 * (size_t)(nwords + VP_CHUNK_TAIL);
+  const unsigned short* gh16 = reinterpret_cast<const unsigned short*>(gh);
+  if (tid == 0) {  // the chunks' min / max and NaN flags (see VP_CHUNK_TAIL); this is also where the frame's flag word starts
+    float mnv[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float mxv[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    uint32_t odd = 0u;
+    for (int c = 0; c < chunks; ++c) {
+      const uint32_t* tail = gh + (size_t)c * (nwords + VP_CHUNK_TAIL) + nwords;
+      odd |= tail[6];
+      if (want_keys) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          mnv[a] = fminf(mnv[a], __uint_as_float(tail[a]));
+          mxv[a] = fmaxf(mxv[a], __uint_as_float(tail[3 + a]));
+        }
+      }
+    }
+    flags[f] = odd;
+    if (warnings) warnings[f] = 0u;
+    if (want_keys) vp_setup_one(mnv, mxv, leaf, vf, f);
+  }
+  __syncthreads();  // (the flag word is written before anyone ORs into it)
   uint32_t* cs_out = chunk_start + (size_t)f * chunks * pl.nb_pad;
   unsigned short* ne_out = ne_bucket + (size_t)f * VP_NB_MAX;
   uint32_t* ns_out = ne_start + (size_t)f * (VP_NB_MAX + 1);  // element start of every non-empty bucket, then M
-  const int nrounds = pl.nb_pad >> 5;
-  // ---- pass 1: per round of 32 buckets, elements and non-empty buckets ------------------------------------------------
+  const int nrounds = (pl.nb_pad + 127) >> 7;  // rounds of 128 buckets: four consecutive buckets per lane
+  // ---- pass 1: per round, elements and non-empty buckets ----------------------------------------------------------------
   bool too_big = false;
   for (int r = warp; r < nrounds; r += VP_SCAN_WARPS) {
-    const int b = 32 * r + lane;
-    unsigned v[VP_MAX_CHUNKS];
-    const unsigned t = (b < pl.nb) ? vp_bucket_total(gh16, pl.nb_pad, chunks, b, v) : 0u;
-    too_big = too_big || t > (unsigned)VP_EMAX;
-    const unsigned sum = __reduce_add_sync(FULL, t);
-    const unsigned ne = (unsigned)__popc(__ballot_sync(FULL, t != 0u));
+    const int b0 = 128 * r + 4 * lane;
+    unsigned v[VP_MAX_CHUNKS][4], t[4] = {0u, 0u, 0u, 0u};
+    if (b0 < pl.nb_pad) vp_bucket_totals4(gh16, chunk_stride16, chunks, b0, v, t);  // (buckets past nb hold zeros)
+    unsigned nz = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      too_big = too_big || t[k] > (unsigned)VP_EMAX;
+      nz += (t[k] != 0u) ? 1u : 0u;
+    }
+    const unsigned sum = __reduce_add_sync(FULL, t[0] + t[1] + t[2] + t[3]);
+    const unsigned ne = __reduce_add_sync(FULL, nz);
     if (lane == 0) {
       s_rt[r] = sum;
       s_rn[r] = ne;
@@ -261,8 +288,8 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   if (too_big) atomicOr(&flags[f], 2u);
   __syncthreads();
   if (warp == 0) {
-    const unsigned m = warp0_excl_scan<VP_MAX_ROUNDS / 32>(s_rt, nrounds);
-    const unsigned ne = warp0_excl_scan<VP_MAX_ROUNDS / 32>(s_rn, nrounds);
+    const unsigned m = warp0_excl_scan<(VP_MAX_ROUNDS / 4 + 31) / 32>(s_rt, nrounds);
+    const unsigned ne = warp0_excl_scan<(VP_MAX_ROUNDS / 4 + 31) / 32>(s_rn, nrounds);
     if (lane == 0) {
       s_total[0] = m;
       s_total[1] = ne;
@@ -274,21 +301,40 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   const int NE = (int)s_total[1];
   // ---- pass 2: bucket starts, per-chunk offsets inside each bucket, the list of non-empty buckets -----------------------
   for (int r = warp; r < nrounds; r += VP_SCAN_WARPS) {
-    const int b = 32 * r + lane;
-    unsigned v[VP_MAX_CHUNKS];
-    const unsigned t = (b < pl.nb) ? vp_bucket_total(gh16, pl.nb_pad, chunks, b, v) : 0u;
-    const unsigned incl = warp_incl_scan(t);
-    unsigned run = s_rt[r] + incl - t;  // the bucket's start (buckets past nb are empty: start = M)
+    const int b0 = 128 * r + 4 * lane;
+    unsigned v[VP_MAX_CHUNKS][4], t[4] = {0u, 0u, 0u, 0u};
+    const bool in_range = b0 < pl.nb_pad;
+    if (in_range) vp_bucket_totals4(gh16, chunk_stride16, chunks, b0, v, t);
+    const unsigned mine = t[0] + t[1] + t[2] + t[3];
+    const unsigned incl = warp_incl_scan(mine);
+    unsigned nz = 0u;
 #pragma unroll
-    for (int c = 0; c < VP_MAX_CHUNKS; ++c) {  // absolute first slot of every (chunk, bucket) range, for the scatter kernel
-      if (c < chunks) cs_out[(size_t)c * pl.nb_pad + b] = run;
-      run += v[c];
-    }
-    const unsigned nz = __ballot_sync(FULL, t != 0u);
-    if (t != 0u) {
-      const unsigned o = s_rn[r] + __popc(nz & lanemask_lt());
-      ne_out[o] = (unsigned short)b;
-      ns_out[o] = s_rt[r] + incl - t;
+    for (int k = 0; k < 4; ++k) nz += (t[k] != 0u) ? 1u : 0u;
+    const unsigned nz_incl = warp_incl_scan(nz);
+    unsigned start[4];  // the buckets' starts (buckets past nb are empty: start = M)
+    start[0] = s_rt[r] + incl - mine;
+    start[1] = start[0] + t[0];
+    start[2] = start[1] + t[1];
+    start[3] = start[2] + t[2];
+    if (in_range) {
+      unsigned run[4] = {start[0], start[1], start[2], start[3]};
+#pragma unroll
+      for (int c = 0; c < VP_MAX_CHUNKS; ++c) {  // absolute first slot of every (chunk, bucket) range, for the scatter kernel
+        if (c < chunks) {
+          *reinterpret_cast<uint4*>(cs_out + (size_t)c * pl.nb_pad + b0) = make_uint4(run[0], run[1], run[2], run[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) run[k] += v[c][k];
+        }
+      }
+      unsigned o = s_rn[r] + nz_incl - nz;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (t[k] != 0u) {
+          ne_out[o] = (unsigned short)(b0 + k);
+          ns_out[o] = start[k];
+          ++o;
+        }
+      }
     }
   }
   if (tid == 0) ns_out[NE] = M;
@@ -692,7 +738,7 @@ int vox_part_group_bound(const VoxFusedPlan& pl, int max_n) {
   const long long b = 2ll * max_n / VP_EMAX + ne / K + 3;  // (two consecutive groups hold more than VP_EMAX elements or K buckets)
   return (int)std::min<long long>(b, 65535);
 }
-size_t vox_part_hist_elems(int B) { return (size_t)B * VP_MAX_CHUNKS * (VP_NB_MAX / 2); }
+size_t vox_part_hist_elems(int B) { return (size_t)B * VP_MAX_CHUNKS * (VP_NB_MAX / 2 + VP_CHUNK_TAIL); }
 size_t vox_part_start_elems(int B) { return (size_t)B * (VP_NB_MAX + 1); }
 size_t vox_part_chunk_start_elems(int B) { return (size_t)B * VP_MAX_CHUNKS * VP_NB_MAX; }
 size_t vox_part_bucket_elems(int B) { return (size_t)B * VP_NB_MAX; }
@@ -702,16 +748,15 @@ void run_voxel_part(const Ctx& c, const VoxelPartArgs& a) {
   const int chunks = vox_part_chunks(c.grid_cap, c.B);
   const int gmax = std::max(1, std::min(a.group_launch, a.group_stride - 1));
   cudaMemsetAsync(a.desc, 0, (size_t)c.B * a.group_stride * sizeof(unsigned), c.stream);
-  KL(c, "k_vp_init", k_vp_init<<<cdiv(c.B, 256), 256, 0, c.stream>>>(a.minmax, a.flags, a.warnings, c.B));
   const size_t hsm = (size_t)(pl.nb_pad / 2) * sizeof(uint32_t);
   if (a.want_keys)
     KL(c, "k_vp_hist", k_vp_hist<true><<<dim3(chunks, c.B), VP_THREADS, hsm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.ghist,
-                                                                                        a.minmax, a.flags, chunks));
+                                                                                        chunks));
   else
     KL(c, "k_vp_hist", k_vp_hist<false><<<dim3(chunks, c.B), VP_THREADS, hsm, c.stream>>>(a.in, a.in_stride, a.n_in, pl, a.ghist,
-                                                                                         a.minmax, a.flags, chunks));
+                                                                                         chunks));
   KL(c, "k_vp_scan", k_vp_scan<<<c.B, VP_SCAN_THREADS, 0, c.stream>>>(a.ghist, a.chunk_start, a.ne_bucket, a.ne_start, a.grec, a.n_groups,
-                                                                      a.n_crop, a.flags, a.minmax, a.leaf, a.vf, pl, chunks,
+                                                                      a.n_crop, a.flags, a.warnings, a.leaf, a.vf, pl, chunks,
                                                                       a.want_keys, gmax, a.group_stride));
   const size_t ssm = (size_t)pl.nb_pad * sizeof(uint32_t);  // (<= 64 KB)
   cudaFuncSetAttribute(k_vp_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm);
@@ -729,7 +774,7 @@ void run_voxel_part(const Ctx& c, const VoxelPartArgs& a) {
                              a.part, a.ne_start, a.ne_bucket, a.grec, a.n_groups, a.flags, pl, a.vf, a.out, a.out_keys,
                              a.n_out, a.desc, c.cap, a.group_stride));
   }
-  count_launch(c, 5);
+  count_launch(c, 4);
 }
 
 }  // namespace pcop
