@@ -209,26 +209,30 @@ __device__ __forceinline__ unsigned warp0_excl_scan(uint32_t* a, int n) {
   return __shfl_sync(FULL, incl, 31);
 }
 
-// per-(chunk, bucket) 16-bit counts of the four buckets b0 .. b0 + 3 (b0 % 4 == 0: one 8-byte load per chunk) ->
-// v[chunk][k]; t[k] = the buckets' totals
+// per-(chunk, bucket) 16-bit counts of the four buckets b0 .. b0 + 3 (b0 % 4 == 0: one 8-byte load per chunk)
+__device__ __forceinline__ void vp_unpack4(const uint2 w, unsigned (&v)[4]) {
+  v[0] = w.x & 0xffffu;
+  v[1] = w.x >> 16;
+  v[2] = w.y & 0xffffu;
+  v[3] = w.y >> 16;
+}
+// t[k] = the buckets' totals over the chunks
 __device__ __forceinline__ void vp_bucket_totals4(const unsigned short* gh16, size_t chunk_stride16, int chunks, int b0,
-                                                  unsigned (&v)[VP_MAX_CHUNKS][4], unsigned (&t)[4]) {
+                                                  unsigned (&t)[4]) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) t[k] = 0u;
 #pragma unroll
   for (int c = 0; c < VP_MAX_CHUNKS; ++c) {
-    uint2 w = make_uint2(0u, 0u);
-    if (c < chunks) w = *reinterpret_cast<const uint2*>(gh16 + (size_t)c * chunk_stride16 + b0);
-    v[c][0] = w.x & 0xffffu;
-    v[c][1] = w.x >> 16;
-    v[c][2] = w.y & 0xffffu;
-    v[c][3] = w.y >> 16;
+    if (c < chunks) {
+      unsigned v[4];
+      vp_unpack4(*reinterpret_cast<const uint2*>(gh16 + (size_t)c * chunk_stride16 + b0), v);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) t[k] += v[c][k];
+      for (int k = 0; k < 4; ++k) t[k] += v[k];
+    }
   }
 }
 
-__global__ void __launch_bounds__(VP_SCAN_THREADS)
+__global__ void __launch_bounds__(VP_SCAN_THREADS, 2)
     k_vp_scan(const uint32_t* __restrict__ ghist, uint32_t* __restrict__ chunk_start, unsigned short* __restrict__ ne_bucket,
               uint32_t* __restrict__ ne_start,
               uint2* __restrict__ grec, int* __restrict__ n_groups, int* __restrict__ n_crop,
@@ -270,8 +274,8 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   bool too_big = false;
   for (int r = warp; r < nrounds; r += VP_SCAN_WARPS) {
     const int b0 = 128 * r + 4 * lane;
-    unsigned v[VP_MAX_CHUNKS][4], t[4] = {0u, 0u, 0u, 0u};
-    if (b0 < pl.nb_pad) vp_bucket_totals4(gh16, chunk_stride16, chunks, b0, v, t);  // (buckets past nb hold zeros)
+    unsigned t[4] = {0u, 0u, 0u, 0u};
+    if (b0 < pl.nb_pad) vp_bucket_totals4(gh16, chunk_stride16, chunks, b0, t);  // (buckets past nb hold zeros)
     unsigned nz = 0u;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -302,9 +306,9 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
   // ---- pass 2: bucket starts, per-chunk offsets inside each bucket, the list of non-empty buckets -----------------------
   for (int r = warp; r < nrounds; r += VP_SCAN_WARPS) {
     const int b0 = 128 * r + 4 * lane;
-    unsigned v[VP_MAX_CHUNKS][4], t[4] = {0u, 0u, 0u, 0u};
+    unsigned t[4] = {0u, 0u, 0u, 0u};
     const bool in_range = b0 < pl.nb_pad;
-    if (in_range) vp_bucket_totals4(gh16, chunk_stride16, chunks, b0, v, t);
+    if (in_range) vp_bucket_totals4(gh16, chunk_stride16, chunks, b0, t);
     const unsigned mine = t[0] + t[1] + t[2] + t[3];
     const unsigned incl = warp_incl_scan(mine);
     unsigned nz = 0u;
@@ -319,12 +323,14 @@ __global__ void __launch_bounds__(VP_SCAN_THREADS)
     if (in_range) {
       unsigned run[4] = {start[0], start[1], start[2], start[3]};
 #pragma unroll
-      for (int c = 0; c < VP_MAX_CHUNKS; ++c) {  // absolute first slot of every (chunk, bucket) range, for the scatter kernel
-        if (c < chunks) {
-          *reinterpret_cast<uint4*>(cs_out + (size_t)c * pl.nb_pad + b0) = make_uint4(run[0], run[1], run[2], run[3]);
+      // absolute first slot of every (chunk, bucket) range, for the scatter kernel (the counts are read a second time --
+      // cache hits -- rather than kept: 32 registers less, two blocks per SM)
+      for (int c = 0; c < chunks; ++c) {
+        *reinterpret_cast<uint4*>(cs_out + (size_t)c * pl.nb_pad + b0) = make_uint4(run[0], run[1], run[2], run[3]);
+        unsigned v[4];
+        vp_unpack4(*reinterpret_cast<const uint2*>(gh16 + (size_t)c * chunk_stride16 + b0), v);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) run[k] += v[c][k];
-        }
+        for (int k = 0; k < 4; ++k) run[k] += v[k];
       }
       unsigned o = s_rn[r] + nz_incl - nz;
 #pragma unroll
