@@ -127,7 +127,7 @@ __device__ __forceinline__ int sor_warp_incl_scan(int v) {
 // scanned 32 at a time.  The k smallest squared distances live one per lane (ascending, lanes >= k hold +inf); a
 // candidate below the k-th is inserted with a ballot (its position) and a shuffle (the shift).  Same candidate set,
 // same float predicate, same termination rule and same summation order as the one-thread-per-point kernel this
-// runs for larger calls (209 -> 57 us on the 8.7 k-point VLP-16 frame: that one walks 35 rows with 13 dependent loads
+// runs for larger calls (209 -> 50 us on the 8.7 k-point VLP-16 frame: that one walks 35 rows with 13 dependent loads
 // each; it wins back once a call holds enough points to fill the GPU with threads, see run_sor).
 constexpr int SOR_WARPS = 8;
 __global__ void __launch_bounds__(SOR_WARPS * 32)

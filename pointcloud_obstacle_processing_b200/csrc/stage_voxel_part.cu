@@ -732,7 +732,7 @@ void vox_part_plan(VoxFusedPlan& pl, size_t max_points) {
 // histogram / scatter blocks per frame: chunks of ~24 576 points (measured: 8 / 4 / 3 chunks per 120 k-point frame 5.53 /
 // 5.46 / 5.40 ms per step; fewer chunks, less per-(chunk, bucket) traffic, but fewer blocks to fill the GPU with)
 // A call of a few frames cannot fill the GPU with four blocks per frame: twice the chunks (half the points per block)
-// while the frames are fewer than 32 (single-frame latency: hist + scatter 54 -> 3x us).
+// while the frames are fewer than 32 (single-frame latency: hist + scatter 54 -> 34 us).
 int vox_part_chunks(int max_n, int B) {
   const int per = (B < 32) ? 12288 : 24576;
   return std::max(1, std::min(VP_MAX_CHUNKS, max_n / per));
