@@ -57,15 +57,40 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md recipe).  The values are NVML's -- what
+    nvidia-smi prints -- read in-process every few milliseconds (the timed region lasts tens of milliseconds; spawning
+    nvidia-smi takes longer than that and competes with the engine's host thread for the rank's cores).  Falls back to
+    the nvidia-smi command line when the NVML binding is missing.  `active` = False: no sampling (ranks other than 0)."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, active=True):
         self.gpu = gpu_index
+        self.active = active
         self.rows = []
+        self.source = None
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        masks = ((8, "hw_slowdown"), (64, "hw_thermal_slowdown"), (32, "sw_thermal_slowdown"), (4, "sw_power_cap"))
+        self.source = "nvml"
+        self._ready.set()
+        while not self._stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append([str(sm), str(mx)] + [("Active" if r & m else "Not Active") for m, _ in masks])
+            self._stop.wait(0.004)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
+            self._ready.set()
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
@@ -80,13 +105,17 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.active:
+            self._ready = threading.Event()
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+            self._ready.wait(timeout=10)  # (NVML initialised before the timed region starts)
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         sm = []
@@ -102,7 +131,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.source}
 
 
 def oracle_frames_per_sec(params, frames, threads):
@@ -344,7 +373,7 @@ def main():
     launches = 0
     alg_bytes = 0.0
     dev_us = 0.0
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, active=(rank == 0)) as clocks:
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
