@@ -245,13 +245,14 @@ def small_config(cfg, batch, reps, local_rank, peak, torch):
     return out
 
 
-# What `value` (every result array delivered to pinned host memory) runs into at N > 1 on the pool's 8-GPU boxes,
-# measured with tools/pcie_probe.sh and tools/n8_probe.sh (profiles/pcie_probe_r02_n8.txt, profiles/n8_probe_r02.txt):
+# What the numbers at N > 1 run into on the pool's 8-GPU boxes, measured with tools/pcie_probe.sh and
+# tools/n8_sync_probe.py (profiles/pcie_probe_r02_n8.txt, profiles/n8_sync_probe_r02.txt):
 HOST_PATH_NOTE = ("result delivery to the host is bound by the box, not by the GPUs: with 8 GPUs copying device-to-host at once "
                   "the box sustains 113 GB/s in total (4 GPUs at 8.8 GB/s, 4 at 19.4 GB/s; one GPU alone 56 GB/s), while 8 "
-                  "ranks at single-GPU speed need 8 x 22 GB/s; 8 independent single-GPU processes (no NCCL) show the same "
-                  "host-mode times, and 5.27 ms per 1024 frames on every GPU with the results left in HBM "
-                  "(`value_results_left_in_hbm`)")
+                  "ranks at single-GPU speed need 8 x 22 GB/s.  With the results left in HBM and the ranks barrier-aligned "
+                  "(no gather) six of the eight GPUs run the 1024-frame call in 5.15-5.25 ms, the single-GPU time, and two "
+                  "(GPUs 3 and 6: same on two boxes, pinned or unpinned host threads, 3 or 4 lanes, 1965 MHz, no throttle "
+                  "reason) take 6.5 ms; the line's time is the slowest rank's, `per_rank_ms_per_step` lists them all")
 
 
 def main():
@@ -383,6 +384,8 @@ def main():
             launches += op.last_launch_count
             alg_bytes += op.last_algorithmic_bytes
         gather_flush()
+        torch.cuda.synchronize()
+        own_wall = time.perf_counter() - t0  # this rank's own K steps (the line's time is the slowest rank's)
         barrier()
         wall = time.perf_counter() - t0
     stage_alg = {}
@@ -404,8 +407,21 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
+    torch.cuda.synchronize()
+    own_wall_dev = time.perf_counter() - t0
     barrier()
     wall_dev_results = time.perf_counter() - t0
+
+    def per_rank_ms(own):
+        """ms per step of every rank's own K steps (rank order); None on one GPU"""
+        if world == 1:
+            return None
+        t = torch.tensor([1000.0 * own / args.steps], dtype=torch.float64, device=dev.device)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [round(float(x.item()), 3) for x in out]
+
+    per_rank = {"results_to_host": per_rank_ms(own_wall), "results_left_in_hbm": per_rank_ms(own_wall_dev)}
     op.set_params(params)
 
     # ---- instrumented pass: the same K steps with a CUDA-event pair around every launch and every stage on the
@@ -617,6 +633,7 @@ def main():
             "frames_per_sec": total_frames / wall,
             "d2h_GBps_aggregate": world * d2h_bytes / (wall / args.steps) / 1e9,
             "host_path": HOST_PATH_NOTE if world > 1 else None,
+            "per_rank_ms_per_step": per_rank if world > 1 else None,
             "value_results_left_in_hbm": {"value": total_points / wall_dev_results, "unit": "points/s",
                                           "ms_per_step": 1000.0 * wall_dev_results / args.steps,
                                           "what": "same K steps with outputs | PCOP_OUT_DEVICE: result arrays stay in HBM for "
