@@ -605,13 +605,13 @@ def main():
                              default=(None, None))[0]
             # DRAM bytes of the stage's kernels from the committed `ncu --set full` capture (profiles/, 256 frames per
             # launch: dram__bytes_read.sum + dram__bytes_write.sum), per frame
-            # (k_vp_hist 498.6 + k_vp_scan 31.6 + k_vp_scatter 958.6 + k_vp_reduce 614.8 MB; k_plane_gen0 5.0 + k_plane_loop 246.5 MB)
-            ncu_dram_per_frame = {"crop+voxel": (498.6e6 + 31.6e6 + 958.6e6 + 614.8e6) / 256.0,
-                                  "plane": 251.5e6 / 256.0, "cluster+centroid": 20.9e6 / 256.0}
+            # (k_vp_hist 498.6 + k_vp_scan 32.5 + k_vp_scatter 958.7 + k_vp_reduce 616.9 MB; k_plane_gen0 5.0 + k_plane_loop 246.7 MB)
+            ncu_dram_per_frame = {"crop+voxel": (498.6e6 + 32.5e6 + 958.7e6 + 616.9e6) / 256.0,
+                                  "plane": 251.7e6 / 256.0, "cluster+centroid": 20.9e6 / 256.0}
             roof = {"bound": "hbm", "stage": name, "kernel": dom_kernel, "achieved": st["achieved_GBps"], "peak": peak,
                     "unit": "GB/s", "frac": st["frac"],
                     "traffic": ncu_dram_per_frame.get(name, 0.0) * B if name in ncu_dram_per_frame else None,
-                    "traffic_source": "profiles/ncu_full_r02b_summary.csv (ncu --set full, 256 frames per launch), scaled "
+                    "traffic_source": "profiles/ncu_full_r02c_summary.csv (ncu --set full, 256 frames per launch), scaled "
                                       "to this step's frames; per step like `algorithmic_bytes_per_step`",
                     "algorithmic_bytes_per_step": st["algorithmic_bytes_per_frame"] * B,
                     "us_per_step": st["us_per_frame"] * B, "peak_source": peak_kind,
