@@ -1731,6 +1731,7 @@ int pcop_create(const pcop_params* params, int device, size_t max_points, int ma
   }
   h->wave_frames = std::min(wave_frames, lane_batch);
   h->trace = getenv("PCOP_TRACE") != nullptr;
+  for (pcop_handle* l : h->extra_lanes) l->trace = h->trace;
   h->ece_small_max = ece_small_limit();
   if (const char* s = getenv("PCOP_PLANE_RESIDENT")) h->plane_resident = (s[0] == '0') ? 0 : 1;  // (the tests cover both paths)
   for (pcop_handle* l : h->extra_lanes) {
