@@ -422,6 +422,32 @@ def main():
         return [round(float(x.item()), 3) for x in out]
 
     per_rank = {"results_to_host": per_rank_ms(own_wall), "results_left_in_hbm": per_rank_ms(own_wall_dev)}
+
+    # ---- extra (N > 1): SURVEY 8(e) as written -- the result arrays stay in HBM and cluster_offsets / cluster_indices /
+    # obstacles of every rank go to rank 0 over NCCL straight from the library's device result buffer (no host copy of
+    # the arrays on any rank).  The staging of a step's arrays has to finish before the next call reuses the buffer, so
+    # it runs on the main thread here (a few dozen device-to-device copies).
+    gathered_dev = None
+    if gather is not None and gthread is not None:
+        for _ in range(2):
+            gather.submit(step_device())
+            gather.wait_staged()
+        gather.flush()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            gather.submit(step_device())
+            gather.wait_staged()
+        gather.flush()
+        torch.cuda.synchronize()
+        own_wall_gd = time.perf_counter() - t0
+        barrier()
+        wall_gd = time.perf_counter() - t0
+        per_rank["results_left_in_hbm_gathered"] = per_rank_ms(own_wall_gd)
+        gathered_dev = {"value": world * args.steps * B * n / wall_gd, "unit": "points/s", "ms_per_step": 1000.0 * wall_gd / args.steps,
+                        "gather_bytes_per_rank_per_step": int(gather.bytes_per_step),
+                        "what": "SURVEY 8(e) as written: result arrays left in HBM on every rank, cluster_offsets / cluster_indices / "
+                                "obstacles of all ranks gathered to rank 0 over NCCL straight from the device result buffers"}
     op.set_params(params)
 
     # ---- instrumented pass: the same K steps with a CUDA-event pair around every launch and every stage on the
@@ -638,6 +664,7 @@ def main():
                                           "ms_per_step": 1000.0 * wall_dev_results / args.steps,
                                           "what": "same K steps with outputs | PCOP_OUT_DEVICE: result arrays stay in HBM for "
                                                   "a GPU-side consumer, only counts and plane records reach the host"},
+            "value_results_left_in_hbm_gathered": gathered_dev,
             "device_ms_per_step": 1000.0 * dev_s / args.steps,
             "instrumented_ms_per_step": 1000.0 * wall_instr / args.steps if wall_instr else None,
             "e2e": {"value": total_points / wall_e2e, "unit": "points/s", "h2d_bytes_per_step": h2d,

@@ -111,7 +111,8 @@ _cudart = None
 
 
 def _cuda_memcpy_h2d_async(dst_dev: int, src_host: int, nbytes: int, stream: int):
-    """cudaMemcpyAsync(host -> device) on raw addresses (the result arrays are library-owned pinned memory)"""
+    """cudaMemcpyAsync(-> device, cudaMemcpyDefault) on raw addresses: the result arrays are library-owned pinned host
+    memory, or device memory when the frames were processed with outputs | OUT_DEVICE (unified addressing tells)"""
     global _cudart
     import ctypes as C
     if _cudart is None:
@@ -128,7 +129,7 @@ def _cuda_memcpy_h2d_async(dst_dev: int, src_host: int, nbytes: int, stream: int
             _cudart = C.CDLL(hits[0])
         _cudart.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         _cudart.cudaMemcpyAsync.restype = C.c_int
-    st = _cudart.cudaMemcpyAsync(C.c_void_p(dst_dev), C.c_void_p(src_host), C.c_size_t(nbytes), 1, C.c_void_p(stream))
+    st = _cudart.cudaMemcpyAsync(C.c_void_p(dst_dev), C.c_void_p(src_host), C.c_size_t(nbytes), 4, C.c_void_p(stream))
     if st != 0:
         raise RuntimeError(f"cudaMemcpyAsync failed with status {st}")
 
@@ -212,7 +213,7 @@ class ResultGather:
         o = 0
         for key, sz in parts:
             if (col64(key)[sz > 0] == 0).any():
-                raise ValueError("ResultGather needs frames processed with outputs | OUT_CLUSTERS | OUT_OBSTACLES (host results)")
+                raise ValueError("ResultGather needs frames processed with outputs | OUT_CLUSTERS | OUT_OBSTACLES")
             for ptr, nbytes in self._runs(col64(key), sz):
                 if on_gpu:
                     _cuda_memcpy_h2d_async(base + o, ptr, nbytes, stream)
