@@ -204,3 +204,32 @@ def test_result_gather_world2_nccl_matches_single_process_results():
         assert got[1][k] == f.cluster_offsets.tolist()
         assert got[2][k] == f.cluster_indices.tolist()
         np.testing.assert_allclose(np.array(got[3][k], np.float32).reshape(-1, 4), f.obstacles, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_result_gather_from_device_resident_results():
+    """outputs | OUT_DEVICE: the result arrays stay in HBM and ResultGather stages them straight from the library's device
+    result buffer (what bench.py's `value_results_left_in_hbm_gathered` runs at N > 1); one rank here, against the oracle"""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import oracle_lib as O
+    from pointcloud_obstacle_processing_b200 import ObstacleProcessor
+    from pointcloud_obstacle_processing_b200 import _ctypes_abi as abi
+    per = 20  # (more than one wave per lane would need a larger batch; 20 frames = one wave)
+    p = synth.params(2)
+    p.outputs = abi.OUT_DEFAULT | abi.OUT_DEVICE
+    clouds = synth.frames(2, 60, per)
+    rg = sharding.ResultGather(per, torch.device("cuda", 0))
+    with ObstacleProcessor(p, clouds.shape[1], max_batch=per, device=0) as op:
+        for _ in range(3):
+            res = op.process_batch_raw(clouds.ctypes.data, clouds.shape[1], np.full(per, clouds.shape[1], np.int32))
+            rg.submit(res)
+            rg.wait_staged()  # the device result buffer is reused by the next call
+        g = rg.last()
+    prm = synth.params(2)
+    ref = [O.process(prm, synth.frame(2, 60 + k)) for k in range(per)]
+    assert g.n_clusters.tolist() == [f.n_clusters for f in ref]
+    for k, f in enumerate(ref):
+        assert g.cluster_offsets[k].tolist() == f.cluster_offsets.tolist()
+        assert g.cluster_indices[k].tolist() == f.cluster_indices.tolist()
+        np.testing.assert_allclose(np.asarray(g.obstacles[k], np.float32).reshape(-1, 4), f.obstacles, rtol=1e-5, atol=1e-5)
