@@ -16,6 +16,11 @@ call per step).
   configs   BASELINE.json configs[0], [2], [3] (single-frame latency + a small batch) and configs[4] (4096 frames
             per GPU per step in one call)
   cpu_baseline  the CPU oracle (PCL-semantics restatement, oracle/) on a bounded sample of the same frames
+  N > 1     frames sharded over the ranks (weak scaling), times = the slowest rank's; `per_rank_ms_per_step` lists every
+            rank; `value` adds the gather of cluster_offsets / cluster_indices / obstacles to rank 0 over NCCL (SURVEY
+            8e), `value_results_left_in_hbm_gathered` is the same gather with the arrays left in HBM on every rank,
+            `host_path` / `d2h_GBps_aggregate` say what the box's host path allows
+  clocks    SM clock + throttle reasons from NVML, sampled every 4 ms inside the timed region (rank 0)
 
 `--impl reference` times that CPU restatement with all host threads on the same config (the reference itself needs
 ROS + PCL and cannot be built in this image).
