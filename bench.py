@@ -255,9 +255,11 @@ def small_config(cfg, batch, reps, local_rank, peak, torch):
 HOST_PATH_NOTE = ("result delivery to the host is bound by the box, not by the GPUs: with 8 GPUs copying device-to-host at once "
                   "the box sustains 113 GB/s in total (4 GPUs at 8.8 GB/s, 4 at 19.4 GB/s; one GPU alone 56 GB/s), while 8 "
                   "ranks at single-GPU speed need 8 x 22 GB/s.  With the results left in HBM and the ranks barrier-aligned "
-                  "(no gather) six of the eight GPUs run the 1024-frame call in 5.15-5.25 ms, the single-GPU time, and two "
-                  "(GPUs 3 and 6: same on two boxes, pinned or unpinned host threads, 3 or 4 lanes, 1965 MHz, no throttle "
-                  "reason) take 6.5 ms; the line's time is the slowest rank's, `per_rank_ms_per_step` lists them all")
+                  "(no gather) six of the eight ranks run the 1024-frame call in 5.15-5.25 ms, the single-GPU time, and two "
+                  "(ranks 3 and 6: same on two boxes, pinned or unpinned host threads, 3 or 4 lanes, 1965 MHz, no throttle "
+                  "reason; rank 3 of a 4-GPU job as well) take 6.5 ms, although GPU 3 runs the same call in 5.2 ms in a "
+                  "process of its own -- cause not identified; the line's time is the slowest rank's, "
+                  "`per_rank_ms_per_step` lists them all")
 
 
 def main():
